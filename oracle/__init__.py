@@ -1,0 +1,206 @@
+"""ctypes bindings for the CPU oracle (oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+METRIC_COSINE, METRIC_L2, METRIC_L2SQ = 0, 1, 2
+TAU_FIXED, TAU_MEDIAN, TAU_MEAN, TAU_PERCENTILE = 0, 1, 2, 3
+LAMBDA_LEGACY_TAUMODE, LAMBDA_ENERGY_NODE, LAMBDA_CORE_F32SEM = 0, 1, 2
+IDX_NONE = 0xFFFFFFFF
+
+_c = ctypes
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    """Compile liboracle.so (gcc, -ffp-contract=off).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        build()
+    L = ctypes.CDLL(_SO)
+    L.orc_num_threads.restype = _c.c_int
+    L.orc_generate_rows.argtypes = [_c.c_int, _c.c_uint64, _c.c_uint64, _c.c_uint64, _c.c_uint32,
+                                    _c.c_uint32, _c.c_double, _dp]
+    L.orc_row_norms.argtypes = [_dp, _c.c_uint64, _c.c_uint32, _dp]
+    L.orc_knn.argtypes = [_dp, _c.c_uint64, _c.c_uint32, _c.c_int, _c.c_uint32, _c.c_double,
+                          _c.c_void_p, _c.c_uint64, _u32p, _dp, _u32p]
+    L.orc_build_adjacency.argtypes = [_u32p, _dp, _u32p, _c.c_uint64, _c.c_uint32, _c.c_double,
+                                      _c.c_double, _c.c_int, _u32p, _dp, _u32p]
+    L.orc_build_adjacency.restype = _c.c_int
+    L.orc_sfgrass.argtypes = [_u32p, _dp, _u32p, _c.c_uint64, _c.c_uint32, _c.c_double]
+    L.orc_sfgrass.restype = _c.c_int
+    L.orc_laplacian_build.argtypes = [_u32p, _dp, _u32p, _c.c_uint64, _c.c_uint32, _c.c_int,
+                                      _c.c_double]
+    L.orc_laplacian_build.restype = _c.c_void_p
+    L.orc_csr_nnz.argtypes = [_c.c_void_p]
+    L.orc_csr_nnz.restype = _c.c_uint64
+    L.orc_csr_copy.argtypes = [_c.c_void_p, _u64p, _u32p, _dp]
+    L.orc_csr_free.argtypes = [_c.c_void_p]
+    L.orc_spmv.argtypes = [_u64p, _u32p, _dp, _c.c_uint64, _dp, _dp]
+    L.orc_rayleigh.argtypes = [_u64p, _u32p, _dp, _c.c_uint64, _dp]
+    L.orc_rayleigh.restype = _c.c_double
+    L.orc_select_tau.argtypes = [_dp, _c.c_uint64, _c.c_int, _c.c_double]
+    L.orc_select_tau.restype = _c.c_double
+    L.orc_lambda.argtypes = [_u64p, _u32p, _dp, _c.c_uint64, _dp, _c.c_uint64, _c.c_int, _c.c_int,
+                             _c.c_double, _dp, _c.c_void_p, _c.c_void_p]
+    L.orc_normalise_lambdas.argtypes = [_dp, _c.c_uint64, _dp]
+    L.orc_diffuse.argtypes = [_u64p, _u32p, _dp, _c.c_uint64, _dp, _c.c_uint64, _c.c_double,
+                              _c.c_uint32]
+    L.orc_transpose.argtypes = [_dp, _c.c_uint64, _c.c_uint64, _dp]
+    _lib = L
+    return L
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def generate_rows(kind, seed, row0, nrows, kdim, n_centres=0, noise=0.0):
+    out = np.empty((nrows, kdim), dtype=np.float64)
+    lib().orc_generate_rows(kind, seed, row0, nrows, kdim, n_centres, noise, out)
+    return out
+
+
+def row_norms(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty(x.shape[0], dtype=np.float64)
+    lib().orc_row_norms(x, x.shape[0], x.shape[1], out)
+    return out
+
+
+def knn(x, k, metric=METRIC_COSINE, eps=np.inf, query_rows=None):
+    """Brute-force kNN (test_helpers.rs:73-133): returns idx (nq,k) u32, dist (nq,k) f64, cnt (nq,)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    m, kd = x.shape
+    if query_rows is None:
+        nq, qp = m, None
+    else:
+        q = np.ascontiguousarray(query_rows, dtype=np.uint64)
+        nq, qp = q.shape[0], q.ctypes.data_as(_c.c_void_p)
+    idx = np.empty((nq, k), dtype=np.uint32)
+    dist = np.empty((nq, k), dtype=np.float64)
+    cnt = np.empty(nq, dtype=np.uint32)
+    lib().orc_knn(x, m, kd, metric, k, float(eps), qp, nq, idx, dist, cnt)
+    return idx, dist, cnt
+
+
+def build_adjacency(idx, dist, cnt, p, sigma, force_sparsify=-1):
+    """laplacian.rs:219-290: kernel weights + inline sparsification.  Returns (adj_idx, adj_w, adj_cnt, applied)."""
+    m, k = idx.shape
+    a_idx = np.empty((m, k), dtype=np.uint32)
+    a_w = np.empty((m, k), dtype=np.float64)
+    a_cnt = np.empty(m, dtype=np.uint32)
+    applied = lib().orc_build_adjacency(np.ascontiguousarray(idx), np.ascontiguousarray(dist),
+                                        np.ascontiguousarray(cnt), m, k, float(p), float(sigma),
+                                        int(force_sparsify), a_idx, a_w, a_cnt)
+    return a_idx, a_w, a_cnt, bool(applied)
+
+
+def sfgrass(a_idx, a_w, a_cnt, ratio=0.5):
+    """sparsification.rs:32-113 on copies.  Returns (adj_idx, adj_w, adj_cnt, applied)."""
+    a_idx, a_w, a_cnt = a_idx.copy(), a_w.copy(), a_cnt.copy()
+    m, k = a_idx.shape
+    applied = lib().orc_sfgrass(a_idx, a_w, a_cnt, m, k, float(ratio))
+    return a_idx, a_w, a_cnt, bool(applied)
+
+
+def laplacian(a_idx, a_w, a_cnt, normalised=False, weight_threshold=1e-9):
+    """laplacian.rs:297-419: symmetrise + L = D - W as CSR (indptr u64, indices u32, data f64)."""
+    m, k = a_idx.shape
+    h = lib().orc_laplacian_build(np.ascontiguousarray(a_idx), np.ascontiguousarray(a_w),
+                                  np.ascontiguousarray(a_cnt), m, k, int(normalised),
+                                  float(weight_threshold))
+    nnz = lib().orc_csr_nnz(h)
+    indptr = np.empty(m + 1, dtype=np.uint64)
+    indices = np.empty(max(nnz, 1), dtype=np.uint32)
+    data = np.empty(max(nnz, 1), dtype=np.float64)
+    lib().orc_csr_copy(h, indptr, indices, data)
+    lib().orc_csr_free(h)
+    return indptr, indices[:nnz], data[:nnz]
+
+
+def _csr_args(indptr, indices, data):
+    return (np.ascontiguousarray(indptr, dtype=np.uint64),
+            np.ascontiguousarray(indices, dtype=np.uint32) if len(indices) else np.zeros(1, np.uint32),
+            np.ascontiguousarray(data, dtype=np.float64) if len(data) else np.zeros(1, np.float64))
+
+
+def spmv(indptr, indices, data, x):
+    ip, ix, dv = _csr_args(indptr, indices, data)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    lib().orc_spmv(ip, ix, dv, len(ip) - 1, x, y)
+    return y
+
+
+def rayleigh(indptr, indices, data, x):
+    ip, ix, dv = _csr_args(indptr, indices, data)
+    return float(lib().orc_rayleigh(ip, ix, dv, len(ip) - 1, np.ascontiguousarray(x, dtype=np.float64)))
+
+
+def select_tau(energies, mode, value=0.0):
+    e = np.ascontiguousarray(energies, dtype=np.float64)
+    if e.size == 0:
+        e = np.zeros(1, dtype=np.float64)
+        n = 0
+    else:
+        n = e.size
+    return float(lib().orc_select_tau(e, n, mode, float(value)))
+
+
+def lambdas(indptr, indices, data, x, variant=LAMBDA_LEGACY_TAUMODE, tau_mode=TAU_MEDIAN,
+            tau_value=0.0, with_parts=False):
+    ip, ix, dv = _csr_args(indptr, indices, data)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n, f = x.shape
+    assert f == len(ip) - 1
+    lam = np.empty(n, dtype=np.float64)
+    e = np.empty(n, dtype=np.float64)
+    g = np.empty(n, dtype=np.float64)
+    lib().orc_lambda(ip, ix, dv, f, x, n, variant, tau_mode, float(tau_value), lam,
+                     e.ctypes.data_as(_c.c_void_p), g.ctypes.data_as(_c.c_void_p))
+    return (lam, e, g) if with_parts else lam
+
+
+def normalise_lambdas(lam):
+    lam = np.array(lam, dtype=np.float64, copy=True)
+    stats = np.empty(3, dtype=np.float64)
+    lib().orc_normalise_lambdas(lam, lam.size, stats)
+    return lam, stats
+
+
+def diffuse(indptr, indices, data, x, eta, steps):
+    ip, ix, dv = _csr_args(indptr, indices, data)
+    x = np.array(x, dtype=np.float64, copy=True, order="C")
+    lib().orc_diffuse(ip, ix, dv, len(ip) - 1, x, x.shape[0], float(eta), int(steps))
+    return x
+
+
+def transpose(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty((x.shape[1], x.shape[0]), dtype=np.float64)
+    lib().orc_transpose(x, x.shape[0], x.shape[1], out)
+    return out

@@ -1,0 +1,794 @@
+/*
+ * oracle.c -- CPU restatement of the reference's graph-wiring arithmetic.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (matternet-rs_b200/,
+ * include/) may include, link or call this file; only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs load liboracle.so, and there
+ * only as the checker / the CPU baseline.
+ *
+ * Parity pin: the reference (tuned-org-uk/matternet-rs, a Rust workspace) cannot be
+ * compiled here (no cargo/rustc; src_legacy is in no crate and needs the un-vendored
+ * `smartcore`).  This restatement is pinned against every known-answer test the
+ * reference holds for the path (tests/test_oracle_kat.py):
+ *   select_tau table            src_legacy/tests/test_taumode.rs:14-160
+ *   L = D - A on 3 points       src_legacy/tests/test_laplacian.rs:655-786
+ *   cosine ordering 45/90/180   src_legacy/tests/test_laplacian.rs:156-213
+ *   chain-graph lambda / R = 0  surfface-core/src/tests/test_spectral.rs:102-144,187-251
+ *   scale invariance            src_legacy/tests/test_taumode.rs:643-682
+ * Neighbour identity at the smartcore CosinePair boundary is "parity unpinned" in the
+ * reference itself (no test pins which neighbours are chosen); the oracle follows the
+ * repo's own brute-force restatement src_legacy/tests/test_helpers.rs:73-133, which
+ * defines distance, eps filter and the (distance, index) order.
+ *
+ * All sums are left folds in ascending index order from 0.0, no FMA contraction
+ * (build with -ffp-contract=off), matching Rust's iter().map().sum().
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_METRIC_COSINE 0 /* rectified cosine distance                    */
+#define ORC_METRIC_L2 1     /* Euclidean: order and report sqrt(sum (a-b)^2) */
+#define ORC_METRIC_L2SQ 2   /* squared Euclidean                             */
+
+#define ORC_TAU_FIXED 0
+#define ORC_TAU_MEDIAN 1
+#define ORC_TAU_MEAN 2
+#define ORC_TAU_PERCENTILE 3
+
+#define ORC_LAMBDA_LEGACY_TAUMODE 0
+#define ORC_LAMBDA_ENERGY_NODE 1
+#define ORC_LAMBDA_CORE_F32SEM 2
+
+#define ORC_IDX_NONE 0xFFFFFFFFu
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic rows: counter-based Philox4x32-10 + Box-Muller with transcendental-free,
+ * bit-reproducible log/sin/cos (only + - * / sqrt in a fixed order), so the CUDA generator
+ * (matternet-rs_b200/csrc/synth.cuh, written independently from the same spec in DESIGN.md)
+ * produces the same bits.  Not part of the reference; the reference's fixtures
+ * (src_legacy/tests/test_data.rs:68-238) use Rust RNG streams that cannot be replayed here,
+ * so the distributions are re-created, not the bit streams.
+ * ------------------------------------------------------------------------------------------ */
+static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                 uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* ln(u) for a normal positive double, via u = m*2^e, m in [sqrt(1/2), sqrt(2)),
+ * ln m = 2*s*(1 + s2/3 + s2^2/5 + ...), s = (m-1)/(m+1). */
+static inline double det_log(double u) {
+    uint64_t bits; memcpy(&bits, &u, 8);
+    int e = (int)((bits >> 52) & 0x7FF) - 1023;
+    bits = (bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m; memcpy(&m, &bits, 8);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double s2 = s * s;
+    double p = 1.0 / 29.0;
+    p = p * s2 + 1.0 / 27.0; p = p * s2 + 1.0 / 25.0; p = p * s2 + 1.0 / 23.0;
+    p = p * s2 + 1.0 / 21.0; p = p * s2 + 1.0 / 19.0; p = p * s2 + 1.0 / 17.0;
+    p = p * s2 + 1.0 / 15.0; p = p * s2 + 1.0 / 13.0; p = p * s2 + 1.0 / 11.0;
+    p = p * s2 + 1.0 / 9.0;  p = p * s2 + 1.0 / 7.0;  p = p * s2 + 1.0 / 5.0;
+    p = p * s2 + 1.0 / 3.0;  p = p * s2 + 1.0;
+    return 2.0 * s * p + (double)e * 0.6931471805599453;
+}
+
+/* sin and cos of 2*pi*v for v = r * 2^-32 (exact), by octant reduction + Taylor. */
+static inline void det_sincos_2pi(uint32_t r, double* sn, double* cs) {
+    uint32_t q = r >> 29;                              /* octant 0..7        */
+    double f = (double)(r & 0x1FFFFFFFu) * (1.0 / 536870912.0); /* frac in [0,1) exact */
+    double a = f * 0.7853981633974483;                 /* phi in [0, pi/4)    */
+    double a2 = a * a;
+    double ps = -1.0 / 121645100408832000.0;           /* -1/19! */
+    ps = ps * a2 + 1.0 / 355687428096000.0;            /* 1/17! */
+    ps = ps * a2 - 1.0 / 1307674368000.0;              /* 1/15! */
+    ps = ps * a2 + 1.0 / 6227020800.0;                 /* 1/13! */
+    ps = ps * a2 - 1.0 / 39916800.0;                   /* 1/11! */
+    ps = ps * a2 + 1.0 / 362880.0;                     /* 1/9!  */
+    ps = ps * a2 - 1.0 / 5040.0;                       /* 1/7!  */
+    ps = ps * a2 + 1.0 / 120.0;                        /* 1/5!  */
+    ps = ps * a2 - 1.0 / 6.0;                          /* 1/3!  */
+    ps = ps * a2 + 1.0;
+    double s0 = a * ps;
+    double pc = 1.0 / 6402373705728000.0;              /* 1/18! */
+    pc = pc * a2 - 1.0 / 20922789888000.0;             /* 1/16! */
+    pc = pc * a2 + 1.0 / 87178291200.0;                /* 1/14! */
+    pc = pc * a2 - 1.0 / 479001600.0;                  /* 1/12! */
+    pc = pc * a2 + 1.0 / 3628800.0;                    /* 1/10! */
+    pc = pc * a2 - 1.0 / 40320.0;                      /* 1/8!  */
+    pc = pc * a2 + 1.0 / 720.0;                        /* 1/6!  */
+    pc = pc * a2 - 1.0 / 24.0;                         /* 1/4!  */
+    pc = pc * a2 + 0.5;
+    double c0 = 1.0 - a2 * pc;
+    const double H = 0.7071067811865476;
+    static const double SQ[8] = {0.0, 1.0, 1.0, 1.0, 0.0, -1.0, -1.0, -1.0};  /* sin(q pi/4)/{1,H} */
+    static const double CQ[8] = {1.0, 1.0, 0.0, -1.0, -1.0, -1.0, 0.0, 1.0};  /* cos(q pi/4)/{1,H} */
+    double sq = SQ[q], cq = CQ[q];
+    if (q & 1u) { sq = sq * H; cq = cq * H; }
+    *sn = sq * c0 + cq * s0;
+    *cs = cq * c0 - sq * s0;
+}
+
+/* Four standard normals for (stream, row, quad): counter = (row_lo, row_hi, quad, stream). */
+static inline void synth_normal4(uint64_t seed, uint32_t stream, uint64_t row, uint32_t quad,
+                                 double z[4]) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), quad, stream, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    for (int h = 0; h < 2; ++h) {
+        double u1 = ((double)r[2 * h] + 0.5) * (1.0 / 4294967296.0);
+        double rad = sqrt(-2.0 * det_log(u1));
+        double sn, cs;
+        det_sincos_2pi(r[2 * h + 1], &sn, &cs);
+        z[2 * h] = rad * cs;
+        z[2 * h + 1] = rad * sn;
+    }
+}
+
+#define SYNTH_STREAM_NOISE 0u
+#define SYNTH_STREAM_CENTRE 1u
+#define SYNTH_STREAM_ASSIGN 2u
+#define SYNTH_STREAM_SHIFT 3u
+
+/* kind 0: x ~ N(0,1) iid.
+ * kind 1: clustered: x_i = c[h(i)] + noise * N(0,I), c_j ~ N(0,I), h(i) = philox(i) mod n_centres
+ *         (the law of make_gaussian_hd / make_energy_test_dataset, test_data.rs:118-238).
+ * kind 2: anisotropic: x_i = N(0,I) + noise * s_i * 1, s_i ~ N(0,1) one shift per row.     */
+void orc_generate_rows(int kind, uint64_t seed, uint64_t row0, uint64_t nrows, uint32_t kdim,
+                       uint32_t n_centres, double noise, double* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t ii = 0; ii < (int64_t)nrows; ++ii) {
+        uint64_t i = row0 + (uint64_t)ii;
+        double* o = out + (size_t)ii * kdim;
+        uint64_t centre = 0; double shift = 0.0;
+        if (kind == 1) {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, SYNTH_STREAM_ASSIGN, (uint32_t)seed,
+                          (uint32_t)(seed >> 32), r);
+            centre = r[0] % (n_centres ? n_centres : 1u);
+        } else if (kind == 2) {
+            double z[4]; synth_normal4(seed, SYNTH_STREAM_SHIFT, i, 0u, z); shift = noise * z[0];
+        }
+        for (uint32_t q = 0; q * 4 < kdim; ++q) {
+            double z[4], c[4];
+            synth_normal4(seed, SYNTH_STREAM_NOISE, i, q, z);
+            if (kind == 1) synth_normal4(seed, SYNTH_STREAM_CENTRE, centre, q, c);
+            for (uint32_t t = 0; t < 4 && q * 4 + t < kdim; ++t) {
+                double v;
+                if (kind == 1) v = c[t] + noise * z[t];
+                else if (kind == 2) v = z[t] + shift;
+                else v = z[t];
+                o[q * 4 + t] = v;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * kNN.  Cosine: src_legacy/tests/test_helpers.rs:77-133 (norms :77-80, denom guard :94-104,
+ * rectification :106, eps filter :107, (distance,index) order :116-120, truncate :122-125) and
+ * src_legacy/laplacian.rs:245-257 (i != j, dist <= eps).  L2: src_legacy/energymaps.rs:875-892
+ * (squared L2, stable sort => ties by index) and surfface-core/src/mst.rs:312-403 (Euclidean
+ * orders by the sqrt value).
+ * ------------------------------------------------------------------------------------------ */
+void orc_row_norms(const double* x, uint64_t m, uint32_t kd, double* norms) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)m; ++i) {
+        const double* r = x + (size_t)i * kd;
+        double s = 0.0;
+        for (uint32_t d = 0; d < kd; ++d) s += r[d] * r[d];
+        norms[i] = sqrt(s);
+    }
+}
+
+static inline double pair_key(const double* a, const double* b, uint32_t kd, int metric, double na,
+                              double nb) {
+    if (metric == ORC_METRIC_COSINE) {
+        double denom = na * nb, cosv = 0.0;
+        if (denom > 1e-12) {
+            double dot = 0.0;
+            for (uint32_t d = 0; d < kd; ++d) dot += a[d] * b[d];
+            cosv = dot / denom;
+            if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0;  /* f64::clamp */
+        }
+        double rect = (cosv > 0.0) ? cosv : 0.0;  /* f64::max(0.0): NaN -> 0.0 */
+        return 1.0 - rect;
+    }
+    double s = 0.0;
+    for (uint32_t d = 0; d < kd; ++d) { double t = a[d] - b[d]; s += t * t; }
+    return metric == ORC_METRIC_L2 ? sqrt(s) : s;
+}
+
+/* 8 corpus rows at a time: eight independent left-fold chains (each pair's own order is
+ * untouched), so the CPU baseline is not artificially latency-bound. */
+static inline void pair_keys8(const double* a, const double* const b[8], uint32_t kd, int metric,
+                              double na, const double nb[8], double out[8]) {
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (metric == ORC_METRIC_COSINE) {
+        for (uint32_t d = 0; d < kd; ++d) {
+            double av = a[d];
+            for (int t = 0; t < 8; ++t) s[t] += av * b[t][d];
+        }
+        for (int t = 0; t < 8; ++t) {
+            double denom = na * nb[t], cosv = 0.0;
+            if (denom > 1e-12) {
+                cosv = s[t] / denom;
+                if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0;
+            }
+            double rect = (cosv > 0.0) ? cosv : 0.0;
+            out[t] = 1.0 - rect;
+        }
+    } else {
+        for (uint32_t d = 0; d < kd; ++d) {
+            double av = a[d];
+            for (int t = 0; t < 8; ++t) { double df = av - b[t][d]; s[t] += df * df; }
+        }
+        for (int t = 0; t < 8; ++t) out[t] = metric == ORC_METRIC_L2 ? sqrt(s[t]) : s[t];
+    }
+}
+
+static inline int key_less(double da, uint32_t ia, double db, uint32_t ib) {
+    return (da < db) || (da == db && ia < ib);
+}
+
+/* Insert (d, j) into the sorted top-k list (dist asc, idx asc). */
+static inline void topk_insert(double* bd, uint32_t* bi, uint32_t* cnt, uint32_t k, double d,
+                               uint32_t j) {
+    uint32_t c = *cnt;
+    if (c == k) {
+        if (!key_less(d, j, bd[k - 1], bi[k - 1])) return;
+        c = k - 1;
+    }
+    uint32_t p = c;
+    while (p > 0 && key_less(d, j, bd[p - 1], bi[p - 1])) { bd[p] = bd[p - 1]; bi[p] = bi[p - 1]; --p; }
+    bd[p] = d; bi[p] = j;
+    *cnt = c + 1;
+}
+
+/* Brute-force kNN of `nq` query rows (query_rows == NULL: rows 0..nq-1) against all m rows.
+ * out_idx/out_dist: nq x k, padded with ORC_IDX_NONE / +inf; out_cnt: nq. */
+void orc_knn(const double* x, uint64_t m, uint32_t kd, int metric, uint32_t k, double eps,
+             const uint64_t* query_rows, uint64_t nq, uint32_t* out_idx, double* out_dist,
+             uint32_t* out_cnt) {
+    double* norms = (double*)malloc(sizeof(double) * (size_t)m);
+    if (metric == ORC_METRIC_COSINE) orc_row_norms(x, m, kd, norms);
+    else memset(norms, 0, sizeof(double) * (size_t)m);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t qq = 0; qq < (int64_t)nq; ++qq) {
+        uint64_t i = query_rows ? query_rows[qq] : (uint64_t)qq;
+        const double* a = x + (size_t)i * kd;
+        double* bd = out_dist + (size_t)qq * k;
+        uint32_t* bi = out_idx + (size_t)qq * k;
+        uint32_t cnt = 0;
+        uint64_t j = 0;
+        for (; j + 8 <= m; j += 8) {
+            const double* b[8]; double nb[8], key[8];
+            for (int t = 0; t < 8; ++t) { b[t] = x + (size_t)(j + t) * kd; nb[t] = norms[j + t]; }
+            pair_keys8(a, b, kd, metric, norms[i], nb, key);
+            for (int t = 0; t < 8; ++t) {
+                if (j + t == i) continue;
+                if (key[t] <= eps) topk_insert(bd, bi, &cnt, k, key[t], (uint32_t)(j + t));
+            }
+        }
+        for (; j < m; ++j) {
+            if (j == i) continue;
+            double key = pair_key(a, x + (size_t)j * kd, kd, metric, norms[i], norms[j]);
+            if (key <= eps) topk_insert(bd, bi, &cnt, k, key, (uint32_t)j);
+        }
+        for (uint32_t t = cnt; t < k; ++t) { bd[t] = INFINITY; bi[t] = ORC_IDX_NONE; }
+        out_cnt[qq] = cnt;
+    }
+    free(norms);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel weights + inline sparsification: src_legacy/laplacian.rs:219-290.
+ *   degrees = #kNN entries with i != j && dist <= eps (:219-229); sparsify iff mean > 10 (:231-232)
+ *   w = 1/(1+(d/sigma)^p), kept iff w > 1e-12 (:255-257)
+ *   score = w*sqrt((deg_i*deg_j) as f64) (:260-261); rows with len > 2 keep max(len/2,1) best (:276-282)
+ * The reference's sort_unstable_by has no tie-break; the contract fixes (score desc, j asc).
+ * adj_idx/adj_w: m x k padded (ORC_IDX_NONE / 0), adj_cnt: m.  force_sparsify: -1 = reference
+ * rule, 0 = never, 1 = always.  Returns 1 when sparsification was applied.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t j; double w; double score; } orc_edge;
+
+static int cmp_score_desc(const void* pa, const void* pb) {
+    const orc_edge* a = (const orc_edge*)pa; const orc_edge* b = (const orc_edge*)pb;
+    if (a->score > b->score) return -1;
+    if (a->score < b->score) return 1;
+    return (a->j > b->j) - (a->j < b->j);
+}
+
+int orc_build_adjacency(const uint32_t* knn_idx, const double* knn_dist, const uint32_t* knn_cnt,
+                        uint64_t m, uint32_t k, double p, double sigma, int force_sparsify,
+                        uint32_t* adj_idx, double* adj_w, uint32_t* adj_cnt) {
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < m; ++i) total += knn_cnt[i];
+    double avg_degree = (double)total / (double)m;
+    int sparsify = force_sparsify < 0 ? (avg_degree > 10.0) : force_sparsify;
+#pragma omp parallel
+    {
+        orc_edge* row = (orc_edge*)malloc(sizeof(orc_edge) * (k ? k : 1));
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < (int64_t)m; ++i) {
+            uint32_t len = 0;
+            for (uint32_t t = 0; t < knn_cnt[i]; ++t) {
+                uint32_t j = knn_idx[(size_t)i * k + t];
+                double d = knn_dist[(size_t)i * k + t];
+                double w = 1.0 / (1.0 + pow(d / sigma, p));
+                if (w > 1e-12) {
+                    double score = w;
+                    if (sparsify)
+                        score = w * sqrt((double)((uint64_t)knn_cnt[i] * (uint64_t)knn_cnt[j]));
+                    row[len].j = j; row[len].w = w; row[len].score = score; ++len;
+                }
+            }
+            if (sparsify && len > 2) {
+                qsort(row, len, sizeof(orc_edge), cmp_score_desc);
+                uint32_t keep = len / 2; if (keep < 1) keep = 1;
+                len = keep;
+            }
+            for (uint32_t t = 0; t < k; ++t) {
+                adj_idx[(size_t)i * k + t] = t < len ? row[t].j : ORC_IDX_NONE;
+                adj_w[(size_t)i * k + t] = t < len ? row[t].w : 0.0;
+            }
+            adj_cnt[i] = len;
+        }
+        free(row);
+    }
+    return sparsify;
+}
+
+/* SF-GRASS standalone sparsifier: src_legacy/sparsification.rs:32-113.
+ *   skip iff mean degree < 10 (:42-52); degrees = row lengths (:60)
+ *   score = w*sqrt((deg_i*deg_j) as f64) (:79-80); keep = clamp(ceil(len*ratio),1,len) (:92-94)
+ * ratio is clamped to [0.1, 1.0] (:26-29).  In place.  Returns 1 when applied. */
+int orc_sfgrass(uint32_t* adj_idx, double* adj_w, uint32_t* adj_cnt, uint64_t m, uint32_t k,
+                double ratio) {
+    if (ratio < 0.1) ratio = 0.1;
+    if (ratio > 1.0) ratio = 1.0;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < m; ++i) total += adj_cnt[i];
+    double avg_degree = (double)total / (double)m;
+    if (avg_degree < 10.0) return 0;
+    uint32_t* deg = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)m);
+    memcpy(deg, adj_cnt, sizeof(uint32_t) * (size_t)m);
+#pragma omp parallel
+    {
+        orc_edge* row = (orc_edge*)malloc(sizeof(orc_edge) * (k ? k : 1));
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < (int64_t)m; ++i) {
+            uint32_t len = deg[i];
+            if (len == 0) continue;
+            for (uint32_t t = 0; t < len; ++t) {
+                uint32_t j = adj_idx[(size_t)i * k + t];
+                double w = adj_w[(size_t)i * k + t];
+                row[t].j = j; row[t].w = w;
+                row[t].score = w * sqrt((double)((uint64_t)deg[i] * (uint64_t)deg[j]));
+            }
+            qsort(row, len, sizeof(orc_edge), cmp_score_desc);
+            uint32_t keep = (uint32_t)ceil((double)len * ratio);
+            if (keep < 1) keep = 1;
+            if (keep > len) keep = len;
+            for (uint32_t t = 0; t < k; ++t) {
+                adj_idx[(size_t)i * k + t] = t < keep ? row[t].j : ORC_IDX_NONE;
+                adj_w[(size_t)i * k + t] = t < keep ? row[t].w : 0.0;
+            }
+            adj_cnt[i] = keep;
+        }
+        free(row);
+    }
+    free(deg);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Symmetrise + Laplacian CSR.
+ *   symmetrise: src_legacy/laplacian.rs:297-348 -- edge set {(i,j,w),(j,i,w)}, src != dst,
+ *     rows sorted by column (:342).  Duplicate (i,j) carry identical w for a symmetric metric;
+ *     the contract takes max (surfface-core/src/laplacian.rs:321-331).
+ *   unnormalised L: src_legacy/laplacian.rs:364-385 -- L_ii = sum_j w_ij in ascending j
+ *     (always stored, :372), L_ij = -w_ij; CSR rows sorted by column (:399, to_csr :161).
+ *   normalised L_sym: surfface-core/src/laplacian.rs:333-372,209-219 -- L_ii = 1 if d_i > thr,
+ *     L_ij = -w/sqrt(d_i d_j) if d_i, d_j > thr; entries |v| <= 1e-9 dropped.
+ * Two-call pattern: orc_laplacian_build returns an opaque handle, nnz read, then copy.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t col; double w; } orc_nb;
+typedef struct {
+    uint64_t m; uint64_t nnz; uint64_t* indptr; uint32_t* indices; double* data;
+} orc_csr;
+
+static int cmp_nb(const void* pa, const void* pb) {
+    const orc_nb* a = (const orc_nb*)pa; const orc_nb* b = (const orc_nb*)pb;
+    if (a->col != b->col) return (a->col > b->col) - (a->col < b->col);
+    return (a->w < b->w) - (a->w > b->w); /* larger w first => max survives dedupe */
+}
+
+orc_csr* orc_laplacian_build(const uint32_t* adj_idx, const double* adj_w, const uint32_t* adj_cnt,
+                             uint64_t m, uint32_t k, int normalised, double weight_threshold) {
+    /* reverse lists by counting sort */
+    uint64_t* cnt = (uint64_t*)calloc((size_t)m + 1, sizeof(uint64_t));
+    for (uint64_t i = 0; i < m; ++i)
+        for (uint32_t t = 0; t < adj_cnt[i]; ++t) {
+            uint32_t j = adj_idx[(size_t)i * k + t];
+            if (j == i) continue;
+            cnt[i + 1]++; cnt[(uint64_t)j + 1]++;
+        }
+    for (uint64_t i = 0; i < m; ++i) cnt[i + 1] += cnt[i];
+    uint64_t tot = cnt[m];
+    orc_nb* nb = (orc_nb*)malloc(sizeof(orc_nb) * (size_t)(tot ? tot : 1));
+    uint64_t* fill = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)m);
+    memcpy(fill, cnt, sizeof(uint64_t) * (size_t)m);
+    for (uint64_t i = 0; i < m; ++i)
+        for (uint32_t t = 0; t < adj_cnt[i]; ++t) {
+            uint32_t j = adj_idx[(size_t)i * k + t];
+            if (j == i) continue;
+            double w = adj_w[(size_t)i * k + t];
+            nb[fill[i]].col = j; nb[fill[i]].w = w; fill[i]++;
+            nb[fill[j]].col = (uint32_t)i; nb[fill[j]].w = w; fill[j]++;
+        }
+    /* sort + dedupe each row in place; ulen[i] = unique neighbours */
+    uint32_t* ulen = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)m);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)m; ++i) {
+        orc_nb* r = nb + cnt[i];
+        uint64_t len = cnt[i + 1] - cnt[i];
+        qsort(r, (size_t)len, sizeof(orc_nb), cmp_nb);
+        uint32_t u = 0;
+        for (uint64_t t = 0; t < len; ++t)
+            if (u == 0 || r[u - 1].col != r[t].col) r[u++] = r[t];
+        ulen[i] = u;
+    }
+    double* deg = (double*)malloc(sizeof(double) * (size_t)m);
+    for (uint64_t i = 0; i < m; ++i) {
+        const orc_nb* r = nb + cnt[i];
+        double s = 0.0;
+        for (uint32_t t = 0; t < ulen[i]; ++t) s += r[t].w;
+        deg[i] = s;
+    }
+    orc_csr* L = (orc_csr*)calloc(1, sizeof(orc_csr));
+    L->m = m;
+    L->indptr = (uint64_t*)calloc((size_t)m + 1, sizeof(uint64_t));
+    /* pass 1: row lengths */
+    for (uint64_t i = 0; i < m; ++i) {
+        const orc_nb* r = nb + cnt[i];
+        uint64_t len = 0;
+        if (!normalised) {
+            len = (uint64_t)ulen[i] + 1;
+        } else {
+            if (deg[i] > weight_threshold) len++;
+            for (uint32_t t = 0; t < ulen[i]; ++t) {
+                double dj = deg[r[t].col];
+                if (deg[i] <= weight_threshold || dj <= weight_threshold) continue;
+                double v = -r[t].w / sqrt(deg[i] * dj);
+                if (fabs(v) > 1e-9) len++;
+            }
+        }
+        L->indptr[i + 1] = L->indptr[i] + len;
+    }
+    L->nnz = L->indptr[m];
+    L->indices = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(L->nnz ? L->nnz : 1));
+    L->data = (double*)malloc(sizeof(double) * (size_t)(L->nnz ? L->nnz : 1));
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)m; ++i) {
+        const orc_nb* r = nb + cnt[i];
+        uint64_t o = L->indptr[i];
+        int diag_done = 0;
+        double dv = normalised ? 1.0 : deg[i];
+        int diag_keep = normalised ? (deg[i] > weight_threshold) : 1;
+        for (uint32_t t = 0; t < ulen[i]; ++t) {
+            if (!diag_done && r[t].col > (uint32_t)i) {
+                if (diag_keep) { L->indices[o] = (uint32_t)i; L->data[o] = dv; ++o; }
+                diag_done = 1;
+            }
+            if (!normalised) {
+                L->indices[o] = r[t].col; L->data[o] = -r[t].w; ++o;
+            } else {
+                double dj = deg[r[t].col];
+                if (deg[i] <= weight_threshold || dj <= weight_threshold) continue;
+                double v = -r[t].w / sqrt(deg[i] * dj);
+                if (fabs(v) > 1e-9) { L->indices[o] = r[t].col; L->data[o] = v; ++o; }
+            }
+        }
+        if (!diag_done && diag_keep) { L->indices[o] = (uint32_t)i; L->data[o] = dv; ++o; }
+    }
+    free(cnt); free(nb); free(fill); free(ulen); free(deg);
+    return L;
+}
+uint64_t orc_csr_nnz(const orc_csr* L) { return L->nnz; }
+void orc_csr_copy(const orc_csr* L, uint64_t* indptr, uint32_t* indices, double* data) {
+    memcpy(indptr, L->indptr, sizeof(uint64_t) * (size_t)(L->m + 1));
+    memcpy(indices, L->indices, sizeof(uint32_t) * (size_t)L->nnz);
+    memcpy(data, L->data, sizeof(double) * (size_t)L->nnz);
+}
+void orc_csr_free(orc_csr* L) {
+    if (!L) return;
+    free(L->indptr); free(L->indices); free(L->data); free(L);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SpMV / Rayleigh: src_legacy/graph.rs:464-501 (row-sequential sum in CSR order), :422-461.
+ * ------------------------------------------------------------------------------------------ */
+void orc_spmv(const uint64_t* indptr, const uint32_t* indices, const double* data, uint64_t m,
+              const double* x, double* y) {
+    for (uint64_t r = 0; r < m; ++r) {
+        double s = 0.0;
+        for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) s += data[e] * x[indices[e]];
+        y[r] = s;
+    }
+}
+
+double orc_rayleigh(const uint64_t* indptr, const uint32_t* indices, const double* data, uint64_t m,
+                    const double* x) {
+    double* lx = (double*)malloc(sizeof(double) * (size_t)m);
+    orc_spmv(indptr, indices, data, m, x, lx);
+    double num = 0.0, den = 0.0;
+    for (uint64_t r = 0; r < m; ++r) num += x[r] * lx[r];
+    for (uint64_t r = 0; r < m; ++r) den += x[r] * x[r];
+    free(lx);
+    return den > 1e-12 ? num / den : 0.0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * tau selection: src_legacy/taumode.rs:29-70 (TAU_FLOOR = 1e-10, :25).
+ * ------------------------------------------------------------------------------------------ */
+static int cmp_f64(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+double orc_select_tau(const double* e, uint64_t n, int mode, double value) {
+    const double FLOOR = 1e-10;
+    if (mode == ORC_TAU_FIXED) return (isfinite(value) && value > 0.0) ? value : FLOOR;
+    if (mode == ORC_TAU_MEAN) {
+        double s = 0.0; uint64_t c = 0;
+        for (uint64_t i = 0; i < n; ++i) if (isfinite(e[i])) { s += e[i]; ++c; }
+        if (c == 0) return FLOOR;
+        double mean = s / (double)c;
+        return mean > FLOOR ? mean : FLOOR;
+    }
+    double* v = (double*)malloc(sizeof(double) * (size_t)(n ? n : 1));
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < n; ++i) if (isfinite(e[i])) v[c++] = e[i];
+    if (c == 0) { free(v); return FLOOR; }
+    qsort(v, (size_t)c, sizeof(double), cmp_f64);
+    double r;
+    if (mode == ORC_TAU_PERCENTILE) {
+        double pp = value;
+        if (pp < 0.0) pp = 0.0; else if (pp > 1.0) pp = 1.0;
+        /* Rust f64::round == C round(): half away from zero */
+        uint64_t idx = (uint64_t)round((double)(c - 1) * pp);
+        r = v[idx];
+    } else {
+        r = (c % 2 == 1) ? v[c / 2] : 0.5 * (v[c / 2 - 1] + v[c / 2]);
+    }
+    free(v);
+    return r > FLOOR ? r : FLOOR;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Per-item lambda.
+ *  LEGACY_TAUMODE  src_legacy/taumode.rs:261-408: zero-vector guard (:268-274, |v| <= 1e-10),
+ *     E = max(num/den, 0) with num = sum_r sum_c (x_r*L_rc)*x_c (:340-352), den > 1e-12 (:356),
+ *     G over both triangles (:366-408), lambda = tau*(E/(E+tau)) + (1-tau)*clamp(G,0,1) (:306-310).
+ *  ENERGY_NODE     src_legacy/energymaps.rs:961-1036: lx = L x (graph.rs:486-493),
+ *     lambda = max(sum x_r*lx_r / sum x_r^2, 0); G over the upper triangle only (not blended);
+ *     out_g receives G when non-NULL.
+ *  CORE_F32SEM     surfface-core/src/spectral/mod.rs:69-181 evaluated in f32:
+ *     R = clamp(num/(den+1e-9), +-1e6); e_i = sum_f max(deg_f x_f^2 - 2 x_f (Wx)_f + (W x^2)_f, 0);
+ *     G_i = clamp(e_i/(sum_i e_i + 1e-12), 0, 1); lambda = R + G.
+ * ------------------------------------------------------------------------------------------ */
+static double lambda_legacy_row(const uint64_t* indptr, const uint32_t* indices, const double* data,
+                                uint64_t f, const double* x, int tau_mode, double tau_value,
+                                double* out_e, double* out_g) {
+    int all_zero = 1;
+    for (uint64_t r = 0; r < f; ++r) if (!(fabs(x[r]) <= 1e-10)) { all_zero = 0; break; }
+    if (all_zero) { if (out_e) *out_e = 0.0; if (out_g) *out_g = 0.0; return 0.0; }
+    double tau = orc_select_tau(x, f, tau_mode, tau_value);
+    double num = 0.0, den = 0.0;
+    for (uint64_t r = 0; r < f; ++r) {
+        double xi = x[r], rs = 0.0;
+        for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) rs += xi * data[e] * x[indices[e]];
+        num += rs;
+    }
+    for (uint64_t r = 0; r < f; ++r) den += x[r] * x[r];
+    double e_raw = 0.0;
+    if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
+    double ssum = 0.0;
+    for (uint64_t r = 0; r < f; ++r)
+        for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+            uint32_t c = indices[e];
+            if (c == r) continue;
+            double w = -data[e]; if (!(w > 0.0)) continue;
+            double d = x[r] - x[c];
+            ssum += w * d * d;
+        }
+    double g = 0.0;
+    if (!(ssum <= 1e-12)) {
+        double acc = 0.0;
+        for (uint64_t r = 0; r < f; ++r)
+            for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+                uint32_t c = indices[e];
+                if (c == r) continue;
+                double w = -data[e]; if (!(w > 0.0)) continue;
+                double d = x[r] - x[c];
+                double share = (w * d * d) / ssum;
+                acc += share * share;
+            }
+        g = acc < 0.0 ? 0.0 : (acc > 1.0 ? 1.0 : acc);
+    }
+    if (out_e) *out_e = e_raw;
+    if (out_g) *out_g = g;
+    double e_bounded = e_raw / (e_raw + tau);
+    return tau * e_bounded + (1.0 - tau) * g;
+}
+
+static double lambda_energy_row(const uint64_t* indptr, const uint32_t* indices, const double* data,
+                                uint64_t f, const double* x, double* lx, double* out_g) {
+    orc_spmv(indptr, indices, data, f, x, lx);
+    double num = 0.0, den = 0.0;
+    for (uint64_t r = 0; r < f; ++r) num += x[r] * lx[r];
+    for (uint64_t r = 0; r < f; ++r) den += x[r] * x[r];
+    double lam = 0.0;
+    if (den > 1e-12) { lam = num / den; if (!(lam > 0.0)) lam = 0.0; }
+    if (out_g) {
+        /* per-row local sums (energymaps.rs:990-1004), then a left fold over rows */
+        double ssum = 0.0;
+        for (uint64_t r = 0; r < f; ++r) {
+            double local = 0.0;
+            for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+                uint32_t c = indices[e];
+                if (c <= r) continue;
+                double w = -data[e]; if (!(w > 0.0)) continue;
+                double d = x[r] - x[c];
+                local += w * d * d;
+            }
+            ssum += local;
+        }
+        double g = 0.0;
+        if (ssum > 1e-12) {
+            double acc = 0.0;
+            for (uint64_t r = 0; r < f; ++r) {
+                double local = 0.0;
+                for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+                    uint32_t c = indices[e];
+                    if (c <= r) continue;
+                    double w = -data[e]; if (!(w > 0.0)) continue;
+                    double d = x[r] - x[c];
+                    double share = (w * d * d) / ssum;
+                    local += share * share;
+                }
+                acc += local;
+            }
+            g = acc < 0.0 ? 0.0 : (acc > 1.0 ? 1.0 : acc);
+        }
+        *out_g = g;
+    }
+    return lam;
+}
+
+/* x: n x f row-major; out_lambda: n; out_e / out_g optional (n each, may be NULL). */
+void orc_lambda(const uint64_t* indptr, const uint32_t* indices, const double* data, uint64_t f,
+                const double* x, uint64_t n, int variant, int tau_mode, double tau_value,
+                double* out_lambda, double* out_e, double* out_g) {
+    if (variant == ORC_LAMBDA_CORE_F32SEM) {
+        /* dense f32 semantics; row sums in ascending feature order */
+        float* W = (float*)calloc((size_t)(f * f), sizeof(float));
+        float* Ld = (float*)calloc((size_t)(f * f), sizeof(float));
+        for (uint64_t r = 0; r < f; ++r)
+            for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+                float v = (float)data[e];
+                Ld[r * f + indices[e]] = v;
+                float w = -v; W[r * f + indices[e]] = w > 0.0f ? w : 0.0f;
+            }
+        float* deg = (float*)calloc((size_t)f, sizeof(float));
+        for (uint64_t r = 0; r < f; ++r) { float s = 0.0f; for (uint64_t c = 0; c < f; ++c) s += W[r * f + c]; deg[r] = s; }
+        float* rq = (float*)malloc(sizeof(float) * (size_t)n);
+        float* en = (float*)malloc(sizeof(float) * (size_t)n);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            const double* xd = x + (size_t)i * f;
+            float num = 0.0f, den = 0.0f, es = 0.0f;
+            for (uint64_t r = 0; r < f; ++r) {
+                float xr = (float)xd[r], lx = 0.0f, wx = 0.0f, wx2 = 0.0f;
+                for (uint64_t c = 0; c < f; ++c) {
+                    float xc = (float)xd[c];
+                    lx += Ld[r * f + c] * xc; wx += W[r * f + c] * xc; wx2 += W[r * f + c] * (xc * xc);
+                }
+                num += xr * lx; den += xr * xr;
+                float ee = deg[r] * (xr * xr) - xr * wx * 2.0f + wx2;
+                es += ee > 0.0f ? ee : 0.0f;
+            }
+            float r = num / (den + 1e-9f);
+            if (r < -1e6f) r = -1e6f; else if (r > 1e6f) r = 1e6f;
+            rq[i] = r; en[i] = es;
+        }
+        float total = 0.0f;
+        for (uint64_t i = 0; i < n; ++i) total += en[i];
+        for (uint64_t i = 0; i < n; ++i) {
+            float g = en[i] / (total + 1e-12f);
+            if (g < 0.0f) g = 0.0f; else if (g > 1.0f) g = 1.0f;
+            out_lambda[i] = (double)(rq[i] + g);
+            if (out_e) out_e[i] = (double)rq[i];
+            if (out_g) out_g[i] = (double)g;
+        }
+        free(W); free(Ld); free(deg); free(rq); free(en);
+        return;
+    }
+#pragma omp parallel
+    {
+        double* lx = (double*)malloc(sizeof(double) * (size_t)(f ? f : 1));
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            const double* xi = x + (size_t)i * f;
+            double e = 0.0, g = 0.0, lam;
+            if (variant == ORC_LAMBDA_LEGACY_TAUMODE) {
+                lam = lambda_legacy_row(indptr, indices, data, f, xi, tau_mode, tau_value, &e, &g);
+            } else {
+                lam = lambda_energy_row(indptr, indices, data, f, xi, lx, out_g ? &g : NULL);
+                e = lam;
+            }
+            out_lambda[i] = lam;
+            if (out_e) out_e[i] = e;
+            if (out_g) out_g[i] = g;
+        }
+        free(lx);
+    }
+}
+
+/* min-max normalisation: src_legacy/core.rs:1341-1355 (max fold starts at 0.0). stats = {min,max,range}. */
+void orc_normalise_lambdas(double* lam, uint64_t n, double* stats) {
+    double mn = INFINITY, mx = 0.0;
+    for (uint64_t i = 0; i < n; ++i) { if (lam[i] < mn) mn = lam[i]; if (lam[i] > mx) mx = lam[i]; }
+    double rng = mx - mn; if (!(rng > 1e-9)) rng = 1e-9;
+    for (uint64_t i = 0; i < n; ++i) lam[i] = (lam[i] - mn) / rng;
+    if (stats) { stats[0] = mn; stats[1] = mx; stats[2] = rng; }
+}
+
+/* diffusion: src_legacy/energymaps.rs:520-546: x_r' = x_r - eta*(L x)_r, `steps` times, in place. */
+void orc_diffuse(const uint64_t* indptr, const uint32_t* indices, const double* data, uint64_t f,
+                 double* x, uint64_t n, double eta, uint32_t steps) {
+    for (uint32_t s = 0; s < steps; ++s) {
+#pragma omp parallel
+        {
+            double* lx = (double*)malloc(sizeof(double) * (size_t)(f ? f : 1));
+#pragma omp for schedule(static)
+            for (int64_t i = 0; i < (int64_t)n; ++i) {
+                double* xi = x + (size_t)i * f;
+                orc_spmv(indptr, indices, data, f, xi, lx);
+                for (uint64_t r = 0; r < f; ++r) xi[r] = xi[r] - eta * lx[r];
+            }
+            free(lx);
+        }
+    }
+}
+
+/* row-major transpose (the reference transposes centroids before the graph build, graph.rs:214-216) */
+void orc_transpose(const double* x, uint64_t rows, uint64_t cols, double* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (int64_t)cols; ++c)
+        for (uint64_t r = 0; r < rows; ++r) out[(size_t)c * rows + r] = x[(size_t)r * cols + c];
+}

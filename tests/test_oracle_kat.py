@@ -1,0 +1,301 @@
+"""Pins the CPU oracle against every known-answer test the reference holds for the hot path
+(SURVEY.md section 8c).  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+FLOOR = 1e-10  # src_legacy/taumode.rs:25
+
+
+# ---- select_tau table: src_legacy/tests/test_taumode.rs:14-160 --------------------------------
+def test_select_tau_fixed(oracle):
+    e = [0.1, 0.5, 1.0]
+    assert oracle.select_tau(e, oracle.TAU_FIXED, 0.3) == 0.3
+    for bad in (-0.1, 0.0, float("nan"), float("inf")):
+        assert oracle.select_tau(e, oracle.TAU_FIXED, bad) == FLOOR
+
+
+def test_select_tau_mean(oracle):
+    assert abs(oracle.select_tau([1.0, 2.0, 3.0], oracle.TAU_MEAN) - 2.0) < 1e-12
+    assert abs(oracle.select_tau([1.0, math.nan, 3.0, math.inf, 2.0], oracle.TAU_MEAN) - 2.0) < 1e-12
+    assert oracle.select_tau([math.nan, math.inf, -math.inf], oracle.TAU_MEAN) == FLOOR
+    assert oracle.select_tau([], oracle.TAU_MEAN) == FLOOR
+
+
+def test_select_tau_median(oracle):
+    assert oracle.select_tau([3.0, 1.0, 2.0], oracle.TAU_MEDIAN) == 2.0
+    assert abs(oracle.select_tau([1.0, 2.0, 3.0, 4.0], oracle.TAU_MEDIAN) - 2.5) < 1e-12
+    assert oracle.select_tau([5.0], oracle.TAU_MEDIAN) == 5.0
+    assert oracle.select_tau([math.nan, 1.0, 3.0, math.inf, 2.0], oracle.TAU_MEDIAN) == 2.0
+    assert oracle.select_tau([math.nan, math.inf], oracle.TAU_MEDIAN) == FLOOR
+    assert oracle.select_tau([], oracle.TAU_MEDIAN) == FLOOR
+
+
+def test_select_tau_percentile(oracle):
+    e = [1.0, 2.0, 3.0, 4.0, 5.0]
+    P = oracle.TAU_PERCENTILE
+    assert oracle.select_tau(e, P, 0.0) == 1.0
+    assert oracle.select_tau(e, P, 1.0) == 5.0
+    assert oracle.select_tau(e, P, 0.5) == 3.0
+    assert oracle.select_tau(e, P, -0.1) == 1.0
+    assert oracle.select_tau(e, P, 1.5) == 5.0
+    assert oracle.select_tau([], P, 0.5) == FLOOR
+
+
+def test_select_tau_floor(oracle):
+    assert oracle.select_tau([FLOOR * 2.0], oracle.TAU_MEAN) == FLOOR * 2.0
+    assert oracle.select_tau([FLOOR / 2.0], oracle.TAU_MEAN) == FLOOR
+    assert oracle.select_tau([0.0], oracle.TAU_MEAN) == FLOOR
+
+
+# ---- pure-Python restatement of test_helpers.rs:73-170 for tiny cases -------------------------
+def helper_adjacency(items, eps, topk, p, sigma):
+    n = len(items)
+    norms = [math.sqrt(sum(v * v for v in it)) for it in items]
+    adj = [dict() for _ in range(n)]
+    for i in range(n):
+        cand = []
+        for j in range(n):
+            if i == j:
+                continue
+            denom = norms[i] * norms[j]
+            if denom > 1e-12:
+                dot = 0.0
+                for a, b in zip(items[i], items[j]):
+                    dot += a * b
+                cos = min(max(dot / denom, -1.0), 1.0)
+            else:
+                cos = 0.0
+            dist = 1.0 - max(cos, 0.0)
+            if dist <= eps:
+                w = 1.0 / (1.0 + (dist / sigma) ** p)
+                if w > 1e-12:
+                    cand.append((dist, j, w))
+        cand.sort()
+        for dist, j, w in cand[:topk]:
+            adj[i][j] = w
+    for i in range(n):
+        for j in list(adj[i].keys()):
+            w = adj[i][j]
+            if w > 1e-12 and adj[j].get(i, 0.0) < 1e-12:
+                adj[j][i] = w
+    return adj
+
+
+def oracle_graph(oracle, items, eps, topk, p, sigma):
+    x = np.array(items, dtype=np.float64)
+    idx, dist, cnt = oracle.knn(x, topk, oracle.METRIC_COSINE, eps)
+    a_idx, a_w, a_cnt, _ = oracle.build_adjacency(idx, dist, cnt, p, sigma)
+    indptr, indices, data = oracle.laplacian(a_idx, a_w, a_cnt)
+    n = len(items)
+    dense = np.zeros((n, n))
+    for r in range(n):
+        for e in range(int(indptr[r]), int(indptr[r + 1])):
+            dense[r, indices[e]] = data[e]
+    return dense, (indptr, indices, data)
+
+
+# ---- L = D - A on 3 points: src_legacy/tests/test_laplacian.rs:655-786 ------------------------
+def test_with_adjacency_output(oracle):
+    items = [[1.0, 0.0], [0.9, 0.1], [0.0, 1.0]]
+    eps, topk, p, sigma = 0.5, 1, 1.0, 0.2
+    adj = helper_adjacency(items, eps, topk, p, sigma)
+    L, (indptr, indices, data) = oracle_graph(oracle, items, eps, topk, p, sigma)
+    # hand-derived: only edge 0-1, d = 1 - 0.9/sqrt(0.82)
+    d01 = 1.0 - 0.9 / math.sqrt(0.9 * 0.9 + 0.1 * 0.1)
+    w01 = 1.0 / (1.0 + d01 / 0.2)
+    assert adj[0] == {1: pytest.approx(w01, rel=1e-15)} and adj[2] == {}
+    for i in range(3):
+        deg = sum(adj[i].values())
+        assert abs(L[i, i] - deg) < 1e-10
+        for j in range(3):
+            if i != j:
+                assert abs(L[i, j] + adj[i].get(j, 0.0)) < 1e-10
+    assert np.allclose(L, L.T, atol=1e-10)
+    # diagonal always stored, even 0 (laplacian.rs:372): 3 diagonals + 2 off-diagonals
+    assert len(data) == 5 and int(indptr[3]) - int(indptr[2]) == 1 and data[-1] == 0.0
+    assert L[0, 1] == -w01
+
+
+# ---- cosine ordering: src_legacy/tests/test_laplacian.rs:156-213 ------------------------------
+def test_cosine_similarity_based_construction(oracle):
+    items = [[1.0, 0.0], [0.707, 0.707], [0.0, 1.0], [-1.0, 0.0]]
+    eps, topk, p, sigma = 2.0, 2, 1.0, 0.5
+    adj = helper_adjacency(items, eps, topk, p, sigma)
+    L, _ = oracle_graph(oracle, items, eps, topk, p, sigma)
+    for i in range(4):
+        for j in range(4):
+            if i != j:
+                assert L[i, j] == -adj[i].get(j, 0.0)
+    a01, a02, a03 = -L[0, 1], -L[0, 2], -L[0, 3]
+    assert a01 > a02
+    assert a02 >= a03
+    assert a01 > a02 + 0.05
+
+
+# ---- Laplacian invariants: src_legacy/tests/test_laplacian.rs:52-154 --------------------------
+def test_laplacian_invariants(oracle):
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(60, 12))
+    k = 5
+    idx, dist, cnt = oracle.knn(x, k, oracle.METRIC_COSINE, np.inf)
+    a_idx, a_w, a_cnt, applied = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0)
+    assert not applied  # mean degree 5 <= 10
+    indptr, indices, data = oracle.laplacian(a_idx, a_w, a_cnt)
+    n = x.shape[0]
+    L = np.zeros((n, n))
+    for r in range(n):
+        cols = indices[int(indptr[r]):int(indptr[r + 1])]
+        assert np.all(np.diff(cols.astype(np.int64)) > 0)  # sorted, unique
+        L[r, cols] = data[int(indptr[r]):int(indptr[r + 1])]
+    assert np.allclose(L.sum(axis=1), 0.0, atol=1e-12)
+    assert np.array_equal(L, L.T)
+    assert np.all(np.diag(L) >= 0.0)
+    assert np.all(L[~np.eye(n, dtype=bool)] <= 0.0)
+    assert len(data) <= n * (2 * k + 1)
+
+
+# ---- Rayleigh / chain graph: surfface-core/src/tests/test_spectral.rs:102-144,187-251 ----------
+def csr_from_dense(d):
+    d = np.asarray(d, dtype=np.float64)
+    indptr, indices, data = [0], [], []
+    for r in range(d.shape[0]):
+        for c in range(d.shape[1]):
+            if d[r, c] != 0.0:
+                indices.append(c)
+                data.append(d[r, c])
+        indptr.append(len(indices))
+    return (np.array(indptr, np.uint64), np.array(indices, np.uint32), np.array(data, np.float64))
+
+
+def test_rayleigh_eigenvector(oracle):
+    L = csr_from_dense([[1.0, -1.0], [-1.0, 1.0]])
+    assert oracle.rayleigh(*L, np.array([1.0, 1.0])) == 0.0
+    lam = oracle.lambdas(*L, np.array([[1.0, 1.0]]), oracle.LAMBDA_CORE_F32SEM)
+    assert abs(lam[0]) < 1e-5
+
+
+def test_dispersion_uniform(oracle):
+    L = csr_from_dense([[1.0, -0.5], [-0.5, 1.0]])
+    x = np.array([[1.0, 1.0], [1.0, 1.0]])
+    for variant in (oracle.LAMBDA_LEGACY_TAUMODE, oracle.LAMBDA_ENERGY_NODE, oracle.LAMBDA_CORE_F32SEM):
+        _, _, g = oracle.lambdas(*L, x, variant, with_parts=True)
+        assert np.all(np.abs(g) < 1e-5)
+
+
+def test_chain_graph_lambda(oracle):
+    L = csr_from_dense([[1, -1, 0], [-1, 2, -1], [0, -1, 1]])
+    x = np.array([[1.0, 1.0, 1.0], [1.0, 0.0, -1.0]])
+    for variant in (oracle.LAMBDA_LEGACY_TAUMODE, oracle.LAMBDA_ENERGY_NODE, oracle.LAMBDA_CORE_F32SEM):
+        lam = oracle.lambdas(*L, x, variant, oracle.TAU_FIXED, 0.5)
+        assert abs(lam[0]) < 1e-5 and lam[1] > lam[0] and np.all(np.isfinite(lam))
+    # hand value: L x = [1, 0, -1], x.Lx = 2, x.x = 2 => E = 1
+    _, e, g = oracle.lambdas(*L, x, oracle.LAMBDA_ENERGY_NODE, with_parts=True)
+    assert e[1] == 1.0
+    # two unit edges with (x_r - x_c)^2 = 1 each => shares 1/2, 1/2 => G = 1/2 (upper triangle)
+    assert g[1] == 0.5
+    # taumode counts both triangles: four shares of 1/4 => 1/4 (exactly half of the energy-node value)
+    _, e2, g2 = oracle.lambdas(*L, x, oracle.LAMBDA_LEGACY_TAUMODE, oracle.TAU_FIXED, 0.5, with_parts=True)
+    assert g2[1] == 0.25 and e2[1] == 1.0
+    lam = oracle.lambdas(*L, x, oracle.LAMBDA_LEGACY_TAUMODE, oracle.TAU_FIXED, 0.5)
+    assert lam[1] == 0.5 * (1.0 / 1.5) + 0.5 * 0.25
+
+
+# ---- scale invariance: src_legacy/tests/test_taumode.rs:643-682 -------------------------------
+def test_scale_invariance(oracle):
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(40, 4))
+    idx, dist, cnt = oracle.knn(oracle.transpose(x), 2, oracle.METRIC_COSINE, np.inf)
+    a = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0)
+    L = oracle.laplacian(*a[:3])
+    v = np.array([[1.0, 2.0, 3.0, 1.0], [2.0, 4.0, 6.0, 2.0]])
+    lam = oracle.lambdas(*L, v, oracle.LAMBDA_LEGACY_TAUMODE, oracle.TAU_FIXED, 0.5)
+    assert abs(lam[0] - lam[1]) <= 1e-10 * max(abs(lam[0]), 1.0)
+
+
+def test_zero_vector_lambda(oracle):
+    L = csr_from_dense([[1, -1, 0], [-1, 2, -1], [0, -1, 1]])
+    lam = oracle.lambdas(*L, np.array([[0.0, 1e-11, -1e-11]]), oracle.LAMBDA_LEGACY_TAUMODE)
+    assert lam[0] == 0.0  # taumode.rs:268-274
+
+
+# ---- normalisation: src_legacy/core.rs:1341-1355 ----------------------------------------------
+def test_normalise_lambdas(oracle):
+    lam, stats = oracle.normalise_lambdas([0.2, 0.5, 0.3])
+    assert stats[0] == 0.2 and stats[1] == 0.5 and lam[0] == 0.0 and lam[1] == 1.0
+    lam, stats = oracle.normalise_lambdas([-2.0, -1.0])  # max fold starts at 0.0
+    assert stats[1] == 0.0 and stats[2] == 2.0 and lam[1] == 0.5
+    lam, stats = oracle.normalise_lambdas([0.3, 0.3])
+    assert stats[2] == 1e-9 and lam[0] == 0.0  # range floor
+
+
+# ---- distances: surfface-core/src/tests/test_distance.rs:254,266,284 --------------------------
+def test_distance_kats(oracle):
+    x = np.array([[0.0, 0.0], [3.0, 4.0]])
+    _, d, _ = oracle.knn(x, 1, oracle.METRIC_L2)
+    assert d[0, 0] == 5.0
+    _, d, _ = oracle.knn(x, 1, oracle.METRIC_L2SQ)
+    assert d[0, 0] == 25.0
+    x = np.array([[1.0, 0.0], [2.0, 0.0], [0.0, 3.0]])
+    idx, d, _ = oracle.knn(x, 2, oracle.METRIC_COSINE)
+    assert idx[0, 0] == 1 and d[0, 0] == 0.0 and d[0, 1] == 1.0  # parallel -> cos 1, orthogonal -> cos 0
+
+
+# ---- ties by index, eps filter, ragged rows ----------------------------------------------------
+def test_knn_ties_and_eps(oracle):
+    x = np.array([[1.0, 0.0], [1.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.0, 0.0]])
+    idx, d, cnt = oracle.knn(x, 3, oracle.METRIC_COSINE)
+    assert list(idx[0]) == [1, 2, 3] and list(d[0]) == [0.0, 0.0, 1.0]
+    assert list(idx[4]) == [0, 1, 2] and list(d[4]) == [1.0, 1.0, 1.0]  # zero row: denom guard -> cos 0
+    idx, d, cnt = oracle.knn(x, 3, oracle.METRIC_COSINE, eps=0.5)
+    assert list(cnt) == [2, 2, 2, 0, 0]
+    assert idx[3, 0] == oracle.IDX_NONE and math.isinf(d[3, 0])
+
+
+# ---- sparsification: laplacian.rs:258-282, sparsification.rs:32-113 ---------------------------
+def test_sparsify_rules(oracle):
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(80, 6))
+    idx, dist, cnt = oracle.knn(x, 12, oracle.METRIC_COSINE)
+    a_idx, a_w, a_cnt, applied = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0)
+    assert applied and np.all(a_cnt == 6)  # mean degree 12 > 10: keep len/2
+    full = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0, force_sparsify=0)
+    assert np.all(full[2] == 12)
+    s_idx, s_w, s_cnt, applied = oracle.sfgrass(*full[:3], ratio=0.3)
+    assert applied and np.all(s_cnt == math.ceil(12 * 0.3))
+    # kept edges are the top scores with (score desc, j asc)
+    deg = full[2]
+    for i in (0, 17, 79):
+        sc = [(-full[1][i, t] * math.sqrt(float(int(deg[i]) * int(deg[full[0][i, t]]))), int(full[0][i, t])) for t in range(12)]
+        sc.sort()
+        assert [j for _, j in sc[:4]] == list(s_idx[i, :4])
+    sparse = oracle.sfgrass(*oracle.build_adjacency(*oracle.knn(x, 5), 2.0, 1.0)[:3])
+    assert not sparse[3]  # mean degree 5 < 10: skipped
+
+
+# ---- diffusion: energymaps.rs:520-546 ---------------------------------------------------------
+def test_diffusion(oracle):
+    L = csr_from_dense([[1, -1, 0], [-1, 2, -1], [0, -1, 1]])
+    x = np.array([[1.0, 0.0, -1.0], [2.0, 2.0, 2.0]])
+    y = oracle.diffuse(*L, x, 0.1, 1)
+    assert np.array_equal(y[0], np.array([1.0 - 0.1 * 1.0, 0.0, -1.0 + 0.1 * 1.0]))
+    assert np.array_equal(y[1], x[1])
+    y4 = oracle.diffuse(*L, x, 0.1, 4)
+    z = x.copy()
+    for _ in range(4):
+        z = oracle.diffuse(*L, z, 0.1, 1)
+    assert np.array_equal(y4, z)
+
+
+# ---- synthetic generator sanity ---------------------------------------------------------------
+def test_generator_statistics(oracle):
+    x = oracle.generate_rows(0, 42, 0, 4000, 64)
+    assert abs(x.mean()) < 0.01 and abs(x.std() - 1.0) < 0.01
+    from scipy import stats
+    assert stats.kstest(x.ravel()[:50000], "norm").pvalue > 1e-3
+    # counter-based: any row range is reproducible
+    y = oracle.generate_rows(0, 42, 1000, 10, 64)
+    assert np.array_equal(x[1000:1010], y)
+    c = oracle.generate_rows(1, 7, 0, 2000, 32, n_centres=8, noise=0.3)
+    assert c.shape == (2000, 32) and np.all(np.isfinite(c))
