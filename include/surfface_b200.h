@@ -1,0 +1,245 @@
+/*
+ * surfface_b200.h -- C ABI of libsurfface_b200.so: the B200 (sm_100a) graph-wiring build path
+ * of surfface (tuned-org-uk/matternet-rs): kNN graph -> sparse Laplacian -> taumode lambda.
+ *
+ * The reference has NO FFI today: the seams are Rust functions.  Every
+ * entry point below names the reference function it stands behind (paths relative to the
+ * reference repo).  A Rust `surfface-b200-sys` crate binds exactly these symbols (see
+ * INTEGRATION.md and matternet-rs_b200/rust/).
+ *
+ * Conventions
+ *   ownership  caller owns every host buffer; the library owns device memory behind opaque
+ *              handles (sfb_mat / sfb_knn / sfb_adj / sfb_csr) released with the matching
+ *              *_free.  Reference: inputs are borrowed slices, outputs owned Vec / CsMat.
+ *   errors     every call returns an sfb_status; sfb_last_error(ctx) holds the message.  The
+ *              reference panics (src_legacy/laplacian.rs:130-135, taumode.rs:329-337); a Rust
+ *              wrapper panics on non-zero to keep those signatures.
+ *   threading  calls are blocking; one sfb_ctx per host thread (not internally locked).
+ *   fallback   there is none: without a CUDA device sfb_ctx_create returns SFB_ECUDA.
+ *   layout     matrices are row-major f64; kNN / adjacency lists are M x k, padded with
+ *              SFB_IDX_NONE (+inf distance / 0 weight) past the row's count; CSR uses u64
+ *              indptr, u32 indices (ascending per row), f64 data.
+ */
+#ifndef SURFFACE_B200_H
+#define SURFFACE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_ABI_VERSION 1
+#define SFB_IDX_NONE 0xFFFFFFFFu
+
+typedef enum {
+    SFB_OK = 0,
+    SFB_EINVAL = 1,       /* bad argument (the reference would assert!/panic!)            */
+    SFB_ECUDA = 2,        /* CUDA runtime / driver error, or no device                    */
+    SFB_ENOMEM = 3,       /* device or host allocation failed                             */
+    SFB_ENCCL = 4,        /* NCCL error / communicator not initialised                    */
+    SFB_EUNCERTIFIED = 5, /* screen could not certify rows and exact fallback was disabled */
+    SFB_EUNSUPPORTED = 6  /* valid request outside what this build implements             */
+} sfb_status;
+
+typedef struct sfb_ctx sfb_ctx;
+typedef struct sfb_mat sfb_mat; /* dense row-major f64 matrix resident in HBM        */
+typedef struct sfb_knn sfb_knn; /* per-row k nearest neighbours (idx, dist, count)   */
+typedef struct sfb_adj sfb_adj; /* weighted directed adjacency lists (idx, w, count) */
+typedef struct sfb_csr sfb_csr; /* CSR matrix (graph Laplacian) resident in HBM      */
+
+/* ---- context -------------------------------------------------------------------------------
+ * Replaces surfface-core/src/backend.rs:18-70 (SurffaceDevice::Cuda / get_device / dispatch). */
+int32_t sfb_abi_version(void);
+int32_t sfb_ctx_create(int32_t device_id, sfb_ctx** out);
+void sfb_ctx_destroy(sfb_ctx* ctx);
+const char* sfb_last_error(const sfb_ctx* ctx);
+/* name: >= 256 bytes; sm_count, hbm_bytes may be NULL */
+int32_t sfb_device_info(const sfb_ctx* ctx, char* name, int32_t* sm_count, uint64_t* hbm_bytes);
+int32_t sfb_synchronize(sfb_ctx* ctx);
+
+/* ---- dense matrices ------------------------------------------------------------------------
+ * The reference moves whole flat Vec copies host<->device (surfface-core/src/laplacian.rs:157-158,
+ * spectral/mod.rs:39-51,170-171).  sfb_mat_from_host is that upload. */
+int32_t sfb_mat_from_host(sfb_ctx* ctx, const double* x, uint64_t rows, uint32_t cols, sfb_mat** out);
+/* Synthetic rows generated on the device: counter-based Philox4x32-10 +
+ * Box-Muller with reproducible arithmetic, so any row can be regenerated on the CPU.
+ * kind 0: N(0,1) iid; 1: clustered (n_centres centres ~ N(0,I), x = c + noise*N(0,I));
+ * 2: N(0,I) + noise * (one N(0,1) shift per row). */
+int32_t sfb_mat_generate(sfb_ctx* ctx, int32_t kind, uint64_t seed, uint64_t rows, uint32_t cols,
+                         uint32_t n_centres, double noise, sfb_mat** out);
+/* GraphFactory::build_laplacian_matrix_from_k_cluster transposes before the graph build
+ * (src_legacy/graph.rs:214-216): nodes become the columns. */
+int32_t sfb_mat_transpose(sfb_ctx* ctx, const sfb_mat* a, sfb_mat** out);
+int32_t sfb_mat_shape(const sfb_mat* a, uint64_t* rows, uint32_t* cols);
+int32_t sfb_mat_copy_rows(sfb_ctx* ctx, const sfb_mat* a, uint64_t row0, uint64_t nrows, double* out);
+void sfb_mat_free(sfb_mat* a);
+
+/* ---- kNN graph -----------------------------------------------------------------------------
+ * Replaces the two CosinePair sweeps of _build_adjacency (src_legacy/laplacian.rs:213-229,245-254),
+ * with the semantics of the repo's brute-force restatement (src_legacy/tests/test_helpers.rs:77-125):
+ *   cosine: d = 1 - max(0, clamp(x_i.x_j / (|x_i||x_j|), -1, 1)), cos := 0 when |x_i||x_j| <= 1e-12
+ *   L2 / L2SQ: surfface-core/src/mst.rs:312-403, src_legacy/energymaps.rs:875-892
+ *   keep j != i with d <= eps, order (d asc, j asc), first k.
+ * Neighbour indices are bit-exact with that definition whichever screen is used: the tensor-core
+ * screen only proposes candidates, every returned distance is the exact f64 value, and rows the
+ * screen cannot certify are recomputed by brute force in f64. */
+typedef enum { SFB_METRIC_COSINE = 0, SFB_METRIC_L2 = 1, SFB_METRIC_L2SQ = 2 } sfb_metric;
+typedef enum {
+    SFB_SCREEN_AUTO = 0,      /* tensor-core screen when the shape allows, else exact       */
+    SFB_SCREEN_EXACT_F64 = 1, /* brute force in f64 (reference arithmetic, no screen)       */
+    SFB_SCREEN_F16 = 2,       /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM  */
+    SFB_SCREEN_BF16 = 3       /* tcgen05 kind::f16, bf16 operands (8x looser margin)        */
+} sfb_screen;
+
+typedef struct {
+    int32_t metric;    /* sfb_metric                                                         */
+    uint32_t k;        /* neighbours kept per row, self excluded (GraphParams.topk)          */
+    double eps;        /* keep d <= eps; +inf disables (GraphParams.eps)                     */
+    int32_t screen;    /* sfb_screen                                                         */
+    uint32_t k_prime;  /* screen candidates per row (0 = default 4k rounded up to 32)        */
+    uint64_t q_begin;  /* query-row shard [q_begin, q_end); q_end = 0 means all rows         */
+    uint64_t q_end;
+    int32_t allow_fallback; /* 0: return SFB_EUNCERTIFIED instead of recomputing rows exactly */
+} sfb_knn_params;
+
+typedef struct {
+    uint64_t rows;            /* query rows computed                                         */
+    uint64_t rows_certified;  /* rows whose screen margin proved the candidate set complete  */
+    uint64_t rows_fallback;   /* rows recomputed by exact f64 brute force                    */
+    uint32_t k_prime;         /* candidates rescored per row                                 */
+    int32_t screen_used;      /* sfb_screen actually run                                     */
+    double ms_prepare;        /* norms + operand conversion                                  */
+    double ms_screen;         /* tensor-core distance screen + top-k' selection              */
+    double ms_rescore;        /* exact f64 rescore + certification                           */
+    double ms_fallback;       /* exact brute force for uncertified rows                      */
+    double max_margin;        /* largest per-row screen margin used                          */
+} sfb_knn_stats;
+
+int32_t sfb_knn_build(sfb_ctx* ctx, const sfb_mat* rows, const sfb_knn_params* params, sfb_knn** out);
+int32_t sfb_knn_shape(const sfb_knn* g, uint64_t* rows, uint32_t* k, uint64_t* q_begin);
+/* idx, dist: rows x k; cnt: rows.  Any pointer may be NULL. */
+int32_t sfb_knn_copy(sfb_ctx* ctx, const sfb_knn* g, uint32_t* idx, double* dist, uint32_t* cnt);
+int32_t sfb_knn_stats_get(const sfb_knn* g, sfb_knn_stats* out);
+int32_t sfb_knn_from_host(sfb_ctx* ctx, const uint32_t* idx, const double* dist, const uint32_t* cnt,
+                          uint64_t rows, uint32_t k, sfb_knn** out);
+void sfb_knn_free(sfb_knn* g);
+
+/* ---- kernel weights + sparsification -------------------------------------------------------
+ * sfb_adjacency_build: src_legacy/laplacian.rs:231-290 -- w = 1/(1+(d/sigma)^p), keep w > 1e-12;
+ *   inline sparsification when mean degree > 10: score = w*sqrt(deg_i*deg_j), rows with more than
+ *   2 edges keep their max(len/2,1) best.  sparsify: -1 reference rule, 0 never, 1 always.
+ *   The reference's sort is unstable with no tie-break; the contract is (score desc, j asc).
+ *   sigma is explicit: the reference has three different defaults.
+ * sfb_sparsify_sfgrass: SfGrassSparsifier::sparsify_graph (src_legacy/sparsification.rs:32-113),
+ *   in place; ratio clamped to [0.1, 1]; skipped when mean degree < 10. */
+typedef struct {
+    double p;
+    double sigma;
+    int32_t sparsify;
+} sfb_adj_params;
+
+int32_t sfb_adjacency_build(sfb_ctx* ctx, const sfb_knn* g, const sfb_adj_params* params,
+                            sfb_adj** out, int32_t* sparsified);
+int32_t sfb_sparsify_sfgrass(sfb_ctx* ctx, sfb_adj* adj, double ratio, int32_t* applied);
+int32_t sfb_adj_shape(const sfb_adj* adj, uint64_t* rows, uint32_t* k);
+int32_t sfb_adj_copy(sfb_ctx* ctx, const sfb_adj* adj, uint32_t* idx, double* w, uint32_t* cnt);
+int32_t sfb_adj_from_host(sfb_ctx* ctx, const uint32_t* idx, const double* w, const uint32_t* cnt,
+                          uint64_t rows, uint32_t k, sfb_adj** out);
+void sfb_adj_free(sfb_adj* adj);
+
+/* ---- symmetrise + Laplacian ----------------------------------------------------------------
+ * _symmetrise_adjancency + _build_sparse_laplacian + to_csr (src_legacy/laplacian.rs:297-419,161):
+ *   undirected edge set {(i,j,w),(j,i,w)}, duplicates -> max, rows sorted by column,
+ *   L_ii = sum_j w_ij (ascending j; stored even when 0), L_ij = -w_ij.
+ * normalised != 0: L_sym = I - D^-1/2 W D^-1/2 (surfface-core/src/laplacian.rs:333-372,209-219):
+ *   L_ii = 1 if d_i > weight_threshold, L_ij = -w/sqrt(d_i d_j), entries |v| <= 1e-9 dropped. */
+typedef struct {
+    int32_t normalised;
+    double weight_threshold;
+} sfb_lap_params;
+
+int32_t sfb_laplacian_build(sfb_ctx* ctx, const sfb_adj* adj, const sfb_lap_params* params, sfb_csr** out);
+int32_t sfb_csr_shape(const sfb_csr* L, uint64_t* rows, uint64_t* nnz);
+int32_t sfb_csr_copy(sfb_ctx* ctx, const sfb_csr* L, uint64_t* indptr, uint32_t* indices, double* data);
+int32_t sfb_csr_from_host(sfb_ctx* ctx, uint64_t rows, const uint64_t* indptr, const uint32_t* indices,
+                          const double* data, sfb_csr** out);
+void sfb_csr_free(sfb_csr* L);
+/* GraphLaplacian::multiply_vector / rayleigh_quotient (src_legacy/graph.rs:464-501,422-461). */
+int32_t sfb_spmv(sfb_ctx* ctx, const sfb_csr* L, const double* x, double* y);
+int32_t sfb_rayleigh_quotient(sfb_ctx* ctx, const sfb_csr* L, const double* x, double* out);
+
+/* ---- per-item lambda -----------------------------------------------------------------------
+ * L is M x M (M = feature nodes), X is R x M: one lambda per row of X, one HBM pass over X.
+ *   LEGACY_TAUMODE  TauMode::compute_taumode_lambdas_parallel (src_legacy/taumode.rs:117-318,326-408)
+ *   ENERGY_NODE     node_energy_and_dispersion (src_legacy/energymaps.rs:923-1045): lambda = E,
+ *                   dispersion over the upper triangle returned separately
+ *   CORE_F32SEM     compute_lambdas_gpu (surfface-core/src/spectral/mod.rs:69-181), f32 semantics
+ * tau: TauMode::select_tau on the ITEM vector (src_legacy/taumode.rs:29-70).
+ * normalise_minmax != 0: ArrowSpace::normalise_lambdas (src_legacy/core.rs:1341-1355);
+ * stats = {min, max, range} of the raw lambdas. */
+typedef enum { SFB_LAMBDA_LEGACY_TAUMODE = 0, SFB_LAMBDA_ENERGY_NODE = 1, SFB_LAMBDA_CORE_F32SEM = 2 } sfb_lambda_variant;
+typedef enum { SFB_TAU_FIXED = 0, SFB_TAU_MEDIAN = 1, SFB_TAU_MEAN = 2, SFB_TAU_PERCENTILE = 3 } sfb_tau_mode;
+
+typedef struct {
+    int32_t variant;
+    int32_t tau_mode;
+    double tau_value; /* Fixed(t) or Percentile(p) */
+    int32_t normalise_minmax;
+} sfb_lambda_params;
+
+/* out_lambda: R (host); out_dispersion: R or NULL; stats: 3 or NULL */
+int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_lambda_params* params,
+                   double* out_lambda, double* out_dispersion, double* stats);
+/* diffusion step of diffuse_and_split_subcentroids (src_legacy/energymaps.rs:520-546):
+ * X <- X - eta * X L^T, `steps` times, in place on the device matrix. */
+int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, double eta, uint32_t steps);
+
+/* ---- reference-shaped one-shot entry points (host buffers in, host buffers out) ------------
+ * sfb_build_laplacian_matrix = build_laplacian_matrix(transposed, &GraphParams, ..)
+ *   (src_legacy/laplacian.rs:122-180): `items` is the already-transposed matrix, nodes = rows.
+ *   normalise must be 0 (the reference's StandardScaler pre-scaling is out of scope).
+ * sfb_compute_taumode_lambdas = TauMode::compute_taumode_lambdas_parallel + update_lambdas
+ *   (src_legacy/taumode.rs:117-214, core.rs:1427-1443): items R x M, lambdas min-max normalised. */
+typedef struct {
+    double eps;
+    uint32_t k;    /* carried for parity with GraphParams; unused, as in the reference */
+    uint32_t topk; /* neighbours kept per node */
+    double p;
+    double sigma;  /* explicit (reference default sigma.unwrap_or(1.0), laplacian.rs:256) */
+    int32_t normalise;
+    int32_t sparsity_check; /* != 0: SFB_EINVAL if sparsity > 0.95 (graph.rs:232-240) */
+} sfb_graph_params;
+
+int32_t sfb_build_laplacian_matrix(sfb_ctx* ctx, const double* items, uint64_t nodes, uint32_t dims,
+                                   const sfb_graph_params* params, int32_t screen, sfb_csr** out);
+int32_t sfb_compute_taumode_lambdas(sfb_ctx* ctx, const sfb_csr* L, const double* items, uint64_t n_items,
+                                    uint32_t n_features, int32_t tau_mode, double tau_value,
+                                    double* out_lambdas);
+
+/* ---- stage timings of the last calls (device time, ms) ------------------------------------- */
+typedef struct {
+    double ms_h2d, ms_knn, ms_adjacency, ms_laplacian, ms_lambda, ms_d2h;
+    uint64_t kernel_launches; /* kernels of this library launched since ctx creation */
+} sfb_stage_times;
+int32_t sfb_timings(const sfb_ctx* ctx, sfb_stage_times* out);
+int32_t sfb_timings_reset(sfb_ctx* ctx);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------
+ * Query rows are sharded across ranks (sfb_knn_params.q_begin/q_end); the exchange steps are the
+ * all-gather of the kNN lists before symmetrisation and the min/max + all-gather of lambda.
+ * id: 128 bytes from sfb_comm_unique_id on rank 0, distributed by the host. */
+int32_t sfb_comm_unique_id(uint8_t id[128]);
+int32_t sfb_comm_init(sfb_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);
+/* gathers equal row shards of every rank into a full-M kNN handle (all ranks get a copy) */
+int32_t sfb_knn_allgather(sfb_ctx* ctx, const sfb_knn* shard, uint64_t total_rows, sfb_knn** out);
+/* lambda over this rank's rows of X, min/max all-reduced, normalised, all-gathered into out (total_rows) */
+int32_t sfb_lambda_allgather(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x_shard, uint64_t row0,
+                             uint64_t total_rows, const sfb_lambda_params* params, double* out_lambda,
+                             double* stats);
+int32_t sfb_comm_barrier(sfb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFFACE_B200_H */

@@ -1,0 +1,490 @@
+"""surfface_b200 -- host-side mirror of the reference's graph-wiring API over the sm_100a C ABI.
+
+Two layers:
+  * handle layer (Context, Matrix, KnnGraph, Adjacency, Csr): one Python object per C-ABI handle;
+  * reference layer: the names and argument meaning of the reference's operator interface for this
+    path -- GraphParams / GraphLaplacian / GraphFactory / build_laplacian_matrix
+    (src_legacy/graph.rs:94-136,193-255, src_legacy/laplacian.rs:122-180), TauMode
+    (src_legacy/taumode.rs:16-23,117-121), SfGrassSparsifier (src_legacy/sparsification.rs:14-36).
+
+The reference is Rust and there is no Rust toolchain here, so the tests drive
+the C ABI through this module; the Rust `-sys` crate a maintainer would add is in rust/ and
+INTEGRATION.md.  Everything computes on the GPU; nothing here falls back to the CPU.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import IDX_NONE, SfbError, lib
+
+METRIC_COSINE, METRIC_L2, METRIC_L2SQ = 0, 1, 2
+SCREEN_AUTO, SCREEN_EXACT_F64, SCREEN_F16, SCREEN_BF16 = 0, 1, 2, 3
+LAMBDA_LEGACY_TAUMODE, LAMBDA_ENERGY_NODE, LAMBDA_CORE_F32SEM = 0, 1, 2
+TAU_FIXED, TAU_MEDIAN, TAU_MEAN, TAU_PERCENTILE = 0, 1, 2, 3
+SYNTH_GAUSSIAN, SYNTH_CLUSTERED, SYNTH_ANISOTROPIC = 0, 1, 2
+
+
+# ------------------------------------------------------------------------------------------------
+# handle layer
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """sfb_ctx: one per host thread; owns the device, its stream and (optionally) an NCCL communicator."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        st = lib().sfb_ctx_create(int(device), C.byref(self._h))
+        if st != _ffi.OK:
+            self._h = C.c_void_p()
+            raise SfbError(st, f"sfb_ctx_create(device={device}) failed (no CUDA device, or not sm_100)")
+        self.device = device
+
+    def check(self, st):
+        if st != _ffi.OK:
+            raise SfbError(st, lib().sfb_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().sfb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self.check(lib().sfb_synchronize(self._h))
+
+    def device_info(self):
+        name = C.create_string_buffer(256)
+        sm = C.c_int32()
+        mem = C.c_uint64()
+        self.check(lib().sfb_device_info(self._h, name, C.byref(sm), C.byref(mem)))
+        return name.value.decode(), sm.value, mem.value
+
+    def timings(self):
+        t = _ffi.StageTimes()
+        self.check(lib().sfb_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in t._fields_}
+
+    def timings_reset(self):
+        self.check(lib().sfb_timings_reset(self._h))
+
+    # -- matrices
+    def matrix(self, x):
+        x = _ffi.f64(x)
+        if x.ndim != 2:
+            raise ValueError("matrix must be 2-D")
+        h = C.c_void_p()
+        self.check(lib().sfb_mat_from_host(self._h, _ffi.ptr(x), x.shape[0], x.shape[1], C.byref(h)))
+        self.synchronize()
+        return Matrix(self, h)
+
+    def generate(self, kind, seed, rows, cols, n_centres=0, noise=0.0):
+        h = C.c_void_p()
+        self.check(lib().sfb_mat_generate(self._h, kind, seed, rows, cols, n_centres, float(noise), C.byref(h)))
+        return Matrix(self, h)
+
+    # -- multi-GPU
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self.check(lib().sfb_comm_init(self._h, buf, rank, world))
+
+    def barrier(self):
+        self.check(lib().sfb_comm_barrier(self._h))
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    st = lib().sfb_comm_unique_id(buf)
+    if st != _ffi.OK:
+        raise SfbError(st, "sfb_comm_unique_id failed (libnccl not loadable?)")
+    return bytes(buf)
+
+
+class _Handle:
+    _free = None
+
+    def __init__(self, ctx, h):
+        self.ctx, self._h = ctx, h
+
+    def free(self):
+        if self._h:
+            getattr(lib(), self._free)(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Matrix(_Handle):
+    _free = "sfb_mat_free"
+
+    @property
+    def shape(self):
+        r, c = C.c_uint64(), C.c_uint32()
+        lib().sfb_mat_shape(self._h, C.byref(r), C.byref(c))
+        return r.value, c.value
+
+    def transpose(self):
+        h = C.c_void_p()
+        self.ctx.check(lib().sfb_mat_transpose(self.ctx._h, self._h, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def rows(self, row0=0, nrows=None):
+        r, c = self.shape
+        nrows = r - row0 if nrows is None else nrows
+        out = np.empty((nrows, c), dtype=np.float64)
+        self.ctx.check(lib().sfb_mat_copy_rows(self.ctx._h, self._h, row0, nrows, _ffi.ptr(out)))
+        return out
+
+    def knn(self, k, metric=METRIC_COSINE, eps=math.inf, screen=SCREEN_AUTO, k_prime=0, q_begin=0, q_end=0,
+            allow_fallback=True):
+        p = _ffi.KnnParams(metric, k, float(eps), screen, k_prime, q_begin, q_end, int(allow_fallback))
+        h = C.c_void_p()
+        self.ctx.check(lib().sfb_knn_build(self.ctx._h, self._h, C.byref(p), C.byref(h)))
+        return KnnGraph(self.ctx, h)
+
+    def diffuse(self, L, eta, steps):
+        self.ctx.check(lib().sfb_diffuse(self.ctx._h, L._h, self._h, float(eta), int(steps)))
+        return self
+
+
+class KnnGraph(_Handle):
+    _free = "sfb_knn_free"
+
+    @property
+    def shape(self):
+        r, k, q = C.c_uint64(), C.c_uint32(), C.c_uint64()
+        lib().sfb_knn_shape(self._h, C.byref(r), C.byref(k), C.byref(q))
+        return r.value, k.value
+
+    @property
+    def q_begin(self):
+        q = C.c_uint64()
+        lib().sfb_knn_shape(self._h, None, None, C.byref(q))
+        return q.value
+
+    def to_host(self):
+        r, k = self.shape
+        idx = np.empty((r, k), np.uint32)
+        dist = np.empty((r, k), np.float64)
+        cnt = np.empty(r, np.uint32)
+        self.ctx.check(lib().sfb_knn_copy(self.ctx._h, self._h, _ffi.ptr(idx), _ffi.ptr(dist), _ffi.ptr(cnt)))
+        self.ctx.synchronize()
+        return idx, dist, cnt
+
+    def stats(self):
+        s = _ffi.KnnStats()
+        lib().sfb_knn_stats_get(self._h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    @staticmethod
+    def from_host(ctx, idx, dist, cnt):
+        idx, dist, cnt = _ffi.u32(idx), _ffi.f64(dist), _ffi.u32(cnt)
+        h = C.c_void_p()
+        ctx.check(lib().sfb_knn_from_host(ctx._h, _ffi.ptr(idx), _ffi.ptr(dist), _ffi.ptr(cnt), idx.shape[0],
+                                           idx.shape[1], C.byref(h)))
+        return KnnGraph(ctx, h)
+
+    def allgather(self, total_rows):
+        h = C.c_void_p()
+        self.ctx.check(lib().sfb_knn_allgather(self.ctx._h, self._h, total_rows, C.byref(h)))
+        return KnnGraph(self.ctx, h)
+
+    def adjacency(self, p=2.0, sigma=1.0, sparsify=-1):
+        prm = _ffi.AdjParams(float(p), float(sigma), int(sparsify))
+        h, applied = C.c_void_p(), C.c_int32()
+        self.ctx.check(lib().sfb_adjacency_build(self.ctx._h, self._h, C.byref(prm), C.byref(h), C.byref(applied)))
+        a = Adjacency(self.ctx, h)
+        a.sparsified = bool(applied.value)
+        return a
+
+
+class Adjacency(_Handle):
+    _free = "sfb_adj_free"
+    sparsified = False
+
+    @property
+    def shape(self):
+        r, k = C.c_uint64(), C.c_uint32()
+        lib().sfb_adj_shape(self._h, C.byref(r), C.byref(k))
+        return r.value, k.value
+
+    def to_host(self):
+        r, k = self.shape
+        idx = np.empty((r, k), np.uint32)
+        w = np.empty((r, k), np.float64)
+        cnt = np.empty(r, np.uint32)
+        self.ctx.check(lib().sfb_adj_copy(self.ctx._h, self._h, _ffi.ptr(idx), _ffi.ptr(w), _ffi.ptr(cnt)))
+        return idx, w, cnt
+
+    @staticmethod
+    def from_host(ctx, idx, w, cnt):
+        idx, w, cnt = _ffi.u32(idx), _ffi.f64(w), _ffi.u32(cnt)
+        h = C.c_void_p()
+        ctx.check(lib().sfb_adj_from_host(ctx._h, _ffi.ptr(idx), _ffi.ptr(w), _ffi.ptr(cnt), idx.shape[0],
+                                           idx.shape[1], C.byref(h)))
+        return Adjacency(ctx, h)
+
+    def sfgrass(self, ratio=0.5):
+        applied = C.c_int32()
+        self.ctx.check(lib().sfb_sparsify_sfgrass(self.ctx._h, self._h, float(ratio), C.byref(applied)))
+        return bool(applied.value)
+
+    def laplacian(self, normalised=False, weight_threshold=1e-9):
+        prm = _ffi.LapParams(int(normalised), float(weight_threshold))
+        h = C.c_void_p()
+        self.ctx.check(lib().sfb_laplacian_build(self.ctx._h, self._h, C.byref(prm), C.byref(h)))
+        return Csr(self.ctx, h)
+
+
+class Csr(_Handle):
+    _free = "sfb_csr_free"
+
+    @property
+    def shape(self):
+        r, nnz = C.c_uint64(), C.c_uint64()
+        lib().sfb_csr_shape(self._h, C.byref(r), C.byref(nnz))
+        return r.value, nnz.value
+
+    def to_host(self):
+        r, nnz = self.shape
+        indptr = np.empty(r + 1, np.uint64)
+        indices = np.empty(max(nnz, 1), np.uint32)
+        data = np.empty(max(nnz, 1), np.float64)
+        self.ctx.check(lib().sfb_csr_copy(self.ctx._h, self._h, _ffi.ptr(indptr), _ffi.ptr(indices), _ffi.ptr(data)))
+        self.ctx.synchronize()
+        return indptr, indices[:nnz], data[:nnz]
+
+    @staticmethod
+    def from_host(ctx, indptr, indices, data):
+        indptr = _ffi.u64(indptr)
+        indices = _ffi.u32(indices) if len(indices) else np.zeros(1, np.uint32)
+        data = _ffi.f64(data) if len(data) else np.zeros(1, np.float64)
+        h = C.c_void_p()
+        ctx.check(lib().sfb_csr_from_host(ctx._h, len(indptr) - 1, _ffi.ptr(indptr), _ffi.ptr(indices),
+                                           _ffi.ptr(data), C.byref(h)))
+        return Csr(ctx, h)
+
+    def spmv(self, x):
+        x = _ffi.f64(x)
+        y = np.empty_like(x)
+        self.ctx.check(lib().sfb_spmv(self.ctx._h, self._h, _ffi.ptr(x), _ffi.ptr(y)))
+        return y
+
+    def rayleigh_quotient(self, x):
+        x = _ffi.f64(x)
+        out = C.c_double()
+        self.ctx.check(lib().sfb_rayleigh_quotient(self.ctx._h, self._h, _ffi.ptr(x), C.byref(out)))
+        return out.value
+
+    def lambdas(self, x: Matrix, variant=LAMBDA_LEGACY_TAUMODE, tau_mode=TAU_MEDIAN, tau_value=0.0,
+                normalise=False, with_dispersion=False):
+        n = x.shape[0]
+        prm = _ffi.LambdaParams(variant, tau_mode, float(tau_value), int(normalise))
+        lam = np.empty(n, np.float64)
+        disp = np.empty(n, np.float64) if with_dispersion else None
+        stats = np.empty(3, np.float64)
+        self.ctx.check(lib().sfb_lambda(self.ctx._h, self._h, x._h, C.byref(prm), _ffi.ptr(lam), _ffi.ptr(disp),
+                                        _ffi.ptr(stats)))
+        self.ctx.synchronize()
+        return (lam, disp, stats) if with_dispersion else (lam, stats)
+
+    def lambdas_allgather(self, x_shard: Matrix, row0, total_rows, variant=LAMBDA_LEGACY_TAUMODE,
+                          tau_mode=TAU_MEDIAN, tau_value=0.0, normalise=True):
+        prm = _ffi.LambdaParams(variant, tau_mode, float(tau_value), int(normalise))
+        lam = np.empty(total_rows, np.float64)
+        stats = np.empty(3, np.float64)
+        self.ctx.check(lib().sfb_lambda_allgather(self.ctx._h, self._h, x_shard._h, row0, total_rows, C.byref(prm),
+                                                  _ffi.ptr(lam), _ffi.ptr(stats)))
+        return lam, stats
+
+
+# ------------------------------------------------------------------------------------------------
+# reference layer
+# ------------------------------------------------------------------------------------------------
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+@dataclass
+class GraphParams:
+    """src_legacy/graph.rs:94-102.  `k` is carried but unused, as in the reference (only `topk`
+    drives the neighbour count, laplacian.rs:213,223,248).  sigma=None means 1.0
+    (`params.sigma.unwrap_or(1.0)`, laplacian.rs:256)."""
+    eps: float = 1e-3
+    k: int = 6
+    topk: int = 3
+    p: float = 2.0
+    sigma: Optional[float] = None
+    normalise: bool = False
+    sparsity_check: bool = False
+
+
+@dataclass
+class GraphLaplacian:
+    """src_legacy/graph.rs:127-136: `matrix` is the CSR Laplacian (here: a device handle plus lazily
+    fetched host arrays), `nnodes` the item count of the original data, `init_data` the matrix the
+    graph was built from."""
+    matrix: Csr
+    nnodes: int
+    graph_params: GraphParams
+    init_data: Optional[np.ndarray] = None
+    energy: bool = False
+    _host: Optional[tuple] = field(default=None, repr=False)
+
+    def csr(self):
+        if self._host is None:
+            self._host = self.matrix.to_host()
+        return self._host
+
+    def shape(self):
+        r, _ = self.matrix.shape
+        return (r, r)
+
+    def nnz(self):
+        return self.matrix.shape[1]
+
+    @staticmethod
+    def sparsity(matrix: Csr):
+        """graph.rs:626-632"""
+        r, nnz = matrix.shape
+        return 1.0 - nnz / float(r * r)
+
+    def degrees(self):
+        """graph.rs:353-373: the diagonal"""
+        indptr, indices, data = self.csr()
+        out = np.zeros(len(indptr) - 1)
+        for r in range(len(out)):
+            s, e = int(indptr[r]), int(indptr[r + 1])
+            hit = np.nonzero(indices[s:e] == r)[0]
+            if len(hit):
+                out[r] = data[s + hit[0]]
+        return out
+
+    def multiply_vector(self, x):
+        """graph.rs:464-501"""
+        if len(x) != self.matrix.shape[0]:
+            raise ValueError(f"Vector length {len(x)} must match number of nodes {self.matrix.shape[0]}")
+        return self.matrix.spmv(x)
+
+    def rayleigh_quotient(self, vector):
+        """graph.rs:422-461"""
+        if len(vector) != self.matrix.shape[0]:
+            raise ValueError(f"Vector length {len(vector)} must match number of nodes {self.matrix.shape[0]}")
+        return self.matrix.rayleigh_quotient(vector)
+
+    def neighbors_of(self, i):
+        """graph.rs:510-525: (j, w) with w = -L_ij > 0"""
+        indptr, indices, data = self.csr()
+        s, e = int(indptr[i]), int(indptr[i + 1])
+        return [(int(j), -float(v)) for j, v in zip(indices[s:e], data[s:e]) if j != i and -v > 0.0]
+
+
+def build_laplacian_matrix(transposed, params: GraphParams, n_items=None, energy=False, screen=SCREEN_AUTO,
+                           ctx=None) -> GraphLaplacian:
+    """src_legacy/laplacian.rs:122-180.  `transposed` has one row per graph node.  Runs through the
+    one-shot C entry point (host buffers in; the CSR stays on the device)."""
+    ctx = ctx or default_context()
+    x = _ffi.f64(transposed)
+    if x.ndim != 2:
+        raise ValueError("items must be a 2-D matrix")
+    n, d = x.shape
+    gp = _ffi.GraphParamsC(float(params.eps), int(params.k), int(params.topk), float(params.p),
+                           float(1.0 if params.sigma is None else params.sigma), int(params.normalise),
+                           int(params.sparsity_check))
+    h = C.c_void_p()
+    ctx.check(lib().sfb_build_laplacian_matrix(ctx._h, _ffi.ptr(x), n, d, C.byref(gp), screen, C.byref(h)))
+    return GraphLaplacian(matrix=Csr(ctx, h), nnodes=n if n_items is None else n_items, graph_params=params,
+                          init_data=x, energy=energy)
+
+
+class GraphFactory:
+    @staticmethod
+    def build_laplacian_matrix_from_k_cluster(clustered, eps, k, topk, p, sigma_override, normalise, sparsity_check,
+                                              n_items, ctx=None) -> GraphLaplacian:
+        """src_legacy/graph.rs:193-255: transposes (features become the nodes) and builds."""
+        clustered = np.asarray(clustered, dtype=np.float64)
+        if clustered.shape[0] > n_items:
+            raise ValueError("clustered.shape().0 <= n_items")  # graph.rs:212
+        params = GraphParams(eps, k, topk, p, sigma_override, normalise, sparsity_check)
+        return build_laplacian_matrix(np.ascontiguousarray(clustered.T), params, n_items, False, ctx=ctx)
+
+
+class TauMode:
+    """src_legacy/taumode.rs:16-23."""
+
+    def __init__(self, kind, value=0.0):
+        self.kind, self.value = kind, value
+
+    @staticmethod
+    def Fixed(t):
+        return TauMode(TAU_FIXED, t)
+
+    @staticmethod
+    def Percentile(p):
+        return TauMode(TAU_PERCENTILE, p)
+
+    def __repr__(self):
+        return {TAU_FIXED: f"Fixed({self.value})", TAU_MEDIAN: "Median", TAU_MEAN: "Mean",
+                TAU_PERCENTILE: f"Percentile({self.value})"}[self.kind]
+
+    @staticmethod
+    def compute_taumode_lambdas_parallel(items, gl: GraphLaplacian, taumode, ctx=None):
+        """taumode.rs:117-214 + ArrowSpace::update_lambdas (core.rs:1427-1443): per-item synthetic
+        lambda against the F x F Laplacian, then min-max normalised.  Returns the lambda vector."""
+        ctx = ctx or gl.matrix.ctx
+        x = _ffi.f64(items)
+        n, f = x.shape
+        out = np.empty(n, np.float64)
+        ctx.check(lib().sfb_compute_taumode_lambdas(ctx._h, gl.matrix._h, _ffi.ptr(x), n, f, taumode.kind,
+                                                    float(taumode.value), _ffi.ptr(out)))
+        return out
+
+    compute_taumode_lambdas = compute_taumode_lambdas_parallel  # taumode.rs:411-413
+
+
+TauMode.Median = TauMode(TAU_MEDIAN)
+TauMode.Mean = TauMode(TAU_MEAN)
+
+
+class SfGrassSparsifier:
+    """src_legacy/sparsification.rs:14-36."""
+
+    def __init__(self):
+        self.target_ratio = 0.5
+
+    def with_target_ratio(self, ratio):
+        self.target_ratio = min(max(ratio, 0.1), 1.0)
+        return self
+
+    def sparsify_graph(self, adj_rows, n_nodes, ctx=None):
+        """adj_rows: list of lists of (j, w).  Returns the same shape."""
+        ctx = ctx or default_context()
+        k = max(1, max((len(r) for r in adj_rows), default=1))
+        idx = np.full((n_nodes, k), IDX_NONE, np.uint32)
+        w = np.zeros((n_nodes, k), np.float64)
+        cnt = np.zeros(n_nodes, np.uint32)
+        for i, r in enumerate(adj_rows):
+            cnt[i] = len(r)
+            for t, (j, wv) in enumerate(r):
+                idx[i, t], w[i, t] = j, wv
+        a = Adjacency.from_host(ctx, idx, w, cnt)
+        a.sfgrass(self.target_ratio)
+        idx, w, cnt = a.to_host()
+        return [[(int(idx[i, t]), float(w[i, t])) for t in range(int(cnt[i]))] for i in range(n_nodes)]

@@ -1,0 +1,410 @@
+// api.cu -- context, dense matrices, handle plumbing, synthetic rows, exclusive scan.
+#include <stdarg.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "synth.cuh"
+
+int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    return code;
+}
+
+extern "C" int32_t sfb_abi_version(void) { return SFB_ABI_VERSION; }
+
+extern "C" int32_t sfb_ctx_create(int32_t device_id, sfb_ctx** out) {
+    if (!out) return SFB_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SFB_ECUDA;  // no CPU fallback
+    if (device_id < 0 || device_id >= n) return SFB_EINVAL;
+    sfb_ctx* ctx = new (std::nothrow) sfb_ctx();
+    if (!ctx) return SFB_ENOMEM;
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SFB_ECUDA;
+    }
+    if (prop.major != 10) {  // sm_100a only: no multi-arch dispatch
+        fprintf(stderr, "surfface_b200: device %d is sm_%d%d, this library is built for sm_100a only\n",
+                device_id, prop.major, prop.minor);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return SFB_EUNSUPPORTED;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return SFB_OK;
+}
+
+extern "C" void sfb_ctx_destroy(sfb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* sfb_last_error(const sfb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" int32_t sfb_device_info(const sfb_ctx* ctx, char* name, int32_t* sm_count, uint64_t* hbm_bytes) {
+    if (!ctx) return SFB_EINVAL;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return SFB_ECUDA;
+    if (name) { strncpy(name, prop.name, 255); name[255] = 0; }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_synchronize(sfb_ctx* ctx) {
+    if (!ctx) return SFB_EINVAL;
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_timings(const sfb_ctx* ctx, sfb_stage_times* out) {
+    if (!ctx || !out) return SFB_EINVAL;
+    *out = ctx->times;
+    return SFB_OK;
+}
+extern "C" int32_t sfb_timings_reset(sfb_ctx* ctx) {
+    if (!ctx) return SFB_EINVAL;
+    uint64_t l = ctx->times.kernel_launches;
+    ctx->times = sfb_stage_times{};
+    ctx->times.kernel_launches = l;
+    return SFB_OK;
+}
+
+// ---- matrices ---------------------------------------------------------------------------------
+static int32_t mat_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t cols, sfb_mat** out) {
+    if (!ctx || !out || rows == 0 || cols == 0) return sfb_fail(ctx, SFB_EINVAL, "matrix must be non-empty");
+    if (rows > 0xFFFFFFFEull) return sfb_fail(ctx, SFB_EINVAL, "rows must fit u32 node indices");
+    sfb_mat* m = new (std::nothrow) sfb_mat();
+    if (!m) return SFB_ENOMEM;
+    m->ctx = ctx; m->rows = rows; m->cols = cols;
+    cudaError_t e = cudaMalloc(&m->d, sizeof(double) * rows * cols);
+    if (e != cudaSuccess) { delete m; return sfb_fail(ctx, SFB_ENOMEM, "cudaMalloc %llu x %u f64: %s", (unsigned long long)rows, cols, cudaGetErrorString(e)); }
+    *out = m;
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_mat_from_host(sfb_ctx* ctx, const double* x, uint64_t rows, uint32_t cols, sfb_mat** out) {
+    if (!x) return sfb_fail(ctx, SFB_EINVAL, "null host pointer");
+    SFB_TRY(mat_alloc(ctx, rows, cols, out));
+    StageTimer t(ctx, &ctx->times.ms_h2d);
+    cudaError_t e = cudaMemcpyAsync((*out)->d, x, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, ctx->stream);
+    t.stop();
+    if (e != cudaSuccess) { sfb_mat_free(*out); *out = nullptr; return sfb_fail(ctx, SFB_ECUDA, "H2D: %s", cudaGetErrorString(e)); }
+    return SFB_OK;
+}
+
+__global__ void generate_rows_kernel(double* __restrict__ out, int kind, uint64_t seed, uint64_t rows, uint32_t cols,
+                                     uint32_t n_centres, double noise) {
+    const uint32_t quads = (cols + 3) / 4;
+    uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= rows * quads) return;
+    uint64_t i = gid / quads;
+    uint32_t q = (uint32_t)(gid % quads);
+    double v[4];
+    synth_row_quad(kind, seed, i, q, n_centres, noise, v);
+    double* o = out + i * cols + (uint64_t)q * 4;
+    for (uint32_t t = 0; t < 4 && q * 4 + t < cols; ++t) o[t] = v[t];
+}
+
+extern "C" int32_t sfb_mat_generate(sfb_ctx* ctx, int32_t kind, uint64_t seed, uint64_t rows, uint32_t cols,
+                                    uint32_t n_centres, double noise, sfb_mat** out) {
+    if (kind < 0 || kind > 2) return sfb_fail(ctx, SFB_EINVAL, "unknown synthetic kind %d", kind);
+    if (kind == 1 && n_centres == 0) return sfb_fail(ctx, SFB_EINVAL, "clustered rows need n_centres > 0");
+    SFB_TRY(mat_alloc(ctx, rows, cols, out));
+    uint64_t total = rows * ((cols + 3) / 4);
+    generate_rows_kernel<<<div_up(total, 256), 256, 0, ctx->stream>>>((*out)->d, kind, seed, rows, cols, n_centres, noise);
+    SFB_LAUNCH_CHECK(ctx);
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+
+// 32x32 tile transpose through shared memory: coalesced on both sides.
+// blockIdx.x walks the (possibly millions of) row tiles, blockIdx.y the column tiles.
+__global__ void transpose_kernel(const double* __restrict__ a, double* __restrict__ b, uint64_t rows, uint32_t cols) {
+    __shared__ double tile[32][33];
+    uint64_t r0 = (uint64_t)blockIdx.x * 32;
+    uint32_t c0 = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        uint64_t r = r0 + dy; uint32_t c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[dy][threadIdx.x] = a[r * cols + c];
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        uint32_t c = c0 + dy; uint64_t r = r0 + threadIdx.x;
+        if (r < rows && c < cols) b[(uint64_t)c * rows + r] = tile[threadIdx.x][dy];
+    }
+}
+
+extern "C" int32_t sfb_mat_transpose(sfb_ctx* ctx, const sfb_mat* a, sfb_mat** out) {
+    if (!a) return sfb_fail(ctx, SFB_EINVAL, "null matrix");
+    if (a->rows > 0xFFFFFFFFull) return sfb_fail(ctx, SFB_EINVAL, "too many rows to transpose");
+    if (a->cols > 65535u * 32u) return sfb_fail(ctx, SFB_EUNSUPPORTED, "transpose supports up to 2M columns");
+    SFB_TRY(mat_alloc(ctx, a->cols, (uint32_t)a->rows, out));
+    dim3 grid(div_up(a->rows, 32), div_up(a->cols, 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, ctx->stream>>>(a->d, (*out)->d, a->rows, a->cols);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_mat_shape(const sfb_mat* a, uint64_t* rows, uint32_t* cols) {
+    if (!a) return SFB_EINVAL;
+    if (rows) *rows = a->rows;
+    if (cols) *cols = a->cols;
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_mat_copy_rows(sfb_ctx* ctx, const sfb_mat* a, uint64_t row0, uint64_t nrows, double* out) {
+    if (!a || !out || row0 + nrows > a->rows) return sfb_fail(ctx, SFB_EINVAL, "row range out of bounds");
+    SFB_CUDA(ctx, cudaMemcpyAsync(out, a->d + row0 * a->cols, sizeof(double) * nrows * a->cols, cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+
+extern "C" void sfb_mat_free(sfb_mat* a) {
+    if (!a) return;
+    cudaFree(a->d);
+    delete a;
+}
+
+// ---- kNN / adjacency / CSR handles ------------------------------------------------------------
+extern "C" int32_t sfb_knn_shape(const sfb_knn* g, uint64_t* rows, uint32_t* k, uint64_t* q_begin) {
+    if (!g) return SFB_EINVAL;
+    if (rows) *rows = g->rows;
+    if (k) *k = g->k;
+    if (q_begin) *q_begin = g->q_begin;
+    return SFB_OK;
+}
+extern "C" int32_t sfb_knn_copy(sfb_ctx* ctx, const sfb_knn* g, uint32_t* idx, double* dist, uint32_t* cnt) {
+    if (!g) return sfb_fail(ctx, SFB_EINVAL, "null kNN handle");
+    StageTimer t(ctx, &ctx->times.ms_d2h);
+    if (idx) SFB_CUDA(ctx, cudaMemcpyAsync(idx, g->idx, sizeof(uint32_t) * g->rows * g->k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist) SFB_CUDA(ctx, cudaMemcpyAsync(dist, g->dist, sizeof(double) * g->rows * g->k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cnt) SFB_CUDA(ctx, cudaMemcpyAsync(cnt, g->cnt, sizeof(uint32_t) * g->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    t.stop();
+    return SFB_OK;
+}
+extern "C" int32_t sfb_knn_stats_get(const sfb_knn* g, sfb_knn_stats* out) {
+    if (!g || !out) return SFB_EINVAL;
+    *out = g->stats;
+    return SFB_OK;
+}
+int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out) {
+    sfb_knn* g = new (std::nothrow) sfb_knn();
+    if (!g) return SFB_ENOMEM;
+    g->ctx = ctx; g->rows = rows; g->k = k; g->total = rows;
+    if (cudaMalloc(&g->idx, sizeof(uint32_t) * rows * k) != cudaSuccess ||
+        cudaMalloc(&g->dist, sizeof(double) * rows * k) != cudaSuccess ||
+        cudaMalloc(&g->cnt, sizeof(uint32_t) * rows) != cudaSuccess) {
+        sfb_knn_free(g);
+        return sfb_fail(ctx, SFB_ENOMEM, "kNN list allocation failed (%llu x %u)", (unsigned long long)rows, k);
+    }
+    *out = g;
+    return SFB_OK;
+}
+extern "C" int32_t sfb_knn_from_host(sfb_ctx* ctx, const uint32_t* idx, const double* dist, const uint32_t* cnt,
+                                     uint64_t rows, uint32_t k, sfb_knn** out) {
+    if (!ctx || !idx || !dist || !cnt || !out || rows == 0 || k == 0) return sfb_fail(ctx, SFB_EINVAL, "bad kNN arrays");
+    SFB_TRY(sfb_knn_alloc(ctx, rows, k, out));
+    sfb_knn* g = *out;
+    SFB_CUDA(ctx, cudaMemcpyAsync(g->idx, idx, sizeof(uint32_t) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
+    SFB_CUDA(ctx, cudaMemcpyAsync(g->dist, dist, sizeof(double) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
+    SFB_CUDA(ctx, cudaMemcpyAsync(g->cnt, cnt, sizeof(uint32_t) * rows, cudaMemcpyHostToDevice, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+extern "C" void sfb_knn_free(sfb_knn* g) {
+    if (!g) return;
+    cudaFree(g->idx); cudaFree(g->dist); cudaFree(g->cnt);
+    delete g;
+}
+
+extern "C" int32_t sfb_adj_shape(const sfb_adj* a, uint64_t* rows, uint32_t* k) {
+    if (!a) return SFB_EINVAL;
+    if (rows) *rows = a->rows;
+    if (k) *k = a->k;
+    return SFB_OK;
+}
+extern "C" int32_t sfb_adj_copy(sfb_ctx* ctx, const sfb_adj* a, uint32_t* idx, double* w, uint32_t* cnt) {
+    if (!a) return sfb_fail(ctx, SFB_EINVAL, "null adjacency handle");
+    if (idx) SFB_CUDA(ctx, cudaMemcpyAsync(idx, a->idx, sizeof(uint32_t) * a->rows * a->k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (w) SFB_CUDA(ctx, cudaMemcpyAsync(w, a->w, sizeof(double) * a->rows * a->k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cnt) SFB_CUDA(ctx, cudaMemcpyAsync(cnt, a->cnt, sizeof(uint32_t) * a->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+int32_t sfb_adj_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_adj** out) {
+    sfb_adj* a = new (std::nothrow) sfb_adj();
+    if (!a) return SFB_ENOMEM;
+    a->ctx = ctx; a->rows = rows; a->k = k;
+    if (cudaMalloc(&a->idx, sizeof(uint32_t) * rows * k) != cudaSuccess ||
+        cudaMalloc(&a->w, sizeof(double) * rows * k) != cudaSuccess ||
+        cudaMalloc(&a->cnt, sizeof(uint32_t) * rows) != cudaSuccess) {
+        sfb_adj_free(a);
+        return sfb_fail(ctx, SFB_ENOMEM, "adjacency allocation failed");
+    }
+    *out = a;
+    return SFB_OK;
+}
+extern "C" int32_t sfb_adj_from_host(sfb_ctx* ctx, const uint32_t* idx, const double* w, const uint32_t* cnt,
+                                     uint64_t rows, uint32_t k, sfb_adj** out) {
+    if (!ctx || !idx || !w || !cnt || !out || rows == 0 || k == 0) return sfb_fail(ctx, SFB_EINVAL, "bad adjacency arrays");
+    SFB_TRY(sfb_adj_alloc(ctx, rows, k, out));
+    sfb_adj* a = *out;
+    SFB_CUDA(ctx, cudaMemcpyAsync(a->idx, idx, sizeof(uint32_t) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
+    SFB_CUDA(ctx, cudaMemcpyAsync(a->w, w, sizeof(double) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
+    SFB_CUDA(ctx, cudaMemcpyAsync(a->cnt, cnt, sizeof(uint32_t) * rows, cudaMemcpyHostToDevice, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+extern "C" void sfb_adj_free(sfb_adj* a) {
+    if (!a) return;
+    cudaFree(a->idx); cudaFree(a->w); cudaFree(a->cnt);
+    delete a;
+}
+
+extern "C" int32_t sfb_csr_shape(const sfb_csr* L, uint64_t* rows, uint64_t* nnz) {
+    if (!L) return SFB_EINVAL;
+    if (rows) *rows = L->rows;
+    if (nnz) *nnz = L->nnz;
+    return SFB_OK;
+}
+extern "C" int32_t sfb_csr_copy(sfb_ctx* ctx, const sfb_csr* L, uint64_t* indptr, uint32_t* indices, double* data) {
+    if (!L) return sfb_fail(ctx, SFB_EINVAL, "null CSR handle");
+    StageTimer t(ctx, &ctx->times.ms_d2h);
+    if (indptr) SFB_CUDA(ctx, cudaMemcpyAsync(indptr, L->indptr, sizeof(uint64_t) * (L->rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (indices && L->nnz) SFB_CUDA(ctx, cudaMemcpyAsync(indices, L->indices, sizeof(uint32_t) * L->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    if (data && L->nnz) SFB_CUDA(ctx, cudaMemcpyAsync(data, L->data, sizeof(double) * L->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    t.stop();
+    return SFB_OK;
+}
+extern "C" int32_t sfb_csr_from_host(sfb_ctx* ctx, uint64_t rows, const uint64_t* indptr, const uint32_t* indices,
+                                     const double* data, sfb_csr** out) {
+    if (!ctx || !indptr || !out || rows == 0) return sfb_fail(ctx, SFB_EINVAL, "bad CSR arrays");
+    uint64_t nnz = indptr[rows];
+    if (nnz && (!indices || !data)) return sfb_fail(ctx, SFB_EINVAL, "bad CSR arrays");
+    for (uint64_t r = 0; r < rows; ++r) {
+        if (indptr[r] > indptr[r + 1]) return sfb_fail(ctx, SFB_EINVAL, "indptr not monotone at row %llu", (unsigned long long)r);
+        for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e)
+            if (indices[e] >= rows || (e > indptr[r] && indices[e] <= indices[e - 1]))
+                return sfb_fail(ctx, SFB_EINVAL, "row %llu: column indices must be ascending and < rows", (unsigned long long)r);
+    }
+    sfb_csr* L = new (std::nothrow) sfb_csr();
+    if (!L) return SFB_ENOMEM;
+    L->ctx = ctx; L->rows = rows; L->nnz = nnz;
+    if (cudaMalloc(&L->indptr, sizeof(uint64_t) * (rows + 1)) != cudaSuccess ||
+        cudaMalloc(&L->indices, sizeof(uint32_t) * (nnz ? nnz : 1)) != cudaSuccess ||
+        cudaMalloc(&L->data, sizeof(double) * (nnz ? nnz : 1)) != cudaSuccess) {
+        sfb_csr_free(L);
+        return sfb_fail(ctx, SFB_ENOMEM, "CSR allocation failed");
+    }
+    SFB_CUDA(ctx, cudaMemcpyAsync(L->indptr, indptr, sizeof(uint64_t) * (rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        SFB_CUDA(ctx, cudaMemcpyAsync(L->indices, indices, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+        SFB_CUDA(ctx, cudaMemcpyAsync(L->data, data, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = L;
+    return SFB_OK;
+}
+extern "C" void sfb_csr_free(sfb_csr* L) {
+    if (!L) return;
+    cudaFree(L->indptr); cudaFree(L->indices); cudaFree(L->data);
+    delete L;
+}
+
+// ---- exclusive scan u32 -> u64 (three kernels: block sums, scan of sums, block scan) ----------
+static constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total) {
+    __shared__ uint64_t warp_sums[SCAN_BLOCK / 32];
+    __shared__ uint64_t block_total;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t s = lane < SCAN_BLOCK / 32 ? warp_sums[lane] : 0, si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < SCAN_BLOCK / 32) warp_sums[lane] = si - s;
+        if (lane == 31) block_total = si;
+    }
+    __syncthreads();
+    *total = block_total;
+    return inc - v + warp_sums[wid];
+}
+
+__global__ void scan_block_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ sums) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint64_t s = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) if (base + t < n) s += in[base + t];
+    uint64_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void scan_sums_serial(uint64_t* sums, uint64_t nb, uint64_t* out_total) {
+    // single block: nb is at most a few thousand
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t b0 = 0; b0 < nb; b0 += SCAN_BLOCK) {
+        uint64_t i = b0 + threadIdx.x;
+        uint64_t v = i < nb ? sums[i] : 0, total;
+        uint64_t ex = block_exclusive_scan(v, &total);
+        if (i < nb) sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_total = carry;
+}
+__global__ void scan_apply(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ sums,
+                           uint64_t* __restrict__ out) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint64_t s = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) { v[t] = base + t < n ? in[base + t] : 0; s += v[t]; }
+    uint64_t total;
+    uint64_t ex = block_exclusive_scan(s, &total) + sums[blockIdx.x];
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) { if (base + t < n) out[base + t] = ex; ex += v[t]; }
+}
+
+int32_t sfb_scan_exclusive_u64(sfb_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out) {
+    uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    DevBuf sums;
+    SFB_CUDA(ctx, sums.alloc(sizeof(uint64_t) * nb));
+    scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, sums.as<uint64_t>());
+    SFB_LAUNCH_CHECK(ctx);
+    scan_sums_serial<<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums.as<uint64_t>(), nb, out + n);
+    SFB_LAUNCH_CHECK(ctx);
+    scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, sums.as<uint64_t>(), out);
+    SFB_LAUNCH_CHECK(ctx);
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}

@@ -1,0 +1,123 @@
+// common.cuh -- context, handles, error plumbing shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/surfface_b200.h"
+
+struct sfb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    sfb_stage_times times{};
+    // NCCL (loaded lazily, comm.cu)
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+struct sfb_mat {
+    sfb_ctx* ctx;
+    double* d = nullptr;  // rows x cols, row-major
+    uint64_t rows = 0;
+    uint32_t cols = 0;
+};
+
+struct sfb_knn {
+    sfb_ctx* ctx;
+    uint32_t* idx = nullptr;  // rows x k
+    double* dist = nullptr;   // rows x k
+    uint32_t* cnt = nullptr;  // rows
+    uint64_t rows = 0;        // query rows held
+    uint64_t q_begin = 0;     // global index of local row 0
+    uint64_t total = 0;       // corpus rows (node count)
+    uint32_t k = 0;
+    sfb_knn_stats stats{};
+};
+
+struct sfb_adj {
+    sfb_ctx* ctx;
+    uint32_t* idx = nullptr;  // rows x k
+    double* w = nullptr;      // rows x k
+    uint32_t* cnt = nullptr;  // rows
+    uint64_t rows = 0;
+    uint32_t k = 0;
+};
+
+struct sfb_csr {
+    sfb_ctx* ctx;
+    uint64_t* indptr = nullptr;  // rows + 1
+    uint32_t* indices = nullptr;
+    double* data = nullptr;
+    uint64_t rows = 0, nnz = 0;
+};
+
+int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...);
+
+#define SFB_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return sfb_fail((ctx), e__ == cudaErrorMemoryAllocation ? SFB_ENOMEM : SFB_ECUDA,    \
+                            "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define SFB_TRY(call)                   \
+    do {                                \
+        int32_t s__ = (call);           \
+        if (s__ != SFB_OK) return s__;  \
+    } while (0)
+
+#define SFB_LAUNCH_CHECK(ctx)                  \
+    do {                                       \
+        (ctx)->times.kernel_launches++;        \
+        SFB_CUDA((ctx), cudaGetLastError());   \
+    } while (0)
+
+// device scratch that frees itself on every return path
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+    void* release() { void* q = p; p = nullptr; return q; }
+};
+
+// device-time stopwatch on the context's stream (own events: timers nest)
+struct StageTimer {
+    sfb_ctx* ctx;
+    double* acc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool done = false;
+    StageTimer(sfb_ctx* c, double* a) : ctx(c), acc(a) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~StageTimer() { if (!done) stop(); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    double stop() {
+        if (done) return 0.0;
+        done = true;
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (acc) *acc += ms;
+        return ms;
+    }
+};
+
+static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- internal entry points between translation units -------------------------------------------
+int32_t sfb_scan_exclusive_u64(sfb_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out /* n+1 */);
+int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int metric, uint32_t k, double eps,
+                      const uint32_t* query_rows /* device, or null */, uint64_t nq, uint64_t q_begin,
+                      uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);
+int32_t sfb_row_norms(sfb_ctx* ctx, const sfb_mat* x, double* norms);
+int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p,
+                         uint64_t q_begin, uint64_t q_end, sfb_knn* out);

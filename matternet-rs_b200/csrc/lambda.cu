@@ -1,0 +1,403 @@
+// lambda.cu -- per-item taumode lambda, min-max normalisation, diffusion.
+//
+// Reference: TauMode::compute_taumode_lambdas_parallel / compute_synthetic_lambda /
+// compute_rayleigh_quotient_from_matrix / compute_item_dispersion / select_tau
+// (src_legacy/taumode.rs:29-70,117-318,326-408), node_energy_and_dispersion
+// (src_legacy/energymaps.rs:923-1045), compute_lambdas_gpu (surfface-core/src/spectral/mod.rs:69-181),
+// normalise_lambdas (src_legacy/core.rs:1341-1355), diffusion (src_legacy/energymaps.rs:520-546).
+//
+// L is F x F (feature graph, a few thousand non-zeros): it stays in L2/L1.  X (R x F, f64) is
+// streamed once: one warp per item row, the row staged in shared memory with coalesced loads, the
+// CSR rows of L dealt round-robin to the lanes.  The reference's dispersion probes all F^2 pairs
+// (taumode.rs:371-383); only the nnz(L) stored pairs are non-zero, which is what is visited here, in
+// the same (r asc, c asc) order per lane.  Cross-lane sums use a fixed butterfly, so results are
+// deterministic and within 1e-12 relative of the reference's left fold.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint64_t sort_key(double v) {
+    uint64_t u = (uint64_t)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(uint64_t k) {
+    uint64_t u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+// Warp radix select over the finite entries of xs[0..f): returns the key of rank `rank` (0-based,
+// ascending).  hist: 256 u32 of shared memory owned by this warp.  Also returns how many finite
+// entries are strictly below / equal to the selected key.
+__device__ uint64_t warp_select(const double* xs, uint32_t f, uint32_t rank, uint32_t* hist, int lane, uint32_t* n_below,
+                                uint32_t* n_equal) {
+    uint64_t prefix = 0, mask = 0;
+    uint32_t below = 0, remaining = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int b = lane; b < 256; b += 32) hist[b] = 0;
+        __syncwarp();
+        for (uint32_t t = lane; t < f; t += 32) {
+            double v = xs[t];
+            if (!isfinite(v)) continue;
+            uint64_t key = sort_key(v);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
+        }
+        __syncwarp();
+        // each lane owns 8 consecutive bins
+        uint32_t c[8], s = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; s += c[b]; }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        uint32_t ex = inc - s;  // finite entries in lower bins (within the current prefix)
+        uint32_t want = rank - below;
+        int found_bin = -1; uint32_t found_below = 0, found_cnt = 0;
+        if (want >= ex && want < ex + s) {
+            uint32_t run = ex;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (found_bin < 0 && want < run + c[b]) { found_bin = lane * 8 + b; found_below = run; found_cnt = c[b]; }
+                run += c[b];
+            }
+        }
+        uint32_t who = __ballot_sync(FULL, found_bin >= 0);
+        int src = __ffs(who) - 1;
+        found_bin = __shfl_sync(FULL, found_bin, src);
+        found_below = __shfl_sync(FULL, found_below, src);
+        found_cnt = __shfl_sync(FULL, found_cnt, src);
+        below += found_below;
+        remaining = found_cnt;
+        prefix |= (uint64_t)found_bin << shift;
+        mask |= 0xFFull << shift;
+        __syncwarp();
+    }
+    *n_below = below; *n_equal = remaining;
+    return prefix;
+}
+
+// tau of one item row held in shared memory: TauMode::select_tau (taumode.rs:29-70)
+__device__ double warp_select_tau(const double* xs, uint32_t f, int mode, double value, uint32_t* hist, int lane) {
+    const double FLOOR = 1e-10;
+    if (mode == SFB_TAU_FIXED) return (isfinite(value) && value > 0.0) ? value : FLOOR;
+    uint32_t n = 0; double s = 0.0;
+    for (uint32_t t = lane; t < f; t += 32) { double v = xs[t]; if (isfinite(v)) { ++n; s += v; } }
+    n = warp_sum_u(n);
+    if (n == 0) return FLOOR;
+    if (mode == SFB_TAU_MEAN) { double mean = warp_sum(s) / (double)n; return mean > FLOOR ? mean : FLOOR; }
+    uint32_t nb, ne;
+    double r;
+    if (mode == SFB_TAU_PERCENTILE) {
+        double pp = value < 0.0 ? 0.0 : (value > 1.0 ? 1.0 : value);
+        uint32_t idx = (uint32_t)round((double)(n - 1) * pp);
+        r = key_value(warp_select(xs, f, idx, hist, lane, &nb, &ne));
+    } else if (n & 1u) {
+        r = key_value(warp_select(xs, f, n / 2, hist, lane, &nb, &ne));
+    } else {
+        uint64_t ka = warp_select(xs, f, n / 2 - 1, hist, lane, &nb, &ne);
+        double a = key_value(ka), b;
+        if (nb + ne > n / 2) b = a;  // duplicates of a reach rank n/2
+        else {
+            uint64_t kb = 0xFFFFFFFFFFFFFFFFull;
+            for (uint32_t t = lane; t < f; t += 32) {
+                double v = xs[t];
+                if (!isfinite(v)) continue;
+                uint64_t kv = sort_key(v);
+                if (kv > ka && kv < kb) kb = kv;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { uint64_t t = __shfl_xor_sync(FULL, kb, o); kb = t < kb ? t : kb; }
+            b = key_value(kb);
+        }
+        r = 0.5 * (a + b);
+    }
+    return r > FLOOR ? r : FLOOR;
+}
+
+struct LambdaArgs {
+    const uint64_t* indptr; const uint32_t* indices; const double* data; uint32_t f;
+    const double* x; uint64_t n;
+    int variant, tau_mode; double tau_value;
+    double* out_lambda; double* out_disp; float* out_energy_f32;
+};
+
+// shared memory: per warp f doubles (the item row) + 256 u32 (select histogram)
+template <int VARIANT>
+__global__ void lambda_kernel(LambdaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* xs = reinterpret_cast<double*>(smem_raw) + (size_t)w * a.f;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)wpb * a.f) + w * 256;
+    const uint32_t f = a.f;
+    for (uint64_t i = (uint64_t)blockIdx.x * wpb + w; i < a.n; i += (uint64_t)gridDim.x * wpb) {
+        const double* xr = a.x + i * f;
+        __syncwarp();
+        bool zero = true;
+        double den = 0.0;
+        for (uint32_t t = lane; t < f; t += 32) {
+            double v = xr[t];
+            xs[t] = v;
+            zero = zero && (fabs(v) <= 1e-10);
+            den += v * v;
+        }
+        __syncwarp();
+        zero = __all_sync(FULL, zero);
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE && zero) {  // taumode.rs:268-274
+            if (lane == 0) { a.out_lambda[i] = 0.0; if (a.out_disp) a.out_disp[i] = 0.0; }
+            continue;
+        }
+        if (VARIANT == SFB_LAMBDA_CORE_F32SEM) {
+            float num = 0.f, den32 = 0.f, es = 0.f;
+            for (uint32_t r = lane; r < f; r += 32) {
+                float xv = (float)xs[r], lx = 0.f, wx = 0.f, wx2 = 0.f, dg = 0.f;
+                for (uint64_t e = a.indptr[r]; e < a.indptr[r + 1]; ++e) {
+                    float lv = (float)a.data[e], xc = (float)xs[a.indices[e]];
+                    float wv = -lv > 0.f ? -lv : 0.f;
+                    lx = __fadd_rn(lx, __fmul_rn(lv, xc));
+                    wx = __fadd_rn(wx, __fmul_rn(wv, xc));
+                    wx2 = __fadd_rn(wx2, __fmul_rn(wv, __fmul_rn(xc, xc)));
+                    dg = __fadd_rn(dg, wv);
+                }
+                num += xv * lx; den32 += xv * xv;
+                float ee = __fadd_rn(__fadd_rn(__fmul_rn(dg, __fmul_rn(xv, xv)), -__fmul_rn(__fmul_rn(xv, wx), 2.0f)), wx2);
+                es += ee > 0.f ? ee : 0.f;
+            }
+            num = warp_sum_f(num); den32 = warp_sum_f(den32); es = warp_sum_f(es);
+            float rq = num / (den32 + 1e-9f);
+            rq = rq < -1e6f ? -1e6f : (rq > 1e6f ? 1e6f : rq);
+            if (lane == 0) { a.out_lambda[i] = (double)rq; a.out_energy_f32[i] = es; }
+            continue;
+        }
+        den = warp_sum(den);
+        double num = 0.0, ssum = 0.0, qsum = 0.0;
+        for (uint32_t r = lane; r < f; r += 32) {
+            const double xv = xs[r];
+            double rs = 0.0;
+            const uint64_t e0 = a.indptr[r], e1 = a.indptr[r + 1];
+            for (uint64_t e = e0; e < e1; ++e) {
+                const uint32_t c = a.indices[e];
+                const double lv = a.data[e], xc = xs[c];
+                if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) rs = __dadd_rn(rs, __dmul_rn(__dmul_rn(xv, lv), xc));  // taumode.rs:348-350
+                else rs = __dadd_rn(rs, __dmul_rn(lv, xc));                                                     // graph.rs:489-491
+                const bool use = VARIANT == SFB_LAMBDA_LEGACY_TAUMODE ? (c != r) : (c > r);
+                const double wv = -lv;
+                if (use && wv > 0.0) {
+                    double d = xv - xc;
+                    double contrib = (wv * d) * d;
+                    ssum += contrib;
+                    qsum = fma(contrib, contrib, qsum);
+                }
+            }
+            num += VARIANT == SFB_LAMBDA_LEGACY_TAUMODE ? rs : xv * rs;
+        }
+        num = warp_sum(num); ssum = warp_sum(ssum); qsum = warp_sum(qsum);
+        double e_raw = 0.0;
+        if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
+        double g = 0.0;
+        if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
+        double lam;
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
+            double tau = warp_select_tau(xs, f, a.tau_mode, a.tau_value, hist, lane);
+            lam = tau * (e_raw / (e_raw + tau)) + (1.0 - tau) * g;  // taumode.rs:306-310
+        } else {
+            lam = e_raw;
+        }
+        if (lane == 0) { a.out_lambda[i] = lam; if (a.out_disp) a.out_disp[i] = g; }
+    }
+}
+
+// CORE_F32SEM second pass: G_i = clamp(e_i / (sum e + 1e-12), 0, 1); lambda = R + G (f32)
+__global__ void core_sum_energy_kernel(const float* __restrict__ e, uint64_t n, float* __restrict__ total) {
+    // single block, ascending chunks: deterministic
+    __shared__ float s[256];
+    float acc = 0.f;
+    for (uint64_t i = threadIdx.x; i < n; i += 256) acc += e[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) { if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) *total = s[0];
+}
+__global__ void core_finish_kernel(const float* __restrict__ e, const float* __restrict__ total, uint64_t n,
+                                   double* __restrict__ lam, double* __restrict__ disp) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = e[i] / (*total + 1e-12f);
+    g = g < 0.f ? 0.f : (g > 1.f ? 1.f : g);
+    lam[i] = (double)((float)lam[i] + g);
+    if (disp) disp[i] = (double)g;
+}
+
+// min / max(0, .) of lambda (core.rs:1345-1346), then (lambda - min) / max(max - min, 1e-9)
+__global__ void minmax_kernel(const double* __restrict__ v, uint64_t n, double* __restrict__ out /* [2*gridDim.x] */) {
+    __shared__ double smin[256], smax[256];
+    double mn = INFINITY, mx = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double x = v[i];
+        mn = fmin(mn, x); mx = fmax(mx, x);
+    }
+    smin[threadIdx.x] = mn; smax[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) { smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + o]); smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + o]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = smin[0]; out[2 * blockIdx.x + 1] = smax[0]; }
+}
+__global__ void normalise_kernel(double* __restrict__ v, uint64_t n, double mn, double rng) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = __ddiv_rn(__dadd_rn(v[i], -mn), rng);
+}
+
+// diffusion: x_r' = x_r - eta * (L x)_r, `steps` times, row resident in shared memory (two slots)
+__global__ void diffuse_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                               const double* __restrict__ data, uint32_t f, double* __restrict__ x, uint64_t n, double eta,
+                               uint32_t steps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* cur = reinterpret_cast<double*>(smem_raw) + (size_t)w * 2 * f;
+    double* nxt = cur + f;
+    for (uint64_t i = (uint64_t)blockIdx.x * wpb + w; i < n; i += (uint64_t)gridDim.x * wpb) {
+        double* xr = x + i * f;
+        __syncwarp();
+        for (uint32_t t = lane; t < f; t += 32) cur[t] = xr[t];
+        __syncwarp();
+        double* a = cur; double* b = nxt;
+        for (uint32_t s = 0; s < steps; ++s) {
+            for (uint32_t r = lane; r < f; r += 32) {
+                double sum = 0.0;
+                for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) sum = __dadd_rn(sum, __dmul_rn(data[e], a[indices[e]]));
+                b[r] = __dadd_rn(a[r], -__dmul_rn(eta, sum));
+            }
+            __syncwarp();
+            double* t = a; a = b; b = t;
+        }
+        for (uint32_t t = lane; t < f; t += 32) xr[t] = a[t];
+    }
+}
+
+}  // namespace
+
+// lambdas of rows [0, n) of a device matrix into a device array; shared by the single- and multi-GPU paths
+int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, uint64_t n, uint32_t f,
+                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp) {
+    if (L->rows != f) return sfb_fail(ctx, SFB_EINVAL, "Matrix rows %llu must match vector length %u", (unsigned long long)L->rows, f);  // taumode.rs:330-337
+    if (prm->variant < 0 || prm->variant > 2) return sfb_fail(ctx, SFB_EINVAL, "unknown lambda variant %d", prm->variant);
+    if (prm->tau_mode < 0 || prm->tau_mode > 3) return sfb_fail(ctx, SFB_EINVAL, "unknown tau mode %d", prm->tau_mode);
+    size_t per_warp = (size_t)f * sizeof(double) + 256 * sizeof(uint32_t);
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    if (per_warp * wpb > ctx->smem_optin) return sfb_fail(ctx, SFB_EUNSUPPORTED, "feature count %u too large for the shared-memory row staging", f);
+    size_t smem = per_warp * wpb;
+    DevBuf e32, tot;
+    LambdaArgs a{L->indptr, L->indices, L->data, f, x_dev, n, prm->variant, prm->tau_mode, prm->tau_value, d_lambda, d_disp, nullptr};
+    // enough resident warps to cover HBM latency; grid = multiple of the SM count
+    int blocks_per_sm = (int)((ctx->smem_optin) / (smem + 1024));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    if (blocks_per_sm > 8) blocks_per_sm = 8;
+    uint64_t want = (n + wpb - 1) / wpb;
+    unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * blocks_per_sm ? want : (uint64_t)ctx->sm_count * blocks_per_sm);
+    if (prm->variant == SFB_LAMBDA_LEGACY_TAUMODE) {
+        SFB_CUDA(ctx, cudaFuncSetAttribute(lambda_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lambda_kernel<0><<<grid, wpb * 32, smem, ctx->stream>>>(a);
+    } else if (prm->variant == SFB_LAMBDA_ENERGY_NODE) {
+        SFB_CUDA(ctx, cudaFuncSetAttribute(lambda_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lambda_kernel<1><<<grid, wpb * 32, smem, ctx->stream>>>(a);
+    } else {
+        SFB_CUDA(ctx, e32.alloc(sizeof(float) * n));
+        SFB_CUDA(ctx, tot.alloc(sizeof(float)));
+        a.out_energy_f32 = e32.as<float>();
+        SFB_CUDA(ctx, cudaFuncSetAttribute(lambda_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lambda_kernel<2><<<grid, wpb * 32, smem, ctx->stream>>>(a);
+        SFB_LAUNCH_CHECK(ctx);
+        core_sum_energy_kernel<<<1, 256, 0, ctx->stream>>>(e32.as<float>(), n, tot.as<float>());
+        SFB_LAUNCH_CHECK(ctx);
+        core_finish_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(e32.as<float>(), tot.as<float>(), n, d_lambda, d_disp);
+    }
+    SFB_LAUNCH_CHECK(ctx);
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+
+// local min / max(0,.) of a device lambda array
+int32_t sfb_minmax_device(sfb_ctx* ctx, const double* d_lambda, uint64_t n, double* mn, double* mx) {
+    const int nb = 128;
+    DevBuf part;
+    SFB_CUDA(ctx, part.alloc(sizeof(double) * 2 * nb));
+    minmax_kernel<<<nb, 256, 0, ctx->stream>>>(d_lambda, n, part.as<double>());
+    SFB_LAUNCH_CHECK(ctx);
+    double h[2 * nb];
+    SFB_CUDA(ctx, cudaMemcpyAsync(h, part.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double a = INFINITY, b = 0.0;
+    for (int i = 0; i < nb; ++i) { a = fmin(a, h[2 * i]); b = fmax(b, h[2 * i + 1]); }
+    *mn = a; *mx = b;
+    return SFB_OK;
+}
+
+int32_t sfb_normalise_device(sfb_ctx* ctx, double* d_lambda, uint64_t n, double mn, double mx, double* stats) {
+    double rng = mx - mn;
+    if (!(rng > 1e-9)) rng = 1e-9;
+    normalise_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(d_lambda, n, mn, rng);
+    SFB_LAUNCH_CHECK(ctx);
+    if (stats) { stats[0] = mn; stats[1] = mx; stats[2] = rng; }
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_lambda_params* prm,
+                              double* out_lambda, double* out_disp, double* stats) {
+    if (!ctx || !L || !x || !prm || !out_lambda) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    StageTimer t(ctx, &ctx->times.ms_lambda);
+    DevBuf lam, disp;
+    SFB_CUDA(ctx, lam.alloc(sizeof(double) * x->rows));
+    if (out_disp) SFB_CUDA(ctx, disp.alloc(sizeof(double) * x->rows));
+    SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, lam.as<double>(), out_disp ? disp.as<double>() : nullptr));
+    if (prm->normalise_minmax || stats) {
+        double mn, mx;
+        SFB_TRY(sfb_minmax_device(ctx, lam.as<double>(), x->rows, &mn, &mx));
+        if (prm->normalise_minmax) SFB_TRY(sfb_normalise_device(ctx, lam.as<double>(), x->rows, mn, mx, stats));
+        else if (stats) { stats[0] = mn; stats[1] = mx; stats[2] = (mx - mn) > 1e-9 ? (mx - mn) : 1e-9; }
+    }
+    t.stop();
+    StageTimer t2(ctx, &ctx->times.ms_d2h);
+    SFB_CUDA(ctx, cudaMemcpyAsync(out_lambda, lam.p, sizeof(double) * x->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_disp) SFB_CUDA(ctx, cudaMemcpyAsync(out_disp, disp.p, sizeof(double) * x->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    t2.stop();
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, double eta, uint32_t steps) {
+    if (!ctx || !L || !x) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (L->rows != x->cols) return sfb_fail(ctx, SFB_EINVAL, "Laplacian rows %llu must match feature count %u", (unsigned long long)L->rows, x->cols);  // energymaps.rs:507-512
+    size_t per_warp = (size_t)x->cols * 2 * sizeof(double);
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    if (per_warp * wpb > ctx->smem_optin) return sfb_fail(ctx, SFB_EUNSUPPORTED, "feature count %u too large", x->cols);
+    size_t smem = per_warp * wpb;
+    SFB_CUDA(ctx, cudaFuncSetAttribute(diffuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t want = (x->rows + wpb - 1) / wpb;
+    unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 4 ? want : (uint64_t)ctx->sm_count * 4);
+    StageTimer t(ctx, &ctx->times.ms_lambda);
+    diffuse_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(L->indptr, L->indices, L->data, x->cols, x->d, x->rows, eta, steps);
+    SFB_LAUNCH_CHECK(ctx);
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}

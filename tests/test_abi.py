@@ -1,0 +1,56 @@
+"""The C-ABI library loads and exports every symbol include/surfface_b200.h declares (CPU only:
+no compute call is made)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "surfface_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sfb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    names = declared_symbols()
+    for must in ("sfb_ctx_create", "sfb_knn_build", "sfb_adjacency_build", "sfb_sparsify_sfgrass",
+                 "sfb_laplacian_build", "sfb_lambda", "sfb_diffuse", "sfb_build_laplacian_matrix",
+                 "sfb_compute_taumode_lambdas", "sfb_knn_allgather", "sfb_lambda_allgather"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(sfb):
+    _ffi = sfb._ffi
+    L = _ffi.lib()
+    names = declared_symbols()
+    assert names, "no declarations parsed"
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+        assert n in _ffi.SYMBOLS, f"{n} has no ctypes signature"
+    assert set(_ffi.SYMBOLS) == set(names)
+    assert L.sfb_abi_version() == 1
+
+
+def test_no_cpu_fallback(sfb):
+    """Without a CUDA device the product refuses to run instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sfb.SfbError):
+        sfb.Context(0)
+
+
+def test_product_does_not_reference_oracle():
+    """Nothing under the product package or include/ may import, include or link the oracle."""
+    bad = []
+    for base in ("matternet-rs_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".rs", "Makefile", ".toml")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"liboracle|import\s+oracle|from\s+oracle|oracle\.c|orc_[a-z]", text):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,334 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): neighbour indices and CSR structure bit-exact, ties by index;
+distances bit-exact (same f64 arithmetic); Laplacian weights and lambda within 1e-9 relative."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9  # the tolerance north_star states for f64 weights and lambda
+
+
+@pytest.fixture(scope="module")
+def ctx(sfb):
+    c = sfb.Context(0)
+    yield c
+    c.close()
+
+
+def assert_knn_equal(got, want):
+    assert np.array_equal(got[2], want[2]), "neighbour counts differ"
+    assert np.array_equal(got[0], want[0]), "neighbour indices differ"
+    assert np.array_equal(got[1], want[1]), "distances differ in bits"
+
+
+# ---- synthetic generator: device rows == CPU replay -------------------------------------------
+@pytest.mark.parametrize("kind,ncent,noise", [(0, 0, 0.0), (1, 16, 0.3), (2, 0, 0.1)])
+def test_generator_bit_exact(sfb, oracle, ctx, kind, ncent, noise):
+    m = ctx.generate(kind, 42, 777, 50, ncent, noise)
+    got = m.rows()
+    want = oracle.generate_rows(kind, 42, 0, 777, 50, ncent, noise)
+    assert np.array_equal(got, want)
+    assert np.array_equal(m.rows(100, 5), oracle.generate_rows(kind, 42, 100, 5, 50, ncent, noise))
+
+
+def test_transpose(sfb, ctx):
+    x = np.random.default_rng(1).normal(size=(77, 45))
+    assert np.array_equal(ctx.matrix(x).transpose().rows(), x.T)
+
+
+# ---- exact kNN --------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [0, 1, 2])
+@pytest.mark.parametrize("m,kd,k", [(50, 7, 3), (257, 33, 16), (1000, 64, 5), (130, 384, 32), (65, 16, 64)])
+def test_knn_exact_parity(sfb, oracle, ctx, metric, m, kd, k):
+    x = np.random.default_rng(m + kd + metric).normal(size=(m, kd))
+    got = ctx.matrix(x).knn(k, metric, screen=sfb.SCREEN_EXACT_F64).to_host()
+    assert_knn_equal(got, oracle.knn(x, k, metric))
+
+
+def test_knn_ties_zero_rows_eps(sfb, oracle, ctx):
+    x = np.array([[1.0, 0.0], [1.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.0, 0.0], [2.0, 0.0], [0.0, 0.0]])
+    for metric in (0, 1, 2):
+        for eps in (math.inf, 0.5, 0.0):
+            got = ctx.matrix(x).knn(3, metric, eps=eps, screen=sfb.SCREEN_EXACT_F64).to_host()
+            assert_knn_equal(got, oracle.knn(x, 3, metric, eps))
+    # duplicated rows: every tie resolved by index
+    rng = np.random.default_rng(9)
+    base = rng.normal(size=(40, 12))
+    x = np.concatenate([base, base, base[:17]])
+    got = ctx.matrix(x).knn(6, 0, screen=sfb.SCREEN_EXACT_F64).to_host()
+    assert_knn_equal(got, oracle.knn(x, 6, 0))
+
+
+def test_knn_query_shard(sfb, oracle, ctx):
+    x = np.random.default_rng(4).normal(size=(500, 24))
+    g = ctx.matrix(x).knn(7, 0, screen=sfb.SCREEN_EXACT_F64, q_begin=120, q_end=333)
+    assert g.shape == (213, 7) and g.q_begin == 120
+    want = oracle.knn(x, 7, 0, query_rows=np.arange(120, 333))
+    assert_knn_equal(g.to_host(), want)
+
+
+def test_knn_argument_errors(sfb, ctx):
+    x = ctx.matrix(np.ones((4, 3)))
+    for bad in (dict(k=0), dict(k=129), dict(k=2, metric=7), dict(k=2, eps=math.nan), dict(k=2, q_begin=3, q_end=2)):
+        with pytest.raises(sfb.SfbError):
+            x.knn(**bad)
+    with pytest.raises(sfb.SfbError):
+        ctx.matrix(np.ones((1, 3))).knn(1)  # assert!(n >= 2), laplacian.rs:130
+
+
+# ---- weights, sparsification ------------------------------------------------------------------
+@pytest.mark.parametrize("p,sigma", [(2.0, 1.0), (1.0, 0.2), (1.7, 0.5)])
+def test_adjacency_parity(sfb, oracle, ctx, p, sigma):
+    x = np.random.default_rng(11).normal(size=(300, 10))
+    for k in (5, 12, 40):  # mean degree <= 10: untouched; > 10: inline sparsification
+        o_knn = oracle.knn(x, k)
+        g = sfb.KnnGraph.from_host(ctx, *o_knn)
+        a = g.adjacency(p, sigma)
+        idx, w, cnt = a.to_host()
+        o_idx, o_w, o_cnt, o_applied = oracle.build_adjacency(*o_knn, p, sigma)
+        assert a.sparsified == o_applied == (k > 10)
+        assert np.array_equal(cnt, o_cnt) and np.array_equal(idx, o_idx)
+        if p in (1.0, 2.0):
+            assert np.array_equal(w, o_w)
+        assert np.allclose(w, o_w, rtol=1e-14, atol=0)
+
+
+def test_adjacency_weight_floor_and_forced(sfb, oracle, ctx):
+    x = np.random.default_rng(12).normal(size=(120, 6))
+    o_knn = oracle.knn(x, 8)
+    g = sfb.KnnGraph.from_host(ctx, *o_knn)
+    # tiny sigma: w = 1/(1+(d/sigma)^p) <= 1e-12 for most edges -> dropped (laplacian.rs:257)
+    got = g.adjacency(4.0, 1e-4).to_host()
+    want = oracle.build_adjacency(*o_knn, 4.0, 1e-4)
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0]) and got[2].sum() < o_knn[2].sum()
+    for force in (0, 1):
+        got = g.adjacency(2.0, 1.0, sparsify=force).to_host()
+        want = oracle.build_adjacency(*o_knn, 2.0, 1.0, force_sparsify=force)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+
+
+@pytest.mark.parametrize("ratio", [0.05, 0.3, 0.5, 1.0])
+def test_sfgrass_parity(sfb, oracle, ctx, ratio):
+    x = np.random.default_rng(13).normal(size=(200, 8))
+    for k in (6, 20, 64):
+        o_adj = oracle.build_adjacency(*oracle.knn(x, k), 2.0, 1.0, force_sparsify=0)
+        a = sfb.Adjacency.from_host(ctx, *o_adj[:3])
+        applied = a.sfgrass(ratio)
+        want = oracle.sfgrass(*o_adj[:3], ratio=ratio)
+        assert applied == want[3] == (k >= 10)
+        got = a.to_host()
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_sfgrass_reference_layer(sfb, oracle, ctx):
+    x = np.random.default_rng(14).normal(size=(60, 5))
+    o_adj = oracle.build_adjacency(*oracle.knn(x, 12), 2.0, 1.0, force_sparsify=0)
+    rows = [[(int(o_adj[0][i, t]), float(o_adj[1][i, t])) for t in range(int(o_adj[2][i]))] for i in range(60)]
+    out = sfb.SfGrassSparsifier().with_target_ratio(0.25).sparsify_graph(rows, 60, ctx=ctx)
+    want = oracle.sfgrass(*o_adj[:3], ratio=0.25)
+    assert [len(r) for r in out] == list(want[2])
+    assert [j for j, _ in out[7]] == list(want[0][7, :want[2][7]])
+
+
+# ---- symmetrise + Laplacian -------------------------------------------------------------------
+def assert_csr_equal(got, want, data_exact=False):
+    assert np.array_equal(got[0], want[0]), "indptr differs"
+    assert np.array_equal(got[1], want[1]), "indices differ"
+    if data_exact:
+        assert np.array_equal(got[2], want[2])
+    assert np.allclose(got[2], want[2], rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("m,kd,k", [(40, 5, 3), (300, 10, 16), (2000, 16, 8), (500, 6, 64)])
+def test_laplacian_parity(sfb, oracle, ctx, m, kd, k):
+    x = np.random.default_rng(m).normal(size=(m, kd))
+    o_adj = oracle.build_adjacency(*oracle.knn(x, k), 2.0, 1.0)
+    a = sfb.Adjacency.from_host(ctx, *o_adj[:3])
+    got = a.laplacian().to_host()
+    assert_csr_equal(got, oracle.laplacian(*o_adj[:3]), data_exact=True)
+    # invariants of src_legacy/tests/test_laplacian.rs:52-154
+    indptr, indices, data = got
+    row = np.repeat(np.arange(m), np.diff(indptr.astype(np.int64)))
+    sums = np.zeros(m)
+    np.add.at(sums, row, data)
+    assert np.all(np.abs(sums) < 1e-12)
+    assert len(data) <= m * (2 * k + 1)
+
+
+def test_laplacian_hub_rows(sfb, oracle, ctx):
+    """A star: node 0 is everybody's neighbour -> one row with M-1 reverse edges (block-sort path)."""
+    m, k = 3000, 2
+    idx = np.zeros((m, k), np.uint32)
+    idx[:, 0] = 0
+    idx[:, 1] = (np.arange(m) + 1) % m
+    idx[0] = [1, 2]
+    w = np.random.default_rng(2).uniform(0.1, 1.0, size=(m, k))
+    cnt = np.full(m, k, np.uint32)
+    a = sfb.Adjacency.from_host(ctx, idx, w, cnt)
+    assert_csr_equal(a.laplacian().to_host(), oracle.laplacian(idx, w, cnt), data_exact=True)
+
+
+def test_laplacian_asymmetric_weights_take_max(sfb, oracle, ctx):
+    idx = np.array([[1, 2], [0, 2], [0, 0xFFFFFFFF]], np.uint32)
+    w = np.array([[0.5, 0.25], [0.75, 0.125], [0.3, 0.0]])
+    cnt = np.array([2, 2, 1], np.uint32)
+    got = sfb.Adjacency.from_host(ctx, idx, w, cnt).laplacian().to_host()
+    assert_csr_equal(got, oracle.laplacian(idx, w, cnt), data_exact=True)
+    assert got[2][1] == -0.75  # L[0][1] = -max(0.5, 0.75)
+
+
+def test_laplacian_empty_and_isolated(sfb, oracle, ctx):
+    idx = np.full((5, 2), 0xFFFFFFFF, np.uint32)
+    w = np.zeros((5, 2))
+    cnt = np.zeros(5, np.uint32)
+    idx[1, 0], w[1, 0], cnt[1] = 3, 0.5, 1
+    got = sfb.Adjacency.from_host(ctx, idx, w, cnt).laplacian().to_host()
+    assert_csr_equal(got, oracle.laplacian(idx, w, cnt), data_exact=True)
+    assert len(got[2]) == 7  # 5 diagonals (zeros stored, laplacian.rs:372) + one undirected edge
+
+
+@pytest.mark.parametrize("thr", [1e-9, 0.8])
+def test_laplacian_normalised(sfb, oracle, ctx, thr):
+    x = np.random.default_rng(21).normal(size=(400, 9))
+    o_adj = oracle.build_adjacency(*oracle.knn(x, 6, eps=0.6), 2.0, 1.0)
+    a = sfb.Adjacency.from_host(ctx, *o_adj[:3])
+    got = a.laplacian(normalised=True, weight_threshold=thr).to_host()
+    assert_csr_equal(got, oracle.laplacian(*o_adj[:3], normalised=True, weight_threshold=thr), data_exact=True)
+
+
+def test_spmv_rayleigh(sfb, oracle, ctx):
+    x = np.random.default_rng(22).normal(size=(250, 7))
+    L = oracle.laplacian(*oracle.build_adjacency(*oracle.knn(x, 5), 2.0, 1.0)[:3])
+    c = sfb.Csr.from_host(ctx, *L)
+    v = np.random.default_rng(23).normal(size=250)
+    assert np.array_equal(c.spmv(v), oracle.spmv(*L, v))
+    assert c.rayleigh_quotient(v) == pytest.approx(oracle.rayleigh(*L, v), rel=1e-12)
+    assert c.rayleigh_quotient(np.zeros(250)) == 0.0
+
+
+# ---- lambda ------------------------------------------------------------------------------------
+def feature_laplacian(oracle, x, topk):
+    idx, dist, cnt = oracle.knn(oracle.transpose(x), topk)
+    a = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0)
+    return oracle.laplacian(*a[:3])
+
+
+@pytest.mark.parametrize("tau", [(1, 0.0), (2, 0.0), (0, 0.35), (0, -1.0), (3, 0.0), (3, 0.37), (3, 1.0)])
+@pytest.mark.parametrize("n,f,topk", [(300, 48, 3), (257, 33, 6), (64, 384, 16)])
+def test_lambda_legacy_parity(sfb, oracle, ctx, tau, n, f, topk):
+    rng = np.random.default_rng(n + f)
+    x = rng.normal(size=(n, f)) + 0.5
+    x[3] = 0.0            # zero vector -> lambda 0 (taumode.rs:268-274)
+    x[4] = 1e-11
+    x[5] = 2.5            # constant vector
+    x[6, :f // 2] = x[6, f // 2: 2 * (f // 2)]  # duplicates around the median
+    L = feature_laplacian(oracle, x, topk)
+    c = sfb.Csr.from_host(ctx, *L)
+    lam, disp, stats = c.lambdas(ctx.matrix(x), sfb.LAMBDA_LEGACY_TAUMODE, tau[0], tau[1], with_dispersion=True)
+    o_lam, o_e, o_g = oracle.lambdas(*L, x, oracle.LAMBDA_LEGACY_TAUMODE, tau[0], tau[1], with_parts=True)
+    assert lam[3] == 0.0 and lam[4] == 0.0
+    assert np.allclose(disp, o_g, rtol=RTOL, atol=1e-15)
+    assert np.allclose(lam, o_lam, rtol=RTOL, atol=1e-14)
+    # normalised: core.rs:1341-1355
+    lam_n, stats = c.lambdas(ctx.matrix(x), sfb.LAMBDA_LEGACY_TAUMODE, tau[0], tau[1], normalise=True)
+    o_n, o_stats = oracle.normalise_lambdas(o_lam)
+    assert np.allclose(stats, o_stats, rtol=RTOL, atol=1e-14)
+    assert np.allclose(lam_n, o_n, rtol=1e-8, atol=1e-12)
+    assert lam_n.min() == 0.0 and lam_n.max() <= 1.0 + 1e-12
+
+
+def test_lambda_tau_nonfinite_entries(sfb, oracle, ctx):
+    """select_tau filters NaN / inf (taumode.rs:41,50); here via an all-finite matrix with huge spread."""
+    x = np.random.default_rng(31).normal(size=(50, 40)) * np.logspace(-3, 3, 40)
+    L = feature_laplacian(oracle, x, 4)
+    c = sfb.Csr.from_host(ctx, *L)
+    for tm, tv in ((1, 0), (3, 0.9)):
+        lam, _ = c.lambdas(ctx.matrix(x), sfb.LAMBDA_LEGACY_TAUMODE, tm, tv)
+        assert np.allclose(lam, oracle.lambdas(*L, x, 0, tm, tv), rtol=RTOL, atol=1e-14)
+
+
+def test_lambda_energy_node_parity(sfb, oracle, ctx):
+    x = np.random.default_rng(32).normal(size=(500, 64))
+    L = feature_laplacian(oracle, x, 4)
+    c = sfb.Csr.from_host(ctx, *L)
+    lam, disp, _ = c.lambdas(ctx.matrix(x), sfb.LAMBDA_ENERGY_NODE, with_dispersion=True)
+    o_lam, _, o_g = oracle.lambdas(*L, x, oracle.LAMBDA_ENERGY_NODE, with_parts=True)
+    assert np.allclose(lam, o_lam, rtol=RTOL, atol=1e-15) and np.allclose(disp, o_g, rtol=RTOL, atol=1e-15)
+    # upper-triangle dispersion == 2x the taumode dispersion for a symmetric L
+    _, disp_t, _ = c.lambdas(ctx.matrix(x), sfb.LAMBDA_LEGACY_TAUMODE, with_dispersion=True)
+    assert np.allclose(disp, 2.0 * disp_t, rtol=1e-12)
+
+
+def test_lambda_core_f32sem(sfb, oracle, ctx):
+    x = np.random.default_rng(33).normal(size=(200, 32))
+    L = feature_laplacian(oracle, x, 4)
+    c = sfb.Csr.from_host(ctx, *L)
+    lam, _ = c.lambdas(ctx.matrix(x), sfb.LAMBDA_CORE_F32SEM)
+    o_lam = oracle.lambdas(*L, x, oracle.LAMBDA_CORE_F32SEM)
+    assert np.allclose(lam, o_lam, rtol=1e-5, atol=1e-6)  # f32 semantics: the reference's own tolerance
+
+
+def test_lambda_kats(sfb, oracle, ctx):
+    """chain graph (test_spectral.rs:187-251) through the CUDA path"""
+    indptr = np.array([0, 2, 5, 7], np.uint64)
+    indices = np.array([0, 1, 0, 1, 2, 1, 2], np.uint32)
+    data = np.array([1.0, -1, -1, 2, -1, -1, 1])
+    c = sfb.Csr.from_host(ctx, indptr, indices, data)
+    x = ctx.matrix(np.array([[1.0, 1.0, 1.0], [1.0, 0.0, -1.0]]))
+    lam, disp, _ = c.lambdas(x, sfb.LAMBDA_LEGACY_TAUMODE, sfb.TAU_FIXED, 0.5, with_dispersion=True)
+    assert lam[0] == 0.0 and disp[1] == 0.25 and lam[1] == 0.5 * (1.0 / 1.5) + 0.5 * 0.25
+    lam, disp, _ = c.lambdas(x, sfb.LAMBDA_ENERGY_NODE, with_dispersion=True)
+    assert lam[1] == 1.0 and disp[1] == 0.5
+    with pytest.raises(sfb.SfbError):  # assert_eq!(matrix.rows(), n), taumode.rs:330-337
+        c.lambdas(ctx.matrix(np.ones((2, 4))))
+
+
+def test_diffusion_bit_exact(sfb, oracle, ctx):
+    x = np.random.default_rng(34).normal(size=(300, 40))
+    L = feature_laplacian(oracle, x, 3)
+    c = sfb.Csr.from_host(ctx, *L)
+    for steps in (1, 4):
+        m = ctx.matrix(x).diffuse(c, 0.1, steps)
+        assert np.array_equal(m.rows(), oracle.diffuse(*L, x, 0.1, steps))
+
+
+# ---- reference-shaped entry points ------------------------------------------------------------
+def test_reference_layer_pipeline(sfb, oracle, ctx):
+    rng = np.random.default_rng(40)
+    centres = rng.normal(size=(5, 24)) * 3
+    x = centres[rng.integers(0, 5, size=600)] + 0.4 * rng.normal(size=(600, 24))
+    params = sfb.GraphParams(eps=math.inf, k=6, topk=3, p=2.0, sigma=None)
+    gl = sfb.GraphFactory.build_laplacian_matrix_from_k_cluster(x, params.eps, params.k, params.topk, params.p,
+                                                                params.sigma, False, False, 600, ctx=ctx)
+    assert gl.shape() == (24, 24) and gl.nnodes == 600
+    L = feature_laplacian(oracle, x, 3)
+    assert_csr_equal(gl.csr(), L, data_exact=True)
+    v = rng.normal(size=24)
+    assert np.array_equal(gl.multiply_vector(v), oracle.spmv(*L, v))
+    assert gl.rayleigh_quotient(v) == pytest.approx(oracle.rayleigh(*L, v), rel=1e-12)
+    assert np.allclose(gl.degrees(), [L[2][int(L[0][r]) + list(L[1][int(L[0][r]):int(L[0][r + 1])]).index(r)] for r in range(24)])
+    for tm in (sfb.TauMode.Median, sfb.TauMode.Mean, sfb.TauMode.Fixed(0.3), sfb.TauMode.Percentile(0.25)):
+        lam = sfb.TauMode.compute_taumode_lambdas_parallel(x, gl, tm)
+        o_lam, _ = oracle.normalise_lambdas(oracle.lambdas(*L, x, 0, tm.kind, tm.value))
+        assert np.allclose(lam, o_lam, rtol=1e-8, atol=1e-12)
+        assert lam.min() >= 0.0 and lam.max() <= 1.0 + 1e-12 and np.all(np.isfinite(lam))
+    with pytest.raises(sfb.SfbError):  # too sparse (graph.rs:232-240)
+        big = rng.normal(size=(50, 200))
+        sfb.GraphFactory.build_laplacian_matrix_from_k_cluster(big, math.inf, 6, 1, 2.0, None, False, True, 50, ctx=ctx)
+
+
+# ---- config C1: 10k x 384 Gaussian, cosine, k = 16 (the reference's CPU-runnable case) --------
+def test_config_c1_exact(sfb, oracle, ctx):
+    m = ctx.generate(sfb.SYNTH_GAUSSIAN, 42, 10000, 384)
+    x = oracle.generate_rows(0, 42, 0, 10000, 384)
+    g = m.knn(16, sfb.METRIC_COSINE, screen=sfb.SCREEN_EXACT_F64)
+    want = oracle.knn(x, 16, oracle.METRIC_COSINE)
+    assert_knn_equal(g.to_host(), want)
+    a = g.adjacency(2.0, 1.0)
+    o_adj = oracle.build_adjacency(*want, 2.0, 1.0)
+    assert a.sparsified and o_adj[3]
+    assert_csr_equal(a.laplacian().to_host(), oracle.laplacian(*o_adj[:3]), data_exact=True)
