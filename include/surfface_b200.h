@@ -217,6 +217,15 @@ int32_t sfb_compute_taumode_lambdas(sfb_ctx* ctx, const sfb_csr* L, const double
                                     uint32_t n_features, int32_t tau_mode, double tau_value,
                                     double* out_lambdas);
 
+/* ---- diagnostics ----------------------------------------------------------------------------
+ * Raw tensor-core accumulators of one 128 x 256 tile of the screen (query rows row0.., corpus rows
+ * from col0 rounded down to a multiple of 256) and the 16-bit operands used, as f32.  Lets the tests
+ * check the tcgen05 path and the accumulation-error model of the certification in isolation.
+ * out_tile: 128*256; q_rows: 128*kpad or NULL; q_cols: 256*kpad or NULL (kpad = cols rounded up to 64). */
+int32_t sfb_debug_screen_tile(sfb_ctx* ctx, const sfb_mat* x, int32_t metric, int32_t screen, uint64_t row0,
+                              uint64_t col0, float* out_tile, float* q_rows, float* q_cols, uint32_t* kpad_out,
+                              double* scale_out);
+
 /* ---- stage timings of the last calls (device time, ms) ------------------------------------- */
 typedef struct {
     double ms_h2d, ms_knn, ms_adjacency, ms_laplacian, ms_lambda, ms_d2h;

@@ -153,6 +153,19 @@ class Matrix(_Handle):
         self.ctx.check(lib().sfb_knn_build(self.ctx._h, self._h, C.byref(p), C.byref(h)))
         return KnnGraph(self.ctx, h)
 
+    def debug_screen_tile(self, metric=METRIC_COSINE, screen=SCREEN_F16, row0=0, col0=0):
+        """Diagnostic: (tile 128x256 f32 accumulators, operands of the 128 rows, operands of the 256 columns, scale)."""
+        r, c = self.shape
+        kpad = (c + 63) // 64 * 64
+        tile = np.empty((128, 256), np.float32)
+        qr = np.empty((128, kpad), np.float32)
+        qc = np.empty((256, kpad), np.float32)
+        kp, sc = C.c_uint32(), C.c_double()
+        self.ctx.check(lib().sfb_debug_screen_tile(self.ctx._h, self._h, metric, screen, row0, col0, _ffi.ptr(tile),
+                                                   _ffi.ptr(qr), _ffi.ptr(qc), C.byref(kp), C.byref(sc)))
+        assert kp.value == kpad
+        return tile, qr, qc, sc.value
+
     def diffuse(self, L, eta, steps):
         self.ctx.check(lib().sfb_diffuse(self.ctx._h, L._h, self._h, float(eta), int(steps)))
         return self

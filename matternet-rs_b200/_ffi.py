@@ -98,6 +98,8 @@ SYMBOLS = {
     "sfb_diffuse": (C.c_int32, [_P, _P, _P, C.c_double, C.c_uint32]),
     "sfb_build_laplacian_matrix": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, C.POINTER(GraphParamsC), C.c_int32, _PP]),
     "sfb_compute_taumode_lambdas": (C.c_int32, [_P, _P, _P, C.c_uint64, C.c_uint32, C.c_int32, C.c_double, _P]),
+    "sfb_debug_screen_tile": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P,
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "sfb_timings": (C.c_int32, [_P, C.POINTER(StageTimes)]),
     "sfb_timings_reset": (C.c_int32, [_P]),
     "sfb_comm_unique_id": (C.c_int32, [_P]),

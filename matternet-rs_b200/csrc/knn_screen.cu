@@ -1,6 +1,731 @@
-// knn_screen.cu -- tensor-core distance screen (placeholder until the tcgen05 kernel lands).
-#include "common.cuh"
+// knn_screen.cu -- tensor-core distance screen (tcgen05 + TMEM + TMA) with fused per-row top-k'
+// selection, exact f64 rescore, per-row certification and exact fallback.
+//
+// Replaces the two CosinePair sweeps of _build_adjacency (src_legacy/laplacian.rs:213-229,245-254)
+// and the brute-force loops of surfface-core/src/mst.rs:312-363 / src_legacy/energymaps.rs:875-892.
+// The RESULT is defined by src_legacy/tests/test_helpers.rs:77-125 (distance in f64, (distance,
+// index) order) and is reproduced bit-for-bit:
+//
+//   1. prepare   rows -> fp16 (or bf16) operands Q (cosine: unit rows * 64; L2: rows * 2^e), with the
+//                exact per-row rounding residual |delta_i| and operand norm |q_i| measured in f64.
+//   2. screen    S = Q Q^T on the tensor cores: TMA (SWIZZLE_128B) -> shared memory ->
+//                tcgen05.mma kind::f16 (M=128, N=256, K=16 per instruction) -> fp32 accumulators in
+//                TMEM (2 x 256 columns, double buffered) -> tcgen05.ld in the epilogue warps.  One
+//                epilogue thread owns one query row: a register threshold filters the 32 values of a
+//                chunk; survivors are appended to the row's candidate buffer (HBM/L2); a full buffer
+//                is pruned to its k' best by a warp-cooperative radix select, tightening the threshold.
+//   3. rescore   every surviving candidate gets the exact f64 distance with the reference's
+//                arithmetic (left-fold, no FMA) and the exact top-k is selected by (distance, index).
+//   4. certify   every candidate the screen dropped had key <= thr_i.  With
+//                  |S~_ij - q_i.q_j| <= gamma |q_i||q_j|            (fp32 accumulation in the tensor core)
+//                  |q_i.q_j - s^2 x^_i.x^_j| <= |delta_i||q_j| + s|delta_j|   (operand rounding, Cauchy-Schwarz)
+//                a lower bound LB_i on the true distance of any dropped candidate follows; row i is
+//                certified iff its exact k-th distance is < LB_i.  Uncertified rows (ties, duplicates,
+//                zero rows, margins too tight for fp16) are recomputed by the exact f64 brute force.
+//   => neighbour sets and distances equal the brute-force reference whatever the screen precision.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
 
-int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat*, const double*, const sfb_knn_params*, uint64_t, uint64_t, sfb_knn*) {
-    return sfb_fail(ctx, SFB_EUNSUPPORTED, "tensor-core screen not built yet");
+#include "common.cuh"
+#include "topk_list.cuh"
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2, B_STAGE_BYTES = BN * BK * 2;
+constexpr int SCREEN_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr double COS_SCALE = 64.0;   // unit rows are scaled by 2^6 so fp16 stays in its normal range
+constexpr uint32_t MAX_CAP = 256;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done, addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 in bits [0,14), SBO (8 rows * 128 B = 1024 B) >> 4 in [32,46), version 1 in [46,48),
+// layout SWIZZLE_128B (2) in [61,64).  LBO is unused for a single 128-byte swizzle atom along K.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint32_t f32_sortable(float v) {
+    uint32_t u = __float_as_uint(v);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sortable_f32(uint32_t k) { return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k); }
+
+// ---- prepare ----------------------------------------------------------------------------------
+__global__ void absmax_kernel(const double* __restrict__ x, uint64_t n, unsigned long long* out) {
+    double m = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = fmax(m, fabs(x[i]));
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));  // non-negative doubles order as integers
+}
+
+// One warp per row.  aux[0..M): |q_i|, [M..2M): |delta_i|, [2M..3M): |q_i|^2 (f64).  gmax[0] = max |q|, gmax[1] = max |delta|.
+template <bool BF16>
+__global__ void prepare_kernel(const double* __restrict__ x, const double* __restrict__ norms, uint64_t m, uint32_t kd,
+                               uint32_t kpad, int cosine, double scale, uint16_t* __restrict__ q, float* __restrict__ nq32,
+                               double* __restrict__ aux, unsigned long long* __restrict__ gmax) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= m) return;
+    double mul = scale;
+    if (cosine) { double nrm = norms[i]; mul = nrm > 0.0 ? scale / nrm : 0.0; }
+    if (!isfinite(mul)) mul = 0.0;
+    double sq = 0.0, sd = 0.0;
+    for (uint32_t d = lane; d < kpad; d += 32) {
+        double t = d < kd ? x[i * kd + d] * mul : 0.0;
+        double qv;
+        uint16_t bits;
+        if (BF16) { __nv_bfloat16 h = __double2bfloat16(t); qv = (double)__bfloat162float(h); bits = __bfloat16_as_ushort(h); }
+        else {
+            __half h = __double2half(t);
+            qv = (double)__half2float(h);
+            if (fabs(qv) < 6.103515625e-05) { qv = 0.0; bits = 0; }  // flush fp16 subnormals ourselves: delta stays exact
+            else bits = __half_as_ushort(h);
+        }
+        if (!isfinite(qv)) { qv = 0.0; bits = 0; }  // overflowed element: dropped from the operand, fully charged to delta
+        q[i * kpad + d] = bits;
+        double dl = qv - t;
+        sq += qv * qv; sd += dl * dl;
+    }
+    for (int o = 16; o; o >>= 1) { sq += __shfl_xor_sync(FULL, sq, o); sd += __shfl_xor_sync(FULL, sd, o); }
+    if (lane == 0) {
+        double qn = sqrt(sq) * (1.0 + 1e-12), dn = sqrt(sd) * (1.0 + 1e-12);
+        if (!isfinite(dn)) dn = INFINITY;
+        aux[i] = qn; aux[m + i] = dn; aux[2 * m + i] = sq;
+        nq32[i] = (float)sq;
+        atomicMax(&gmax[0], (unsigned long long)__double_as_longlong(qn));
+        atomicMax(&gmax[1], (unsigned long long)__double_as_longlong(dn));
+    }
+}
+
+// ---- the screen -------------------------------------------------------------------------------
+struct ScreenArgs {
+    uint64_t n_rows;        // corpus rows M (columns of S beyond it are padding)
+    uint64_t q_begin, nq;   // query rows [q_begin, q_begin + nq)
+    uint32_t kblocks;       // kpad / 64
+    uint32_t tiles_total, tiles_per_split, n_splits;
+    uint32_t idesc;
+    uint32_t kprime, cap;
+    const float* nq32;      // |q_j|^2 as f32 (L2 keys)
+    float* buf_key; uint32_t* buf_idx;  // [(row_local * n_splits + split) * cap]
+    uint32_t* out_cnt; float* out_thr;  // [row_local * n_splits + split]
+    float* dump;            // DUMP mode: 128 x 256 accumulators of the CTA's first tile
+};
+
+// Warp-cooperative prune of the candidate buffers of the lanes in `need`: keep the k' largest keys.
+template <int E>
+__device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_t* my_idx, uint32_t& cnt, float& thr,
+                                           uint32_t kprime, int lane) {
+    while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        float* kp = reinterpret_cast<float*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(my_key), L));
+        uint32_t* ip = reinterpret_cast<uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(my_idx), L));
+        const uint32_t n = __shfl_sync(FULL, cnt, L);
+        uint32_t key[E], idx[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            uint32_t e = lane + 32 * u;
+            bool v = e < n;
+            key[u] = v ? f32_sortable(__ldcg(kp + e)) : 0u;  // 0 sorts below every real key
+            idx[u] = v ? __ldcg(ip + e) : 0u;
+        }
+        // k'-th largest key by MSB-first radix select
+        uint32_t prefix = 0, want = kprime;
+#pragma unroll 1
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t bit = 1u << b, hi = b == 31 ? 0u : ~((bit << 1) - 1u);
+            uint32_t c = 0;
+#pragma unroll
+            for (int u = 0; u < E; ++u) c += __popc(__ballot_sync(FULL, (key[u] & hi) == (prefix & hi) && (key[u] & bit)));
+            if (c >= want) prefix |= bit; else want -= c;
+        }
+        // keep key > T and `want` of the entries equal to T
+        uint32_t base = 0, eq_seen = 0;
+        uint32_t pos[E]; bool keep[E];
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            bool gt = key[u] > prefix, eq = key[u] == prefix && (uint32_t)(lane + 32 * u) < n;
+            uint32_t beq = __ballot_sync(FULL, eq);
+            uint32_t my_eq_rank = eq_seen + __popc(beq & ((1u << lane) - 1u));
+            keep[u] = gt || (eq && my_eq_rank < want);
+            eq_seen += __popc(beq);
+            uint32_t bk = __ballot_sync(FULL, keep[u]);
+            pos[u] = base + __popc(bk & ((1u << lane) - 1u));
+            base += __popc(bk);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < E; ++u)
+            if (keep[u]) { __stcg(kp + pos[u], sortable_f32(key[u])); __stcg(ip + pos[u], idx[u]); }
+        __syncwarp();
+        if (lane == L) { cnt = base; thr = sortable_f32(prefix); }
+    }
+}
+
+template <bool L2, bool DUMP>
+__global__ void __launch_bounds__(SCREEN_THREADS, 1)
+knn_screen_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ScreenArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // carve: A stages | B stages | barriers | tmem ptr | nq tile (L2)
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_nq = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t mb = blockIdx.x, split = blockIdx.y;
+    const uint32_t t0 = split * a.tiles_per_split;
+    uint32_t t1 = t0 + a.tiles_per_split;
+    if (t1 > a.tiles_total) t1 = a.tiles_total;
+    const uint32_t n_my_tiles = t1 > t0 ? t1 - t0 : 0;
+    const int m_row0 = (int)(a.q_begin + (uint64_t)mb * BM);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = 0; t < n_my_tiles; ++t) {
+                const int n0 = (int)((t0 + t) * BN);
+                for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, (int)(kb * BK), m_row0, &full_bar[stage]);
+                    tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, (int)(kb * BK), n0, &full_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = 0; t < n_my_tiles; ++t) {
+                const uint32_t as = t & 1, aphase = (t >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES), b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), a.idesc, (kb | (uint32_t)k) != 0u);
+                    umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                    if (kb + 1 == a.kblocks) umma_commit(&tfull_bar[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: thread = query row =====
+        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are this warp's
+        const int row_in_tile = quarter * 32 + lane;
+        const uint64_t row_local = (uint64_t)mb * BM + row_in_tile;
+        const bool row_valid = row_local < a.nq;
+        const size_t slot = (size_t)(row_valid ? row_local : 0) * a.n_splits + split;
+        float* my_key = a.buf_key + slot * a.cap;
+        uint32_t* my_idx = a.buf_idx + slot * a.cap;
+        uint32_t cnt = 0;
+        float thr = -INFINITY;
+        const int etid = threadIdx.x - 64;            // 0..127 among the epilogue threads
+        for (uint32_t t = 0; t < n_my_tiles; ++t) {
+            const uint32_t as = t & 1, aphase = (t >> 1) & 1;
+            const uint32_t n0 = (t0 + t) * BN;
+            if (L2) {
+                // |q_j|^2 of this tile's 256 columns, double buffered with the accumulator stage
+                float* dst = s_nq + as * BN;
+                for (int c = etid; c < BN; c += 128) dst[c] = (uint64_t)n0 + c < a.n_rows ? __ldg(a.nq32 + n0 + c) : INFINITY;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ch * 32, v);
+                tmem_ld_wait();
+                if (DUMP) {
+                    if (t == 0)
+                        for (int c = 0; c < 32; ++c) a.dump[(size_t)row_in_tile * BN + ch * 32 + c] = __uint_as_float(v[c]);
+                    continue;
+                }
+                const float* nqv = s_nq + as * BN + ch * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    float key = __uint_as_float(v[c]);
+                    if (L2) key = fmaf(2.0f, key, -nqv[c]);  // -(|q_j|^2 - 2 q_i.q_j): larger is nearer
+                    if (key > thr) {
+                        uint32_t j = n0 + ch * 32 + c;
+                        if (row_valid && j < a.n_rows) { __stcg(my_key + cnt, key); __stcg(my_idx + cnt, j); ++cnt; }
+                    }
+                }
+                // a chunk appends at most 32 entries: prune whenever fewer than 32 slots remain
+                uint32_t need = __ballot_sync(FULL, cnt + 32 > a.cap);
+                if (need) {
+                    __syncwarp();
+                    if (a.cap <= 128) prune_rows<4>(need, my_key, my_idx, cnt, thr, a.kprime, lane);
+                    else prune_rows<8>(need, my_key, my_idx, cnt, thr, a.kprime, lane);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (!DUMP && row_valid) { a.out_cnt[slot] = cnt; a.out_thr[slot] = thr; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- rescore + certify ------------------------------------------------------------------------
+struct RescoreArgs {
+    const double* x; const double* norms; uint64_t m; uint32_t kd; int metric; uint32_t k; double eps;
+    uint64_t q_begin, nq; uint32_t n_splits, cap;
+    const float* buf_key; const uint32_t* buf_idx; const uint32_t* cnt; const float* thr;
+    const double* aux;      // |q|, |delta|, |q|^2
+    double nmax, dmax, gamma, scale;
+    uint32_t* out_idx; double* out_dist; uint32_t* out_cnt;
+    uint32_t* fb_rows; uint32_t* fb_count;  // uncertified rows (global indices)
+    double* max_margin;
+};
+
+// One warp per query row.  Candidate rows are staged 32 at a time through a padded shared tile so
+// global loads are coalesced and every lane runs its candidate's left fold in dimension order.
+template <bool COS>
+__global__ void __launch_bounds__(128) knn_rescore_kernel(RescoreArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* tile = reinterpret_cast<double*>(smem_raw) + (size_t)w * (33 * 32 + 32);  // [32][33] + query chunk [32]
+    double* qch = tile + 33 * 32;
+    double* ld = reinterpret_cast<double*>(smem_raw) + (size_t)wpb * (33 * 32 + 32) + (size_t)w * a.k;
+    uint32_t* li = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)wpb * (33 * 32 + 32 + a.k)) + (size_t)w * a.k;
+
+    const uint64_t rl = (uint64_t)blockIdx.x * wpb + w;
+    if (rl >= a.nq) return;
+    const uint32_t gi = (uint32_t)(a.q_begin + rl);
+    const double* xi = a.x + (uint64_t)gi * a.kd;
+    const double ni = COS ? a.norms[gi] : 0.0;
+    uint32_t c = 0;
+    float thr = -INFINITY;
+    for (uint32_t s = 0; s < a.n_splits; ++s) {
+        const size_t slot = (size_t)rl * a.n_splits + s;
+        const uint32_t n = a.cnt[slot];
+        thr = fmaxf(thr, a.thr[slot]);
+        const uint32_t* cand = a.buf_idx + slot * a.cap;
+        for (uint32_t b = 0; b < n; b += 32) {
+            const uint32_t mine = b + lane < n ? cand[b + lane] : SFB_IDX_NONE;
+            const uint32_t nb = n - b < 32 ? n - b : 32;
+            double acc = 0.0;
+            for (uint32_t d0 = 0; d0 < a.kd; d0 += 32) {
+                __syncwarp();
+                for (uint32_t r = 0; r < nb; ++r) {
+                    uint32_t j = __shfl_sync(FULL, mine, r);
+                    tile[r * 33 + lane] = d0 + lane < a.kd ? a.x[(uint64_t)j * a.kd + d0 + lane] : 0.0;
+                }
+                qch[lane] = d0 + lane < a.kd ? xi[d0 + lane] : 0.0;
+                __syncwarp();
+                const uint32_t lim = a.kd - d0 < 32 ? a.kd - d0 : 32;
+                if (lane < (int)nb) {
+                    for (uint32_t d = 0; d < lim; ++d) {
+                        if (COS) acc = __dadd_rn(acc, __dmul_rn(qch[d], tile[lane * 33 + d]));
+                        else { double t = __dadd_rn(qch[d], -tile[lane * 33 + d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
+                    }
+                }
+            }
+            double key = INFINITY;
+            if (mine != SFB_IDX_NONE) {
+                if (COS) {
+                    double denom = __dmul_rn(ni, a.norms[mine]), cosv = 0.0;
+                    if (denom > 1e-12) { cosv = __ddiv_rn(acc, denom); if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0; }
+                    double rect = cosv > 0.0 ? cosv : 0.0;
+                    key = __dadd_rn(1.0, -rect);
+                } else key = a.metric == SFB_METRIC_L2 ? __dsqrt_rn(acc) : acc;
+            }
+            double td = c == a.k ? ld[a.k - 1] : INFINITY;
+            uint32_t ti = c == a.k ? li[a.k - 1] : SFB_IDX_NONE;
+            bool pass = mine != SFB_IDX_NONE && mine != gi && key <= a.eps && topk_key_less(key, mine, td, ti);
+            uint32_t bal = __ballot_sync(FULL, pass);
+            while (bal) {
+                int src = __ffs(bal) - 1; bal &= bal - 1;
+                double kd_ = __shfl_sync(FULL, key, src);
+                uint32_t jj = __shfl_sync(FULL, mine, src);
+                warp_list_insert(ld, li, c, a.k, kd_, jj, lane);
+            }
+        }
+    }
+    // certification
+    const double bound = c == a.k ? ld[a.k - 1] : a.eps;  // every dropped candidate must be farther than this
+    bool certified;
+    double margin = 0.0;
+    if (thr == -INFINITY) certified = true;               // the screen never dropped anything for this row
+    else {
+        const double qn = a.aux[gi], dn = a.aux[a.m + gi], q2 = a.aux[2 * a.m + gi];
+        if (COS) {
+            const double s2 = a.scale * a.scale;
+            margin = ((a.gamma * qn + dn) * a.nmax + a.scale * a.dmax) * (1.0 + 1e-6) + s2 * 1e-9;
+            double cos_ub = ((double)thr + margin) / s2;
+            double lb = 1.0 - (cos_ub > 0.0 ? (cos_ub < 1.0 ? cos_ub : 1.0) : 0.0);
+            certified = bound < lb;
+            margin /= s2;
+        } else {
+            // dropped: 2 S~ - nq32_j <= thr  =>  |q_i - q_j|^2 >= |q_i|^2 - thr - eta
+            const double eta = (1.2e-7 * a.nmax * a.nmax + (2.0 * a.gamma + 1.2e-7) * qn * a.nmax) * (1.0 + 1e-6) + 2.4e-7 * fabs((double)thr);
+            const double rho = (dn + a.dmax) * (1.0 + 1e-9);
+            double d2 = q2 - (double)thr - eta;
+            double lbs = (d2 > 0.0 ? sqrt(d2) * (1.0 - 1e-12) : 0.0) - rho;  // scaled lower bound on |y_i - y_j|
+            double lb = lbs > 0.0 ? lbs / a.scale : 0.0;
+            double b = bound * (1.0 + 1e-12);
+            certified = a.metric == SFB_METRIC_L2 ? b < lb : b < lb * lb;
+            margin = rho / a.scale;
+        }
+    }
+    if (!(margin == margin)) certified = false;
+    if (certified) {
+        for (uint32_t t = lane; t < a.k; t += 32) {
+            a.out_idx[rl * a.k + t] = t < c ? li[t] : SFB_IDX_NONE;
+            a.out_dist[rl * a.k + t] = t < c ? ld[t] : INFINITY;
+        }
+        if (lane == 0) a.out_cnt[rl] = c;
+    } else if (lane == 0) {
+        a.fb_rows[atomicAdd(a.fb_count, 1u)] = gi;
+    }
+    if (lane == 0 && margin > 0.0 && isfinite(margin)) atomicMax(reinterpret_cast<unsigned long long*>(a.max_margin), (unsigned long long)__double_as_longlong(margin));
+}
+
+__global__ void scatter_rows_kernel(const uint32_t* __restrict__ rows, uint32_t n, uint64_t q_begin, uint32_t k,
+                                    const uint32_t* __restrict__ t_idx, const double* __restrict__ t_dist, const uint32_t* __restrict__ t_cnt,
+                                    uint32_t* __restrict__ out_idx, double* __restrict__ out_dist, uint32_t* __restrict__ out_cnt) {
+    uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)n * k) return;
+    uint32_t r = (uint32_t)(gid / k), t = (uint32_t)(gid % k);
+    uint64_t dst = (uint64_t)rows[r] - q_begin;
+    out_idx[dst * k + t] = t_idx[gid]; out_dist[dst * k + t] = t_dist[gid];
+    if (t == 0) out_cnt[dst] = t_cnt[r];
+}
+
+// ---- host -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int32_t make_tmap(sfb_ctx* ctx, CUtensorMap* map, void* base, uint64_t rows, uint32_t kpad, uint32_t box_rows, bool bf16) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !p) return sfb_fail(ctx, SFB_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    cuuint64_t dims[2] = {kpad, rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sfb_fail(ctx, SFB_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SFB_OK;
+}
+
+uint32_t make_idesc(bool bf16) {
+    // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format (F16 0 / BF16 1) @7 / @10, K-major A and B,
+    // N >> 3 @17, M >> 4 @24
+    uint32_t fmt = bf16 ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+size_t screen_smem_bytes() { return (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 16 * 8 + 16 + 2 * BN * sizeof(float) + 1024; }
+
+struct Prepared {
+    DevBuf q, nq32, aux, gmax;
+    uint64_t mpad = 0; uint32_t kpad = 0;
+    double scale = 1.0, nmax = 0.0, dmax = 0.0;
+    bool bf16 = false;
+};
+
+int32_t prepare_operands(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int metric, bool bf16, Prepared* P) {
+    const uint64_t m = x->rows;
+    P->bf16 = bf16;
+    P->kpad = (x->cols + BK - 1) / BK * BK;
+    P->mpad = (m + BN - 1) / BN * BN;
+    SFB_CUDA(ctx, P->q.alloc((size_t)P->mpad * P->kpad * 2));
+    SFB_CUDA(ctx, P->nq32.alloc(sizeof(float) * P->mpad));
+    SFB_CUDA(ctx, P->aux.alloc(sizeof(double) * 3 * m));
+    SFB_CUDA(ctx, P->gmax.alloc(4 * sizeof(unsigned long long)));
+    SFB_CUDA(ctx, cudaMemsetAsync(P->q.p, 0, (size_t)P->mpad * P->kpad * 2, ctx->stream));
+    SFB_CUDA(ctx, cudaMemsetAsync(P->gmax.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const bool cosine = metric == SFB_METRIC_COSINE;
+    P->scale = COS_SCALE;
+    if (!cosine) {
+        absmax_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(x->d, m * x->cols, P->gmax.as<unsigned long long>() + 2);
+        SFB_LAUNCH_CHECK(ctx);
+        double amax = 0.0;
+        SFB_CUDA(ctx, cudaMemcpyAsync(&amax, P->gmax.as<unsigned long long>() + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!isfinite(amax)) return sfb_fail(ctx, SFB_EINVAL, "matrix holds non-finite values");
+        // power-of-two scale that puts the largest |x| in [128, 256): exact in f64, far from fp16 overflow
+        int e = 0;
+        if (amax > 0.0) { frexp(amax, &e); e = 8 - e; }
+        P->scale = ldexp(1.0, e);
+    }
+    if (bf16)
+        prepare_kernel<true><<<div_up(m * 32, 256), 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, P->kpad, cosine, P->scale, P->q.as<uint16_t>(),
+                                                                            P->nq32.as<float>(), P->aux.as<double>(), P->gmax.as<unsigned long long>());
+    else
+        prepare_kernel<false><<<div_up(m * 32, 256), 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, P->kpad, cosine, P->scale, P->q.as<uint16_t>(),
+                                                                             P->nq32.as<float>(), P->aux.as<double>(), P->gmax.as<unsigned long long>());
+    SFB_LAUNCH_CHECK(ctx);
+    double g[2];
+    SFB_CUDA(ctx, cudaMemcpyAsync(g, P->gmax.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    P->nmax = g[0]; P->dmax = g[1];
+    return SFB_OK;
+}
+
+template <bool DUMP>
+int32_t launch_screen(sfb_ctx* ctx, const Prepared& P, int metric, ScreenArgs& sa, uint32_t m_blocks) {
+    CUtensorMap tmA, tmB;
+    SFB_TRY(make_tmap(ctx, &tmA, P.q.p, P.mpad, P.kpad, BM, P.bf16));
+    SFB_TRY(make_tmap(ctx, &tmB, P.q.p, P.mpad, P.kpad, BN, P.bf16));
+    sa.idesc = make_idesc(P.bf16);
+    size_t smem = screen_smem_bytes();
+    dim3 grid(m_blocks, sa.n_splits);
+    if (metric == SFB_METRIC_COSINE) {
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_kernel<false, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_screen_kernel<false, DUMP><<<grid, SCREEN_THREADS, smem, ctx->stream>>>(tmA, tmB, sa);
+    } else {
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_kernel<true, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_screen_kernel<true, DUMP><<<grid, SCREEN_THREADS, smem, ctx->stream>>>(tmA, tmB, sa);
+    }
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
+}  // namespace
+
+int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p, uint64_t q_begin,
+                         uint64_t q_end, sfb_knn* out) {
+    const uint64_t m = x->rows, nq = q_end - q_begin;
+    const bool bf16 = p->screen == SFB_SCREEN_BF16;
+    const bool cosine = p->metric == SFB_METRIC_COSINE;
+    if (m > 0xFFFFFF00ull) return sfb_fail(ctx, SFB_EUNSUPPORTED, "too many rows for the screen");
+    sfb_knn_stats& st = out->stats;
+    st.screen_used = p->screen;
+
+    // k' candidates survive per row and corpus split; the buffer has 64 slots of slack between prunes
+    uint32_t kprime = p->k_prime ? p->k_prime : (3 * p->k + 16 + 31) / 32 * 32;
+    if (kprime < p->k + 1) kprime = p->k + 1;
+    if (kprime < 64 && !p->k_prime) kprime = 64;
+    if (kprime > MAX_CAP - 64) kprime = MAX_CAP - 64;
+    if (kprime < p->k + 1) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k too large for the screen buffers");
+    const uint32_t cap = (kprime + 64 + 31) / 32 * 32;
+    st.k_prime = kprime;
+
+    Prepared P;
+    {
+        StageTimer t(ctx, nullptr);
+        SFB_TRY(prepare_operands(ctx, x, norms, p->metric, bf16, &P));
+        st.ms_prepare = t.stop();
+    }
+    const uint32_t m_blocks = (uint32_t)((nq + BM - 1) / BM);
+    ScreenArgs sa{};
+    sa.n_rows = m; sa.q_begin = q_begin; sa.nq = nq; sa.kblocks = P.kpad / BK;
+    sa.tiles_total = (uint32_t)(P.mpad / BN);
+    uint32_t want_ctas = 2u * (uint32_t)ctx->sm_count;
+    uint32_t n_splits = m_blocks >= want_ctas ? 1u : (want_ctas + m_blocks - 1) / m_blocks;
+    if (n_splits > sa.tiles_total) n_splits = sa.tiles_total;
+    sa.tiles_per_split = (sa.tiles_total + n_splits - 1) / n_splits;
+    sa.n_splits = (sa.tiles_total + sa.tiles_per_split - 1) / sa.tiles_per_split;
+    sa.kprime = kprime; sa.cap = cap; sa.nq32 = P.nq32.as<float>();
+
+    const size_t slots = (size_t)nq * sa.n_splits;
+    DevBuf buf_key, buf_idx, cnt, thr, fb_rows, fb_count;
+    SFB_CUDA(ctx, buf_key.alloc(slots * cap * sizeof(float)));
+    SFB_CUDA(ctx, buf_idx.alloc(slots * cap * sizeof(uint32_t)));
+    SFB_CUDA(ctx, cnt.alloc(slots * sizeof(uint32_t)));
+    SFB_CUDA(ctx, thr.alloc(slots * sizeof(float)));
+    SFB_CUDA(ctx, fb_rows.alloc(nq * sizeof(uint32_t)));
+    SFB_CUDA(ctx, fb_count.alloc(4 * sizeof(uint64_t)));
+    SFB_CUDA(ctx, cudaMemsetAsync(fb_count.p, 0, 4 * sizeof(uint64_t), ctx->stream));
+    SFB_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, slots * sizeof(uint32_t), ctx->stream));
+    sa.buf_key = buf_key.as<float>(); sa.buf_idx = buf_idx.as<uint32_t>(); sa.out_cnt = cnt.as<uint32_t>(); sa.out_thr = thr.as<float>();
+    {
+        StageTimer t(ctx, nullptr);
+        SFB_TRY(launch_screen<false>(ctx, P, p->metric, sa, m_blocks));
+        st.ms_screen = t.stop();
+        SFB_CUDA(ctx, cudaGetLastError());
+    }
+    // tensor-core fp32 accumulation: K products, each partial sum off by at most 2 ulp of the running bound
+    const double gamma = ((double)P.kpad + 64.0) * ldexp(1.0, -23);
+    RescoreArgs ra{x->d, norms, m, x->cols, p->metric, p->k, p->eps, q_begin, nq, sa.n_splits, cap,
+                   sa.buf_key, sa.buf_idx, sa.out_cnt, sa.out_thr, P.aux.as<double>(), P.nmax, P.dmax, gamma, P.scale,
+                   out->idx, out->dist, out->cnt, fb_rows.as<uint32_t>(), fb_count.as<uint32_t>(),
+                   reinterpret_cast<double*>(fb_count.as<uint64_t>() + 1)};
+    {
+        StageTimer t(ctx, nullptr);
+        const int wpb = 4;
+        size_t smem = (size_t)wpb * ((33 * 32 + 32 + p->k) * sizeof(double) + p->k * sizeof(uint32_t));
+        if (cosine) {
+            SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knn_rescore_kernel<true><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);
+        } else {
+            SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            knn_rescore_kernel<false><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);
+        }
+        SFB_LAUNCH_CHECK(ctx);
+        st.ms_rescore = t.stop();
+    }
+    uint64_t h[2];
+    SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_fb = (uint32_t)(h[0] & 0xFFFFFFFFu);
+    memcpy(&st.max_margin, &h[1], 8);
+    st.rows_fallback = n_fb;
+    st.rows_certified = nq - n_fb;
+    if (n_fb) {
+        if (!p->allow_fallback) return sfb_fail(ctx, SFB_EUNCERTIFIED, "%u of %llu rows not certified by the screen", n_fb, (unsigned long long)nq);
+        StageTimer t(ctx, nullptr);
+        DevBuf t_idx, t_dist, t_cnt;
+        SFB_CUDA(ctx, t_idx.alloc((size_t)n_fb * p->k * sizeof(uint32_t)));
+        SFB_CUDA(ctx, t_dist.alloc((size_t)n_fb * p->k * sizeof(double)));
+        SFB_CUDA(ctx, t_cnt.alloc((size_t)n_fb * sizeof(uint32_t)));
+        SFB_TRY(sfb_knn_exact(ctx, x, norms, p->metric, p->k, p->eps, fb_rows.as<uint32_t>(), n_fb, 0, t_idx.as<uint32_t>(),
+                              t_dist.as<double>(), t_cnt.as<uint32_t>()));
+        scatter_rows_kernel<<<div_up((uint64_t)n_fb * p->k, 256), 256, 0, ctx->stream>>>(fb_rows.as<uint32_t>(), n_fb, q_begin, p->k,
+                                                                                         t_idx.as<uint32_t>(), t_dist.as<double>(), t_cnt.as<uint32_t>(),
+                                                                                         out->idx, out->dist, out->cnt);
+        SFB_LAUNCH_CHECK(ctx);
+        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        st.ms_fallback = t.stop();
+    }
+    return SFB_OK;
+}
+
+// Diagnostic: the raw tensor-core accumulators of one 128 x 256 tile (rows row0.., columns col0.. rounded
+// down to a multiple of 256) plus the operands the screen used, for validating the MMA path and the
+// accumulation-error model in tests.  q_out: mpad x kpad operand values as f32 (may be NULL).
+extern "C" int32_t sfb_debug_screen_tile(sfb_ctx* ctx, const sfb_mat* x, int32_t metric, int32_t screen, uint64_t row0,
+                                         uint64_t col0, float* out_tile /* 128*256 */, float* q_rows /* 128*kpad */,
+                                         float* q_cols /* 256*kpad */, uint32_t* kpad_out, double* scale_out) {
+    if (!ctx || !x || !out_tile) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    DevBuf norms, dump;
+    SFB_CUDA(ctx, norms.alloc(sizeof(double) * x->rows));
+    if (metric == SFB_METRIC_COSINE) SFB_TRY(sfb_row_norms(ctx, x, norms.as<double>()));
+    Prepared P;
+    SFB_TRY(prepare_operands(ctx, x, norms.as<double>(), metric, screen == SFB_SCREEN_BF16, &P));
+    SFB_CUDA(ctx, dump.alloc(sizeof(float) * BM * BN));
+    ScreenArgs sa{};
+    sa.n_rows = x->rows; sa.q_begin = row0; sa.nq = BM; sa.kblocks = P.kpad / BK;
+    sa.tiles_total = (uint32_t)(col0 / BN) + 1; sa.tiles_per_split = sa.tiles_total; sa.n_splits = 1;
+    // run only the requested tile: start the split at it
+    sa.tiles_per_split = 1; sa.n_splits = sa.tiles_total;
+    sa.kprime = 64; sa.cap = 128; sa.nq32 = P.nq32.as<float>(); sa.dump = dump.as<float>();
+    // grid.y = n_splits CTAs would all dump; launch a single CTA positioned on the tile instead
+    {
+        CUtensorMap tmA, tmB;
+        SFB_TRY(make_tmap(ctx, &tmA, P.q.p, P.mpad, P.kpad, BM, P.bf16));
+        SFB_TRY(make_tmap(ctx, &tmB, (uint8_t*)P.q.p + (col0 / BN) * BN * (size_t)P.kpad * 2, P.mpad - (col0 / BN) * BN, P.kpad, BN, P.bf16));
+        sa.idesc = make_idesc(P.bf16);
+        sa.tiles_total = 1; sa.n_splits = 1;
+        size_t smem = screen_smem_bytes();
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_screen_kernel<false, true><<<dim3(1, 1), SCREEN_THREADS, smem, ctx->stream>>>(tmA, tmB, sa);
+        SFB_LAUNCH_CHECK(ctx);
+    }
+    SFB_CUDA(ctx, cudaMemcpyAsync(out_tile, dump.p, sizeof(float) * BM * BN, cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (kpad_out) *kpad_out = P.kpad;
+    if (scale_out) *scale_out = P.scale;
+    // operands back as f32 (host converts): copy raw 16-bit rows
+    auto copy_rows = [&](uint64_t r0, uint32_t nr, float* dst) -> int32_t {
+        if (!dst) return SFB_OK;
+        std::string tmp;
+        tmp.resize((size_t)nr * P.kpad * 2);
+        uint64_t avail = P.mpad > r0 ? P.mpad - r0 : 0;
+        uint32_t take = avail < nr ? (uint32_t)avail : nr;
+        memset(&tmp[0], 0, tmp.size());
+        if (take) SFB_CUDA(ctx, cudaMemcpy(&tmp[0], (uint8_t*)P.q.p + r0 * (size_t)P.kpad * 2, (size_t)take * P.kpad * 2, cudaMemcpyDeviceToHost));
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(tmp.data());
+        for (size_t e = 0; e < (size_t)nr * P.kpad; ++e) {
+            if (P.bf16) { uint32_t u = (uint32_t)h[e] << 16; memcpy(&dst[e], &u, 4); }
+            else dst[e] = __half2float(__ushort_as_half(h[e]));
+        }
+        return SFB_OK;
+    };
+    SFB_TRY(copy_rows(row0, BM, q_rows));
+    SFB_TRY(copy_rows(col0 / BN * BN, BN, q_cols));
+    return SFB_OK;
 }

@@ -331,4 +331,5 @@ def test_config_c1_exact(sfb, oracle, ctx):
     a = g.adjacency(2.0, 1.0)
     o_adj = oracle.build_adjacency(*want, 2.0, 1.0)
     assert a.sparsified and o_adj[3]
-    assert_csr_equal(a.laplacian().to_host(), oracle.laplacian(*o_adj[:3]), data_exact=True)
+    # weights: glibc pow(r, 2.0) vs the device's exactly rounded r*r may differ in the last bit
+    assert_csr_equal(a.laplacian().to_host(), oracle.laplacian(*o_adj[:3]))
