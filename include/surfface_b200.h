@@ -57,6 +57,9 @@ const char* sfb_last_error(const sfb_ctx* ctx);
 /* name: >= 256 bytes; sm_count, hbm_bytes may be NULL */
 int32_t sfb_device_info(const sfb_ctx* ctx, char* name, int32_t* sm_count, uint64_t* hbm_bytes);
 int32_t sfb_synchronize(sfb_ctx* ctx);
+/* page-locked host memory for the host<->device copies of the one-shot entry points */
+int32_t sfb_pinned_alloc(sfb_ctx* ctx, uint64_t bytes, void** out);
+void sfb_pinned_free(void* p);
 
 /* ---- dense matrices ------------------------------------------------------------------------
  * The reference moves whole flat Vec copies host<->device (surfface-core/src/laplacian.rs:157-158,
@@ -71,6 +74,8 @@ int32_t sfb_mat_generate(sfb_ctx* ctx, int32_t kind, uint64_t seed, uint64_t row
 /* GraphFactory::build_laplacian_matrix_from_k_cluster transposes before the graph build
  * (src_legacy/graph.rs:214-216): nodes become the columns. */
 int32_t sfb_mat_transpose(sfb_ctx* ctx, const sfb_mat* a, sfb_mat** out);
+/* non-owning view of rows [row0, row0 + nrows) (the parent must outlive it); free with sfb_mat_free */
+int32_t sfb_mat_view_rows(sfb_ctx* ctx, const sfb_mat* a, uint64_t row0, uint64_t nrows, sfb_mat** out);
 int32_t sfb_mat_shape(const sfb_mat* a, uint64_t* rows, uint32_t* cols);
 int32_t sfb_mat_copy_rows(sfb_ctx* ctx, const sfb_mat* a, uint64_t row0, uint64_t nrows, double* out);
 void sfb_mat_free(sfb_mat* a);
@@ -232,6 +237,9 @@ typedef struct {
     uint64_t kernel_launches; /* kernels of this library launched since ctx creation */
 } sfb_stage_times;
 int32_t sfb_timings(const sfb_ctx* ctx, sfb_stage_times* out);
+/* device stopwatch on the context's stream (CUDA events): start, run any calls, stop -> ms */
+int32_t sfb_timer_start(sfb_ctx* ctx);
+int32_t sfb_timer_stop(sfb_ctx* ctx, double* ms);
 int32_t sfb_timings_reset(sfb_ctx* ctx);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) -------------------------------------

@@ -28,6 +28,9 @@ TAU_FIXED, TAU_MEDIAN, TAU_MEAN, TAU_PERCENTILE = 0, 1, 2, 3
 SYNTH_GAUSSIAN, SYNTH_CLUSTERED, SYNTH_ANISOTROPIC = 0, 1, 2
 
 
+_PINNED = {}  # page-locked buffers stay alive for the life of the process
+
+
 # ------------------------------------------------------------------------------------------------
 # handle layer
 # ------------------------------------------------------------------------------------------------
@@ -72,8 +75,26 @@ class Context:
         self.check(lib().sfb_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in t._fields_}
 
+    def timer_start(self):
+        self.check(lib().sfb_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.check(lib().sfb_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def timings_reset(self):
         self.check(lib().sfb_timings_reset(self._h))
+
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array over page-locked host memory (kept alive by the returned array's base)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self.check(lib().sfb_pinned_alloc(self._h, n, C.byref(p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        _PINNED[p.value] = buf
+        return arr
 
     # -- matrices
     def matrix(self, x):
@@ -139,6 +160,13 @@ class Matrix(_Handle):
         self.ctx.check(lib().sfb_mat_transpose(self.ctx._h, self._h, C.byref(h)))
         return Matrix(self.ctx, h)
 
+    def view_rows(self, row0, nrows):
+        h = C.c_void_p()
+        self.ctx.check(lib().sfb_mat_view_rows(self.ctx._h, self._h, row0, nrows, C.byref(h)))
+        v = Matrix(self.ctx, h)
+        v._parent = self  # keep the parent alive
+        return v
+
     def rows(self, row0=0, nrows=None):
         r, c = self.shape
         nrows = r - row0 if nrows is None else nrows
@@ -186,11 +214,11 @@ class KnnGraph(_Handle):
         lib().sfb_knn_shape(self._h, None, None, C.byref(q))
         return q.value
 
-    def to_host(self):
+    def to_host(self, out=None):
         r, k = self.shape
-        idx = np.empty((r, k), np.uint32)
-        dist = np.empty((r, k), np.float64)
-        cnt = np.empty(r, np.uint32)
+        if out is None:
+            out = (np.empty((r, k), np.uint32), np.empty((r, k), np.float64), np.empty(r, np.uint32))
+        idx, dist, cnt = out
         self.ctx.check(lib().sfb_knn_copy(self.ctx._h, self._h, _ffi.ptr(idx), _ffi.ptr(dist), _ffi.ptr(cnt)))
         self.ctx.synchronize()
         return idx, dist, cnt
@@ -269,11 +297,12 @@ class Csr(_Handle):
         lib().sfb_csr_shape(self._h, C.byref(r), C.byref(nnz))
         return r.value, nnz.value
 
-    def to_host(self):
+    def to_host(self, out=None):
         r, nnz = self.shape
-        indptr = np.empty(r + 1, np.uint64)
-        indices = np.empty(max(nnz, 1), np.uint32)
-        data = np.empty(max(nnz, 1), np.float64)
+        if out is None:
+            out = (np.empty(r + 1, np.uint64), np.empty(max(nnz, 1), np.uint32), np.empty(max(nnz, 1), np.float64))
+        indptr, indices, data = out
+        assert len(indices) >= nnz and len(data) >= nnz
         self.ctx.check(lib().sfb_csr_copy(self.ctx._h, self._h, _ffi.ptr(indptr), _ffi.ptr(indices), _ffi.ptr(data)))
         self.ctx.synchronize()
         return indptr, indices[:nnz], data[:nnz]

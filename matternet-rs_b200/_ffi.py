@@ -69,9 +69,12 @@ SYMBOLS = {
     "sfb_last_error": (C.c_char_p, [_P]),
     "sfb_device_info": (C.c_int32, [_P, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "sfb_synchronize": (C.c_int32, [_P]),
+    "sfb_pinned_alloc": (C.c_int32, [_P, C.c_uint64, _PP]),
+    "sfb_pinned_free": (None, [_P]),
     "sfb_mat_from_host": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, _PP]),
     "sfb_mat_generate": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, _PP]),
     "sfb_mat_transpose": (C.c_int32, [_P, _P, _PP]),
+    "sfb_mat_view_rows": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, _PP]),
     "sfb_mat_shape": (C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "sfb_mat_copy_rows": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "sfb_mat_free": (None, [_P]),
@@ -102,6 +105,8 @@ SYMBOLS = {
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "sfb_timings": (C.c_int32, [_P, C.POINTER(StageTimes)]),
     "sfb_timings_reset": (C.c_int32, [_P]),
+    "sfb_timer_start": (C.c_int32, [_P]),
+    "sfb_timer_stop": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "sfb_comm_unique_id": (C.c_int32, [_P]),
     "sfb_comm_init": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
     "sfb_knn_allgather": (C.c_int32, [_P, _P, C.c_uint64, _PP]),

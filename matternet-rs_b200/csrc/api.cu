@@ -50,6 +50,8 @@ extern "C" void sfb_ctx_destroy(sfb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    sfb_comm_destroy(ctx);
+    if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -71,6 +73,30 @@ extern "C" int32_t sfb_synchronize(sfb_ctx* ctx) {
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SFB_OK;
 }
+
+extern "C" int32_t sfb_timer_start(sfb_ctx* ctx) {
+    if (!ctx) return SFB_EINVAL;
+    if (!ctx->timer0) { SFB_CUDA(ctx, cudaEventCreate(&ctx->timer0)); SFB_CUDA(ctx, cudaEventCreate(&ctx->timer1)); }
+    SFB_CUDA(ctx, cudaEventRecord(ctx->timer0, ctx->stream));
+    return SFB_OK;
+}
+extern "C" int32_t sfb_timer_stop(sfb_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->timer0) return sfb_fail(ctx, SFB_EINVAL, "timer not started");
+    SFB_CUDA(ctx, cudaEventRecord(ctx->timer1, ctx->stream));
+    SFB_CUDA(ctx, cudaEventSynchronize(ctx->timer1));
+    float f = 0.f;
+    SFB_CUDA(ctx, cudaEventElapsedTime(&f, ctx->timer0, ctx->timer1));
+    *ms = f;
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_pinned_alloc(sfb_ctx* ctx, uint64_t bytes, void** out) {
+    if (!ctx || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault);
+    if (e != cudaSuccess) return sfb_fail(ctx, SFB_ENOMEM, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return SFB_OK;
+}
+extern "C" void sfb_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" int32_t sfb_timings(const sfb_ctx* ctx, sfb_stage_times* out) {
     if (!ctx || !out) return SFB_EINVAL;
@@ -175,9 +201,18 @@ extern "C" int32_t sfb_mat_copy_rows(sfb_ctx* ctx, const sfb_mat* a, uint64_t ro
     return SFB_OK;
 }
 
+extern "C" int32_t sfb_mat_view_rows(sfb_ctx* ctx, const sfb_mat* a, uint64_t row0, uint64_t nrows, sfb_mat** out) {
+    if (!a || !out || nrows == 0 || row0 + nrows > a->rows) return sfb_fail(ctx, SFB_EINVAL, "row range out of bounds");
+    sfb_mat* v = new (std::nothrow) sfb_mat();
+    if (!v) return SFB_ENOMEM;
+    v->ctx = ctx; v->d = a->d + row0 * a->cols; v->rows = nrows; v->cols = a->cols; v->owns = false;
+    *out = v;
+    return SFB_OK;
+}
+
 extern "C" void sfb_mat_free(sfb_mat* a) {
     if (!a) return;
-    cudaFree(a->d);
+    if (a->owns) cudaFree(a->d);
     delete a;
 }
 

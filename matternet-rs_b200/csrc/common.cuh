@@ -14,6 +14,7 @@ struct sfb_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;  // sfb_timer_start / stop
     std::string last_error;
     sfb_stage_times times{};
     // NCCL (loaded lazily, comm.cu)
@@ -26,6 +27,7 @@ struct sfb_mat {
     double* d = nullptr;  // rows x cols, row-major
     uint64_t rows = 0;
     uint32_t cols = 0;
+    bool owns = true;  // false: a row-range view into another matrix
 };
 
 struct sfb_knn {
@@ -118,6 +120,7 @@ int32_t sfb_scan_exclusive_u64(sfb_ctx* ctx, const uint32_t* in, uint64_t n, uin
 int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int metric, uint32_t k, double eps,
                       const uint32_t* query_rows /* device, or null */, uint64_t nq, uint64_t q_begin,
                       uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);
+void sfb_comm_destroy(sfb_ctx* ctx);
 int32_t sfb_row_norms(sfb_ctx* ctx, const sfb_mat* x, double* norms);
 int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p,
                          uint64_t q_begin, uint64_t q_end, sfb_knn* out);

@@ -207,6 +207,80 @@ __global__ void knn_merge_kernel(const uint32_t* __restrict__ pidx, const double
     if (lane == 0) out_cnt[qi] = c;
 }
 
+// ---- few nodes, very long rows (the feature graph: D nodes x N dims, graph.rs:214-216) ----------
+// The 64x64 tile kernel above would launch a handful of CTAs, each walking millions of dimensions.
+// Here every (i, j) pair gets its own thread: 16 x 16 pair tiles, the dimension streamed through
+// shared memory 32 at a time (coalesced 256-byte row segments), one left fold per pair.  For a
+// self-kNN only tiles on or above the diagonal are computed and mirrored (products commute, so
+// key(i,j) and key(j,i) have the same bits).  FP64-pipe bound: nodes^2 * dims multiply-adds.
+template <bool COS>
+__global__ void __launch_bounds__(256) knn_dense_keys_kernel(const double* __restrict__ x, const double* __restrict__ norms,
+                                                             uint32_t m, uint32_t kd, int metric, double* __restrict__ keys) {
+    __shared__ double qs[16][33], cs[16][33];
+    const uint32_t ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;  // mirrored
+    const int tid = threadIdx.x, qi = tid >> 4, cj = tid & 15;
+    const uint32_t gi = ti * 16 + qi, gj = tj * 16 + cj;
+    double acc = 0.0;
+    for (uint32_t d0 = 0; d0 < kd; d0 += 32) {
+        __syncthreads();
+        for (int e = tid; e < 16 * 32; e += 256) {
+            int r = e >> 5, d = e & 31;
+            uint32_t ri = ti * 16 + r, rj = tj * 16 + r;
+            qs[r][d] = (ri < m && d0 + d < kd) ? __ldg(x + (uint64_t)ri * kd + d0 + d) : 0.0;
+            cs[r][d] = (rj < m && d0 + d < kd) ? __ldg(x + (uint64_t)rj * kd + d0 + d) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int d = 0; d < 32; ++d) {
+            if (COS) acc = __dadd_rn(acc, __dmul_rn(qs[qi][d], cs[cj][d]));
+            else { double t = __dadd_rn(qs[qi][d], -cs[cj][d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
+        }
+    }
+    if (gi >= m || gj >= m) return;
+    double key;
+    if (COS) {
+        double denom = __dmul_rn(norms[gi], norms[gj]), cosv = 0.0;
+        if (denom > 1e-12) { cosv = __ddiv_rn(acc, denom); if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0; }
+        double rect = cosv > 0.0 ? cosv : 0.0;
+        key = __dadd_rn(1.0, -rect);
+    } else key = metric == SFB_METRIC_L2 ? __dsqrt_rn(acc) : acc;
+    keys[(uint64_t)gi * m + gj] = key;
+    keys[(uint64_t)gj * m + gi] = key;
+}
+
+// one warp per query row: scan the dense key row, keep the (distance, index) top-k
+__global__ void knn_dense_select_kernel(const double* __restrict__ keys, uint32_t m, uint64_t q_begin, uint64_t nq, uint32_t k,
+                                        double eps, uint32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                        uint32_t* __restrict__ out_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* ld = reinterpret_cast<double*>(smem_raw) + (size_t)w * k;
+    uint32_t* li = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)wpb * k) + (size_t)w * k;
+    const uint64_t qi = (uint64_t)blockIdx.x * wpb + w;
+    if (qi >= nq) return;
+    const uint32_t g = (uint32_t)(q_begin + qi);
+    uint32_t c = 0;
+    for (uint32_t j0 = 0; j0 < m; j0 += 32) {
+        uint32_t j = j0 + lane;
+        double key = j < m ? keys[(uint64_t)g * m + j] : INFINITY;
+        double td = c == k ? ld[k - 1] : INFINITY;
+        uint32_t ti = c == k ? li[k - 1] : SFB_IDX_NONE;
+        bool pass = j < m && j != g && key <= eps && topk_key_less(key, j, td, ti);
+        uint32_t bal = __ballot_sync(0xffffffffu, pass);
+        while (bal) {
+            int src = __ffs(bal) - 1; bal &= bal - 1;
+            double kd_ = __shfl_sync(0xffffffffu, key, src);
+            warp_list_insert(ld, li, c, k, kd_, j0 + src, lane);
+        }
+    }
+    for (uint32_t t = lane; t < k; t += 32) {
+        out_idx[qi * k + t] = t < c ? li[t] : SFB_IDX_NONE;
+        out_dist[qi * k + t] = t < c ? ld[t] : INFINITY;
+    }
+    if (lane == 0) out_cnt[qi] = c;
+}
+
 size_t exact_smem_bytes(uint32_t k) {
     return sizeof(double) * (2 * KC * TP + TQ * (TC + 1) + TQ + TC + (size_t)TQ * k) + sizeof(uint32_t) * ((size_t)TQ * k + 2 * TQ);
 }
@@ -224,6 +298,22 @@ int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int m
                       uint32_t* out_cnt) {
     if (nq == 0) return SFB_OK;
     if (k == 0 || k > 128) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k must be in 1..128 (got %u)", k);
+    // feature-graph shape: few nodes with very long rows -> one thread per pair over a dense key matrix
+    if (!query_rows && x->rows <= 4096 && (uint64_t)x->cols >= 8ull * x->rows) {
+        const uint32_t m = (uint32_t)x->rows;
+        DevBuf keys;
+        SFB_CUDA(ctx, keys.alloc(sizeof(double) * (size_t)m * m));
+        dim3 grid(div_up(m, 16), div_up(m, 16));
+        if (metric == SFB_METRIC_COSINE) knn_dense_keys_kernel<true><<<grid, 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, metric, keys.as<double>());
+        else knn_dense_keys_kernel<false><<<grid, 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, metric, keys.as<double>());
+        SFB_LAUNCH_CHECK(ctx);
+        const int wpb = 4;
+        size_t ssm = (size_t)wpb * k * (sizeof(double) + sizeof(uint32_t));
+        knn_dense_select_kernel<<<div_up(nq, wpb), wpb * 32, ssm, ctx->stream>>>(keys.as<double>(), m, q_begin, nq, k, eps, out_idx, out_dist, out_cnt);
+        SFB_LAUNCH_CHECK(ctx);
+        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SFB_OK;
+    }
     const uint64_t q_tiles = (nq + TQ - 1) / TQ, n_tiles = (x->rows + TC - 1) / TC;
     uint64_t want = 2ull * ctx->sm_count;
     uint32_t csplits = 1;

@@ -77,7 +77,9 @@ def test_knn_screen_duplicates_zero_rows_eps(sfb, oracle, ctx):
         for eps in (math.inf, 0.7):
             g = ctx.matrix(x).knn(10, metric, eps=eps, screen=sfb.SCREEN_F16)
             assert_knn_equal(g.to_host(), oracle.knn(x, 10, metric, eps))
-            assert g.stats()["rows_fallback"] > 0
+            if metric == 0 and eps == math.inf:
+                # a zero row ties with everything at distance 1: the margin cannot separate -> exact fallback
+                assert g.stats()["rows_fallback"] >= 7
 
 
 def test_knn_screen_query_shard_and_kprime(sfb, oracle, ctx):
