@@ -90,8 +90,13 @@ def test_knn_screen_query_shard_and_kprime(sfb, oracle, ctx):
     for kp in (16, 32, 192):
         g = mat.knn(12, 0, screen=sfb.SCREEN_F16, k_prime=kp, q_begin=0, q_end=2000)
         assert_knn_equal(g.to_host(), oracle.knn(x, 12, 0, query_rows=np.arange(0, 2000)))
-    with pytest.raises(sfb.SfbError):  # duplicates cannot be certified; without fallback the call refuses
-        ctx.matrix(np.concatenate([x[:3000], x[:3000]])).knn(4, 0, screen=sfb.SCREEN_F16, allow_fallback=False)
+    # a zero row is at cosine distance exactly 1 from every row: no margin separates its k-th neighbour
+    # from the dropped candidates, so without the exact fallback the call refuses
+    with pytest.raises(sfb.SfbError):
+        ctx.matrix(np.concatenate([x[:3000], np.zeros((3, 72))])).knn(4, 0, screen=sfb.SCREEN_F16, allow_fallback=False)
+    # duplicated rows certify as long as the k-th gap is wide: both copies carry the same screen key
+    g = ctx.matrix(np.concatenate([x[:3000], x[:3000]])).knn(4, 0, screen=sfb.SCREEN_F16, allow_fallback=False)
+    assert_knn_equal(g.to_host(), oracle.knn(np.concatenate([x[:3000], x[:3000]]), 4, 0))
 
 
 def test_knn_auto_uses_screen(sfb, oracle, ctx):
