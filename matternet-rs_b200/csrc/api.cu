@@ -1,7 +1,9 @@
 // api.cu -- context, dense matrices, handle plumbing, synthetic rows, exclusive scan.
 #include <stdarg.h>
 
+#include <mutex>
 #include <new>
+#include <set>
 
 #include "common.cuh"
 #include "synth.cuh"
@@ -14,6 +16,22 @@ int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...) {
     va_end(ap);
     if (ctx) ctx->last_error = buf;
     return code;
+}
+
+thread_local sfb_ctx* sfb_tls_ctx = nullptr;
+
+cudaError_t sfb_dev_alloc(sfb_ctx* ctx, void** p, size_t bytes) {
+    if (!ctx) return cudaMalloc(p, bytes ? bytes : 16);
+    sfb_tls_ctx = ctx;
+    return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream);
+}
+// handles may outlive their context (garbage-collected host languages): only live contexts are dereferenced
+static std::mutex g_live_mu;
+static std::set<const sfb_ctx*> g_live;
+static bool ctx_live(const sfb_ctx* c) { std::lock_guard<std::mutex> l(g_live_mu); return g_live.count(c) != 0; }
+void sfb_dev_free(sfb_ctx* ctx, void* p) {
+    if (!p) return;
+    if (ctx && ctx_live(ctx)) cudaFreeAsync(p, ctx->stream); else cudaFree(p);
 }
 
 extern "C" int32_t sfb_abi_version(void) { return SFB_ABI_VERSION; }
@@ -40,14 +58,22 @@ extern "C" int32_t sfb_ctx_create(int32_t device_id, sfb_ctx** out) {
         delete ctx;
         return SFB_EUNSUPPORTED;
     }
+    {   // keep freed blocks in the pool instead of returning them to the driver at every synchronise
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    { std::lock_guard<std::mutex> l(g_live_mu); g_live.insert(ctx); }
     *out = ctx;
     return SFB_OK;
 }
 
 extern "C" void sfb_ctx_destroy(sfb_ctx* ctx) {
     if (!ctx) return;
+    { std::lock_guard<std::mutex> l(g_live_mu); g_live.erase(ctx); }
+    if (sfb_tls_ctx == ctx) sfb_tls_ctx = nullptr;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     sfb_comm_destroy(ctx);
@@ -118,7 +144,7 @@ static int32_t mat_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t cols, sfb_mat** o
     sfb_mat* m = new (std::nothrow) sfb_mat();
     if (!m) return SFB_ENOMEM;
     m->ctx = ctx; m->rows = rows; m->cols = cols;
-    cudaError_t e = cudaMalloc(&m->d, sizeof(double) * rows * cols);
+    cudaError_t e = sfb_dev_alloc(ctx, (void**)&m->d, sizeof(double) * rows * cols);
     if (e != cudaSuccess) { delete m; return sfb_fail(ctx, SFB_ENOMEM, "cudaMalloc %llu x %u f64: %s", (unsigned long long)rows, cols, cudaGetErrorString(e)); }
     *out = m;
     return SFB_OK;
@@ -212,7 +238,7 @@ extern "C" int32_t sfb_mat_view_rows(sfb_ctx* ctx, const sfb_mat* a, uint64_t ro
 
 extern "C" void sfb_mat_free(sfb_mat* a) {
     if (!a) return;
-    if (a->owns) cudaFree(a->d);
+    if (a->owns) sfb_dev_free(a->ctx, a->d);
     delete a;
 }
 
@@ -242,9 +268,9 @@ int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out) {
     sfb_knn* g = new (std::nothrow) sfb_knn();
     if (!g) return SFB_ENOMEM;
     g->ctx = ctx; g->rows = rows; g->k = k; g->total = rows;
-    if (cudaMalloc(&g->idx, sizeof(uint32_t) * rows * k) != cudaSuccess ||
-        cudaMalloc(&g->dist, sizeof(double) * rows * k) != cudaSuccess ||
-        cudaMalloc(&g->cnt, sizeof(uint32_t) * rows) != cudaSuccess) {
+    if (sfb_dev_alloc(ctx, (void**)&g->idx, sizeof(uint32_t) * rows * k) != cudaSuccess ||
+        sfb_dev_alloc(ctx, (void**)&g->dist, sizeof(double) * rows * k) != cudaSuccess ||
+        sfb_dev_alloc(ctx, (void**)&g->cnt, sizeof(uint32_t) * rows) != cudaSuccess) {
         sfb_knn_free(g);
         return sfb_fail(ctx, SFB_ENOMEM, "kNN list allocation failed (%llu x %u)", (unsigned long long)rows, k);
     }
@@ -264,7 +290,7 @@ extern "C" int32_t sfb_knn_from_host(sfb_ctx* ctx, const uint32_t* idx, const do
 }
 extern "C" void sfb_knn_free(sfb_knn* g) {
     if (!g) return;
-    cudaFree(g->idx); cudaFree(g->dist); cudaFree(g->cnt);
+    sfb_dev_free(g->ctx, g->idx); sfb_dev_free(g->ctx, g->dist); sfb_dev_free(g->ctx, g->cnt);
     delete g;
 }
 
@@ -286,9 +312,9 @@ int32_t sfb_adj_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_adj** out) {
     sfb_adj* a = new (std::nothrow) sfb_adj();
     if (!a) return SFB_ENOMEM;
     a->ctx = ctx; a->rows = rows; a->k = k;
-    if (cudaMalloc(&a->idx, sizeof(uint32_t) * rows * k) != cudaSuccess ||
-        cudaMalloc(&a->w, sizeof(double) * rows * k) != cudaSuccess ||
-        cudaMalloc(&a->cnt, sizeof(uint32_t) * rows) != cudaSuccess) {
+    if (sfb_dev_alloc(ctx, (void**)&a->idx, sizeof(uint32_t) * rows * k) != cudaSuccess ||
+        sfb_dev_alloc(ctx, (void**)&a->w, sizeof(double) * rows * k) != cudaSuccess ||
+        sfb_dev_alloc(ctx, (void**)&a->cnt, sizeof(uint32_t) * rows) != cudaSuccess) {
         sfb_adj_free(a);
         return sfb_fail(ctx, SFB_ENOMEM, "adjacency allocation failed");
     }
@@ -308,7 +334,7 @@ extern "C" int32_t sfb_adj_from_host(sfb_ctx* ctx, const uint32_t* idx, const do
 }
 extern "C" void sfb_adj_free(sfb_adj* a) {
     if (!a) return;
-    cudaFree(a->idx); cudaFree(a->w); cudaFree(a->cnt);
+    sfb_dev_free(a->ctx, a->idx); sfb_dev_free(a->ctx, a->w); sfb_dev_free(a->ctx, a->cnt);
     delete a;
 }
 
@@ -341,9 +367,9 @@ extern "C" int32_t sfb_csr_from_host(sfb_ctx* ctx, uint64_t rows, const uint64_t
     sfb_csr* L = new (std::nothrow) sfb_csr();
     if (!L) return SFB_ENOMEM;
     L->ctx = ctx; L->rows = rows; L->nnz = nnz;
-    if (cudaMalloc(&L->indptr, sizeof(uint64_t) * (rows + 1)) != cudaSuccess ||
-        cudaMalloc(&L->indices, sizeof(uint32_t) * (nnz ? nnz : 1)) != cudaSuccess ||
-        cudaMalloc(&L->data, sizeof(double) * (nnz ? nnz : 1)) != cudaSuccess) {
+    if (sfb_dev_alloc(ctx, (void**)&L->indptr, sizeof(uint64_t) * (rows + 1)) != cudaSuccess ||
+        sfb_dev_alloc(ctx, (void**)&L->indices, sizeof(uint32_t) * (nnz ? nnz : 1)) != cudaSuccess ||
+        sfb_dev_alloc(ctx, (void**)&L->data, sizeof(double) * (nnz ? nnz : 1)) != cudaSuccess) {
         sfb_csr_free(L);
         return sfb_fail(ctx, SFB_ENOMEM, "CSR allocation failed");
     }
@@ -358,7 +384,7 @@ extern "C" int32_t sfb_csr_from_host(sfb_ctx* ctx, uint64_t rows, const uint64_t
 }
 extern "C" void sfb_csr_free(sfb_csr* L) {
     if (!L) return;
-    cudaFree(L->indptr); cudaFree(L->indices); cudaFree(L->data);
+    sfb_dev_free(L->ctx, L->indptr); sfb_dev_free(L->ctx, L->indices); sfb_dev_free(L->ctx, L->data);
     delete L;
 }
 

@@ -61,8 +61,17 @@ struct sfb_csr {
 
 int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...);
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync on the context's stream,
+// release threshold = never): a build allocates and frees GB-sized scratch at every stage, and plain
+// cudaMalloc / cudaFree synchronise the device and cost hundreds of milliseconds per step.
+// All work of a context runs on its one stream, so stream order is program order.
+extern thread_local sfb_ctx* sfb_tls_ctx;  // the context of the call in flight (set by SFB_CUDA / sfb_dev_alloc)
+cudaError_t sfb_dev_alloc(sfb_ctx* ctx, void** p, size_t bytes);
+void sfb_dev_free(sfb_ctx* ctx, void* p);
+
 #define SFB_CUDA(ctx, call)                                                                      \
     do {                                                                                         \
+        sfb_tls_ctx = (ctx);                                                                     \
         cudaError_t e__ = (call);                                                                \
         if (e__ != cudaSuccess)                                                                  \
             return sfb_fail((ctx), e__ == cudaErrorMemoryAllocation ? SFB_ENOMEM : SFB_ECUDA,    \
@@ -84,8 +93,9 @@ int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...);
 // device scratch that frees itself on every return path
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    sfb_ctx* owner = nullptr;
+    ~DevBuf() { if (p) sfb_dev_free(owner, p); }
+    cudaError_t alloc(size_t bytes) { owner = sfb_tls_ctx; return sfb_dev_alloc(owner, &p, bytes); }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
     void* release() { void* q = p; p = nullptr; return q; }
 };

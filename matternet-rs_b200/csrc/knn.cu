@@ -26,6 +26,7 @@ extern "C" int32_t sfb_knn_build(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_p
 
     StageTimer total(ctx, &ctx->times.ms_knn);
     DevBuf norms;
+    sfb_tls_ctx = ctx;
     cudaError_t e = norms.alloc(sizeof(double) * x->rows);
     if (e != cudaSuccess) { sfb_knn_free(g); *out = nullptr; return sfb_fail(ctx, SFB_ENOMEM, "norms: %s", cudaGetErrorString(e)); }
     int32_t st = SFB_OK;

@@ -524,13 +524,13 @@ extern "C" int32_t sfb_laplacian_build(sfb_ctx* ctx, const sfb_adj* a, const sfb
     sfb_csr* L = new (std::nothrow) sfb_csr();
     if (!L) return SFB_ENOMEM;
     L->ctx = ctx; L->rows = m;
-    if (cudaMalloc(&L->indptr, sizeof(uint64_t) * (m + 1)) != cudaSuccess) { sfb_csr_free(L); return sfb_fail(ctx, SFB_ENOMEM, "indptr"); }
+    if (sfb_dev_alloc(ctx, (void**)&L->indptr, sizeof(uint64_t) * (m + 1)) != cudaSuccess) { sfb_csr_free(L); return sfb_fail(ctx, SFB_ENOMEM, "indptr"); }
     int32_t st = sfb_scan_exclusive_u64(ctx, row_nnz.as<uint32_t>(), m, L->indptr);
     if (st != SFB_OK) { sfb_csr_free(L); return st; }
     cudaMemcpyAsync(&L->nnz, L->indptr + m, 8, cudaMemcpyDeviceToHost, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    if (cudaMalloc(&L->indices, sizeof(uint32_t) * (L->nnz ? L->nnz : 1)) != cudaSuccess ||
-        cudaMalloc(&L->data, sizeof(double) * (L->nnz ? L->nnz : 1)) != cudaSuccess) {
+    if (sfb_dev_alloc(ctx, (void**)&L->indices, sizeof(uint32_t) * (L->nnz ? L->nnz : 1)) != cudaSuccess ||
+        sfb_dev_alloc(ctx, (void**)&L->data, sizeof(double) * (L->nnz ? L->nnz : 1)) != cudaSuccess) {
         sfb_csr_free(L);
         return sfb_fail(ctx, SFB_ENOMEM, "CSR arrays (%llu nnz)", (unsigned long long)L->nnz);
     }
