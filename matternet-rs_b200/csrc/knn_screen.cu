@@ -84,6 +84,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants ----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA's share of a pair operand; the transaction bytes complete on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this shared offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start address >> 4 in bits [0,14), SBO (8 rows * 128 B = 1024 B) >> 4 in [32,46), version 1 in [46,48),
 // layout SWIZZLE_128B (2) in [61,64).  LBO is unused for a single 128-byte swizzle atom along K.
@@ -209,6 +239,52 @@ __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_
     }
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+    return d;
+}
+
+// Filters one 32-column chunk of a thread's query row against its threshold.  Hits are rare once the
+// threshold has tightened (a few percent of chunks), so the common case is a branch-free FMNMX3 tree
+// (20 instructions) and one warp vote; per-element compares run only inside groups of 4 whose max passes.
+template <bool L2>
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const float* __restrict__ nqv, uint32_t col0, uint64_t n_rows,
+                                             bool row_valid, float* my_key, uint32_t* my_idx, uint32_t& cnt, float& thr,
+                                             uint32_t cap, uint32_t kprime, int lane) {
+    float key[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        key[c] = __uint_as_float(v[c]);
+        if (L2) key[c] = fmaf(2.0f, key[c], -nqv[c]);  // -(|q_j|^2 - 2 q_i.q_j): larger is nearer
+    }
+    float g[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmax3(key[4 * q], key[4 * q + 1], key[4 * q + 2]), key[4 * q + 3]);
+    const float m = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
+    const bool hit = m > thr;
+    if (!__any_sync(FULL, hit)) return;
+    if (hit && row_valid) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (g[q] > thr) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t j = col0 + 4 * q + e;
+                    if (key[4 * q + e] > thr && j < n_rows) { __stcg(my_key + cnt, key[4 * q + e]); __stcg(my_idx + cnt, j); ++cnt; }
+                }
+            }
+        }
+    }
+    // a chunk appends at most 32 entries: prune whenever fewer than 32 slots remain
+    const uint32_t need = __ballot_sync(FULL, cnt + 32 > cap);
+    if (need) {
+        __syncwarp();
+        if (cap <= 128) prune_rows<4>(need, my_key, my_idx, cnt, thr, kprime, lane);
+        else prune_rows<8>(need, my_key, my_idx, cnt, thr, kprime, lane);
+    }
+}
+
 template <bool L2, bool DUMP>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1)
 knn_screen_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ScreenArgs a) {
@@ -317,23 +393,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int c = 0; c < 32; ++c) a.dump[(size_t)row_in_tile * BN + ch * 32 + c] = __uint_as_float(v[c]);
                     continue;
                 }
-                const float* nqv = s_nq + as * BN + ch * 32;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    float key = __uint_as_float(v[c]);
-                    if (L2) key = fmaf(2.0f, key, -nqv[c]);  // -(|q_j|^2 - 2 q_i.q_j): larger is nearer
-                    if (key > thr) {
-                        uint32_t j = n0 + ch * 32 + c;
-                        if (row_valid && j < a.n_rows) { __stcg(my_key + cnt, key); __stcg(my_idx + cnt, j); ++cnt; }
-                    }
-                }
-                // a chunk appends at most 32 entries: prune whenever fewer than 32 slots remain
-                uint32_t need = __ballot_sync(FULL, cnt + 32 > a.cap);
-                if (need) {
-                    __syncwarp();
-                    if (a.cap <= 128) prune_rows<4>(need, my_key, my_idx, cnt, thr, a.kprime, lane);
-                    else prune_rows<8>(need, my_key, my_idx, cnt, thr, a.kprime, lane);
-                }
+                filter_chunk<L2>(v, s_nq + as * BN + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -346,6 +406,194 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- the screen, CTA-pair version -------------------------------------------------------------
+// The single-CTA kernel above re-streams both operands for every 128 x 256 tile: 48 KB of L2 -> shared
+// traffic per 512 tensor-core cycles and SM, more than twice what the L2 can deliver to 148 SMs, and the
+// fp16 corpus (0.77 GB at 1M x 384) falls out of the 126 MB L2 between two sweeps.  This version
+//   * pairs two CTAs (cluster of 2, tcgen05.mma.cta_group::2, M = 256): each CTA stages only HALF of
+//     every corpus tile (128 of the 256 rows) and the pair's tensor cores read both halves;
+//   * keeps the CTA's 128 query rows (all of K) resident in shared memory for a whole work item, so only
+//     the corpus streams: 16 KB per k-block and CTA -- a third of the single-CTA traffic;
+//   * walks the corpus in L2-sized chunks: every pair sweeps chunk c for all of its query blocks before
+//     any pair touches chunk c + 1 (persistent CTAs, static schedule), so corpus tiles are read from HBM
+//     once per chunk instead of once per query block.  The per-row state (threshold, candidate count)
+//     lives in HBM between chunks; the candidate buffers already do.
+struct Screen2Args {
+    uint64_t n_rows;
+    uint64_t q_begin, nq;
+    uint32_t kblocks, stages;
+    uint32_t tiles_total, tiles_per_split, n_splits, chunk_tiles, n_chunks;
+    uint32_t n_mb2;         // 256-row query blocks
+    uint32_t idesc;
+    uint32_t kprime, cap;
+    const float* nq32;
+    float* buf_key; uint32_t* buf_idx;
+    uint32_t* out_cnt; float* out_thr;
+};
+
+constexpr int P_BM = 128, P_BNH = 128, P_SLAB_BYTES = 128 * BK * 2;  // 16 KB: one k-block of 128 rows
+
+template <bool L2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SCREEN_THREADS, 1)
+knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // carve: A slabs [kblocks] | B stages [stages] | barriers | tmem ptr | nq tiles (L2)
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)a.kblocks * P_SLAB_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)a.stages * P_SLAB_BYTES);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tfull_bar = empty_bar + 8;     // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;    // [2]
+    uint64_t* afull_bar = tempty_bar + 2;    // [1]
+    uint64_t* aempty_bar = afull_bar + 1;    // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty_bar + 1);
+    float* s_nq = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const uint32_t n_slots = a.n_mb2 * a.n_splits;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
+        for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }  // 4 epilogue warps x 2 CTAs
+        mbar_init(afull_bar, 1); mbar_init(aempty_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // Work items in schedule order; every role of both CTAs walks the same sequence.
+#define SFB_FOR_EACH_ITEM                                                                              \
+    for (uint32_t chunk = 0; chunk < a.n_chunks; ++chunk)                                              \
+        for (uint32_t s2 = pair; s2 < n_slots; s2 += n_pairs)
+#define SFB_ITEM_RANGE                                                                                 \
+    const uint32_t mb2 = s2 / a.n_splits, split = s2 - mb2 * a.n_splits;                               \
+    const uint32_t t_lo = split * a.tiles_per_split + chunk * a.chunk_tiles;                           \
+    uint32_t t_hi = t_lo + a.chunk_tiles;                                                              \
+    { uint32_t e = (split + 1) * a.tiles_per_split; if (e > a.tiles_total) e = a.tiles_total; if (t_hi > e) t_hi = e; } \
+    if (t_lo >= t_hi) continue;
+
+    if (warp == 0) {
+        // ===== TMA producer (one thread per CTA) =====
+        if (lane == 0) {
+            const uint32_t l_afull = mapa_u32(afull_bar, 0);
+            uint32_t stage = 0, phase = 0, iphase = 0;
+            SFB_FOR_EACH_ITEM {
+                SFB_ITEM_RANGE
+                const int row0 = (int)(a.q_begin + (uint64_t)mb2 * 256 + rank * P_BM);
+                mbar_wait(aempty_bar, iphase ^ 1);   // the previous item's MMAs have retired
+                if (leader) mbar_expect_tx(afull_bar, 2u * a.kblocks * P_SLAB_BYTES);
+                for (uint32_t kb = 0; kb < a.kblocks; ++kb)
+                    tma_load_2d_pair(sA + (size_t)kb * P_SLAB_BYTES, &tm, (int)(kb * BK), row0, l_afull);
+                iphase ^= 1;
+                for (uint32_t t = t_lo; t < t_hi; ++t) {
+                    const int n0 = (int)(t * BN + rank * P_BNH);
+                    for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (leader) mbar_expect_tx(&full_bar[stage], 2u * P_SLAB_BYTES);
+                        tma_load_2d_pair(sB + (size_t)stage * P_SLAB_BYTES, &tm, (int)(kb * BK), n0, mapa_u32(&full_bar[stage], 0));
+                        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+        if (leader && lane == 0) {
+            uint32_t stage = 0, phase = 0, iphase = 0, tc = 0;
+            SFB_FOR_EACH_ITEM {
+                SFB_ITEM_RANGE
+                mbar_wait(afull_bar, iphase);
+                iphase ^= 1;
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(sA);
+                for (uint32_t t = t_lo; t < t_hi; ++t, ++tc) {
+                    const uint32_t as = tc & 1, aphase = (tc >> 1) & 1;
+                    mbar_wait(&tempty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * BN;
+                    for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = a_base + kb * P_SLAB_BYTES, b_addr = smem_u32(sB + (size_t)stage * P_SLAB_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_pair(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), a.idesc, (kb | (uint32_t)k) != 0u);
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (kb + 1 == a.kblocks) umma_commit_pair(&tfull_bar[as]);
+                        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit_pair(aempty_bar);   // A may be overwritten once every MMA of this item has retired
+            }
+        }
+    } else {
+        // ===== epilogue: thread = query row =====
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const int etid = threadIdx.x - 64;
+        const uint32_t l_tempty0 = mapa_u32(&tempty_bar[0], 0), l_tempty1 = mapa_u32(&tempty_bar[1], 0);
+        uint32_t tc = 0;
+        SFB_FOR_EACH_ITEM {
+            SFB_ITEM_RANGE
+            const uint64_t row_local = (uint64_t)mb2 * 256 + rank * P_BM + row_in_tile;
+            const bool row_valid = row_local < a.nq;
+            const size_t slot = (size_t)(row_valid ? row_local : 0) * a.n_splits + split;
+            float* my_key = a.buf_key + slot * a.cap;
+            uint32_t* my_idx = a.buf_idx + slot * a.cap;
+            uint32_t cnt = 0;
+            float thr = -INFINITY;
+            if (chunk != 0 && row_valid) { cnt = a.out_cnt[slot]; thr = a.out_thr[slot]; }
+            for (uint32_t t = t_lo; t < t_hi; ++t, ++tc) {
+                const uint32_t as = tc & 1, aphase = (tc >> 1) & 1;
+                const uint32_t n0 = t * BN;
+                if (L2) {
+                    float* dst = s_nq + as * BN;
+                    for (int c = etid; c < BN; c += 128) dst[c] = (uint64_t)n0 + c < a.n_rows ? __ldg(a.nq32 + n0 + c) : INFINITY;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
+                const float* nqt = s_nq + as * BN;
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch += 2) {
+                    tmem_ld_wait();
+                    tmem_ld32(taddr + (ch + 1) * 32, vb);   // in flight while chunk ch is filtered
+                    filter_chunk<L2>(va, nqt + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
+                    tmem_ld_wait();
+                    if (ch + 2 < BN / 32) tmem_ld32(taddr + (ch + 2) * 32, va);
+                    filter_chunk<L2>(vb, nqt + (ch + 1) * 32, n0 + (ch + 1) * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(as ? l_tempty1 : l_tempty0);
+            }
+            if (row_valid) { a.out_cnt[slot] = cnt; a.out_thr[slot] = thr; }
+        }
+    }
+#undef SFB_FOR_EACH_ITEM
+#undef SFB_ITEM_RANGE
+    __syncwarp();         // the single-thread roles rejoin their warps before the aligned cluster barrier
+    tc_fence_before();
+    cluster_sync_all();   // no CTA may leave while its peer can still signal its barriers or read its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -574,6 +822,39 @@ int32_t launch_screen(sfb_ctx* ctx, const Prepared& P, int metric, ScreenArgs& s
     return SFB_OK;
 }
 
+int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2Args& sa) {
+    CUtensorMap tm;
+    SFB_TRY(make_tmap(ctx, &tm, P.q.p, P.mpad, P.kpad, P_BM, P.bf16));
+    // M = 256 across the pair, N = 256
+    const uint32_t fmt = P.bf16 ? 1u : 0u;
+    sa.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const size_t fixed = 1024 + 22 * 8 + 16 + 2 * BN * sizeof(float);
+    const size_t budget = ctx->smem_optin ? ctx->smem_optin : 232448;
+    size_t stages = (budget - fixed - (size_t)sa.kblocks * P_SLAB_BYTES) / P_SLAB_BYTES;
+    if (stages > 8) stages = 8;
+    sa.stages = (uint32_t)stages;
+    const size_t smem = fixed + ((size_t)sa.kblocks + stages) * P_SLAB_BYTES;
+    const uint32_t n_slots = sa.n_mb2 * sa.n_splits;
+    uint32_t pairs = (uint32_t)ctx->sm_count / 2;
+    if (pairs > n_slots) pairs = n_slots;
+    if (metric == SFB_METRIC_COSINE) {
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_screen_pair_kernel<false><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, sa);
+    } else {
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_screen_pair_kernel<true><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, sa);
+    }
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
+// the pair kernel keeps all of K for 128 rows in shared memory: K <= 512 (8 slabs of 16 KB) leaves >= 5 stages
+bool pair_kernel_applies(const Prepared& P) {
+    const char* v1 = getenv("SFB_SCREEN_V1");
+    if (v1 && v1[0] == '1') return false;
+    return P.kpad / BK <= 8;
+}
+
 }  // namespace
 
 int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p, uint64_t q_begin,
@@ -600,18 +881,44 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
         SFB_TRY(prepare_operands(ctx, x, norms, p->metric, bf16, &P));
         st.ms_prepare = t.stop();
     }
-    const uint32_t m_blocks = (uint32_t)((nq + BM - 1) / BM);
+    const uint32_t tiles_total = (uint32_t)(P.mpad / BN);
+    const bool use_pair = pair_kernel_applies(P);
     ScreenArgs sa{};
-    sa.n_rows = m; sa.q_begin = q_begin; sa.nq = nq; sa.kblocks = P.kpad / BK;
-    sa.tiles_total = (uint32_t)(P.mpad / BN);
-    uint32_t want_ctas = 2u * (uint32_t)ctx->sm_count;
-    uint32_t n_splits = m_blocks >= want_ctas ? 1u : (want_ctas + m_blocks - 1) / m_blocks;
-    if (n_splits > sa.tiles_total) n_splits = sa.tiles_total;
-    sa.tiles_per_split = (sa.tiles_total + n_splits - 1) / n_splits;
-    sa.n_splits = (sa.tiles_total + sa.tiles_per_split - 1) / sa.tiles_per_split;
-    sa.kprime = kprime; sa.cap = cap; sa.nq32 = P.nq32.as<float>();
+    Screen2Args s2{};
+    uint32_t n_splits_used = 1;
+    uint32_t m_blocks = (uint32_t)((nq + BM - 1) / BM);
+    if (use_pair) {
+        s2.n_rows = m; s2.q_begin = q_begin; s2.nq = nq; s2.kblocks = P.kpad / BK;
+        s2.tiles_total = tiles_total;
+        s2.n_mb2 = (uint32_t)((nq + 255) / 256);
+        const uint32_t pairs = (uint32_t)ctx->sm_count / 2;
+        uint32_t n_splits = s2.n_mb2 >= 4 * pairs ? 1u : (2 * pairs + s2.n_mb2 - 1) / s2.n_mb2;
+        if (n_splits > tiles_total) n_splits = tiles_total;
+        s2.tiles_per_split = (tiles_total + n_splits - 1) / n_splits;
+        s2.n_splits = (tiles_total + s2.tiles_per_split - 1) / s2.tiles_per_split;
+        // corpus chunk that stays L2-resident while every pair sweeps it
+        double chunk_mb = 24.0;
+        if (const char* e = getenv("SFB_SCREEN_CHUNK_MB")) { double v = atof(e); if (v > 0.0) chunk_mb = v; }
+        uint64_t ct = (uint64_t)(chunk_mb * 1048576.0 / ((double)BN * P.kpad * 2.0));
+        if (ct < 4) ct = 4;
+        if (ct > s2.tiles_per_split) ct = s2.tiles_per_split;
+        s2.chunk_tiles = (uint32_t)ct;
+        s2.n_chunks = (s2.tiles_per_split + s2.chunk_tiles - 1) / s2.chunk_tiles;
+        s2.kprime = kprime; s2.cap = cap; s2.nq32 = P.nq32.as<float>();
+        n_splits_used = s2.n_splits;
+    } else {
+        sa.n_rows = m; sa.q_begin = q_begin; sa.nq = nq; sa.kblocks = P.kpad / BK;
+        sa.tiles_total = tiles_total;
+        uint32_t want_ctas = 2u * (uint32_t)ctx->sm_count;
+        uint32_t n_splits = m_blocks >= want_ctas ? 1u : (want_ctas + m_blocks - 1) / m_blocks;
+        if (n_splits > sa.tiles_total) n_splits = sa.tiles_total;
+        sa.tiles_per_split = (sa.tiles_total + n_splits - 1) / n_splits;
+        sa.n_splits = (sa.tiles_total + sa.tiles_per_split - 1) / sa.tiles_per_split;
+        sa.kprime = kprime; sa.cap = cap; sa.nq32 = P.nq32.as<float>();
+        n_splits_used = sa.n_splits;
+    }
 
-    const size_t slots = (size_t)nq * sa.n_splits;
+    const size_t slots = (size_t)nq * n_splits_used;
     DevBuf buf_key, buf_idx, cnt, thr, fb_rows, fb_count;
     SFB_CUDA(ctx, buf_key.alloc(slots * cap * sizeof(float)));
     SFB_CUDA(ctx, buf_idx.alloc(slots * cap * sizeof(uint32_t)));
@@ -621,10 +928,13 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     SFB_CUDA(ctx, fb_count.alloc(4 * sizeof(uint64_t)));
     SFB_CUDA(ctx, cudaMemsetAsync(fb_count.p, 0, 4 * sizeof(uint64_t), ctx->stream));
     SFB_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, slots * sizeof(uint32_t), ctx->stream));
-    sa.buf_key = buf_key.as<float>(); sa.buf_idx = buf_idx.as<uint32_t>(); sa.out_cnt = cnt.as<uint32_t>(); sa.out_thr = thr.as<float>();
+    sa.buf_key = s2.buf_key = buf_key.as<float>(); sa.buf_idx = s2.buf_idx = buf_idx.as<uint32_t>();
+    sa.out_cnt = s2.out_cnt = cnt.as<uint32_t>(); sa.out_thr = s2.out_thr = thr.as<float>();
+    sa.n_splits = n_splits_used;
     {
         StageTimer t(ctx, nullptr);
-        SFB_TRY(launch_screen<false>(ctx, P, p->metric, sa, m_blocks));
+        if (use_pair) SFB_TRY(launch_screen_pair(ctx, P, p->metric, s2));
+        else SFB_TRY(launch_screen<false>(ctx, P, p->metric, sa, m_blocks));
         st.ms_screen = t.stop();
         SFB_CUDA(ctx, cudaGetLastError());
     }
