@@ -188,7 +188,13 @@ struct ScreenArgs {
     float* dump;            // DUMP mode: 128 x 256 accumulators of the CTA's first tile
 };
 
-// Warp-cooperative prune of the candidate buffers of the lanes in `need`: keep the k' largest keys.
+// Warp-cooperative prune of the candidate buffers of the lanes in `need`: keep (at least) the k' largest keys
+// and raise the row's threshold to the largest key dropped.
+//   fast path  the keys are quantised to 8 bits over the buffer's [min, max] and the cut is found by an
+//              8-step binary search on ballot counts: keeps k' plus the few entries sharing the cut's bin.
+//              Quantisation is monotone, so every kept key is strictly greater than every dropped key.
+//   exact path MSB-first radix select of the k'-th largest key (32 steps); taken when the fast cut would
+//              drop nothing (all keys equal, or one outlier stretching the range).
 template <int E>
 __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_t* my_idx, uint32_t& cnt, float& thr,
                                            uint32_t kprime, int lane) {
@@ -198,34 +204,82 @@ __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_
         float* kp = reinterpret_cast<float*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(my_key), L));
         uint32_t* ip = reinterpret_cast<uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(my_idx), L));
         const uint32_t n = __shfl_sync(FULL, cnt, L);
-        uint32_t key[E], idx[E];
+        float kf[E];
+        uint32_t idx[E];
+        float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
         for (int u = 0; u < E; ++u) {
-            uint32_t e = lane + 32 * u;
-            bool v = e < n;
-            key[u] = v ? f32_sortable(__ldcg(kp + e)) : 0u;  // 0 sorts below every real key
+            const uint32_t e = lane + 32 * u;
+            const bool v = e < n;
+            kf[u] = v ? __ldcg(kp + e) : -INFINITY;
             idx[u] = v ? __ldcg(ip + e) : 0u;
+            if (v) mn = fminf(mn, kf[u]);
+            mx = fmaxf(mx, kf[u]);
         }
-        // k'-th largest key by MSB-first radix select
-        uint32_t prefix = 0, want = kprime;
-#pragma unroll 1
-        for (int b = 31; b >= 0; --b) {
-            const uint32_t bit = 1u << b, hi = b == 31 ? 0u : ~((bit << 1) - 1u);
-            uint32_t c = 0;
 #pragma unroll
-            for (int u = 0; u < E; ++u) c += __popc(__ballot_sync(FULL, (key[u] & hi) == (prefix & hi) && (key[u] & bit)));
-            if (c >= want) prefix |= bit; else want -= c;
+        for (int o = 16; o; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o)); }
+        bool keep[E];
+        uint32_t kept = 0;
+        float new_thr = -INFINITY;
+        {
+            const float scale = 255.0f / (mx - mn);   // inf / NaN when all keys are equal: the cut below then drops nothing
+            uint32_t q[E];
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                float t = (kf[u] - mn) * scale;
+                q[u] = (uint32_t)(lane + 32 * u) < n ? (uint32_t)fminf(fmaxf(t, 0.0f), 255.0f) : 0u;  // NaN -> 0
+            }
+            uint32_t cut = 0;
+#pragma unroll
+            for (int b = 7; b >= 0; --b) {
+                const uint32_t trial = cut | (1u << b);
+                uint32_t c = 0;
+#pragma unroll
+                for (int u = 0; u < E; ++u) c += __popc(__ballot_sync(FULL, q[u] >= trial));   // invalid entries hold q = 0 < trial
+                if (c >= kprime) cut = trial;
+            }
+            float dropped_max = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const bool v = (uint32_t)(lane + 32 * u) < n;
+                keep[u] = v && q[u] >= cut;
+                kept += __popc(__ballot_sync(FULL, keep[u]));
+                if (v && !keep[u]) dropped_max = fmaxf(dropped_max, kf[u]);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) dropped_max = fmaxf(dropped_max, __shfl_xor_sync(FULL, dropped_max, o));
+            new_thr = dropped_max;
         }
-        // keep key > T and `want` of the entries equal to T
-        uint32_t base = 0, eq_seen = 0;
-        uint32_t pos[E]; bool keep[E];
+        if (kept == n) {
+            // exact path: k'-th largest key by MSB-first radix select
+            uint32_t key[E];
+#pragma unroll
+            for (int u = 0; u < E; ++u) key[u] = (uint32_t)(lane + 32 * u) < n ? f32_sortable(kf[u]) : 0u;  // 0 sorts below every real key
+            uint32_t prefix = 0, want = kprime;
+#pragma unroll 1
+            for (int b = 31; b >= 0; --b) {
+                const uint32_t bit = 1u << b, hi = b == 31 ? 0u : ~((bit << 1) - 1u);
+                uint32_t c = 0;
+#pragma unroll
+                for (int u = 0; u < E; ++u) c += __popc(__ballot_sync(FULL, (key[u] & hi) == (prefix & hi) && (key[u] & bit)));
+                if (c >= want) prefix |= bit; else want -= c;
+            }
+            // keep key > T and `want` of the entries equal to T
+            uint32_t eq_seen = 0;
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                bool gt = key[u] > prefix, eq = key[u] == prefix && (uint32_t)(lane + 32 * u) < n;
+                uint32_t beq = __ballot_sync(FULL, eq);
+                uint32_t my_eq_rank = eq_seen + __popc(beq & ((1u << lane) - 1u));
+                keep[u] = gt || (eq && my_eq_rank < want);
+                eq_seen += __popc(beq);
+            }
+            new_thr = sortable_f32(prefix);
+        }
+        uint32_t base = 0;
+        uint32_t pos[E];
 #pragma unroll
         for (int u = 0; u < E; ++u) {
-            bool gt = key[u] > prefix, eq = key[u] == prefix && (uint32_t)(lane + 32 * u) < n;
-            uint32_t beq = __ballot_sync(FULL, eq);
-            uint32_t my_eq_rank = eq_seen + __popc(beq & ((1u << lane) - 1u));
-            keep[u] = gt || (eq && my_eq_rank < want);
-            eq_seen += __popc(beq);
             uint32_t bk = __ballot_sync(FULL, keep[u]);
             pos[u] = base + __popc(bk & ((1u << lane) - 1u));
             base += __popc(bk);
@@ -233,9 +287,9 @@ __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < E; ++u)
-            if (keep[u]) { __stcg(kp + pos[u], sortable_f32(key[u])); __stcg(ip + pos[u], idx[u]); }
+            if (keep[u]) { __stcg(kp + pos[u], kf[u]); __stcg(ip + pos[u], idx[u]); }
         __syncwarp();
-        if (lane == L) { cnt = base; thr = sortable_f32(prefix); }
+        if (lane == L) { cnt = base; thr = fmaxf(thr, new_thr); }
     }
 }
 
