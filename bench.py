@@ -8,7 +8,7 @@ One "step" = one full build over one synthetic embedding matrix (BASELINE.json c
 1M x 384 clustered, cosine k=16, + Laplacian + taumode lambda):
     item graph     kNN (tcgen05 screen + exact f64 rescore) -> kernel weights / sparsification
                    -> symmetrise + CSR Laplacian                       (src_legacy/laplacian.rs:122-419)
-    feature graph  the reference's own call shape: transpose, kNN over the D feature nodes, Laplacian
+    feature graph  the reference's own call shape: kNN over the D feature nodes (the columns), Laplacian
                    (src_legacy/graph.rs:193-255)
     lambda         per-item taumode lambda against the D x D feature Laplacian, min-max normalised
                    (src_legacy/taumode.rs:117-318, core.rs:1341-1355)
@@ -24,9 +24,7 @@ import argparse
 import json
 import math
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -60,49 +58,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every 200 ms DURING the timed region, through NVML in a
+    thread of this process.  (An `nvidia-smi -lms 200` child process was measured to slow the timed step
+    by ~25 %: every query stalls the CUDA calls of the process being measured.)"""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, gpu_index, period=0.2):
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[gpu_index]) if gpu_index < len(ids) else gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    for name, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                self._stop.wait(period)
+
+        self._t = threading.Thread(target=loop, daemon=True)
+        self._t.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            parts = [s.strip() for s in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        self.f.close()
-        os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-        return out
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm),
+                "sm_mhz_min": sm[0], "how": "NVML in-process thread, 200 ms period, timed region only"}
 
 
 def shard(n, rank, world):
@@ -114,32 +115,47 @@ def shard(n, rank, world):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+_TRACE = bool(os.environ.get("SFB_BENCH_TRACE"))
+
+
+def _timed(ctx, name, f):
+    """SFB_BENCH_TRACE=1: wall time of every public call, to stderr (development aid; adds synchronisation)."""
+    if not _TRACE:
+        return f()
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    r = f()
+    ctx.synchronize()
+    sys.stderr.write(f"  {name:14s} {(time.perf_counter() - t0) * 1e3:9.2f} ms\n")
+    return r
+
+
 def build_once(sfb, ctx, X, wl, rank, world, out_lambda=None, keep=False):
     """One full build on device-resident X.  Returns (handles or None, stats)."""
     n, d = X.shape
     lo, hi = shard(n, rank, world)
-    g = X.knn(wl["k"], wl["metric"], q_begin=lo, q_end=hi)
+    g = _timed(ctx, "knn", lambda: X.knn(wl["k"], wl["metric"], q_begin=lo, q_end=hi))
     st = g.stats()
     if world > 1:
-        g_all = g.allgather(n)
+        g_all = _timed(ctx, "allgather", lambda: g.allgather(n))
         g.free()
         g = g_all
-    adj = g.adjacency(P_WEIGHT, SIGMA)
-    L = adj.laplacian()
+    adj = _timed(ctx, "adjacency", lambda: g.adjacency(P_WEIGHT, SIGMA))
+    L = _timed(ctx, "laplacian", lambda: adj.laplacian())
     # feature graph (the reference's call shape) + per-item lambda
-    Xt = X.transpose()
-    gf = Xt.knn(min(wl["k"], d - 1), sfb.METRIC_COSINE)
-    adjf = gf.adjacency(P_WEIGHT, SIGMA)
-    Lf = adjf.laplacian()
+    gf = _timed(ctx, "knn_columns", lambda: X.knn_columns(min(wl["k"], d - 1), sfb.METRIC_COSINE))
+    adjf = _timed(ctx, "adjacency_f", lambda: gf.adjacency(P_WEIGHT, SIGMA))
+    Lf = _timed(ctx, "laplacian_f", lambda: adjf.laplacian())
     xs = X.view_rows(lo, hi - lo)
-    lam, lstats = Lf.lambdas_allgather(xs, lo, n, normalise=True)
+    lam, lstats = _timed(ctx, "lambda", lambda: Lf.lambdas_allgather(xs, lo, n, normalise=True))
     if out_lambda is not None:
         out_lambda[:] = lam
-    for h in (xs, adjf, gf, Xt, adj, g):
-        h.free()
+    _timed(ctx, "free", lambda: [h.free() for h in (xs, adjf, gf, adj, g)])
     if keep:
         return (L, Lf, lam), st
     L.free(); Lf.free()
+    if _TRACE:
+        sys.stderr.write(f"  knn stats: prepare {st['ms_prepare']:.2f} screen {st['ms_screen']:.2f} rescore {st['ms_rescore']:.2f} fallback {st['ms_fallback']:.2f}\n")
     return None, st
 
 
@@ -184,13 +200,16 @@ def run_ours(args):
         build_once(sfb, ctx, X, wl, rank, world)
     barrier()
     ctx.timings_reset()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not args.no_clocks else None
     stats = []
     t_wall = time.perf_counter()
     ctx.timer_start()
+    step_wall = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         _, st = build_once(sfb, ctx, X, wl, rank, world)
         stats.append(st)
+        step_wall.append((time.perf_counter() - t_s) * 1e3)  # every step ends with a synchronising D2H of lambda
     ms = ctx.timer_stop()
     barrier()
     t_wall = time.perf_counter() - t_wall
@@ -265,7 +284,8 @@ def run_ours(args):
             "config": {"workload": wl["name"], "rows": n, "cols": d, "k": k, "metric": ["cosine", "l2", "l2sq"][wl["metric"]],
                        "p": P_WEIGHT, "sigma": SIGMA, "sharding": f"query rows / {world}, corpus replicated" if world > 1 else "single GPU",
                        "l2_policy": f"inputs larger than L2 ({n * d * 8 / 1e9:.2f} GB f64 matrix streamed every step)"},
-            "impl": "surfface_b200", "wall_ms_per_step": wall_ms / args.steps,
+            "impl": "surfface_b200", "wall_ms_per_step": wall_ms / args.steps, "wall_ms_steps": [round(v, 2) for v in step_wall],
+            "knn_ms_steps": [[round(s_[k_], 2) for k_ in ("ms_prepare", "ms_screen", "ms_rescore")] for s_ in stats],
             "stages_ms_per_step": {kk: tm[kk] / args.steps for kk in ("ms_knn", "ms_adjacency", "ms_laplacian", "ms_lambda")},
             "knn": {kk: stats[-1][kk] for kk in ("rows", "rows_certified", "rows_fallback", "k_prime", "screen_used", "ms_prepare",
                                                  "ms_screen", "ms_rescore", "ms_fallback", "max_margin")},
@@ -386,6 +406,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of one sampled kNN pass")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (diagnosis)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -122,6 +122,10 @@ typedef struct {
 } sfb_knn_stats;
 
 int32_t sfb_knn_build(sfb_ctx* ctx, const sfb_mat* rows, const sfb_knn_params* params, sfb_knn** out);
+/* The same graph over the COLUMNS of x (x is dims x nodes): the feature graph of
+ * GraphFactory::build_laplacian_matrix_from_k_cluster (src_legacy/graph.rs:193-216) straight from the
+ * item matrix, without materialising the transposed copy the reference makes. */
+int32_t sfb_knn_build_columns(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* params, sfb_knn** out);
 int32_t sfb_knn_shape(const sfb_knn* g, uint64_t* rows, uint32_t* k, uint64_t* q_begin);
 /* idx, dist: rows x k; cnt: rows.  Any pointer may be NULL. */
 int32_t sfb_knn_copy(sfb_ctx* ctx, const sfb_knn* g, uint32_t* idx, double* dist, uint32_t* cnt);

@@ -20,10 +20,33 @@ int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...) {
 
 thread_local sfb_ctx* sfb_tls_ctx = nullptr;
 
+static void cache_release_all(sfb_ctx* ctx) {
+    for (auto& kv : ctx->free_blocks) { cudaFree(kv.second); ctx->block_size.erase(kv.second); }
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
+}
+
 cudaError_t sfb_dev_alloc(sfb_ctx* ctx, void** p, size_t bytes) {
-    if (!ctx) return cudaMalloc(p, bytes ? bytes : 16);
+    if (!bytes) bytes = 16;
+    if (!ctx) return cudaMalloc(p, bytes);
     sfb_tls_ctx = ctx;
-    return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream);
+    const size_t want = (bytes + 511) & ~(size_t)511;
+    auto it = ctx->free_blocks.lower_bound(want);
+    if (it != ctx->free_blocks.end() && it->first <= want + want / 4 + (1u << 20)) {   // best fit, bounded waste
+        *p = it->second;
+        ctx->cached_bytes -= it->first;
+        ctx->free_blocks.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e == cudaErrorMemoryAllocation && !ctx->free_blocks.empty()) {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        cache_release_all(ctx);
+        e = cudaMalloc(p, want);
+    }
+    if (e == cudaSuccess) ctx->block_size[*p] = want;
+    return e;
 }
 // handles may outlive their context (garbage-collected host languages): only live contexts are dereferenced
 static std::mutex g_live_mu;
@@ -31,7 +54,11 @@ static std::set<const sfb_ctx*> g_live;
 static bool ctx_live(const sfb_ctx* c) { std::lock_guard<std::mutex> l(g_live_mu); return g_live.count(c) != 0; }
 void sfb_dev_free(sfb_ctx* ctx, void* p) {
     if (!p) return;
-    if (ctx && ctx_live(ctx)) cudaFreeAsync(p, ctx->stream); else cudaFree(p);
+    if (ctx && ctx_live(ctx)) {
+        auto it = ctx->block_size.find(p);
+        if (it != ctx->block_size.end()) { ctx->free_blocks.emplace(it->second, p); ctx->cached_bytes += it->second; return; }
+    }
+    cudaFree(p);
 }
 
 extern "C" int32_t sfb_abi_version(void) { return SFB_ABI_VERSION; }
@@ -58,11 +85,6 @@ extern "C" int32_t sfb_ctx_create(int32_t device_id, sfb_ctx** out) {
         delete ctx;
         return SFB_EUNSUPPORTED;
     }
-    {   // keep freed blocks in the pool instead of returning them to the driver at every synchronise
-        cudaMemPool_t pool;
-        unsigned long long keep = ~0ull;
-        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     { std::lock_guard<std::mutex> l(g_live_mu); g_live.insert(ctx); }
@@ -77,6 +99,7 @@ extern "C" void sfb_ctx_destroy(sfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     sfb_comm_destroy(ctx);
+    cache_release_all(ctx);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -185,32 +208,36 @@ extern "C" int32_t sfb_mat_generate(sfb_ctx* ctx, int32_t kind, uint64_t seed, u
     return SFB_OK;
 }
 
-// 32x32 tile transpose through shared memory: coalesced on both sides.
-// blockIdx.x walks the (possibly millions of) row tiles, blockIdx.y the column tiles.
-__global__ void transpose_kernel(const double* __restrict__ a, double* __restrict__ b, uint64_t rows, uint32_t cols) {
+// 32x32 tile transpose through shared memory: coalesced on both sides.  One block per tile, tiles
+// numbered along the LONGER side first so either shape (few rows x millions of columns, or the reverse) fits.
+__global__ void transpose_kernel(const double* __restrict__ a, double* __restrict__ b, uint64_t rows, uint64_t cols, uint64_t tiles_r) {
     __shared__ double tile[32][33];
-    uint64_t r0 = (uint64_t)blockIdx.x * 32;
-    uint32_t c0 = blockIdx.y * 32;
+    const uint64_t t = blockIdx.x;
+    const uint64_t r0 = (t % tiles_r) * 32, c0 = (t / tiles_r) * 32;
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
-        uint64_t r = r0 + dy; uint32_t c = c0 + threadIdx.x;
+        uint64_t r = r0 + dy, c = c0 + threadIdx.x;
         if (r < rows && c < cols) tile[dy][threadIdx.x] = a[r * cols + c];
     }
     __syncthreads();
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
-        uint32_t c = c0 + dy; uint64_t r = r0 + threadIdx.x;
-        if (r < rows && c < cols) b[(uint64_t)c * rows + r] = tile[threadIdx.x][dy];
+        uint64_t c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) b[c * rows + r] = tile[threadIdx.x][dy];
     }
+}
+
+int32_t sfb_transpose_device(sfb_ctx* ctx, const double* a, uint64_t rows, uint64_t cols, double* b) {
+    const uint64_t tiles_r = (rows + 31) / 32, tiles_c = (cols + 31) / 32;
+    if (tiles_r * tiles_c > 0x7FFFFFFFull) return sfb_fail(ctx, SFB_EUNSUPPORTED, "matrix too large to transpose in one launch");
+    transpose_kernel<<<(unsigned)(tiles_r * tiles_c), dim3(32, 8), 0, ctx->stream>>>(a, b, rows, cols, tiles_r);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
 }
 
 extern "C" int32_t sfb_mat_transpose(sfb_ctx* ctx, const sfb_mat* a, sfb_mat** out) {
     if (!a) return sfb_fail(ctx, SFB_EINVAL, "null matrix");
     if (a->rows > 0xFFFFFFFFull) return sfb_fail(ctx, SFB_EINVAL, "too many rows to transpose");
-    if (a->cols > 65535u * 32u) return sfb_fail(ctx, SFB_EUNSUPPORTED, "transpose supports up to 2M columns");
     SFB_TRY(mat_alloc(ctx, a->cols, (uint32_t)a->rows, out));
-    dim3 grid(div_up(a->rows, 32), div_up(a->cols, 32)), block(32, 8);
-    transpose_kernel<<<grid, block, 0, ctx->stream>>>(a->d, (*out)->d, a->rows, a->cols);
-    SFB_LAUNCH_CHECK(ctx);
-    return SFB_OK;
+    return sfb_transpose_device(ctx, a->d, a->rows, a->cols, (*out)->d);
 }
 
 extern "C" int32_t sfb_mat_shape(const sfb_mat* a, uint64_t* rows, uint32_t* cols) {

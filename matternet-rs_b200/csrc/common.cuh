@@ -5,7 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/surfface_b200.h"
 
@@ -17,6 +19,10 @@ struct sfb_ctx {
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;  // sfb_timer_start / stop
     std::string last_error;
     sfb_stage_times times{};
+    // device-memory cache (api.cu: sfb_dev_alloc / sfb_dev_free)
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> block_size;
+    size_t cached_bytes = 0;
     // NCCL (loaded lazily, comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -61,10 +67,13 @@ struct sfb_csr {
 
 int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...);
 
-// Device memory comes from the device's stream-ordered pool (cudaMallocAsync on the context's stream,
-// release threshold = never): a build allocates and frees GB-sized scratch at every stage, and plain
-// cudaMalloc / cudaFree synchronise the device and cost hundreds of milliseconds per step.
-// All work of a context runs on its one stream, so stream order is program order.
+// Device memory comes from a per-context cache of cudaMalloc'ed blocks: a build allocates and frees
+// GB-sized scratch at every stage, and plain cudaMalloc / cudaFree synchronise the device and cost
+// hundreds of milliseconds per step.  (cudaMallocAsync was tried first: its reuse-or-grow decision
+// depends on whether earlier frees have retired, which made one step in five stall for up to a second.)
+// All work of a context runs on its one stream, so a freed block can be handed out again at once:
+// stream order is program order.  Blocks are returned to the driver when an allocation fails and when
+// the context is destroyed.
 extern thread_local sfb_ctx* sfb_tls_ctx;  // the context of the call in flight (set by SFB_CUDA / sfb_dev_alloc)
 cudaError_t sfb_dev_alloc(sfb_ctx* ctx, void** p, size_t bytes);
 void sfb_dev_free(sfb_ctx* ctx, void* p);

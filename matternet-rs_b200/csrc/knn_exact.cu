@@ -208,45 +208,103 @@ __global__ void knn_merge_kernel(const uint32_t* __restrict__ pidx, const double
 }
 
 // ---- few nodes, very long rows (the feature graph: D nodes x N dims, graph.rs:214-216) ----------
-// The 64x64 tile kernel above would launch a handful of CTAs, each walking millions of dimensions.
-// Here every (i, j) pair gets its own thread: 16 x 16 pair tiles, the dimension streamed through
-// shared memory 32 at a time (coalesced 256-byte row segments), one left fold per pair.  For a
-// self-kNN only tiles on or above the diagonal are computed and mirrored (products commute, so
-// key(i,j) and key(j,i) have the same bits).  FP64-pipe bound: nodes^2 * dims multiply-adds.
-template <bool COS>
-__global__ void __launch_bounds__(256) knn_dense_keys_kernel(const double* __restrict__ x, const double* __restrict__ norms,
-                                                             uint32_t m, uint32_t kd, int metric, double* __restrict__ keys) {
-    __shared__ double qs[16][33], cs[16][33];
-    const uint32_t ti = blockIdx.y, tj = blockIdx.x;
-    if (tj < ti) return;  // mirrored
-    const int tid = threadIdx.x, qi = tid >> 4, cj = tid & 15;
-    const uint32_t gi = ti * 16 + qi, gj = tj * 16 + cj;
-    double acc = 0.0;
-    for (uint32_t d0 = 0; d0 < kd; d0 += 32) {
-        __syncthreads();
-        for (int e = tid; e < 16 * 32; e += 256) {
-            int r = e >> 5, d = e & 31;
-            uint32_t ri = ti * 16 + r, rj = tj * 16 + r;
-            qs[r][d] = (ri < m && d0 + d < kd) ? __ldg(x + (uint64_t)ri * kd + d0 + d) : 0.0;
-            cs[r][d] = (rj < m && d0 + d < kd) ? __ldg(x + (uint64_t)rj * kd + d0 + d) : 0.0;
+// Input layout: DIMS-MAJOR, xd[n * m + i] = node i at dimension n -- i.e. the item matrix itself (N x D);
+// the reference transposes it first (graph.rs:216), here the transposed copy is never needed.
+// Every (i, j) pair is one left fold over the N dimensions with separately rounded multiply and add,
+// so each sum has the bits of the CPU restatement; the pairs are the parallelism.  A CTA of 64 threads
+// owns a 16 x 16 pair tile (thread = 2 x 2 pairs: four independent FP64 chains), streams the two
+// 16-column strips of xd through shared memory 64 dimensions at a time (cp.async, double buffered)
+// and writes the raw sums G[i][j] (= G[j][i]: products commute) for tiles on or above the diagonal.
+// The diagonal G[i][i] is the squared norm with the same fold as orc_row_norms.
+// FP64-pipe bound: m^2/2 * N multiply + add pairs; at m = 384 the 300 tiles fill 148 SMs.
+constexpr int GT = 16, GCH = 64;
+
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, int bytes, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? bytes : 0;   // src-size 0: the destination is zero-filled
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+template <bool COS, int VEC>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
+__global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G) {
+    __shared__ __align__(16) double sa[2][GCH][GT], sb[2][GCH][GT];
+    // decode the upper-triangular tile index
+    const uint32_t T = (m + GT - 1) / GT;
+    uint32_t ti = 0, rem = blockIdx.x;
+    while (rem >= T - ti) { rem -= T - ti; ++ti; }
+    const uint32_t tj = ti + rem;
+    const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+    const uint32_t ci = ti * GT, cj = tj * GT;
+
+    auto stage = [&](int buf, uint64_t n0) {
+        constexpr int PIECES = GT / VEC;            // pieces per 16-column strip row
+        for (int e = tid; e < GCH * PIECES; e += 64) {
+            const int r = e / PIECES, pc = (e % PIECES) * VEC;
+            const uint64_t n = n0 + r;
+            const bool rv = n < kd;
+            const double* src = xd + (rv ? n : 0) * m;
+            const bool va = rv && ci + pc + VEC <= m, vb = rv && cj + pc + VEC <= m;
+            cp_async_zfill(&sa[buf][r][pc], va ? src + ci + pc : xd, VEC * 8, va);
+            cp_async_zfill(&sb[buf][r][pc], vb ? src + cj + pc : xd, VEC * 8, vb);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+    const uint64_t n_chunks = (kd + GCH - 1) / GCH;
+    stage(0, 0);
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const int buf = (int)(c & 1);
+        if (c + 1 < n_chunks) { stage(buf ^ 1, (c + 1) * GCH); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        const uint64_t left = kd - c * GCH;
+        const int lim = left < (uint64_t)GCH ? (int)left : GCH;
 #pragma unroll 8
-        for (int d = 0; d < 32; ++d) {
-            if (COS) acc = __dadd_rn(acc, __dmul_rn(qs[qi][d], cs[cj][d]));
-            else { double t = __dadd_rn(qs[qi][d], -cs[cj][d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
+        for (int n = 0; n < lim; ++n) {
+            const double2 a = *reinterpret_cast<const double2*>(&sa[buf][n][2 * ty]);
+            const double2 b = *reinterpret_cast<const double2*>(&sb[buf][n][2 * tx]);
+            if (COS) {
+                a00 = __dadd_rn(a00, __dmul_rn(a.x, b.x)); a01 = __dadd_rn(a01, __dmul_rn(a.x, b.y));
+                a10 = __dadd_rn(a10, __dmul_rn(a.y, b.x)); a11 = __dadd_rn(a11, __dmul_rn(a.y, b.y));
+            } else {
+                double t;
+                t = __dadd_rn(a.x, -b.x); a00 = __dadd_rn(a00, __dmul_rn(t, t));
+                t = __dadd_rn(a.x, -b.y); a01 = __dadd_rn(a01, __dmul_rn(t, t));
+                t = __dadd_rn(a.y, -b.x); a10 = __dadd_rn(a10, __dmul_rn(t, t));
+                t = __dadd_rn(a.y, -b.y); a11 = __dadd_rn(a11, __dmul_rn(t, t));
+            }
         }
+        __syncthreads();
     }
-    if (gi >= m || gj >= m) return;
+    const uint32_t i0 = ci + 2 * ty, j0 = cj + 2 * tx;
+    const double acc[2][2] = {{a00, a01}, {a10, a11}};
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj) {
+            const uint32_t i = i0 + di, j = j0 + dj;
+            if (i < m && j < m) { G[(uint64_t)i * m + j] = acc[di][dj]; G[(uint64_t)j * m + i] = acc[di][dj]; }
+        }
+}
+
+// raw sums G -> distance keys, written behind G (cosine: the norms are the square roots of the diagonal)
+template <bool COS>
+__global__ void gram_keys_kernel(double* __restrict__ G, uint32_t m, int metric, double* __restrict__ norms) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= m) return;
+    const double acc = G[(uint64_t)i * m + j];
     double key;
     if (COS) {
-        double denom = __dmul_rn(norms[gi], norms[gj]), cosv = 0.0;
+        const double ni = __dsqrt_rn(G[(uint64_t)i * m + i]), nj = __dsqrt_rn(G[(uint64_t)j * m + j]);
+        double denom = __dmul_rn(ni, nj), cosv = 0.0;
         if (denom > 1e-12) { cosv = __ddiv_rn(acc, denom); if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0; }
-        double rect = cosv > 0.0 ? cosv : 0.0;
+        const double rect = cosv > 0.0 ? cosv : 0.0;
         key = __dadd_rn(1.0, -rect);
+        if (i == 0 && norms) norms[j] = nj;
     } else key = metric == SFB_METRIC_L2 ? __dsqrt_rn(acc) : acc;
-    keys[(uint64_t)gi * m + gj] = key;
-    keys[(uint64_t)gj * m + gi] = key;
+    G[(uint64_t)m * m + (uint64_t)i * m + j] = key;
 }
 
 // one warp per query row: scan the dense key row, keep the (distance, index) top-k
@@ -293,27 +351,36 @@ int32_t sfb_row_norms(sfb_ctx* ctx, const sfb_mat* x, double* norms) {
     return SFB_OK;
 }
 
+bool sfb_dense_shape(uint64_t nodes, uint64_t dims) { return nodes <= 4096 && dims >= 8ull * nodes; }
+
+// kNN over few nodes with very long rows, from the DIMS-MAJOR matrix xd[kd][m] (see gram_tile_kernel).
+int32_t sfb_knn_dense(sfb_ctx* ctx, const double* xd, uint32_t m, uint64_t kd, int metric, uint32_t k, double eps,
+                      uint64_t q_begin, uint64_t nq, uint32_t* out_idx, double* out_dist, uint32_t* out_cnt) {
+    if (nq == 0) return SFB_OK;
+    if (k == 0 || k > 128) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k must be in 1..128 (got %u)", k);
+    DevBuf g;  // [0, m*m): raw sums, [m*m, 2*m*m): keys
+    SFB_CUDA(ctx, g.alloc(sizeof(double) * 2 * (size_t)m * m));
+    const uint32_t T = (m + GT - 1) / GT, tiles = T * (T + 1) / 2;
+    const bool cos = metric == SFB_METRIC_COSINE, even = (m & 1u) == 0 && (reinterpret_cast<uintptr_t>(xd) & 15u) == 0;
+    if (cos) { if (even) gram_tile_kernel<true, 2><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); else gram_tile_kernel<true, 1><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); }
+    else { if (even) gram_tile_kernel<false, 2><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); else gram_tile_kernel<false, 1><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); }
+    SFB_LAUNCH_CHECK(ctx);
+    dim3 kgrid(div_up(m, 128), m);
+    if (cos) gram_keys_kernel<true><<<kgrid, 128, 0, ctx->stream>>>(g.as<double>(), m, metric, nullptr);
+    else gram_keys_kernel<false><<<kgrid, 128, 0, ctx->stream>>>(g.as<double>(), m, metric, nullptr);
+    SFB_LAUNCH_CHECK(ctx);
+    const int wpb = 4;
+    size_t ssm = (size_t)wpb * k * (sizeof(double) + sizeof(uint32_t));
+    knn_dense_select_kernel<<<div_up(nq, wpb), wpb * 32, ssm, ctx->stream>>>(g.as<double>() + (size_t)m * m, m, q_begin, nq, k, eps, out_idx, out_dist, out_cnt);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
 int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int metric, uint32_t k, double eps,
                       const uint32_t* query_rows, uint64_t nq, uint64_t q_begin, uint32_t* out_idx, double* out_dist,
                       uint32_t* out_cnt) {
     if (nq == 0) return SFB_OK;
     if (k == 0 || k > 128) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k must be in 1..128 (got %u)", k);
-    // feature-graph shape: few nodes with very long rows -> one thread per pair over a dense key matrix
-    if (!query_rows && x->rows <= 4096 && (uint64_t)x->cols >= 8ull * x->rows) {
-        const uint32_t m = (uint32_t)x->rows;
-        DevBuf keys;
-        SFB_CUDA(ctx, keys.alloc(sizeof(double) * (size_t)m * m));
-        dim3 grid(div_up(m, 16), div_up(m, 16));
-        if (metric == SFB_METRIC_COSINE) knn_dense_keys_kernel<true><<<grid, 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, metric, keys.as<double>());
-        else knn_dense_keys_kernel<false><<<grid, 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, metric, keys.as<double>());
-        SFB_LAUNCH_CHECK(ctx);
-        const int wpb = 4;
-        size_t ssm = (size_t)wpb * k * (sizeof(double) + sizeof(uint32_t));
-        knn_dense_select_kernel<<<div_up(nq, wpb), wpb * 32, ssm, ctx->stream>>>(keys.as<double>(), m, q_begin, nq, k, eps, out_idx, out_dist, out_cnt);
-        SFB_LAUNCH_CHECK(ctx);
-        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return SFB_OK;
-    }
     const uint64_t q_tiles = (nq + TQ - 1) / TQ, n_tiles = (x->rows + TC - 1) / TC;
     uint64_t want = 2ull * ctx->sm_count;
     uint32_t csplits = 1;

@@ -71,6 +71,29 @@ def test_knn_query_shard(sfb, oracle, ctx):
     assert_knn_equal(g.to_host(), want)
 
 
+# ---- feature graph: few nodes with very long rows (graph.rs:193-216) ----------------------------
+@pytest.mark.parametrize("metric", [0, 1, 2])
+@pytest.mark.parametrize("n_items,n_feat,k", [(3000, 48, 5), (2001, 33, 3), (5000, 130, 16), (777, 17, 16)])
+def test_knn_columns_feature_graph(sfb, oracle, ctx, metric, n_items, n_feat, k):
+    """Nodes = columns of the item matrix; Gram-tile kernel (dims-major input, odd / even widths, ragged
+    tiles and chunks) and the rows-as-nodes entry point on the transposed copy agree with the oracle."""
+    x = np.random.default_rng(n_items + n_feat + metric).normal(size=(n_items, n_feat))
+    x[:, 3] = x[:, 1]          # duplicated feature: exact ties, broken by index
+    x[:, 5] = 0.0              # a zero feature: cosine := 0 -> distance 1 to everything
+    want = oracle.knn(oracle.transpose(x), k, metric)
+    m = ctx.matrix(x)
+    assert_knn_equal(m.knn_columns(k, metric).to_host(), want)
+    assert_knn_equal(m.transpose().knn(k, metric).to_host(), want)
+    eps = float(np.median(want[1][np.isfinite(want[1])]))
+    assert_knn_equal(m.knn_columns(k, metric, eps=eps).to_host(), oracle.knn(oracle.transpose(x), k, metric, eps))
+
+
+def test_knn_columns_many_nodes(sfb, oracle, ctx):
+    """Columns as nodes when the shape is NOT the feature-graph shape: falls back to a node-major copy."""
+    x = np.random.default_rng(77).normal(size=(40, 600))
+    assert_knn_equal(ctx.matrix(x).knn_columns(9, 0).to_host(), oracle.knn(oracle.transpose(x), 9, 0))
+
+
 def test_knn_argument_errors(sfb, ctx):
     x = ctx.matrix(np.ones((4, 3)))
     for bad in (dict(k=0), dict(k=129), dict(k=2, metric=7), dict(k=2, eps=math.nan), dict(k=2, q_begin=3, q_end=2)):
