@@ -663,88 +663,204 @@ struct RescoreArgs {
     double* max_margin;
 };
 
-// One warp per query row.  Candidate rows are staged 32 at a time through a padded shared tile so
-// global loads are coalesced and every lane runs its candidate's left fold in dimension order.
+// One warp per query row.
+//   filter   the screen hands over k' .. cap candidates per row, but only those whose screen key is within
+//            the error margin of the k-th best key can be among the exact k nearest: with S_k the k-th
+//            largest key (self excluded) every candidate below S_k - 3 * margin (cosine; the L2 form goes
+//            through the distance bounds) is provably farther than k others.  That cuts the rows gathered
+//            in f64 -- the cost of this kernel -- from ~100 to ~k + a few.  Excluded candidates join the
+//            screen's dropped set: the certificate below is evaluated against the larger threshold.
+//   rescore  candidate rows are staged 32 at a time through a padded shared tile so global loads are
+//            coalesced and every lane runs its candidate's left fold in dimension order (reference bits).
+//   certify  row i is certified iff its exact k-th distance is below the proven lower bound on the
+//            distance of everything that was not rescored; otherwise it goes to the exact fallback.
+constexpr uint32_t RS_MAXC = 256;  // candidates a row can bring to the filter; beyond that all are rescored
+constexpr int RS_TILE = 33 * 32 + 32;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+    const int n = valid ? 8 : 0;   // src-size 0: zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+
 template <bool COS>
-__global__ void __launch_bounds__(128) knn_rescore_kernel(RescoreArgs a) {
+__global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double* tile = reinterpret_cast<double*>(smem_raw) + (size_t)w * (33 * 32 + 32);  // [32][33] + query chunk [32]
-    double* qch = tile + 33 * 32;
-    double* ld = reinterpret_cast<double*>(smem_raw) + (size_t)wpb * (33 * 32 + 32) + (size_t)w * a.k;
-    uint32_t* li = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)wpb * (33 * 32 + 32 + a.k)) + (size_t)w * a.k;
+    double* dbase = reinterpret_cast<double*>(smem_raw);
+    double* tile = dbase + (size_t)w * (2 * RS_TILE);   // 2 x { [32][33] candidate tile + query chunk [32] }
+    double* ld = dbase + (size_t)wpb * (2 * RS_TILE) + (size_t)w * a.k;
+    uint32_t* ubase = reinterpret_cast<uint32_t*>(dbase + (size_t)wpb * (2 * RS_TILE + a.k));
+    uint32_t* li = ubase + (size_t)w * a.k;
+    float* skey = reinterpret_cast<float*>(ubase + (size_t)wpb * a.k) + (size_t)w * RS_MAXC;
+    uint32_t* sidx = ubase + (size_t)wpb * (a.k + RS_MAXC) + (size_t)w * RS_MAXC;
 
     const uint64_t rl = (uint64_t)blockIdx.x * wpb + w;
     if (rl >= a.nq) return;
     const uint32_t gi = (uint32_t)(a.q_begin + rl);
     const double* xi = a.x + (uint64_t)gi * a.kd;
     const double ni = COS ? a.norms[gi] : 0.0;
-    uint32_t c = 0;
+    const double qn = a.aux[gi], dn = a.aux[a.m + gi], q2 = a.aux[2 * a.m + gi];
+    const double s2 = a.scale * a.scale;
+    // error model of the screen key (see the header comment of this file)
+    const double cos_margin = ((a.gamma * qn + dn) * a.nmax + a.scale * a.dmax) * (1.0 + 1e-6) + s2 * 1e-9;  // key units
+    const double eta_base = (1.2e-7 * a.nmax * a.nmax + (2.0 * a.gamma + 1.2e-7) * qn * a.nmax) * (1.0 + 1e-6);
+    const double rho = (dn + a.dmax) * (1.0 + 1e-9);
+
+    uint32_t total = 0;
     float thr = -INFINITY;
     for (uint32_t s = 0; s < a.n_splits; ++s) {
         const size_t slot = (size_t)rl * a.n_splits + s;
-        const uint32_t n = a.cnt[slot];
+        total += a.cnt[slot];
         thr = fmaxf(thr, a.thr[slot]);
-        const uint32_t* cand = a.buf_idx + slot * a.cap;
-        for (uint32_t b = 0; b < n; b += 32) {
-            const uint32_t mine = b + lane < n ? cand[b + lane] : SFB_IDX_NONE;
-            const uint32_t nb = n - b < 32 ? n - b : 32;
-            double acc = 0.0;
-            for (uint32_t d0 = 0; d0 < a.kd; d0 += 32) {
-                __syncwarp();
-                for (uint32_t r = 0; r < nb; ++r) {
-                    uint32_t j = __shfl_sync(FULL, mine, r);
-                    tile[r * 33 + lane] = d0 + lane < a.kd ? a.x[(uint64_t)j * a.kd + d0 + lane] : 0.0;
-                }
-                qch[lane] = d0 + lane < a.kd ? xi[d0 + lane] : 0.0;
-                __syncwarp();
-                const uint32_t lim = a.kd - d0 < 32 ? a.kd - d0 : 32;
-                if (lane < (int)nb) {
-                    for (uint32_t d = 0; d < lim; ++d) {
-                        if (COS) acc = __dadd_rn(acc, __dmul_rn(qch[d], tile[lane * 33 + d]));
-                        else { double t = __dadd_rn(qch[d], -tile[lane * 33 + d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
-                    }
-                }
-            }
-            double key = INFINITY;
-            if (mine != SFB_IDX_NONE) {
-                if (COS) {
-                    double denom = __dmul_rn(ni, a.norms[mine]), cosv = 0.0;
-                    if (denom > 1e-12) { cosv = __ddiv_rn(acc, denom); if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0; }
-                    double rect = cosv > 0.0 ? cosv : 0.0;
-                    key = __dadd_rn(1.0, -rect);
-                } else key = a.metric == SFB_METRIC_L2 ? __dsqrt_rn(acc) : acc;
-            }
-            double td = c == a.k ? ld[a.k - 1] : INFINITY;
-            uint32_t ti = c == a.k ? li[a.k - 1] : SFB_IDX_NONE;
-            bool pass = mine != SFB_IDX_NONE && mine != gi && key <= a.eps && topk_key_less(key, mine, td, ti);
-            uint32_t bal = __ballot_sync(FULL, pass);
-            while (bal) {
-                int src = __ffs(bal) - 1; bal &= bal - 1;
-                double kd_ = __shfl_sync(FULL, key, src);
-                uint32_t jj = __shfl_sync(FULL, mine, src);
-                warp_list_insert(ld, li, c, a.k, kd_, jj, lane);
+    }
+
+    // ---- filter -------------------------------------------------------------------------------
+    const bool use_list = total <= RS_MAXC;
+    uint32_t n_list = 0;
+    if (use_list) {
+        for (uint32_t s = 0; s < a.n_splits; ++s) {
+            const size_t slot = (size_t)rl * a.n_splits + s;
+            const uint32_t n = a.cnt[slot];
+            for (uint32_t b = 0; b < n; b += 32) {
+                const bool v = b + lane < n;
+                const uint32_t j = v ? __ldcg(a.buf_idx + slot * a.cap + b + lane) : SFB_IDX_NONE;
+                const float kf = v ? __ldcg(a.buf_key + slot * a.cap + b + lane) : -INFINITY;
+                const bool keep = v && j != gi;
+                const uint32_t bal = __ballot_sync(FULL, keep);
+                if (keep) { const uint32_t pos = n_list + __popc(bal & ((1u << lane) - 1u)); skey[pos] = kf; sidx[pos] = j; }
+                n_list += __popc(bal);
             }
         }
+        __syncwarp();
+        if (n_list > a.k) {
+            uint32_t key[RS_MAXC / 32];
+#pragma unroll
+            for (int u = 0; u < (int)(RS_MAXC / 32); ++u) { const uint32_t e = lane + 32 * u; key[u] = e < n_list ? f32_sortable(skey[e]) : 0u; }
+            uint32_t prefix = 0, want = a.k;
+#pragma unroll 1
+            for (int b = 31; b >= 0; --b) {
+                const uint32_t bit = 1u << b, hi = b == 31 ? 0u : ~((bit << 1) - 1u);
+                uint32_t c = 0;
+#pragma unroll
+                for (int u = 0; u < (int)(RS_MAXC / 32); ++u) c += __popc(__ballot_sync(FULL, (key[u] & hi) == (prefix & hi) && (key[u] & bit)));
+                if (c >= want) prefix |= bit; else want -= c;
+            }
+            const double sk = (double)sortable_f32(prefix);   // k-th largest screen key among the other rows
+            double tf;
+            if (COS) tf = sk - 3.0 * cos_margin;
+            else {
+                // the k rows with key >= sk are within T of row i (scaled units); exclude what is provably farther
+                const double eta_k = eta_base + 2.4e-7 * (fabs(sk) + q2);
+                const double d2k = q2 - sk + eta_k;
+                const double T = (d2k > 0.0 ? sqrt(d2k) : 0.0) * (1.0 + 1e-9) + 2.0 * rho * (1.0 + 1e-6) + 1e-300;
+                const double t2 = T * T * (1.0 + 1e-9);
+                tf = q2 - t2 - (eta_base + 2.4e-7 * (q2 + t2)) * (1.0 + 1e-6);
+            }
+            const float thr_filter = isfinite(tf) ? __double2float_rd(tf) : -INFINITY;
+            // compact in place (output position <= input position), remember the largest key excluded
+            uint32_t out = 0;
+            float ex_max = -INFINITY;
+            for (uint32_t b = 0; b < n_list; b += 32) {
+                const bool v = b + lane < n_list;
+                const float kf = v ? skey[b + lane] : -INFINITY;
+                const uint32_t j = v ? sidx[b + lane] : SFB_IDX_NONE;
+                const bool keep = v && kf >= thr_filter;
+                if (v && !keep) ex_max = fmaxf(ex_max, kf);
+                const uint32_t bal = __ballot_sync(FULL, keep);
+                __syncwarp();
+                if (keep) sidx[out + __popc(bal & ((1u << lane) - 1u))] = j;
+                out += __popc(bal);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ex_max = fmaxf(ex_max, __shfl_xor_sync(FULL, ex_max, o));
+            n_list = out;
+            thr = fmaxf(thr, ex_max);   // the excluded candidates join the dropped set
+            __syncwarp();
+        }
     }
-    // certification
-    const double bound = c == a.k ? ld[a.k - 1] : a.eps;  // every dropped candidate must be farther than this
+
+    // ---- exact rescore ------------------------------------------------------------------------
+    uint32_t c = 0;
+    auto run_batch = [&](uint32_t mine, uint32_t nb) {
+        double acc = 0.0;
+        // cp.async (8 bytes per lane: one 256-byte row segment per instruction), two tiles in flight:
+        // the gather of chunk c + 1 overlaps the folds of chunk c
+        auto issue = [&](int buf, uint32_t d0) {
+            double* tb = tile + buf * RS_TILE;
+            const bool dv = d0 + lane < a.kd;
+            const uint32_t dd = dv ? d0 + lane : 0u;
+            for (uint32_t r = 0; r < nb; ++r) {
+                const uint32_t j = __shfl_sync(FULL, mine, r);
+                cp_async8(&tb[r * 33 + lane], a.x + (uint64_t)j * a.kd + dd, dv);
+            }
+            cp_async8(&tb[33 * 32 + lane], xi + dd, dv);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        const uint32_t n_chunks = (a.kd + 31) / 32;
+        issue(0, 0);
+        for (uint32_t ci = 0; ci < n_chunks; ++ci) {
+            const int buf = (int)(ci & 1u);
+            if (ci + 1 < n_chunks) { issue(buf ^ 1, (ci + 1) * 32); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const double* tb = tile + buf * RS_TILE;
+            const double* qc = tb + 33 * 32;
+            const uint32_t d0 = ci * 32, lim = a.kd - d0 < 32 ? a.kd - d0 : 32;
+            if (lane < (int)nb) {
+                for (uint32_t d = 0; d < lim; ++d) {
+                    if (COS) acc = __dadd_rn(acc, __dmul_rn(qc[d], tb[lane * 33 + d]));
+                    else { double t = __dadd_rn(qc[d], -tb[lane * 33 + d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
+                }
+            }
+            __syncwarp();   // the tile is rewritten two iterations from now
+        }
+        double key = INFINITY;
+        if (mine != SFB_IDX_NONE) {
+            if (COS) {
+                double denom = __dmul_rn(ni, a.norms[mine]), cosv = 0.0;
+                if (denom > 1e-12) { cosv = __ddiv_rn(acc, denom); if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0; }
+                double rect = cosv > 0.0 ? cosv : 0.0;
+                key = __dadd_rn(1.0, -rect);
+            } else key = a.metric == SFB_METRIC_L2 ? __dsqrt_rn(acc) : acc;
+        }
+        double td = c == a.k ? ld[a.k - 1] : INFINITY;
+        uint32_t ti = c == a.k ? li[a.k - 1] : SFB_IDX_NONE;
+        bool pass = mine != SFB_IDX_NONE && mine != gi && key <= a.eps && topk_key_less(key, mine, td, ti);
+        uint32_t bal = __ballot_sync(FULL, pass);
+        while (bal) {
+            int src = __ffs(bal) - 1; bal &= bal - 1;
+            double kd_ = __shfl_sync(FULL, key, src);
+            uint32_t jj = __shfl_sync(FULL, mine, src);
+            warp_list_insert(ld, li, c, a.k, kd_, jj, lane);
+        }
+    };
+    if (use_list) {
+        for (uint32_t b = 0; b < n_list; b += 32)
+            run_batch(b + lane < n_list ? sidx[b + lane] : SFB_IDX_NONE, n_list - b < 32 ? n_list - b : 32);
+    } else {
+        for (uint32_t s = 0; s < a.n_splits; ++s) {
+            const size_t slot = (size_t)rl * a.n_splits + s;
+            const uint32_t n = a.cnt[slot];
+            const uint32_t* cand = a.buf_idx + slot * a.cap;
+            for (uint32_t b = 0; b < n; b += 32) run_batch(b + lane < n ? cand[b + lane] : SFB_IDX_NONE, n - b < 32 ? n - b : 32);
+        }
+    }
+
+    // ---- certification ------------------------------------------------------------------------
+    const double bound = c == a.k ? ld[a.k - 1] : a.eps;  // everything not rescored must be farther than this
     bool certified;
     double margin = 0.0;
-    if (thr == -INFINITY) certified = true;               // the screen never dropped anything for this row
+    if (thr == -INFINITY) certified = true;               // nothing was dropped or excluded for this row
     else {
-        const double qn = a.aux[gi], dn = a.aux[a.m + gi], q2 = a.aux[2 * a.m + gi];
         if (COS) {
-            const double s2 = a.scale * a.scale;
-            margin = ((a.gamma * qn + dn) * a.nmax + a.scale * a.dmax) * (1.0 + 1e-6) + s2 * 1e-9;
+            margin = cos_margin;
             double cos_ub = ((double)thr + margin) / s2;
             double lb = 1.0 - (cos_ub > 0.0 ? (cos_ub < 1.0 ? cos_ub : 1.0) : 0.0);
             certified = bound < lb;
             margin /= s2;
         } else {
-            // dropped: 2 S~ - nq32_j <= thr  =>  |q_i - q_j|^2 >= |q_i|^2 - thr - eta
-            const double eta = (1.2e-7 * a.nmax * a.nmax + (2.0 * a.gamma + 1.2e-7) * qn * a.nmax) * (1.0 + 1e-6) + 2.4e-7 * fabs((double)thr);
-            const double rho = (dn + a.dmax) * (1.0 + 1e-9);
+            // not rescored: 2 S~ - nq32_j <= thr  =>  |q_i - q_j|^2 >= |q_i|^2 - thr - eta
+            const double eta = eta_base + 2.4e-7 * fabs((double)thr);
             double d2 = q2 - (double)thr - eta;
             double lbs = (d2 > 0.0 ? sqrt(d2) * (1.0 - 1e-12) : 0.0) - rho;  // scaled lower bound on |y_i - y_j|
             double lb = lbs > 0.0 ? lbs / a.scale : 0.0;
@@ -1001,7 +1117,7 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     {
         StageTimer t(ctx, nullptr);
         const int wpb = 4;
-        size_t smem = (size_t)wpb * ((33 * 32 + 32 + p->k) * sizeof(double) + p->k * sizeof(uint32_t));
+        size_t smem = (size_t)wpb * ((2 * RS_TILE + p->k) * sizeof(double) + (p->k + 2 * RS_MAXC) * sizeof(uint32_t));
         if (cosine) {
             SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             knn_rescore_kernel<true><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);
