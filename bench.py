@@ -272,8 +272,14 @@ def run_ours(args):
     if screened and scr_ms > 0:
         ach = flops / (scr_ms * 1e-3) / 1e12
         peak = pk["tc_sustained"] if scr_ms > 100 else pk["tc_burst"]
-        roof = {"kernel": "knn_screen_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "ms_per_launch": scr_ms, "flops_per_launch": flops,
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_screen_traffic.json")
+        if args.config == "c2" and not args.rows and world == 1 and os.path.exists(tpath):
+            tj = json.load(open(tpath))   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+        roof = {"kernel": "knn_screen_pair_kernel" if d <= 512 else "knn_screen_kernel", "bound": "tensor", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "ms_per_launch": scr_ms, "flops_per_launch": flops,
                 "peak_source": pk["source"] + (", sustained" if scr_ms > 100 else ", burst")}
 
     if rank == 0:

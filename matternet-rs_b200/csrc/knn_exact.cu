@@ -215,7 +215,7 @@ __global__ void knn_merge_kernel(const uint32_t* __restrict__ pidx, const double
 // owns a 16 x 16 pair tile (thread = 2 x 2 pairs: four independent FP64 chains), streams the two
 // 16-column strips of xd through shared memory 64 dimensions at a time (cp.async, double buffered)
 // and writes the raw sums G[i][j] (= G[j][i]: products commute) for tiles on or above the diagonal.
-// The diagonal G[i][i] is the squared norm with the same fold as orc_row_norms.
+// The diagonal G[i][i] is the squared norm, the same left fold as row_norms_kernel.
 // FP64-pipe bound: m^2/2 * N multiply + add pairs; at m = 384 the 300 tiles fill 148 SMs.
 constexpr int GT = 16, GCH = 64;
 
