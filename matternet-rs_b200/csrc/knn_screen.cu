@@ -1037,9 +1037,13 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     st.screen_used = p->screen;
 
     // k' candidates survive per row and corpus split; the buffer has 64 slots of slack between prunes
-    uint32_t kprime = p->k_prime ? p->k_prime : (3 * p->k + 16 + 31) / 32 * 32;
+    // k' = 3k: measured at C2 (k = 16) -- k' = 96 / 64 / 48 / 32 / 24 take 814 / 717 / 689 / 662 / 645 ms of screen with
+    // 0 / 0 / 0 / 9 / 3366 uncertified rows (an uncertified row costs 0.1 ms of f64 brute force)
+    uint32_t kprime = p->k_prime ? p->k_prime : (3 * p->k + 15) / 16 * 16;
+    bool kp_forced = p->k_prime != 0;
+    if (const char* e = getenv("SFB_SCREEN_KPRIME")) { int v = atoi(e); if (v > 0 && !p->k_prime) { kprime = (uint32_t)v; kp_forced = true; } }  // tuning aid
     if (kprime < p->k + 1) kprime = p->k + 1;
-    if (kprime < 64 && !p->k_prime) kprime = 64;
+    if (kprime < 48 && !kp_forced) kprime = 48;
     if (kprime > MAX_CAP - 64) kprime = MAX_CAP - 64;
     if (kprime < p->k + 1) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k too large for the screen buffers");
     const uint32_t cap = (kprime + 64 + 31) / 32 * 32;
