@@ -479,6 +479,8 @@ struct Screen2Args {
     uint64_t n_rows;
     uint64_t q_begin, nq;
     uint32_t kblocks, stages;
+    uint32_t resident;      // k-blocks of the query rows that stay in shared memory for a whole work item (all of them when K <= 512)
+    uint32_t stage_bytes;   // 16 KB (corpus half-tile) when every k-block is resident, else 32 KB (+ the streamed query slab)
     uint32_t tiles_total, tiles_per_split, n_splits, chunk_tiles, n_chunks;
     uint32_t n_mb2;         // 256-row query blocks
     uint32_t idesc;
@@ -496,8 +498,8 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // carve: A slabs [kblocks] | B stages [stages] | barriers | tmem ptr | nq tiles (L2)
     uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)a.kblocks * P_SLAB_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)a.stages * P_SLAB_BYTES);
+    uint8_t* sB = smem + (size_t)a.resident * P_SLAB_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)a.stages * a.stage_bytes);
     uint64_t* empty_bar = full_bar + 8;
     uint64_t* tfull_bar = empty_bar + 8;     // [2]
     uint64_t* tempty_bar = tfull_bar + 2;    // [2]
@@ -548,16 +550,20 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
                 SFB_ITEM_RANGE
                 const int row0 = (int)(a.q_begin + (uint64_t)mb2 * 256 + rank * P_BM);
                 mbar_wait(aempty_bar, iphase ^ 1);   // the previous item's MMAs have retired
-                if (leader) mbar_expect_tx(afull_bar, 2u * a.kblocks * P_SLAB_BYTES);
-                for (uint32_t kb = 0; kb < a.kblocks; ++kb)
+                if (leader) mbar_expect_tx(afull_bar, 2u * a.resident * P_SLAB_BYTES);
+                for (uint32_t kb = 0; kb < a.resident; ++kb)
                     tma_load_2d_pair(sA + (size_t)kb * P_SLAB_BYTES, &tm, (int)(kb * BK), row0, l_afull);
                 iphase ^= 1;
                 for (uint32_t t = t_lo; t < t_hi; ++t) {
                     const int n0 = (int)(t * BN + rank * P_BNH);
                     for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (leader) mbar_expect_tx(&full_bar[stage], 2u * P_SLAB_BYTES);
-                        tma_load_2d_pair(sB + (size_t)stage * P_SLAB_BYTES, &tm, (int)(kb * BK), n0, mapa_u32(&full_bar[stage], 0));
+                        const bool stream_a = kb >= a.resident;   // this k-block of the query rows rides along with the corpus
+                        if (leader) mbar_expect_tx(&full_bar[stage], stream_a ? 4u * P_SLAB_BYTES : 2u * P_SLAB_BYTES);
+                        const uint32_t l_full = mapa_u32(&full_bar[stage], 0);
+                        uint8_t* st = sB + (size_t)stage * a.stage_bytes;
+                        tma_load_2d_pair(st, &tm, (int)(kb * BK), n0, l_full);
+                        if (stream_a) tma_load_2d_pair(st + P_SLAB_BYTES, &tm, (int)(kb * BK), row0, l_full);
                         if (++stage == a.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -581,7 +587,8 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
                     for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_addr = a_base + kb * P_SLAB_BYTES, b_addr = smem_u32(sB + (size_t)stage * P_SLAB_BYTES);
+                        const uint32_t b_addr = smem_u32(sB + (size_t)stage * a.stage_bytes);
+                        const uint32_t a_addr = kb < a.resident ? a_base + kb * P_SLAB_BYTES : b_addr + P_SLAB_BYTES;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             umma_f16_pair(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), a.idesc, (kb | (uint32_t)k) != 0u);
@@ -1000,10 +1007,19 @@ int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2A
     sa.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     const size_t fixed = 1024 + 22 * 8 + 16 + 2 * BN * sizeof(float);
     const size_t budget = ctx->smem_optin ? ctx->smem_optin : 232448;
-    size_t stages = (budget - fixed - (size_t)sa.kblocks * P_SLAB_BYTES) / P_SLAB_BYTES;
-    if (stages > 8) stages = 8;
-    sa.stages = (uint32_t)stages;
-    const size_t smem = fixed + ((size_t)sa.kblocks + stages) * P_SLAB_BYTES;
+    const size_t room = (budget - fixed) / P_SLAB_BYTES;   // 16 KB slabs that fit
+    if (sa.kblocks + 5 <= room) {
+        // every k-block of the query rows is resident; the stages carry corpus half-tiles only
+        sa.resident = sa.kblocks; sa.stage_bytes = P_SLAB_BYTES;
+        size_t stages = room - sa.kblocks;
+        sa.stages = (uint32_t)(stages > 8 ? 8 : stages);
+    } else {
+        // K > 512: keep what fits beside four 32 KB stages, stream the remaining query slabs with the corpus
+        sa.stages = 4; sa.stage_bytes = 2 * P_SLAB_BYTES;
+        sa.resident = (uint32_t)(room - 2 * sa.stages);
+        if (sa.resident > sa.kblocks) sa.resident = sa.kblocks;
+    }
+    const size_t smem = fixed + (size_t)sa.resident * P_SLAB_BYTES + (size_t)sa.stages * sa.stage_bytes;
     const uint32_t n_slots = sa.n_mb2 * sa.n_splits;
     uint32_t pairs = (uint32_t)ctx->sm_count / 2;
     if (pairs > n_slots) pairs = n_slots;
@@ -1018,11 +1034,10 @@ int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2A
     return SFB_OK;
 }
 
-// the pair kernel keeps all of K for 128 rows in shared memory: K <= 512 (8 slabs of 16 KB) leaves >= 5 stages
+// SFB_SCREEN_V1=1 forces the single-CTA kernel (A/B comparisons)
 bool pair_kernel_applies(const Prepared& P) {
     const char* v1 = getenv("SFB_SCREEN_V1");
-    if (v1 && v1[0] == '1') return false;
-    return P.kpad / BK <= 8;
+    return !(v1 && v1[0] == '1');
 }
 
 }  // namespace

@@ -49,7 +49,7 @@ def test_tile_accumulators_match_operands(sfb, ctx, screen, m, kd, row0, col0):
 
 @pytest.mark.parametrize("screen", [2, 3])
 @pytest.mark.parametrize("metric", [0, 1, 2])
-@pytest.mark.parametrize("m,kd,k", [(5000, 96, 16), (4097, 50, 8), (6000, 384, 32)])
+@pytest.mark.parametrize("m,kd,k", [(5000, 96, 16), (4097, 50, 8), (6000, 384, 32), (4500, 700, 8), (4200, 1030, 5)])
 def test_knn_screen_parity_gaussian(sfb, oracle, ctx, screen, metric, m, kd, k):
     x = np.random.default_rng(m + kd + metric).normal(size=(m, kd))
     g = ctx.matrix(x).knn(k, metric, screen=screen)
