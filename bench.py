@@ -143,13 +143,17 @@ def build_once(sfb, ctx, X, wl, rank, world, out_lambda=None, keep=False):
     adj = _timed(ctx, "adjacency", lambda: g.adjacency(P_WEIGHT, SIGMA))
     L = _timed(ctx, "laplacian", lambda: adj.laplacian())
     # feature graph (the reference's call shape) + per-item lambda
-    gf = _timed(ctx, "knn_columns", lambda: X.knn_columns(min(wl["k"], d - 1), sfb.METRIC_COSINE))
+    gf = _timed(ctx, "knn_columns", lambda: X.knn_columns(min(wl["k"], d - 1), sfb.METRIC_COSINE, sharded=world > 1))
     adjf = _timed(ctx, "adjacency_f", lambda: gf.adjacency(P_WEIGHT, SIGMA))
     Lf = _timed(ctx, "laplacian_f", lambda: adjf.laplacian())
     xs = X.view_rows(lo, hi - lo)
     lam, lstats = _timed(ctx, "lambda", lambda: Lf.lambdas_allgather(xs, lo, n, normalise=True))
     if out_lambda is not None:
         out_lambda[:] = lam
+    if keep == "all":
+        for h in (xs, adjf, gf, adj):
+            h.free()
+        return (L, Lf, lam, g), st
     _timed(ctx, "free", lambda: [h.free() for h in (xs, adjf, gf, adj, g)])
     if keep:
         return (L, Lf, lam), st
@@ -221,6 +225,11 @@ def run_ours(args):
     ms_total, wall_ms = float(t[0]), float(t[1])
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3)
+
+    # ---- parity at full size (--verify): sampled rows against the CPU oracle, structural invariants ---
+    verify = None
+    if args.verify:
+        verify = verify_build(sfb, ctx, X, wl, rank, world)
 
     # ---- end to end: pinned host matrix in, CSR + lambda out ----------------------------------
     e2e = None
@@ -298,12 +307,69 @@ def run_ours(args):
             "gpu_launches": int(tm["kernel_launches"]),
             "clocks": clocks, "roofline": roof, "e2e": e2e,
         }
+        if verify is not None:
+            line["verify"] = verify
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_sample(wl, args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def verify_build(sfb, ctx, X, wl, rank, world, n_sample=48):
+    """Full-size parity (every rank runs the build; rank 0 checks): kNN lists of sampled rows bit-exact against
+    the oracle's brute force over the FULL corpus; CSR invariants of the item Laplacian (sorted columns, stored
+    diagonal, row sums 0, symmetry on sampled entries); feature Laplacian and sampled lambdas against the oracle."""
+    import numpy as np
+    import oracle
+    oracle.build()
+    oracle.use_all_threads()
+    n, d, k = wl["rows"], wl["cols"], wl["k"]
+    (L, Lf, lam, g), _ = build_once(sfb, ctx, X, wl, rank, world, keep="all")
+    out = None
+    if rank == 0:
+        xh = np.empty((n, d))
+        step = 1 << 16
+        for r0 in range(0, n, step):
+            xh[r0:r0 + step] = X.rows(r0, min(step, n - r0))
+        rows = np.unique(np.random.default_rng(1).integers(0, n, n_sample))
+        idx, dist_, cnt = g.to_host()
+        o_idx, o_dist, o_cnt = oracle.knn(xh, k, wl["metric"], query_rows=rows)
+        knn_ok = bool(np.array_equal(idx[rows], o_idx) and np.array_equal(dist_[rows], o_dist) and np.array_equal(cnt[rows], o_cnt))
+        indptr, indices, data = L.to_host()
+        ip = indptr.astype(np.int64)
+        deg = np.diff(ip)
+        row_of = np.repeat(np.arange(n), deg)
+        sorted_ok = bool(np.all((np.diff(indices.astype(np.int64)) > 0) | (np.diff(row_of) > 0)))
+        diag_ok = bool(np.count_nonzero(indices == row_of) == n)
+        rs = np.add.reduceat(data, ip[:-1])
+        scale = np.add.reduceat(np.abs(data), ip[:-1]) + 1e-300
+        rowsum_ok = bool(np.max(np.abs(rs) / scale) < 1e-12)
+        sym_ok = True
+        for r in rows[:16]:
+            for e in range(ip[r], ip[r + 1]):
+                c = int(indices[e])
+                pos = ip[c] + np.searchsorted(indices[ip[c]:ip[c + 1]], r)
+                sym_ok = sym_ok and pos < ip[c + 1] and indices[pos] == r and data[pos] == data[e]
+        # the item graph from the gathered lists == the oracle's assembly of the same lists
+        a = oracle.build_adjacency(idx, dist_, cnt, P_WEIGHT, SIGMA)
+        o_ptr, o_ind, o_dat = oracle.laplacian(*a[:3])
+        lap_ok = bool(np.array_equal(indptr, o_ptr) and np.array_equal(indices, o_ind) and np.allclose(data, o_dat, rtol=1e-9, atol=0))
+        # feature graph + lambda
+        f = oracle.knn(oracle.transpose(xh), min(k, d - 1), oracle.METRIC_COSINE)
+        fl = oracle.laplacian(*oracle.build_adjacency(*f, P_WEIGHT, SIGMA)[:3])
+        fptr, find, fdat = Lf.to_host()
+        flap_ok = bool(np.array_equal(fptr, fl[0]) and np.array_equal(find, fl[1]) and np.allclose(fdat, fl[2], rtol=1e-9, atol=0))
+        o_lam, _ = oracle.normalise_lambdas(oracle.lambdas(*fl, xh))
+        lam_ok = bool(np.allclose(lam, o_lam, rtol=1e-9, atol=1e-12))
+        out = {"knn_rows_checked": int(len(rows)), "knn_bit_exact": knn_ok, "csr_sorted": sorted_ok, "csr_diagonal_stored": diag_ok,
+               "csr_row_sums_zero": rowsum_ok, "csr_symmetric_sample": bool(sym_ok), "item_laplacian_matches_oracle": lap_ok,
+               "feature_laplacian_matches_oracle": flap_ok, "lambda_all_rows_within_1e-9": lam_ok}
+        out["ok"] = all(v for kk, v in out.items() if kk != "knn_rows_checked")
+    for h in (L, Lf, g):
+        h.free()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -317,6 +383,7 @@ def cpu_setup(wl):
     import numpy as np
     import oracle
     oracle.build()
+    oracle.use_all_threads()
     key = (wl["rows"], wl["cols"], wl["seed"])
     if key in _CPU_CACHE:
         return _CPU_CACHE[key]
@@ -409,8 +476,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the row count (development only)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of one sampled kNN pass")
+    ap.add_argument("--cpu-seconds", type=float, default=25.0, help="CPU time budget of one sampled kNN pass")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="after timing, check the full-size build against the CPU oracle (adds ~1 min)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (diagnosis)")
     args = ap.parse_args()

@@ -252,6 +252,10 @@ int32_t sfb_timings_reset(sfb_ctx* ctx);
  * id: 128 bytes from sfb_comm_unique_id on rank 0, distributed by the host. */
 int32_t sfb_comm_unique_id(uint8_t id[128]);
 int32_t sfb_comm_init(sfb_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);
+/* sfb_knn_build_columns as a COLLECTIVE: every rank passes the same matrix; when it has the feature-graph shape
+ * (few columns, many rows) the exact f64 pair sums are split across the ranks and all-reduced (each sum is
+ * produced by exactly one rank, so the result has the same bits as the single-GPU build). */
+int32_t sfb_knn_build_columns_sharded(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* params, sfb_knn** out);
 /* gathers equal row shards of every rank into a full-M kNN handle (all ranks get a copy) */
 int32_t sfb_knn_allgather(sfb_ctx* ctx, const sfb_knn* shard, uint64_t total_rows, sfb_knn** out);
 /* lambda over this rank's rows of X, min/max all-reduced, normalised, all-gathered into out (total_rows) */

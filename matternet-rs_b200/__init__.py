@@ -181,11 +181,13 @@ class Matrix(_Handle):
         self.ctx.check(lib().sfb_knn_build(self.ctx._h, self._h, C.byref(p), C.byref(h)))
         return KnnGraph(self.ctx, h)
 
-    def knn_columns(self, k, metric=METRIC_COSINE, eps=math.inf, screen=SCREEN_AUTO):
-        """kNN graph over the COLUMNS of this matrix (the feature graph, graph.rs:193-216), no transposed copy."""
+    def knn_columns(self, k, metric=METRIC_COSINE, eps=math.inf, screen=SCREEN_AUTO, sharded=False):
+        """kNN graph over the COLUMNS of this matrix (the feature graph, graph.rs:193-216), no transposed copy.
+        sharded=True: collective over the context's communicator (every rank holds the same matrix)."""
         p = _ffi.KnnParams(metric, k, float(eps), screen, 0, 0, 0, 1)
         h = C.c_void_p()
-        self.ctx.check(lib().sfb_knn_build_columns(self.ctx._h, self._h, C.byref(p), C.byref(h)))
+        fn = lib().sfb_knn_build_columns_sharded if sharded else lib().sfb_knn_build_columns
+        self.ctx.check(fn(self.ctx._h, self._h, C.byref(p), C.byref(h)))
         return KnnGraph(self.ctx, h)
 
     def debug_screen_tile(self, metric=METRIC_COSINE, screen=SCREEN_F16, row0=0, col0=0):

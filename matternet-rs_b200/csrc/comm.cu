@@ -89,6 +89,13 @@ void sfb_comm_destroy(sfb_ctx* ctx) {
     if (ctx && ctx->nccl_comm && nccl() && nccl()->CommDestroy) { nccl()->CommDestroy((ncclComm_t)ctx->nccl_comm); ctx->nccl_comm = nullptr; }
 }
 
+int32_t sfb_comm_allreduce_sum_f64(sfb_ctx* ctx, double* buf, size_t n) {
+    if (ctx->world == 1) return SFB_OK;
+    if (!ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    SFB_NCCL(ctx, nccl()->AllReduce(buf, buf, n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return SFB_OK;
+}
+
 extern "C" int32_t sfb_comm_barrier(sfb_ctx* ctx) {
     if (!ctx) return SFB_EINVAL;
     if (ctx->world == 1) { SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return SFB_OK; }

@@ -6,13 +6,13 @@
 int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out);
 
 int32_t sfb_knn_dense(sfb_ctx* ctx, const double* xd, uint32_t m, uint64_t kd, int metric, uint32_t k, double eps,
-                      uint64_t q_begin, uint64_t nq, uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);
+                      uint64_t q_begin, uint64_t nq, uint32_t* out_idx, double* out_dist, uint32_t* out_cnt, int collective);
 bool sfb_dense_shape(uint64_t nodes, uint64_t dims);
 int32_t sfb_transpose_device(sfb_ctx* ctx, const double* a, uint64_t rows, uint64_t cols, double* b);
 
 // `x` holds the nodes as ROWS (columns_are_nodes == false) or as COLUMNS (true: x is dims x nodes, the
 // untransposed item matrix of GraphFactory::build_laplacian_matrix_from_k_cluster, graph.rs:193-216).
-static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_nodes, const sfb_knn_params* p, sfb_knn** out) {
+static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_nodes, const sfb_knn_params* p, sfb_knn** out, int collective) {
     if (!ctx || !x || !p || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
     *out = nullptr;
     const uint64_t nodes = columns_are_nodes ? x->cols : x->rows, dims = columns_are_nodes ? x->rows : x->cols;
@@ -48,7 +48,7 @@ static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_no
             else st = sfb_transpose_device(ctx, x->d, nodes, dims, tmp.as<double>());
             xd = tmp.as<double>();
         }
-        if (st == SFB_OK) st = sfb_knn_dense(ctx, xd, (uint32_t)nodes, dims, p->metric, p->k, p->eps, q_begin, nq, g->idx, g->dist, g->cnt);
+        if (st == SFB_OK) st = sfb_knn_dense(ctx, xd, (uint32_t)nodes, dims, p->metric, p->k, p->eps, q_begin, nq, g->idx, g->dist, g->cnt, collective);
         if (st == SFB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = sfb_fail(ctx, SFB_ECUDA, "dense kNN failed");
         g->stats.ms_fallback = tf.stop();
         g->stats.rows_fallback = nq;
@@ -98,9 +98,13 @@ static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_no
 }
 
 extern "C" int32_t sfb_knn_build(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, sfb_knn** out) {
-    return knn_build_any(ctx, x, false, p, out);
+    return knn_build_any(ctx, x, false, p, out, 0);
 }
 
 extern "C" int32_t sfb_knn_build_columns(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, sfb_knn** out) {
-    return knn_build_any(ctx, x, true, p, out);
+    return knn_build_any(ctx, x, true, p, out, 0);
+}
+
+extern "C" int32_t sfb_knn_build_columns_sharded(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, sfb_knn** out) {
+    return knn_build_any(ctx, x, true, p, out, 1);
 }

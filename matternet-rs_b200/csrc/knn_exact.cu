@@ -227,11 +227,11 @@ __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc,
 }
 
 template <bool COS, int VEC>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
-__global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G) {
+__global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G, uint32_t tile0) {
     __shared__ __align__(16) double sa[2][GCH][GT], sb[2][GCH][GT];
     // decode the upper-triangular tile index
     const uint32_t T = (m + GT - 1) / GT;
-    uint32_t ti = 0, rem = blockIdx.x;
+    uint32_t ti = 0, rem = blockIdx.x + tile0;
     while (rem >= T - ti) { rem -= T - ti; ++ti; }
     const uint32_t tj = ti + rem;
     const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
@@ -354,17 +354,33 @@ int32_t sfb_row_norms(sfb_ctx* ctx, const sfb_mat* x, double* norms) {
 bool sfb_dense_shape(uint64_t nodes, uint64_t dims) { return nodes <= 4096 && dims >= 8ull * nodes; }
 
 // kNN over few nodes with very long rows, from the DIMS-MAJOR matrix xd[kd][m] (see gram_tile_kernel).
+int32_t sfb_comm_allreduce_sum_f64(sfb_ctx* ctx, double* buf, size_t n);
+
+// `collective` != 0: every rank of the communicator calls this with the same matrix; the pair tiles are split
+// across the ranks and the raw sums all-reduced (each entry is non-zero on exactly one rank: x + 0 is exact).
 int32_t sfb_knn_dense(sfb_ctx* ctx, const double* xd, uint32_t m, uint64_t kd, int metric, uint32_t k, double eps,
-                      uint64_t q_begin, uint64_t nq, uint32_t* out_idx, double* out_dist, uint32_t* out_cnt) {
+                      uint64_t q_begin, uint64_t nq, uint32_t* out_idx, double* out_dist, uint32_t* out_cnt, int collective) {
     if (nq == 0) return SFB_OK;
     if (k == 0 || k > 128) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k must be in 1..128 (got %u)", k);
     DevBuf g;  // [0, m*m): raw sums, [m*m, 2*m*m): keys
     SFB_CUDA(ctx, g.alloc(sizeof(double) * 2 * (size_t)m * m));
     const uint32_t T = (m + GT - 1) / GT, tiles = T * (T + 1) / 2;
+    uint32_t t0 = 0, t1 = tiles;
+    const bool split = collective && ctx->world > 1;
+    if (split) {
+        const uint32_t per = (tiles + (uint32_t)ctx->world - 1) / (uint32_t)ctx->world;
+        t0 = (uint32_t)ctx->rank * per; if (t0 > tiles) t0 = tiles;
+        t1 = t0 + per < tiles ? t0 + per : tiles;
+        SFB_CUDA(ctx, cudaMemsetAsync(g.p, 0, sizeof(double) * (size_t)m * m, ctx->stream));
+    }
     const bool cos = metric == SFB_METRIC_COSINE, even = (m & 1u) == 0 && (reinterpret_cast<uintptr_t>(xd) & 15u) == 0;
-    if (cos) { if (even) gram_tile_kernel<true, 2><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); else gram_tile_kernel<true, 1><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); }
-    else { if (even) gram_tile_kernel<false, 2><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); else gram_tile_kernel<false, 1><<<tiles, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>()); }
-    SFB_LAUNCH_CHECK(ctx);
+    if (t1 > t0) {
+        const uint32_t nt = t1 - t0;
+        if (cos) { if (even) gram_tile_kernel<true, 2><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); else gram_tile_kernel<true, 1><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); }
+        else { if (even) gram_tile_kernel<false, 2><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); else gram_tile_kernel<false, 1><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); }
+        SFB_LAUNCH_CHECK(ctx);
+    }
+    if (split) SFB_TRY(sfb_comm_allreduce_sum_f64(ctx, g.as<double>(), (size_t)m * m));
     dim3 kgrid(div_up(m, 128), m);
     if (cos) gram_keys_kernel<true><<<kgrid, 128, 0, ctx->stream>>>(g.as<double>(), m, metric, nullptr);
     else gram_keys_kernel<false><<<kgrid, 128, 0, ctx->stream>>>(g.as<double>(), m, metric, nullptr);

@@ -42,6 +42,7 @@ def lib():
         build()
     L = ctypes.CDLL(_SO)
     L.orc_num_threads.restype = _c.c_int
+    L.orc_set_num_threads.argtypes = [_c.c_int]
     L.orc_generate_rows.argtypes = [_c.c_int, _c.c_uint64, _c.c_uint64, _c.c_uint64, _c.c_uint32,
                                     _c.c_uint32, _c.c_double, _dp]
     L.orc_row_norms.argtypes = [_dp, _c.c_uint64, _c.c_uint32, _dp]
@@ -76,6 +77,13 @@ def lib():
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def use_all_threads():
+    """OpenMP threads = host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 def generate_rows(kind, seed, row0, nrows, kdim, n_centres=0, noise=0.0):

@@ -46,6 +46,15 @@
 
 #define ORC_IDX_NONE 0xFFFFFFFFu
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline must still use all host threads */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
