@@ -303,7 +303,7 @@ def run_ours(args):
             "knn_ms_steps": [[round(s_[k_], 2) for k_ in ("ms_prepare", "ms_screen", "ms_rescore")] for s_ in stats],
             "stages_ms_per_step": {kk: tm[kk] / args.steps for kk in ("ms_knn", "ms_adjacency", "ms_laplacian", "ms_lambda")},
             "knn": {kk: stats[-1][kk] for kk in ("rows", "rows_certified", "rows_fallback", "k_prime", "screen_used", "ms_prepare",
-                                                 "ms_screen", "ms_rescore", "ms_fallback", "max_margin")},
+                                                 "ms_screen", "ms_rescore", "ms_fallback", "max_margin", "rows_rescreened", "ms_rescreen")},
             "gpu_launches": int(tm["kernel_launches"]),
             "clocks": clocks, "roofline": roof, "e2e": e2e,
         }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 1
+#define SFB_ABI_VERSION 2
 #define SFB_IDX_NONE 0xFFFFFFFFu
 
 typedef enum {
@@ -102,7 +102,7 @@ typedef struct {
     uint32_t k;        /* neighbours kept per row, self excluded (GraphParams.topk)          */
     double eps;        /* keep d <= eps; +inf disables (GraphParams.eps)                     */
     int32_t screen;    /* sfb_screen                                                         */
-    uint32_t k_prime;  /* screen candidates per row (0 = default 4k rounded up to 32)        */
+    uint32_t k_prime;  /* screen candidates per row at the first level (0 = default max(2k, 32)) */
     uint64_t q_begin;  /* query-row shard [q_begin, q_end); q_end = 0 means all rows         */
     uint64_t q_end;
     int32_t allow_fallback; /* 0: return SFB_EUNCERTIFIED instead of recomputing rows exactly */
@@ -119,6 +119,8 @@ typedef struct {
     double ms_rescore;        /* exact f64 rescore + certification                           */
     double ms_fallback;       /* exact brute force for uncertified rows                      */
     double max_margin;        /* largest per-row screen margin used                          */
+    uint64_t rows_rescreened; /* rows the first screen level left to the k' = 192 re-screen   */
+    double ms_rescreen;       /* gather + re-screen + rescore of those rows                   */
 } sfb_knn_stats;
 
 int32_t sfb_knn_build(sfb_ctx* ctx, const sfb_mat* rows, const sfb_knn_params* params, sfb_knn** out);

@@ -105,7 +105,7 @@ struct DevBuf {
     sfb_ctx* owner = nullptr;
     ~DevBuf() { if (p) sfb_dev_free(owner, p); }
     cudaError_t alloc(size_t bytes) { owner = sfb_tls_ctx; return sfb_dev_alloc(owner, &p, bytes); }
-    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
     void* release() { void* q = p; p = nullptr; return q; }
 };
 

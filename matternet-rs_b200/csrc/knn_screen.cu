@@ -477,7 +477,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //     lives in HBM between chunks; the candidate buffers already do.
 struct Screen2Args {
     uint64_t n_rows;
-    uint64_t q_begin, nq;
+    uint64_t q_begin, nq;   // q_begin: first row of the QUERY operand (tmA) this launch covers
     uint32_t kblocks, stages;
     uint32_t resident;      // k-blocks of the query rows that stay in shared memory for a whole work item (all of them when K <= 512)
     uint32_t stage_bytes;   // 16 KB (corpus half-tile) when every k-block is resident, else 32 KB (+ the streamed query slab)
@@ -494,7 +494,7 @@ constexpr int P_BM = 128, P_BNH = 128, P_SLAB_BYTES = 128 * BK * 2;  // 16 KB: o
 
 template <bool L2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SCREEN_THREADS, 1)
-knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
+knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmA, Screen2Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // carve: A slabs [kblocks] | B stages [stages] | barriers | tmem ptr | nq tiles (L2)
     uint8_t* sA = smem;
@@ -516,6 +516,7 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }  // 4 epilogue warps x 2 CTAs
         mbar_init(afull_bar, 1); mbar_init(aempty_bar, 1);
@@ -552,7 +553,7 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
                 mbar_wait(aempty_bar, iphase ^ 1);   // the previous item's MMAs have retired
                 if (leader) mbar_expect_tx(afull_bar, 2u * a.resident * P_SLAB_BYTES);
                 for (uint32_t kb = 0; kb < a.resident; ++kb)
-                    tma_load_2d_pair(sA + (size_t)kb * P_SLAB_BYTES, &tm, (int)(kb * BK), row0, l_afull);
+                    tma_load_2d_pair(sA + (size_t)kb * P_SLAB_BYTES, &tmA, (int)(kb * BK), row0, l_afull);
                 iphase ^= 1;
                 for (uint32_t t = t_lo; t < t_hi; ++t) {
                     const int n0 = (int)(t * BN + rank * P_BNH);
@@ -563,7 +564,7 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, Screen2Args a) {
                         const uint32_t l_full = mapa_u32(&full_bar[stage], 0);
                         uint8_t* st = sB + (size_t)stage * a.stage_bytes;
                         tma_load_2d_pair(st, &tm, (int)(kb * BK), n0, l_full);
-                        if (stream_a) tma_load_2d_pair(st + P_SLAB_BYTES, &tm, (int)(kb * BK), row0, l_full);
+                        if (stream_a) tma_load_2d_pair(st + P_SLAB_BYTES, &tmA, (int)(kb * BK), row0, l_full);
                         if (++stage == a.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -668,6 +669,8 @@ struct RescoreArgs {
     uint32_t* out_idx; double* out_dist; uint32_t* out_cnt;
     uint32_t* fb_rows; uint32_t* fb_count;  // uncertified rows (global indices)
     double* max_margin;
+    const uint32_t* qlist;  // null: query row rl is global row q_begin + rl; else global row qlist[rl] (re-screen of uncertified rows)
+    uint64_t out_base;      // results of global row g go to output row g - out_base
 };
 
 // One warp per query row.
@@ -703,7 +706,8 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
 
     const uint64_t rl = (uint64_t)blockIdx.x * wpb + w;
     if (rl >= a.nq) return;
-    const uint32_t gi = (uint32_t)(a.q_begin + rl);
+    const uint32_t gi = a.qlist ? a.qlist[rl] : (uint32_t)(a.q_begin + rl);
+    const uint64_t orow = (uint64_t)gi - a.out_base;
     const double* xi = a.x + (uint64_t)gi * a.kd;
     const double ni = COS ? a.norms[gi] : 0.0;
     const double qn = a.aux[gi], dn = a.aux[a.m + gi], q2 = a.aux[2 * a.m + gi];
@@ -879,14 +883,24 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
     if (!(margin == margin)) certified = false;
     if (certified) {
         for (uint32_t t = lane; t < a.k; t += 32) {
-            a.out_idx[rl * a.k + t] = t < c ? li[t] : SFB_IDX_NONE;
-            a.out_dist[rl * a.k + t] = t < c ? ld[t] : INFINITY;
+            a.out_idx[orow * a.k + t] = t < c ? li[t] : SFB_IDX_NONE;
+            a.out_dist[orow * a.k + t] = t < c ? ld[t] : INFINITY;
         }
-        if (lane == 0) a.out_cnt[rl] = c;
+        if (lane == 0) a.out_cnt[orow] = c;
     } else if (lane == 0) {
         a.fb_rows[atomicAdd(a.fb_count, 1u)] = gi;
     }
     if (lane == 0 && margin > 0.0 && isfinite(margin)) atomicMax(reinterpret_cast<unsigned long long*>(a.max_margin), (unsigned long long)__double_as_longlong(margin));
+}
+
+// query operand of the re-screen: the 16-bit rows of the uncertified queries, packed
+__global__ void gather_rows16_kernel(const uint16_t* __restrict__ q, uint32_t kpad, const uint32_t* __restrict__ rows, uint32_t n,
+                                     uint16_t* __restrict__ out) {
+    const uint32_t per = kpad / 8;   // uint4 = 8 halves; kpad is a multiple of 64
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)n * per) return;
+    const uint32_t r = (uint32_t)(gid / per), c = (uint32_t)(gid % per);
+    reinterpret_cast<uint4*>(out)[(uint64_t)r * per + c] = __ldg(reinterpret_cast<const uint4*>(q) + (uint64_t)rows[r] * per + c);
 }
 
 __global__ void scatter_rows_kernel(const uint32_t* __restrict__ rows, uint32_t n, uint64_t q_begin, uint32_t k,
@@ -981,9 +995,9 @@ int32_t prepare_operands(sfb_ctx* ctx, const sfb_mat* x, const double* norms, in
 }
 
 template <bool DUMP>
-int32_t launch_screen(sfb_ctx* ctx, const Prepared& P, int metric, ScreenArgs& sa, uint32_t m_blocks) {
+int32_t launch_screen(sfb_ctx* ctx, const Prepared& P, int metric, ScreenArgs& sa, uint32_t m_blocks, void* a_base = nullptr, uint64_t a_rows = 0) {
     CUtensorMap tmA, tmB;
-    SFB_TRY(make_tmap(ctx, &tmA, P.q.p, P.mpad, P.kpad, BM, P.bf16));
+    SFB_TRY(make_tmap(ctx, &tmA, a_base ? a_base : P.q.p, a_base ? a_rows : P.mpad, P.kpad, BM, P.bf16));
     SFB_TRY(make_tmap(ctx, &tmB, P.q.p, P.mpad, P.kpad, BN, P.bf16));
     sa.idesc = make_idesc(P.bf16);
     size_t smem = screen_smem_bytes();
@@ -999,9 +1013,10 @@ int32_t launch_screen(sfb_ctx* ctx, const Prepared& P, int metric, ScreenArgs& s
     return SFB_OK;
 }
 
-int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2Args& sa) {
-    CUtensorMap tm;
+int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2Args& sa, void* a_base, uint64_t a_rows) {
+    CUtensorMap tm, tmA;
     SFB_TRY(make_tmap(ctx, &tm, P.q.p, P.mpad, P.kpad, P_BM, P.bf16));
+    SFB_TRY(make_tmap(ctx, &tmA, a_base, a_rows, P.kpad, P_BM, P.bf16));
     // M = 256 across the pair, N = 256
     const uint32_t fmt = P.bf16 ? 1u : 0u;
     sa.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -1025,10 +1040,10 @@ int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2A
     if (pairs > n_slots) pairs = n_slots;
     if (metric == SFB_METRIC_COSINE) {
         SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_screen_pair_kernel<false><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, sa);
+        knn_screen_pair_kernel<false><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, tmA, sa);
     } else {
         SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_screen_pair_kernel<true><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, sa);
+        knn_screen_pair_kernel<true><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, tmA, sa);
     }
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
@@ -1042,42 +1057,27 @@ bool pair_kernel_applies(const Prepared& P) {
 
 }  // namespace
 
-int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p, uint64_t q_begin,
-                         uint64_t q_end, sfb_knn* out) {
-    const uint64_t m = x->rows, nq = q_end - q_begin;
-    const bool bf16 = p->screen == SFB_SCREEN_BF16;
+namespace {
+
+// One screen + rescore + certify pass over `nq` query rows.  The query operand is `a_base` (a_rows rows of
+// 16-bit operands; query row rl is its row a_row0 + rl); qlist == null: query rl is global row a_row0 + rl,
+// else global row qlist[rl].  Certified rows are written to `out` (row g - out_base); the global indices of the
+// rest are appended to fb_rows / fb_count.
+int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p, const Prepared& P,
+                     uint32_t kprime, void* a_base, uint64_t a_rows, uint64_t a_row0, uint64_t nq, const uint32_t* qlist,
+                     uint64_t out_base, sfb_knn* out, uint32_t* fb_rows, uint64_t* fb_count /* [0] count, [1] max margin */,
+                     double* ms_screen, double* ms_rescore) {
+    const uint64_t m = x->rows;
     const bool cosine = p->metric == SFB_METRIC_COSINE;
-    if (m > 0xFFFFFF00ull) return sfb_fail(ctx, SFB_EUNSUPPORTED, "too many rows for the screen");
-    sfb_knn_stats& st = out->stats;
-    st.screen_used = p->screen;
-
-    // k' candidates survive per row and corpus split; the buffer has 64 slots of slack between prunes
-    // k' = 3k: measured at C2 (k = 16) -- k' = 96 / 64 / 48 / 32 / 24 take 814 / 717 / 689 / 662 / 645 ms of screen with
-    // 0 / 0 / 0 / 9 / 3366 uncertified rows (an uncertified row costs 0.1 ms of f64 brute force)
-    uint32_t kprime = p->k_prime ? p->k_prime : (3 * p->k + 15) / 16 * 16;
-    bool kp_forced = p->k_prime != 0;
-    if (const char* e = getenv("SFB_SCREEN_KPRIME")) { int v = atoi(e); if (v > 0 && !p->k_prime) { kprime = (uint32_t)v; kp_forced = true; } }  // tuning aid
-    if (kprime < p->k + 1) kprime = p->k + 1;
-    if (kprime < 48 && !kp_forced) kprime = 48;
-    if (kprime > MAX_CAP - 64) kprime = MAX_CAP - 64;
-    if (kprime < p->k + 1) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k too large for the screen buffers");
     const uint32_t cap = (kprime + 64 + 31) / 32 * 32;
-    st.k_prime = kprime;
-
-    Prepared P;
-    {
-        StageTimer t(ctx, nullptr);
-        SFB_TRY(prepare_operands(ctx, x, norms, p->metric, bf16, &P));
-        st.ms_prepare = t.stop();
-    }
     const uint32_t tiles_total = (uint32_t)(P.mpad / BN);
     const bool use_pair = pair_kernel_applies(P);
     ScreenArgs sa{};
     Screen2Args s2{};
     uint32_t n_splits_used = 1;
-    uint32_t m_blocks = (uint32_t)((nq + BM - 1) / BM);
+    const uint32_t m_blocks = (uint32_t)((nq + BM - 1) / BM);
     if (use_pair) {
-        s2.n_rows = m; s2.q_begin = q_begin; s2.nq = nq; s2.kblocks = P.kpad / BK;
+        s2.n_rows = m; s2.q_begin = a_row0; s2.nq = nq; s2.kblocks = P.kpad / BK;
         s2.tiles_total = tiles_total;
         s2.n_mb2 = (uint32_t)((nq + 255) / 256);
         const uint32_t pairs = (uint32_t)ctx->sm_count / 2;
@@ -1096,7 +1096,7 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
         s2.kprime = kprime; s2.cap = cap; s2.nq32 = P.nq32.as<float>();
         n_splits_used = s2.n_splits;
     } else {
-        sa.n_rows = m; sa.q_begin = q_begin; sa.nq = nq; sa.kblocks = P.kpad / BK;
+        sa.n_rows = m; sa.q_begin = a_row0; sa.nq = nq; sa.kblocks = P.kpad / BK;
         sa.tiles_total = tiles_total;
         uint32_t want_ctas = 2u * (uint32_t)ctx->sm_count;
         uint32_t n_splits = m_blocks >= want_ctas ? 1u : (want_ctas + m_blocks - 1) / m_blocks;
@@ -1108,31 +1108,28 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     }
 
     const size_t slots = (size_t)nq * n_splits_used;
-    DevBuf buf_key, buf_idx, cnt, thr, fb_rows, fb_count;
+    DevBuf buf_key, buf_idx, cnt, thr;
     SFB_CUDA(ctx, buf_key.alloc(slots * cap * sizeof(float)));
     SFB_CUDA(ctx, buf_idx.alloc(slots * cap * sizeof(uint32_t)));
     SFB_CUDA(ctx, cnt.alloc(slots * sizeof(uint32_t)));
     SFB_CUDA(ctx, thr.alloc(slots * sizeof(float)));
-    SFB_CUDA(ctx, fb_rows.alloc(nq * sizeof(uint32_t)));
-    SFB_CUDA(ctx, fb_count.alloc(4 * sizeof(uint64_t)));
-    SFB_CUDA(ctx, cudaMemsetAsync(fb_count.p, 0, 4 * sizeof(uint64_t), ctx->stream));
     SFB_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, slots * sizeof(uint32_t), ctx->stream));
     sa.buf_key = s2.buf_key = buf_key.as<float>(); sa.buf_idx = s2.buf_idx = buf_idx.as<uint32_t>();
     sa.out_cnt = s2.out_cnt = cnt.as<uint32_t>(); sa.out_thr = s2.out_thr = thr.as<float>();
     sa.n_splits = n_splits_used;
     {
         StageTimer t(ctx, nullptr);
-        if (use_pair) SFB_TRY(launch_screen_pair(ctx, P, p->metric, s2));
-        else SFB_TRY(launch_screen<false>(ctx, P, p->metric, sa, m_blocks));
-        st.ms_screen = t.stop();
+        if (use_pair) SFB_TRY(launch_screen_pair(ctx, P, p->metric, s2, a_base, a_rows));
+        else SFB_TRY(launch_screen<false>(ctx, P, p->metric, sa, m_blocks, a_base, a_rows));
+        *ms_screen += t.stop();
         SFB_CUDA(ctx, cudaGetLastError());
     }
     // tensor-core fp32 accumulation: K products, each partial sum off by at most 2 ulp of the running bound
     const double gamma = ((double)P.kpad + 64.0) * ldexp(1.0, -23);
-    RescoreArgs ra{x->d, norms, m, x->cols, p->metric, p->k, p->eps, q_begin, nq, sa.n_splits, cap,
+    RescoreArgs ra{x->d, norms, m, x->cols, p->metric, p->k, p->eps, a_row0, nq, sa.n_splits, cap,
                    sa.buf_key, sa.buf_idx, sa.out_cnt, sa.out_thr, P.aux.as<double>(), P.nmax, P.dmax, gamma, P.scale,
-                   out->idx, out->dist, out->cnt, fb_rows.as<uint32_t>(), fb_count.as<uint32_t>(),
-                   reinterpret_cast<double*>(fb_count.as<uint64_t>() + 1)};
+                   out->idx, out->dist, out->cnt, fb_rows, reinterpret_cast<uint32_t*>(fb_count),
+                   reinterpret_cast<double*>(fb_count + 1), qlist, out_base};
     {
         StageTimer t(ctx, nullptr);
         const int wpb = 4;
@@ -1145,13 +1142,84 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
             knn_rescore_kernel<false><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);
         }
         SFB_LAUNCH_CHECK(ctx);
-        st.ms_rescore = t.stop();
+        *ms_rescore += t.stop();   // synchronises: the candidate buffers may be released on return
     }
-    uint64_t h[2];
-    SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    return SFB_OK;
+}
+
+}  // namespace
+
+// Screen in up to three levels, each exact for the rows it certifies:
+//   1. every query row with a small k' (cheap epilogue: the cost of the screen grows with k');
+//   2. the rows level 1 could not certify -- near-ties at the margin, tight clusters -- once more through the tensor
+//      cores with k' = 192, their 16-bit rows packed into a small query operand;
+//   3. what is left (exact ties, zero rows, duplicates) by f64 brute force.
+int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p, uint64_t q_begin,
+                         uint64_t q_end, sfb_knn* out) {
+    const uint64_t m = x->rows, nq = q_end - q_begin;
+    const bool bf16 = p->screen == SFB_SCREEN_BF16;
+    if (m > 0xFFFFFF00ull) return sfb_fail(ctx, SFB_EUNSUPPORTED, "too many rows for the screen");
+    sfb_knn_stats& st = out->stats;
+    st.screen_used = p->screen;
+
+    // k' candidates survive per row and corpus split; the buffer has 64 slots of slack between prunes.
+    // Measured at C2 (k = 16): k' = 96 / 64 / 48 / 32 / 24 take 814 / 717 / 689 / 662 / 645 ms of screen and leave
+    // 0 / 0 / 0 / 9 / 3366 rows to the next level.
+    const uint32_t kp_max = MAX_CAP - 64;
+    uint32_t kprime = p->k_prime ? p->k_prime : (2 * p->k + 7) / 8 * 8;
+    bool kp_forced = p->k_prime != 0;
+    if (const char* e = getenv("SFB_SCREEN_KPRIME")) { int v = atoi(e); if (v > 0 && !p->k_prime) { kprime = (uint32_t)v; kp_forced = true; } }  // tuning aid
+    if (kprime < 32 && !kp_forced) kprime = 32;
+    if (kprime < p->k + 1) kprime = p->k + 1;
+    if (kprime > kp_max) kprime = kp_max;
+    if (kprime < p->k + 1) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k too large for the screen buffers");
+    st.k_prime = kprime;
+
+    Prepared P;
+    {
+        StageTimer t(ctx, nullptr);
+        SFB_TRY(prepare_operands(ctx, x, norms, p->metric, bf16, &P));
+        st.ms_prepare = t.stop();
+    }
+    DevBuf fb_rows, fb_rows2, fb_count;
+    SFB_CUDA(ctx, fb_rows.alloc(nq * sizeof(uint32_t)));
+    SFB_CUDA(ctx, fb_count.alloc(4 * sizeof(uint64_t)));
+    SFB_CUDA(ctx, cudaMemsetAsync(fb_count.p, 0, 4 * sizeof(uint64_t), ctx->stream));
+    uint64_t* fbc = fb_count.as<uint64_t>();
+
+    // level 1
+    SFB_TRY(screen_level(ctx, x, norms, p, P, kprime, P.q.p, P.mpad, q_begin, nq, nullptr, q_begin, out, fb_rows.as<uint32_t>(), fbc,
+                         &st.ms_screen, &st.ms_rescore));
+    uint64_t h[4];
+    SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const uint32_t n_fb = (uint32_t)(h[0] & 0xFFFFFFFFu);
+    uint32_t n_fb = (uint32_t)(h[0] & 0xFFFFFFFFu);
     memcpy(&st.max_margin, &h[1], 8);
+    const uint32_t* fb_final = fb_rows.as<uint32_t>();
+
+    // level 2: re-screen the uncertified rows with the widest k'
+    const bool rescreen_off = getenv("SFB_SCREEN_NO_RESCREEN") != nullptr;
+    if (n_fb && kprime < kp_max && !rescreen_off && kp_max >= p->k + 1) {
+        StageTimer t(ctx, nullptr);
+        st.rows_rescreened = n_fb;
+        DevBuf qa;
+        const uint64_t a_rows = ((uint64_t)n_fb + 255) / 256 * 256;
+        SFB_CUDA(ctx, qa.alloc(a_rows * P.kpad * 2));
+        SFB_CUDA(ctx, cudaMemsetAsync(qa.p, 0, a_rows * P.kpad * 2, ctx->stream));
+        gather_rows16_kernel<<<div_up((uint64_t)n_fb * (P.kpad / 8), 256), 256, 0, ctx->stream>>>(P.q.as<uint16_t>(), P.kpad, fb_rows.as<uint32_t>(), n_fb,
+                                                                                                 qa.as<uint16_t>());
+        SFB_LAUNCH_CHECK(ctx);
+        SFB_CUDA(ctx, fb_rows2.alloc((size_t)n_fb * sizeof(uint32_t)));
+        SFB_CUDA(ctx, cudaMemsetAsync(fbc + 2, 0, 2 * sizeof(uint64_t), ctx->stream));
+        double ms_s = 0.0, ms_r = 0.0;
+        SFB_TRY(screen_level(ctx, x, norms, p, P, kp_max, qa.p, a_rows, 0, n_fb, fb_rows.as<uint32_t>(), q_begin, out, fb_rows2.as<uint32_t>(),
+                             fbc + 2, &ms_s, &ms_r));
+        SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        n_fb = (uint32_t)(h[2] & 0xFFFFFFFFu);
+        fb_final = fb_rows2.as<uint32_t>();
+        st.ms_rescreen = t.stop();
+    }
     st.rows_fallback = n_fb;
     st.rows_certified = nq - n_fb;
     if (n_fb) {
@@ -1161,9 +1229,9 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
         SFB_CUDA(ctx, t_idx.alloc((size_t)n_fb * p->k * sizeof(uint32_t)));
         SFB_CUDA(ctx, t_dist.alloc((size_t)n_fb * p->k * sizeof(double)));
         SFB_CUDA(ctx, t_cnt.alloc((size_t)n_fb * sizeof(uint32_t)));
-        SFB_TRY(sfb_knn_exact(ctx, x, norms, p->metric, p->k, p->eps, fb_rows.as<uint32_t>(), n_fb, 0, t_idx.as<uint32_t>(),
+        SFB_TRY(sfb_knn_exact(ctx, x, norms, p->metric, p->k, p->eps, fb_final, n_fb, 0, t_idx.as<uint32_t>(),
                               t_dist.as<double>(), t_cnt.as<uint32_t>()));
-        scatter_rows_kernel<<<div_up((uint64_t)n_fb * p->k, 256), 256, 0, ctx->stream>>>(fb_rows.as<uint32_t>(), n_fb, q_begin, p->k,
+        scatter_rows_kernel<<<div_up((uint64_t)n_fb * p->k, 256), 256, 0, ctx->stream>>>(fb_final, n_fb, q_begin, p->k,
                                                                                          t_idx.as<uint32_t>(), t_dist.as<double>(), t_cnt.as<uint32_t>(),
                                                                                          out->idx, out->dist, out->cnt);
         SFB_LAUNCH_CHECK(ctx);
