@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <map>
 #include <string>
@@ -130,6 +132,14 @@ struct StageTimer {
         if (acc) *acc += ms;
         return ms;
     }
+};
+
+// SFB_TRACE=1: host wall-clock checkpoints to stderr (synchronises the stream at every checkpoint)
+struct HostTrace {
+    sfb_ctx* ctx; const char* what; bool on; double t0 = 0.0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    HostTrace(sfb_ctx* c, const char* w) : ctx(c), what(w) { static const bool e = getenv("SFB_TRACE") != nullptr; on = e; if (on) { cudaStreamSynchronize(ctx->stream); t0 = now(); } }
+    void mark(const char* label) { if (!on) return; cudaStreamSynchronize(ctx->stream); double t = now(); fprintf(stderr, "[sfb] %-14s %-18s %9.3f ms\n", what, label, t - t0); t0 = t; }
 };
 
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }

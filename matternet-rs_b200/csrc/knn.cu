@@ -33,6 +33,7 @@ static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_no
     g->stats = sfb_knn_stats{};
     g->stats.rows = nq;
 
+    HostTrace tr(ctx, "knn_build");
     StageTimer total(ctx, &ctx->times.ms_knn);
     int32_t st = SFB_OK;
     int screen = p->screen;
@@ -69,6 +70,7 @@ static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_no
             if (e != cudaSuccess) st = sfb_fail(ctx, SFB_ENOMEM, "norms: %s", cudaGetErrorString(e));
         }
         if (st == SFB_OK && p->metric == SFB_METRIC_COSINE) st = sfb_row_norms(ctx, &view, norms.as<double>());
+        tr.mark("norms");
         if (screen == SFB_SCREEN_AUTO) {
             // the screen pays off once the pair count dwarfs its fixed costs and k' stays small
             bool big = nodes >= 4096 && dims >= 32 && p->k <= 64;
@@ -93,6 +95,7 @@ static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_no
         }
     }
     total.stop();
+    tr.mark("rest");
     if (st != SFB_OK) { sfb_knn_free(g); *out = nullptr; }
     return st;
 }

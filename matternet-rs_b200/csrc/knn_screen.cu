@@ -1081,7 +1081,10 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
         s2.tiles_total = tiles_total;
         s2.n_mb2 = (uint32_t)((nq + 255) / 256);
         const uint32_t pairs = (uint32_t)ctx->sm_count / 2;
+        // corpus splits give small launches parallelism, but every split keeps its own k' candidates per row and the
+        // rescore gathers all of them: more than 8 made the re-screen of 9 rows take 17 ms (148 x 192 candidates each)
         uint32_t n_splits = s2.n_mb2 >= 4 * pairs ? 1u : (2 * pairs + s2.n_mb2 - 1) / s2.n_mb2;
+        if (n_splits > 8) n_splits = 8;
         if (n_splits > tiles_total) n_splits = tiles_total;
         s2.tiles_per_split = (tiles_total + n_splits - 1) / n_splits;
         s2.n_splits = (tiles_total + s2.tiles_per_split - 1) / s2.tiles_per_split;
@@ -1100,6 +1103,7 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
         sa.tiles_total = tiles_total;
         uint32_t want_ctas = 2u * (uint32_t)ctx->sm_count;
         uint32_t n_splits = m_blocks >= want_ctas ? 1u : (want_ctas + m_blocks - 1) / m_blocks;
+        if (n_splits > 8) n_splits = 8;
         if (n_splits > sa.tiles_total) n_splits = sa.tiles_total;
         sa.tiles_per_split = (sa.tiles_total + n_splits - 1) / n_splits;
         sa.n_splits = (sa.tiles_total + sa.tiles_per_split - 1) / sa.tiles_per_split;
@@ -1175,12 +1179,14 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     if (kprime < p->k + 1) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k too large for the screen buffers");
     st.k_prime = kprime;
 
+    HostTrace tr(ctx, "knn_screened");
     Prepared P;
     {
         StageTimer t(ctx, nullptr);
         SFB_TRY(prepare_operands(ctx, x, norms, p->metric, bf16, &P));
         st.ms_prepare = t.stop();
     }
+    tr.mark("prepare");
     DevBuf fb_rows, fb_rows2, fb_count;
     SFB_CUDA(ctx, fb_rows.alloc(nq * sizeof(uint32_t)));
     SFB_CUDA(ctx, fb_count.alloc(4 * sizeof(uint64_t)));
@@ -1196,6 +1202,7 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     uint32_t n_fb = (uint32_t)(h[0] & 0xFFFFFFFFu);
     memcpy(&st.max_margin, &h[1], 8);
     const uint32_t* fb_final = fb_rows.as<uint32_t>();
+    tr.mark("level 1");
 
     // level 2: re-screen the uncertified rows with the widest k'
     const bool rescreen_off = getenv("SFB_SCREEN_NO_RESCREEN") != nullptr;
@@ -1219,6 +1226,7 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
         n_fb = (uint32_t)(h[2] & 0xFFFFFFFFu);
         fb_final = fb_rows2.as<uint32_t>();
         st.ms_rescreen = t.stop();
+        tr.mark("level 2");
     }
     st.rows_fallback = n_fb;
     st.rows_certified = nq - n_fb;
