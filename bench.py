@@ -246,7 +246,12 @@ def run_ours(args):
 
         def e2e_step():
             nonlocal d2h
-            Xd = ctx.matrix(xh)
+            if world > 1:   # upload this rank's rows only; the corpus is replicated over NVLink, not PCIe
+                xs_ = ctx.matrix(xh[lo:hi])
+                Xd = xs_.allgather_rows(n)
+                xs_.free()
+            else:
+                Xd = ctx.matrix(xh)
             (L, Lf, lam), _ = build_once(sfb, ctx, Xd, wl, rank, world, out_lambda=out_lam, keep=True)
             indptr, indices, data = L.to_host(out_csr)
             d2h = indptr.nbytes + indices.nbytes + data.nbytes + out_lam.nbytes
@@ -267,8 +272,9 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         ms_e_step = float(te[0]) / e2e_steps
         e2e = {"value": n / (ms_e_step * 1e-3), "unit": UNIT, "ms_per_step": ms_e_step, "steps": e2e_steps,
-               "h2d_bytes_per_step": int(n) * d * 8, "d2h_bytes_per_step": int(d2h),
-               "api": "Context.matrix(host f64) -> Matrix.knn -> adjacency -> laplacian -> Csr.to_host; Csr.lambdas_allgather -> host"}
+               "h2d_bytes_per_step": int(hi - lo) * d * 8 * world, "d2h_bytes_per_step": int(d2h) * world,
+               "api": "Context.matrix(host f64 rows of this rank) [-> Matrix.allgather_rows] -> Matrix.knn -> adjacency -> laplacian -> Csr.to_host; "
+                      "Csr.lambdas_allgather -> host (every rank fetches the full CSR and lambda)"}
     else:
         X.free()
 

@@ -254,6 +254,9 @@ int32_t sfb_timings_reset(sfb_ctx* ctx);
  * id: 128 bytes from sfb_comm_unique_id on rank 0, distributed by the host. */
 int32_t sfb_comm_unique_id(uint8_t id[128]);
 int32_t sfb_comm_init(sfb_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);
+/* every rank uploads only its own row shard (same ceil split as below); the full matrix is assembled on every GPU
+ * by one all-gather over NVLink instead of eight uploads of the whole matrix over PCIe */
+int32_t sfb_mat_allgather_rows(sfb_ctx* ctx, const sfb_mat* shard, uint64_t total_rows, sfb_mat** out);
 /* sfb_knn_build_columns as a COLLECTIVE: every rank passes the same matrix; when it has the feature-graph shape
  * (few columns, many rows) the exact f64 pair sums are split across the ranks and all-reduced (each sum is
  * produced by exactly one rank, so the result has the same bits as the single-GPU build). */

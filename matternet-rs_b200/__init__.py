@@ -160,6 +160,12 @@ class Matrix(_Handle):
         self.ctx.check(lib().sfb_mat_transpose(self.ctx._h, self._h, C.byref(h)))
         return Matrix(self.ctx, h)
 
+    def allgather_rows(self, total_rows):
+        """Collective: this rank's row shard -> the full matrix on every GPU (all-gather over NVLink)."""
+        h = C.c_void_p()
+        self.ctx.check(lib().sfb_mat_allgather_rows(self.ctx._h, self._h, total_rows, C.byref(h)))
+        return Matrix(self.ctx, h)
+
     def view_rows(self, row0, nrows):
         h = C.c_void_p()
         self.ctx.check(lib().sfb_mat_view_rows(self.ctx._h, self._h, row0, nrows, C.byref(h)))

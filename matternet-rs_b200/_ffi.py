@@ -75,6 +75,7 @@ SYMBOLS = {
     "sfb_mat_generate": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, _PP]),
     "sfb_mat_transpose": (C.c_int32, [_P, _P, _PP]),
     "sfb_mat_view_rows": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, _PP]),
+    "sfb_mat_allgather_rows": (C.c_int32, [_P, _P, C.c_uint64, _PP]),
     "sfb_mat_shape": (C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "sfb_mat_copy_rows": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "sfb_mat_free": (None, [_P]),

@@ -11,6 +11,8 @@
 #include <math.h>
 #include <nccl.h>
 
+#include <new>
+
 #include "common.cuh"
 
 int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out);
@@ -142,6 +144,36 @@ extern "C" int32_t sfb_knn_allgather(sfb_ctx* ctx, const sfb_knn* shard, uint64_
     SFB_NCCL(ctx, nccl()->AllGather(my_dist, g->dist, S * k, ncclFloat64, comm, ctx->stream));
     SFB_NCCL(ctx, nccl()->AllGather(my_cnt, g->cnt, S, ncclUint32, comm, ctx->stream));
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+
+// The corpus over NVLink instead of PCIe: every rank uploads only its own row shard and the full matrix is
+// assembled on every GPU by one all-gather (north_star: "the corpus is ring-passed or replicated over NVLink").
+extern "C" int32_t sfb_mat_allgather_rows(sfb_ctx* ctx, const sfb_mat* shard, uint64_t total_rows, sfb_mat** out) {
+    if (!ctx || !shard || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    *out = nullptr;
+    const uint64_t world = (uint64_t)ctx->world, S = (total_rows + world - 1) / world;
+    const uint64_t lo = (uint64_t)ctx->rank * S < total_rows ? (uint64_t)ctx->rank * S : total_rows;
+    const uint64_t hi = lo + S < total_rows ? lo + S : total_rows;
+    if (shard->rows != hi - lo) return sfb_fail(ctx, SFB_EINVAL, "rank %d must hold rows [%llu, %llu) of %llu", ctx->rank, (unsigned long long)lo, (unsigned long long)hi, (unsigned long long)total_rows);
+    if (world > 1 && !ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    sfb_mat* m = new (std::nothrow) sfb_mat();
+    if (!m) return SFB_ENOMEM;
+    m->ctx = ctx; m->rows = total_rows; m->cols = shard->cols;
+    const size_t row_bytes = sizeof(double) * shard->cols;
+    cudaError_t e = sfb_dev_alloc(ctx, (void**)&m->d, world * S * row_bytes);
+    if (e != cudaSuccess) { delete m; return sfb_fail(ctx, SFB_ENOMEM, "all-gathered matrix: %s", cudaGetErrorString(e)); }
+    double* mine = m->d + lo * shard->cols;
+    StageTimer t(ctx, &ctx->times.ms_h2d);
+    int32_t st = SFB_OK;
+    if (cudaMemcpyAsync(mine, shard->d, shard->rows * row_bytes, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) st = sfb_fail(ctx, SFB_ECUDA, "shard copy failed");
+    if (st == SFB_OK && world > 1) {
+        ncclResult_t r = nccl()->AllGather(m->d + (uint64_t)ctx->rank * S * shard->cols, m->d, S * shard->cols, ncclFloat64, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+        if (r != ncclSuccess) st = sfb_fail(ctx, SFB_ENCCL, "ncclAllGather: %s", nccl()->GetErrorString(r));
+    }
+    if (st == SFB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = sfb_fail(ctx, SFB_ECUDA, "matrix all-gather failed");
+    if (st != SFB_OK) { sfb_mat_free(m); return st; }
+    *out = m;
     return SFB_OK;
 }
 

@@ -1206,7 +1206,8 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
 
     // level 2: re-screen the uncertified rows with the widest k'
     const bool rescreen_off = getenv("SFB_SCREEN_NO_RESCREEN") != nullptr;
-    if (n_fb && kprime < kp_max && !rescreen_off && kp_max >= p->k + 1) {
+    // a re-screen launch has ~4 ms of fixed cost; below a few dozen rows the f64 brute force (0.1 ms / row at 1M x 384) is cheaper
+    if (n_fb >= 32 && kprime < kp_max && !rescreen_off && kp_max >= p->k + 1) {
         StageTimer t(ctx, nullptr);
         st.rows_rescreened = n_fb;
         DevBuf qa;
