@@ -293,6 +293,11 @@ __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_
     }
 }
 
+// SFB_SCREEN_DBG=4: [0] cycles in the slow (hit) path, [1] slow-path entries, [2] cycles in prunes, [3] prune calls,
+// [4] rows pruned, [5] cycles waiting for a full accumulator, [6] tiles -- summed over warp 2 of every CTA
+__device__ unsigned long long g_screen_dbg[8];
+__device__ volatile int g_prof_on = 0;
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
@@ -305,7 +310,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 template <bool L2>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const float* __restrict__ nqv, uint32_t col0, uint64_t n_rows,
                                              bool row_valid, float* my_key, uint32_t* my_idx, uint32_t& cnt, float& thr,
-                                             uint32_t cap, uint32_t kprime, int lane) {
+                                             uint32_t cap, uint32_t kprime, int lane, bool prof_on = false) {
     float key[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
@@ -318,6 +323,10 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     const float m = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
     const bool hit = m > thr;
     if (!__any_sync(FULL, hit)) return;
+    const bool prof = prof_on && lane == 0 && (threadIdx.x >> 5) == 2;
+    long long t_in = 0;
+    if (prof) t_in = clock64();
+    // (A warp-uniform variant -- one vote per group of 4, predicated appends -- was measured slower: 705 vs 658 ms.)
     if (hit && row_valid) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -334,9 +343,13 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     const uint32_t need = __ballot_sync(FULL, cnt + 32 > cap);
     if (need) {
         __syncwarp();
+        long long t_p = 0;
+        if (prof) t_p = clock64();
         if (cap <= 128) prune_rows<4>(need, my_key, my_idx, cnt, thr, kprime, lane);
         else prune_rows<8>(need, my_key, my_idx, cnt, thr, kprime, lane);
+        if (prof) { atomicAdd(&g_screen_dbg[2], (unsigned long long)(clock64() - t_p)); atomicAdd(&g_screen_dbg[3], 1ull); atomicAdd(&g_screen_dbg[4], (unsigned long long)__popc(need)); }
     }
+    if (prof) { atomicAdd(&g_screen_dbg[0], (unsigned long long)(clock64() - t_in)); atomicAdd(&g_screen_dbg[1], 1ull); }
 }
 
 template <bool L2, bool DUMP>
@@ -488,6 +501,7 @@ struct Screen2Args {
     const float* nq32;
     float* buf_key; uint32_t* buf_idx;
     uint32_t* out_cnt; float* out_thr;
+    uint32_t dbg;           // SFB_SCREEN_DBG (timing experiments, results invalid): 1 = tcgen05.ld only, 2 = no epilogue work
 };
 
 constexpr int P_BM = 128, P_BNH = 128, P_SLAB_BYTES = 128 * BK * 2;  // 16 KB: one k-block of 128 rows
@@ -618,6 +632,7 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
             uint32_t cnt = 0;
             float thr = -INFINITY;
             if (chunk != 0 && row_valid) { cnt = a.out_cnt[slot]; thr = a.out_thr[slot]; }
+            if (a.dbg == 3) thr = INFINITY;   // timing experiment: the fast path only, nothing ever passes
             for (uint32_t t = t_lo; t < t_hi; ++t, ++tc) {
                 const uint32_t as = tc & 1, aphase = (tc >> 1) & 1;
                 const uint32_t n0 = t * BN;
@@ -626,25 +641,42 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
                     for (int c = etid; c < BN; c += 128) dst[c] = (uint64_t)n0 + c < a.n_rows ? __ldg(a.nq32 + n0 + c) : INFINITY;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
+                const bool prof = a.dbg == 4 && lane == 0 && warp == 2;
+                long long t_w = 0;
+                if (prof) t_w = clock64();
                 mbar_wait(&tfull_bar[as], aphase);
+                if (prof) { atomicAdd(&g_screen_dbg[5], (unsigned long long)(clock64() - t_w)); atomicAdd(&g_screen_dbg[6], 1ull); }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
                 const float* nqt = s_nq + as * BN;
                 uint32_t va[32], vb[32];
-                tmem_ld32(taddr, va);
+                if (a.dbg == 0 || a.dbg >= 3) {
+                    tmem_ld32(taddr, va);
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch += 2) {
-                    tmem_ld_wait();
-                    tmem_ld32(taddr + (ch + 1) * 32, vb);   // in flight while chunk ch is filtered
-                    filter_chunk<L2>(va, nqt + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
-                    tmem_ld_wait();
-                    if (ch + 2 < BN / 32) tmem_ld32(taddr + (ch + 2) * 32, va);
-                    filter_chunk<L2>(vb, nqt + (ch + 1) * 32, n0 + (ch + 1) * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
+                    for (int ch = 0; ch < BN / 32; ch += 2) {
+                        tmem_ld_wait();
+                        tmem_ld32(taddr + (ch + 1) * 32, vb);   // in flight while chunk ch is filtered
+                        filter_chunk<L2>(va, nqt + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane, a.dbg == 4);
+                        tmem_ld_wait();
+                        if (ch + 2 < BN / 32) tmem_ld32(taddr + (ch + 2) * 32, va);
+                        filter_chunk<L2>(vb, nqt + (ch + 1) * 32, n0 + (ch + 1) * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane, a.dbg == 4);
+                    }
+                } else if (a.dbg == 1) {
+                    uint32_t acc = 0;
+#pragma unroll 1
+                    for (int ch = 0; ch < BN / 32; ++ch) {
+                        tmem_ld32(taddr + ch * 32, va);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc ^= va[c];
+                    }
+                    if (acc == 0x12345678u) thr = 0.0f;   // keeps the loads alive
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(as ? l_tempty1 : l_tempty0);
             }
+            if (a.dbg == 3) { cnt = 0; thr = -INFINITY; }
             if (row_valid) { a.out_cnt[slot] = cnt; a.out_thr[slot] = thr; }
         }
     }
@@ -1069,7 +1101,10 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
                      double* ms_screen, double* ms_rescore) {
     const uint64_t m = x->rows;
     const bool cosine = p->metric == SFB_METRIC_COSINE;
-    const uint32_t cap = (kprime + 64 + 31) / 32 * 32;
+    uint32_t slack = 64;   // appends a row's buffer takes between two prunes (minus the 32 a chunk may add)
+    if (const char* e = getenv("SFB_SCREEN_SLACK")) { int v = atoi(e); if (v >= 64) slack = (uint32_t)v; }
+    uint32_t cap = (kprime + slack + 31) / 32 * 32;
+    if (cap > MAX_CAP) cap = MAX_CAP;
     const uint32_t tiles_total = (uint32_t)(P.mpad / BN);
     const bool use_pair = pair_kernel_applies(P);
     ScreenArgs sa{};
@@ -1097,6 +1132,7 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
         s2.chunk_tiles = (uint32_t)ct;
         s2.n_chunks = (s2.tiles_per_split + s2.chunk_tiles - 1) / s2.chunk_tiles;
         s2.kprime = kprime; s2.cap = cap; s2.nq32 = P.nq32.as<float>();
+        if (const char* e = getenv("SFB_SCREEN_DBG")) s2.dbg = (uint32_t)atoi(e);
         n_splits_used = s2.n_splits;
     } else {
         sa.n_rows = m; sa.q_begin = a_row0; sa.nq = nq; sa.kblocks = P.kpad / BK;
@@ -1123,7 +1159,20 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
     sa.n_splits = n_splits_used;
     {
         StageTimer t(ctx, nullptr);
+        if (use_pair && s2.dbg == 4) {
+            unsigned long long z[8] = {0}; int on = 1;
+            cudaMemcpyToSymbol(g_screen_dbg, z, sizeof z); cudaMemcpyToSymbol(g_prof_on, &on, sizeof on);
+        }
         if (use_pair) SFB_TRY(launch_screen_pair(ctx, P, p->metric, s2, a_base, a_rows));
+        if (use_pair && s2.dbg == 4) {
+            unsigned long long z[8]; int off = 0;
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpyFromSymbol(z, g_screen_dbg, sizeof z); cudaMemcpyToSymbol(g_prof_on, &off, sizeof off);
+            fprintf(stderr, "[sfb] screen dbg (warp 2 of %d CTAs): tiles %llu, wait-for-accumulator %.0f cyc/tile, slow path %.2f entries/tile at %.0f cyc, "
+                    "prunes %.3f calls/tile (%.2f rows each) at %.0f cyc\n", 2 * (ctx->sm_count / 2), z[6], z[6] ? (double)z[5] / z[6] : 0.0,
+                    z[6] ? (double)z[1] / z[6] : 0.0, z[1] ? (double)z[0] / z[1] : 0.0, z[6] ? (double)z[3] / z[6] : 0.0, z[3] ? (double)z[4] / z[3] : 0.0,
+                    z[3] ? (double)z[2] / z[3] : 0.0);
+        }
         else SFB_TRY(launch_screen<false>(ctx, P, p->metric, sa, m_blocks, a_base, a_rows));
         *ms_screen += t.stop();
         SFB_CUDA(ctx, cudaGetLastError());
