@@ -293,10 +293,11 @@ __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_
     }
 }
 
+// Cycle counters of the epilogue, compiled in only with -DSFB_SCREEN_PROFILE (they cost ~50 ms at C2 even when idle).
 // SFB_SCREEN_DBG=4: [0] cycles in the slow (hit) path, [1] slow-path entries, [2] cycles in prunes, [3] prune calls,
 // [4] rows pruned, [5] cycles waiting for a full accumulator, [6] tiles -- summed over warp 2 of every CTA
 __device__ unsigned long long g_screen_dbg[8];
-__device__ volatile int g_prof_on = 0;
+__device__ int g_prof_on = 0;
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
@@ -310,7 +311,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 template <bool L2>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const float* __restrict__ nqv, uint32_t col0, uint64_t n_rows,
                                              bool row_valid, float* my_key, uint32_t* my_idx, uint32_t& cnt, float& thr,
-                                             uint32_t cap, uint32_t kprime, int lane, bool prof_on = false) {
+                                             uint32_t cap, uint32_t kprime, int lane) {
     float key[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
@@ -323,9 +324,11 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     const float m = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
     const bool hit = m > thr;
     if (!__any_sync(FULL, hit)) return;
-    const bool prof = prof_on && lane == 0 && (threadIdx.x >> 5) == 2;
+#ifdef SFB_SCREEN_PROFILE
+    const bool prof = g_prof_on && lane == 0 && (threadIdx.x >> 5) == 2;
     long long t_in = 0;
     if (prof) t_in = clock64();
+#endif
     // (A warp-uniform variant -- one vote per group of 4, predicated appends -- was measured slower: 705 vs 658 ms.)
     if (hit && row_valid) {
 #pragma unroll
@@ -343,13 +346,19 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     const uint32_t need = __ballot_sync(FULL, cnt + 32 > cap);
     if (need) {
         __syncwarp();
+#ifdef SFB_SCREEN_PROFILE
         long long t_p = 0;
         if (prof) t_p = clock64();
+#endif
         if (cap <= 128) prune_rows<4>(need, my_key, my_idx, cnt, thr, kprime, lane);
         else prune_rows<8>(need, my_key, my_idx, cnt, thr, kprime, lane);
+#ifdef SFB_SCREEN_PROFILE
         if (prof) { atomicAdd(&g_screen_dbg[2], (unsigned long long)(clock64() - t_p)); atomicAdd(&g_screen_dbg[3], 1ull); atomicAdd(&g_screen_dbg[4], (unsigned long long)__popc(need)); }
+#endif
     }
+#ifdef SFB_SCREEN_PROFILE
     if (prof) { atomicAdd(&g_screen_dbg[0], (unsigned long long)(clock64() - t_in)); atomicAdd(&g_screen_dbg[1], 1ull); }
+#endif
 }
 
 template <bool L2, bool DUMP>
@@ -641,11 +650,15 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
                     for (int c = etid; c < BN; c += 128) dst[c] = (uint64_t)n0 + c < a.n_rows ? __ldg(a.nq32 + n0 + c) : INFINITY;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
+#ifdef SFB_SCREEN_PROFILE
                 const bool prof = a.dbg == 4 && lane == 0 && warp == 2;
                 long long t_w = 0;
                 if (prof) t_w = clock64();
+#endif
                 mbar_wait(&tfull_bar[as], aphase);
+#ifdef SFB_SCREEN_PROFILE
                 if (prof) { atomicAdd(&g_screen_dbg[5], (unsigned long long)(clock64() - t_w)); atomicAdd(&g_screen_dbg[6], 1ull); }
+#endif
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
                 const float* nqt = s_nq + as * BN;
@@ -656,10 +669,10 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
                     for (int ch = 0; ch < BN / 32; ch += 2) {
                         tmem_ld_wait();
                         tmem_ld32(taddr + (ch + 1) * 32, vb);   // in flight while chunk ch is filtered
-                        filter_chunk<L2>(va, nqt + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane, a.dbg == 4);
+                        filter_chunk<L2>(va, nqt + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
                         tmem_ld_wait();
                         if (ch + 2 < BN / 32) tmem_ld32(taddr + (ch + 2) * 32, va);
-                        filter_chunk<L2>(vb, nqt + (ch + 1) * 32, n0 + (ch + 1) * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane, a.dbg == 4);
+                        filter_chunk<L2>(vb, nqt + (ch + 1) * 32, n0 + (ch + 1) * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
                     }
                 } else if (a.dbg == 1) {
                     uint32_t acc = 0;
