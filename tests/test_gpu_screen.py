@@ -104,3 +104,51 @@ def test_knn_auto_uses_screen(sfb, oracle, ctx):
     g = ctx.matrix(x).knn(16, 0)
     assert g.stats()["screen_used"] == sfb.SCREEN_F16
     assert_knn_equal(g.to_host(), oracle.knn(x, 16, 0))
+
+
+def test_knn_screen_edge_shapes(sfb, oracle, ctx):
+    """Ragged and extreme shapes through the screen: k at the ABI maximum, more neighbours asked than rows can supply
+    under eps (counts < k, padded with IDX_NONE / +inf), a one-row query shard, a corpus that is not a multiple of the
+    256-row tile, K = 1 and a K that is not a multiple of 64."""
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(4321, 70))
+    mat = ctx.matrix(x)
+    # k = 128 (ABI maximum): k' = 192 leaves k + 64
+    assert_knn_equal(mat.knn(128, 1, screen=sfb.SCREEN_F16, q_begin=100, q_end=400).to_host(),
+                     oracle.knn(x, 128, 1, query_rows=np.arange(100, 400)))
+    # tight eps: most rows keep fewer than k neighbours
+    d = oracle.knn(x, 8, 0)[1]
+    eps = float(np.quantile(d[:, 3], 0.5))
+    got = mat.knn(8, 0, eps=eps, screen=sfb.SCREEN_F16).to_host()
+    want = oracle.knn(x, 8, 0, eps)
+    assert_knn_equal(got, want)
+    assert (got[2] < 8).any() and np.all(got[0][got[2] == 0] == sfb.IDX_NONE if (got[2] == 0).any() else True)
+    # single query row, last row of the matrix
+    assert_knn_equal(mat.knn(5, 2, screen=sfb.SCREEN_F16, q_begin=4320, q_end=4321).to_host(),
+                     oracle.knn(x, 5, 2, query_rows=np.array([4320])))
+    # one-dimensional rows: cosine is +-1 everywhere (ties by index), L2 is |a - b|
+    y = rng.normal(size=(4200, 1))
+    for metric in (0, 1):
+        assert_knn_equal(ctx.matrix(y).knn(4, metric, screen=sfb.SCREEN_F16).to_host(), oracle.knn(y, 4, metric))
+
+
+def test_knn_screen_non_finite_input(sfb, ctx):
+    """The reference would propagate NaN through its sort; the screen refuses non-finite rows for L2 instead of
+    returning an arbitrary order (cosine rows with non-finite norms become zero operands and fall back)."""
+    x = np.random.default_rng(12).normal(size=(4200, 16))
+    x[17, 3] = np.inf
+    with pytest.raises(sfb.SfbError):
+        ctx.matrix(x).knn(4, 1, screen=sfb.SCREEN_F16)
+
+
+def test_knn_three_levels(sfb, oracle, ctx):
+    """Tight clusters with a deliberately small k': level 1 leaves many rows uncertified, the k' = 192 re-screen
+    certifies most of them, the rest go to f64 brute force -- and the result is still the oracle's, bit for bit."""
+    m = ctx.generate(sfb.SYNTH_CLUSTERED, 3, 30000, 64, 16, 0.05)
+    x = oracle.generate_rows(1, 3, 0, 30000, 64, 16, 0.05)
+    g = m.knn(8, 0, screen=sfb.SCREEN_F16, k_prime=9)
+    st = g.stats()
+    assert st["rows_rescreened"] >= 32 and st["rows_fallback"] < st["rows_rescreened"]
+    assert st["rows_certified"] + st["rows_fallback"] == 30000
+    assert_knn_equal(g.to_host(), oracle.knn(x, 8, 0))
+    print(st)
