@@ -228,6 +228,28 @@ int32_t sfb_compute_taumode_lambdas(sfb_ctx* ctx, const sfb_csr* L, const double
                                     uint32_t n_features, int32_t tau_mode, double tau_value,
                                     double* out_lambdas);
 
+/* ---- successor Stage C: Bhattacharyya feature graph (f32 semantics) ---------------------------
+ * sfb_bc_adjacency_build = compute_bhattacharyya_weights (surfface-core/src/laplacian.rs:254-298) with
+ *   bhattacharyya_coefficient (surfface-core/src/distance.rs:260-290): means / variances are the centroid
+ *   state [C, F] row-major on the HOST (the reference pulls them to the CPU, laplacian.rs:157-158); nodes are
+ *   the F features; per node the k.min(F-1) largest BC > weight_threshold, order (BC desc, j asc).
+ *   Follow with sfb_laplacian_build {normalised, weight_threshold}: max-symmetrisation and L_sym / L as in
+ *   build_laplacian_flat (laplacian.rs:312-394).  Values are f32-exact numbers carried in f64.
+ * sfb_laplacian_stage_execute = LaplacianStage::execute (laplacian.rs:135-219) in one call. */
+typedef struct {
+    uint32_t k_neighbors;       /* default 15   (LaplacianConfig, laplacian.rs:49-77) */
+    float variance_regularizer; /* default 1e-6 */
+    int32_t normalize;          /* default 1    */
+    float weight_threshold;     /* default 1e-9 */
+} sfb_laplacian_config;
+
+int32_t sfb_bc_adjacency_build(sfb_ctx* ctx, const float* means, const float* variances, uint32_t n_centroids,
+                               uint32_t n_features, uint32_t k, float variance_regularizer, float weight_threshold,
+                               sfb_adj** out);
+/* degrees: n_features floats or NULL */
+int32_t sfb_laplacian_stage_execute(sfb_ctx* ctx, const float* means, const float* variances, uint32_t n_centroids,
+                                    uint32_t n_features, const sfb_laplacian_config* cfg, sfb_csr** out, float* degrees);
+
 /* ---- diagnostics ----------------------------------------------------------------------------
  * Raw tensor-core accumulators of one 128 x 256 tile of the screen (query rows row0.., corpus rows
  * from col0 rounded down to a multiple of 256) and the 16-bit operands used, as f32.  Lets the tests

@@ -545,3 +545,63 @@ class SfGrassSparsifier:
         a.sfgrass(self.target_ratio)
         idx, w, cnt = a.to_host()
         return [[(int(idx[i, t]), float(w[i, t])) for t in range(int(cnt[i]))] for i in range(n_nodes)]
+
+
+# ---- successor Stage C (surfface-core/src/laplacian.rs) ---------------------------------------------------------
+@dataclass
+class LaplacianConfig:
+    """surfface-core/src/laplacian.rs:49-77."""
+    k_neighbors: int = 15
+    variance_regularizer: float = 1e-6
+    normalize: bool = True
+    weight_threshold: float = 1e-9
+
+
+@dataclass
+class LaplacianOutput:
+    """surfface-core/src/laplacian.rs:84-99 (`matrix` is a device CSR handle; values are f32-exact)."""
+    matrix: Csr
+    n_features: int
+    nnz: int
+    degrees: np.ndarray
+    sparsity: float
+
+
+def bc_adjacency(means, variances, k, reg=1e-6, thr=1e-9, ctx=None) -> Adjacency:
+    """compute_bhattacharyya_weights (laplacian.rs:254-298): directed top-k Bhattacharyya affinities per feature."""
+    ctx = ctx or default_context()
+    m = np.ascontiguousarray(means, dtype=np.float32)
+    v = np.ascontiguousarray(variances, dtype=np.float32)
+    if m.ndim != 2 or m.shape != v.shape:
+        raise ValueError("means and variances must be [C, F] arrays of the same shape")
+    h = C.c_void_p()
+    ctx.check(lib().sfb_bc_adjacency_build(ctx._h, _ffi.ptr(m), _ffi.ptr(v), m.shape[0], m.shape[1], int(k), float(reg),
+                                           float(thr), C.byref(h)))
+    return Adjacency(ctx, h)
+
+
+class LaplacianStage:
+    """LaplacianStage (surfface-core/src/laplacian.rs:101-219)."""
+
+    def __init__(self, config: Optional[LaplacianConfig] = None):
+        self.config = config or LaplacianConfig()
+
+    @staticmethod
+    def with_defaults():
+        return LaplacianStage(LaplacianConfig())
+
+    def execute(self, means, variances, ctx=None) -> LaplacianOutput:
+        ctx = ctx or default_context()
+        m = np.ascontiguousarray(means, dtype=np.float32)
+        v = np.ascontiguousarray(variances, dtype=np.float32)
+        if m.ndim != 2 or m.shape != v.shape:
+            raise ValueError("means and variances must be [C, F] arrays of the same shape")
+        c, f = m.shape
+        cfg = _ffi.LaplacianConfigC(int(self.config.k_neighbors), float(self.config.variance_regularizer),
+                                    int(self.config.normalize), float(self.config.weight_threshold))
+        deg = np.empty(f, np.float32)
+        h = C.c_void_p()
+        ctx.check(lib().sfb_laplacian_stage_execute(ctx._h, _ffi.ptr(m), _ffi.ptr(v), c, f, C.byref(cfg), C.byref(h), _ffi.ptr(deg)))
+        L = Csr(ctx, h)
+        nnz = L.shape[1]
+        return LaplacianOutput(matrix=L, n_features=f, nnz=nnz, degrees=deg, sparsity=1.0 - nnz / float(f * f))

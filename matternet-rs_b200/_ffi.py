@@ -53,6 +53,11 @@ class GraphParamsC(C.Structure):
                 ("sigma", C.c_double), ("normalise", C.c_int32), ("sparsity_check", C.c_int32)]
 
 
+class LaplacianConfigC(C.Structure):
+    _fields_ = [("k_neighbors", C.c_uint32), ("variance_regularizer", C.c_float), ("normalize", C.c_int32),
+                ("weight_threshold", C.c_float)]
+
+
 class StageTimes(C.Structure):
     _fields_ = [("ms_h2d", C.c_double), ("ms_knn", C.c_double), ("ms_adjacency", C.c_double),
                 ("ms_laplacian", C.c_double), ("ms_lambda", C.c_double), ("ms_d2h", C.c_double),
@@ -106,6 +111,8 @@ SYMBOLS = {
     "sfb_compute_taumode_lambdas": (C.c_int32, [_P, _P, _P, C.c_uint64, C.c_uint32, C.c_int32, C.c_double, _P]),
     "sfb_debug_screen_tile": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P,
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
+    "sfb_bc_adjacency_build": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _PP]),
+    "sfb_laplacian_stage_execute": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(LaplacianConfigC), _PP, _P]),
     "sfb_timings": (C.c_int32, [_P, C.POINTER(StageTimes)]),
     "sfb_timings_reset": (C.c_int32, [_P]),
     "sfb_timer_start": (C.c_int32, [_P]),

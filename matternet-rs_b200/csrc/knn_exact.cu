@@ -351,6 +351,16 @@ int32_t sfb_row_norms(sfb_ctx* ctx, const sfb_mat* x, double* norms) {
     return SFB_OK;
 }
 
+// top-k (key asc, index asc) of every row of a dense m x m key matrix (shared with the Bhattacharyya graph, bc.cu)
+int32_t sfb_dense_select(sfb_ctx* ctx, const double* keys, uint32_t m, uint64_t q_begin, uint64_t nq, uint32_t k, double eps,
+                         uint32_t* out_idx, double* out_dist, uint32_t* out_cnt) {
+    const int wpb = 4;
+    size_t ssm = (size_t)wpb * k * (sizeof(double) + sizeof(uint32_t));
+    knn_dense_select_kernel<<<div_up(nq, wpb), wpb * 32, ssm, ctx->stream>>>(keys, m, q_begin, nq, k, eps, out_idx, out_dist, out_cnt);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
 bool sfb_dense_shape(uint64_t nodes, uint64_t dims) { return nodes <= 4096 && dims >= 8ull * nodes; }
 
 // kNN over few nodes with very long rows, from the DIMS-MAJOR matrix xd[kd][m] (see gram_tile_kernel).

@@ -71,6 +71,11 @@ def lib():
     L.orc_diffuse.argtypes = [_u64p, _u32p, _dp, _c.c_uint64, _dp, _c.c_uint64, _c.c_double,
                               _c.c_uint32]
     L.orc_transpose.argtypes = [_dp, _c.c_uint64, _c.c_uint64, _dp]
+    _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    L.orc_bc.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_float]
+    L.orc_bc.restype = _c.c_float
+    L.orc_bc_matrix.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_float, _fp]
+    L.orc_bc_knn.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_float, _c.c_float, _u32p, _fp, _u32p]
     _lib = L
     return L
 
@@ -212,3 +217,32 @@ def transpose(x):
     out = np.empty((x.shape[1], x.shape[0]), dtype=np.float64)
     lib().orc_transpose(x, x.shape[0], x.shape[1], out)
     return out
+
+
+# ---- successor Stage C: Bhattacharyya-coefficient feature graph (f32) --------------------------
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def bc(means, variances, i, j, reg=1e-6):
+    """bhattacharyya_coefficient (surfface-core/src/distance.rs:260-290) of features i, j of a [C, F] state."""
+    m, v = _f32(means), _f32(variances)
+    return float(lib().orc_bc(m, v, m.shape[0], m.shape[1], i, j, reg))
+
+
+def bc_matrix(means, variances, reg=1e-6):
+    m, v = _f32(means), _f32(variances)
+    out = np.empty((m.shape[1], m.shape[1]), np.float32)
+    lib().orc_bc_matrix(m, v, m.shape[0], m.shape[1], reg, out)
+    return out
+
+
+def bc_knn(means, variances, k, reg=1e-6, thr=1e-9):
+    """compute_bhattacharyya_weights (surfface-core/src/laplacian.rs:254-298): (idx [F,k], w [F,k] f32, cnt [F])."""
+    m, v = _f32(means), _f32(variances)
+    f = m.shape[1]
+    idx = np.empty((f, k), np.uint32)
+    w = np.empty((f, k), np.float32)
+    cnt = np.empty(f, np.uint32)
+    lib().orc_bc_knn(m, v, m.shape[0], f, k, reg, thr, idx, w, cnt)
+    return idx, w, cnt

@@ -801,3 +801,74 @@ void orc_transpose(const double* x, uint64_t rows, uint64_t cols, double* out) {
     for (int64_t c = 0; c < (int64_t)cols; ++c)
         for (uint64_t r = 0; r < rows; ++r) out[(size_t)c * rows + r] = x[(size_t)r * cols + c];
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Successor Stage C ("next" row of the scope table): Bhattacharyya-coefficient kNN over the feature
+ * nodes, f32 arithmetic as in the reference.
+ *   bhattacharyya_coefficient      surfface-core/src/distance.rs:260-290
+ *   compute_bhattacharyya_weights  surfface-core/src/laplacian.rs:254-298
+ * means / vars are the centroid state [C, F] row-major (feature i at centroid c = a[c*F + i]); the
+ * reference transposes first (laplacian.rs:165-166), the arithmetic per pair is the same left fold over c.
+ * The reference's sort is unstable with no tie-break; the contract is (BC desc, j asc).
+ * libm: logf / expf here are glibc's, the reference's are the platform's -- its own tests compare at 1e-5.
+ * ------------------------------------------------------------------------------------------ */
+float orc_bc(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t i, uint32_t j, float reg) {
+    float db = 0.0f;
+    for (uint32_t cc = 0; cc < c; ++cc) {
+        float vi = vars[(size_t)cc * f + i], vj = vars[(size_t)cc * f + j];
+        vi = vi > reg ? vi : reg;                       /* f32::max: NaN-ignoring, like fmaxf */
+        vj = vj > reg ? vj : reg;
+        if (vars[(size_t)cc * f + i] != vars[(size_t)cc * f + i]) vi = reg;
+        if (vars[(size_t)cc * f + j] != vars[(size_t)cc * f + j]) vj = reg;
+        float v_sum = vi + vj;
+        float dm = means[(size_t)cc * f + i] - means[(size_t)cc * f + j];
+        float mean_term = (dm * dm) / (4.0f * v_sum);
+        float log_term = 0.5f * logf(v_sum / (2.0f * sqrtf(vi * vj)));
+        db += mean_term + log_term;
+    }
+    float bc = expf(-db);
+    if (bc < 0.0f) bc = 0.0f;
+    if (bc > 1.0f) bc = 1.0f;
+    return bc;
+}
+
+void orc_bc_matrix(const float* means, const float* vars, uint32_t c, uint32_t f, float reg, float* out /* f*f */) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < (int64_t)f; ++i)
+        for (uint32_t j = 0; j < f; ++j) out[(size_t)i * f + j] = orc_bc(means, vars, c, f, (uint32_t)i, j, reg);
+}
+
+typedef struct { float w; uint32_t j; } orc_bc_pair;
+static int orc_bc_cmp(const void* a, const void* b) {
+    const orc_bc_pair* x = (const orc_bc_pair*)a; const orc_bc_pair* y = (const orc_bc_pair*)b;
+    if (x->w > y->w) return -1;
+    if (x->w < y->w) return 1;
+    return x->j < y->j ? -1 : (x->j > y->j ? 1 : 0);
+}
+
+/* out_idx / out_w: f x k (padded with IDX_NONE / 0), out_cnt: f */
+void orc_bc_knn(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t k, float reg, float thr,
+                uint32_t* out_idx, float* out_w, uint32_t* out_cnt) {
+    uint32_t kk = k < (f ? f - 1 : 0) ? k : (f ? f - 1 : 0);
+#pragma omp parallel
+    {
+        orc_bc_pair* sc = (orc_bc_pair*)malloc(sizeof(orc_bc_pair) * (size_t)(f ? f : 1));
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t i = 0; i < (int64_t)f; ++i) {
+            uint32_t n = 0;
+            for (uint32_t j = 0; j < f; ++j) {
+                if (j == (uint32_t)i) continue;
+                float w = orc_bc(means, vars, c, f, (uint32_t)i, j, reg);
+                if (w > thr) { sc[n].w = w; sc[n].j = j; ++n; }
+            }
+            qsort(sc, n, sizeof(orc_bc_pair), orc_bc_cmp);
+            uint32_t keep = n < kk ? n : kk;
+            for (uint32_t t = 0; t < k; ++t) {
+                out_idx[(size_t)i * k + t] = t < keep ? sc[t].j : ORC_IDX_NONE;
+                out_w[(size_t)i * k + t] = t < keep ? sc[t].w : 0.0f;
+            }
+            out_cnt[i] = keep;
+        }
+        free(sc);
+    }
+}

@@ -356,3 +356,51 @@ def test_config_c1_exact(sfb, oracle, ctx):
     assert a.sparsified and o_adj[3]
     # weights: glibc pow(r, 2.0) vs the device's exactly rounded r*r may differ in the last bit
     assert_csr_equal(a.laplacian().to_host(), oracle.laplacian(*o_adj[:3]))
+
+
+# ---- successor Stage C: Bhattacharyya feature graph (f32 semantics, 1e-5 like the reference's own tests) ------
+def _bc_state(seed, c, f):
+    rng = np.random.default_rng(seed)
+    means = rng.normal(size=(c, f)).astype(np.float32)
+    variances = rng.uniform(0.05, 2.0, size=(c, f)).astype(np.float32)
+    variances[0, :5] = 0.0          # below the variance floor
+    means[:, 7] = means[:, 3]; variances[:, 7] = variances[:, 3]   # a duplicated feature: BC = 1, ties by index
+    return means, variances
+
+
+@pytest.mark.parametrize("c,f,k", [(40, 150, 15), (7, 33, 40), (300, 64, 5)])
+def test_bc_adjacency_parity(sfb, oracle, ctx, c, f, k):
+    means, variances = _bc_state(c + f, c, f)
+    idx, w, cnt = sfb.bc_adjacency(means, variances, k, ctx=ctx).to_host()
+    kk = min(k, f - 1)
+    o_idx, o_w, o_cnt = oracle.bc_knn(means, variances, kk)
+    assert idx.shape == (f, kk) and np.array_equal(cnt, o_cnt)
+    np.testing.assert_allclose(w, o_w.astype(np.float64), rtol=1e-5, atol=1e-12)
+    B = oracle.bc_matrix(means, variances).astype(np.float64)
+    differ = np.argwhere(idx != o_idx)
+    for r, t in differ:   # only near-ties (logf / expf last-bit differences) may swap places
+        assert abs(B[r, idx[r, t]] - B[r, o_idx[r, t]]) <= 1e-5 * B[r, o_idx[r, t]]
+    assert len(differ) <= 0.02 * idx.size
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_laplacian_stage_execute(sfb, oracle, ctx, normalize):
+    """LaplacianStage::execute (laplacian.rs:135-219): BC kNN -> max-symmetrise -> L_sym or D - W."""
+    means, variances = _bc_state(5, 30, 90)
+    cfg = sfb.LaplacianConfig(k_neighbors=12, normalize=normalize)
+    out = sfb.LaplacianStage(cfg).execute(means, variances, ctx=ctx)
+    assert out.n_features == 90 and out.matrix.shape[0] == 90
+    indptr, indices, data = out.matrix.to_host()
+    o_idx, o_w, o_cnt = oracle.bc_knn(means, variances, 12)
+    o_ptr, o_ind, o_dat = oracle.laplacian(o_idx, o_w.astype(np.float64), o_cnt, normalised=normalize, weight_threshold=1e-9)
+    assert np.array_equal(indptr, o_ptr) and np.array_equal(indices, o_ind)
+    np.testing.assert_allclose(data, o_dat, rtol=1e-5, atol=1e-9)
+    u_ptr, u_ind, u_dat = oracle.laplacian(o_idx, o_w.astype(np.float64), o_cnt, normalised=False)
+    deg = np.array([u_dat[s:e][u_ind[s:e] == r][0] for r, (s, e) in enumerate(zip(u_ptr[:-1].astype(int), u_ptr[1:].astype(int)))])
+    np.testing.assert_allclose(out.degrees, deg, rtol=1e-5)
+    if normalize:   # diag = 1, Rayleigh quotients in [0, 2] (tests/test_laplacian.rs:16-114)
+        row_of = np.repeat(np.arange(90), np.diff(indptr.astype(np.int64)))
+        assert np.allclose(data[indices == row_of], 1.0)
+        x = np.random.default_rng(0).normal(size=90)
+        r = out.matrix.rayleigh_quotient(x)
+        assert -1e-6 <= r <= 2.0 + 1e-6

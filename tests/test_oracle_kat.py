@@ -299,3 +299,33 @@ def test_generator_statistics(oracle):
     assert np.array_equal(x[1000:1010], y)
     c = oracle.generate_rows(1, 7, 0, 2000, 32, n_centres=8, noise=0.3)
     assert c.shape == (2000, 32) and np.all(np.isfinite(c))
+
+
+# ---- successor Stage C: Bhattacharyya coefficient (surfface-core/src/distance.rs:260-290) --------------------
+def test_bhattacharyya_kats(oracle):
+    """Identical distributions => BC = 1 (tests/test_distance.rs:10-25); unit variances, mean gap d => exp(-d^2/8);
+    equal means, variances (1, 4) => sqrt(2*1*2/(1+4)) per centroid; symmetric; decays with separation
+    (tests/test_distance.rs:412-470); variances below the floor are clamped to it."""
+    m = np.array([[0.0, 0.0, 1.0, 3.0]], np.float32)
+    v = np.array([[1.0, 1.0, 1.0, 1.0]], np.float32)
+    assert oracle.bc(m, v, 0, 1) == 1.0
+    assert oracle.bc(m, v, 0, 2) == pytest.approx(math.exp(-1.0 / 8.0), rel=1e-6)
+    assert oracle.bc(m, v, 0, 3) == pytest.approx(math.exp(-9.0 / 8.0), rel=1e-6)
+    assert oracle.bc(m, v, 0, 2) == oracle.bc(m, v, 2, 0)
+    assert oracle.bc(m, v, 0, 1) > oracle.bc(m, v, 0, 2) > oracle.bc(m, v, 0, 3)
+    m2 = np.zeros((3, 2), np.float32)
+    v2 = np.array([[1.0, 4.0]] * 3, np.float32)
+    assert oracle.bc(m2, v2, 0, 1) == pytest.approx((2.0 * 1.0 * 2.0 / 5.0) ** 1.5, rel=1e-6)   # (2 s_i s_j / (v_i + v_j))^(C/2)
+    v3 = np.array([[0.0, 1e-9]], np.float32)
+    assert oracle.bc(np.zeros((1, 2), np.float32), v3, 0, 1, reg=1e-6) == 1.0
+
+
+def test_bhattacharyya_knn_order_and_threshold(oracle):
+    """Top-k by (BC desc, j asc), k.min(F-1), BC <= threshold dropped (laplacian.rs:254-298)."""
+    m = np.array([[0.0, 0.5, 0.5, 40.0, 0.1]], np.float32)
+    v = np.ones((1, 5), np.float32)
+    idx, w, cnt = oracle.bc_knn(m, v, 3, thr=1e-9)
+    assert list(idx[0]) == [4, 1, 2] and cnt[0] == 3          # 1 and 2 tie: index order
+    assert cnt[3] == 0 and np.all(idx[3] == oracle.IDX_NONE)  # BC(3, .) ~ exp(-200) underflows below the threshold
+    idx, w, cnt = oracle.bc_knn(m, v, 10)
+    assert cnt[0] == 3 and idx.shape == (5, 10)               # feature 3 is out of reach of everyone
