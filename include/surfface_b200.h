@@ -102,7 +102,7 @@ typedef struct {
     uint32_t k;        /* neighbours kept per row, self excluded (GraphParams.topk)          */
     double eps;        /* keep d <= eps; +inf disables (GraphParams.eps)                     */
     int32_t screen;    /* sfb_screen                                                         */
-    uint32_t k_prime;  /* screen candidates per row at the first level (0 = default max(2k, 32)) */
+    uint32_t k_prime;  /* screen candidates per row at the first level (0 = default max(1.5k, 32)) */
     uint64_t q_begin;  /* query-row shard [q_begin, q_end); q_end = 0 means all rows         */
     uint64_t q_end;
     int32_t allow_fallback; /* 0: return SFB_EUNCERTIFIED instead of recomputing rows exactly */

@@ -1232,7 +1232,7 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     // Measured at C2 (k = 16): k' = 96 / 64 / 48 / 32 / 24 take 814 / 717 / 689 / 662 / 645 ms of screen and leave
     // 0 / 0 / 0 / 9 / 3366 rows to the next level.
     const uint32_t kp_max = MAX_CAP - 64;
-    uint32_t kprime = p->k_prime ? p->k_prime : (2 * p->k + 7) / 8 * 8;
+    uint32_t kprime = p->k_prime ? p->k_prime : (3 * p->k / 2 + 7) / 8 * 8;   // 1.5k (C5-like, k = 64: k' = 128 / 96 -> 980 / 895 ms), at least 32
     bool kp_forced = p->k_prime != 0;
     if (const char* e = getenv("SFB_SCREEN_KPRIME")) { int v = atoi(e); if (v > 0 && !p->k_prime) { kprime = (uint32_t)v; kp_forced = true; } }  // tuning aid
     if (kprime < 32 && !kp_forced) kprime = 32;
