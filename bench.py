@@ -40,6 +40,8 @@ WORKLOADS = {
                metric=0, k=16),
     "c2": dict(name="C2 1M x 384 clustered, cosine k=16 + Laplacian + taumode lambda", rows=1_000_000, cols=384, kind=1,
                seed=7, centres=1024, noise=0.3, metric=0, k=16),
+    "c3": dict(name="C3 10M x 768 clustered, L2 k=16 + lambda, query-row sharded", rows=10_000_000, cols=768, kind=1, seed=11,
+               centres=4096, noise=0.3, metric=1, k=16),
     "c4": dict(name="C4 100k x 3072 anisotropic, cosine k=32", rows=100_000, cols=3072, kind=2, seed=13, centres=0,
                noise=0.1, metric=0, k=32),
     "c5": dict(name="C5 5M x 128 clustered, L2 k=64", rows=5_000_000, cols=128, kind=1, seed=17, centres=2048, noise=0.5,

@@ -1073,6 +1073,7 @@ int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2A
         sa.resident = sa.kblocks; sa.stage_bytes = P_SLAB_BYTES;
         size_t stages = room - sa.kblocks;
         sa.stages = (uint32_t)(stages > 8 ? 8 : stages);
+        if (const char* e = getenv("SFB_SCREEN_STAGES")) { int v = atoi(e); if (v >= 2 && (uint32_t)v <= sa.stages) sa.stages = (uint32_t)v; }
     } else {
         // K > 512: keep what fits beside four 32 KB stages, stream the remaining query slabs with the corpus
         sa.stages = 4; sa.stage_bytes = 2 * P_SLAB_BYTES;
