@@ -294,7 +294,7 @@ def run_ours(args):
         if args.config == "c2" and not args.rows and world == 1 and os.path.exists(tpath):
             tj = json.load(open(tpath))   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
-        roof = {"kernel": "knn_screen_pair_kernel" if d <= 512 else "knn_screen_kernel", "bound": "tensor", "achieved": ach,
+        roof = {"kernel": "knn_screen_pair_kernel", "bound": "tensor", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "ms_per_launch": scr_ms, "flops_per_launch": flops,
                 "peak_source": pk["source"] + (", sustained" if scr_ms > 100 else ", burst")}
