@@ -206,6 +206,14 @@ int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_l
  * X <- X - eta * X L^T, `steps` times, in place on the device matrix. */
 int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, double eta, uint32_t steps);
 
+/* Energy pipeline, item -> sub-centroid mapping (src_legacy/energymaps.rs:1246-1342): nearest sub-centroid in
+ * lambda space (first strict minimum of |lambda_item - lambda_s|), ties within epsilon (1e-11 in the reference)
+ * broken by the strictly largest cosine in ascending s.  item_lambdas: N, sub_lambdas: S (host).  out_idx: N;
+ * out_lambda (the chosen sub-centroid's lambda) and out_norm (|item|): N or NULL. */
+int32_t sfb_map_items_to_subcentroids(sfb_ctx* ctx, const sfb_mat* items, const double* item_lambdas,
+                                      const sfb_mat* sub_centroids, const double* sub_lambdas, double epsilon,
+                                      uint32_t* out_idx, double* out_lambda, double* out_norm);
+
 /* ---- reference-shaped one-shot entry points (host buffers in, host buffers out) ------------
  * sfb_build_laplacian_matrix = build_laplacian_matrix(transposed, &GraphParams, ..)
  *   (src_legacy/laplacian.rs:122-180): `items` is the already-transposed matrix, nodes = rows.

@@ -209,6 +209,15 @@ class Matrix(_Handle):
         assert kp.value == kpad
         return tile, qr, qc, sc.value
 
+    def map_to_subcentroids(self, item_lambdas, sub_centroids, sub_lambdas, epsilon=1e-11):
+        """Energy pipeline (energymaps.rs:1246-1342): (index of the chosen sub-centroid, its lambda, |item|) per row."""
+        n = self.shape[0]
+        il, sl = _ffi.f64(item_lambdas), _ffi.f64(sub_lambdas)
+        idx = np.empty(n, np.uint32); lam = np.empty(n, np.float64); norm = np.empty(n, np.float64)
+        self.ctx.check(lib().sfb_map_items_to_subcentroids(self.ctx._h, self._h, _ffi.ptr(il), sub_centroids._h, _ffi.ptr(sl),
+                                                           float(epsilon), _ffi.ptr(idx), _ffi.ptr(lam), _ffi.ptr(norm)))
+        return idx, lam, norm
+
     def diffuse(self, L, eta, steps):
         self.ctx.check(lib().sfb_diffuse(self.ctx._h, L._h, self._h, float(eta), int(steps)))
         return self

@@ -113,6 +113,7 @@ SYMBOLS = {
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_double)]),
     "sfb_bc_adjacency_build": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _PP]),
     "sfb_laplacian_stage_execute": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(LaplacianConfigC), _PP, _P]),
+    "sfb_map_items_to_subcentroids": (C.c_int32, [_P, _P, _P, _P, _P, C.c_double, _P, _P, _P]),
     "sfb_timings": (C.c_int32, [_P, C.POINTER(StageTimes)]),
     "sfb_timings_reset": (C.c_int32, [_P]),
     "sfb_timer_start": (C.c_int32, [_P]),

@@ -384,6 +384,88 @@ extern "C" int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, 
     return SFB_OK;
 }
 
+// ---- energy pipeline: item -> sub-centroid mapping (src_legacy/energymaps.rs:1246-1342) ----------------------
+// One warp per item.  The |delta lambda| scan over the S sub-centroids is a lexicographic (distance, index) warp
+// minimum, i.e. the reference's "first strictly smaller"; ties within epsilon are rare, and only then are cosines
+// computed: lane = candidate, each lane running the reference's left folds (dot, |centroid|^2) so the strict
+// comparison between candidates sees the reference's bits.
+namespace {
+__global__ void map_items_kernel(const double* __restrict__ x, uint64_t n, uint32_t f, const double* __restrict__ item_lam,
+                                 const double* __restrict__ subc, uint32_t s, const double* __restrict__ sub_lam, double eps,
+                                 uint32_t* __restrict__ out_idx, double* __restrict__ out_lam, double* __restrict__ out_norm) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const double* xi = x + i * f;
+    const double li = item_lam[i];
+    double bd = INFINITY; uint32_t bi = 0xFFFFFFFFu;
+    for (uint32_t c = lane; c < s; c += 32) { double d = fabs(li - sub_lam[c]); if (d < bd) { bd = d; bi = c; } }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        double od = __shfl_xor_sync(FULL, bd, o); uint32_t oi = __shfl_xor_sync(FULL, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    // |item| = sqrt of the left-fold sum of squares: lane 0 folds (F steps), the others count candidates meanwhile
+    double nsq = 0.0;
+    if (lane == 0) for (uint32_t t = 0; t < f; ++t) nsq = __dadd_rn(nsq, __dmul_rn(xi[t], xi[t]));
+    nsq = __shfl_sync(FULL, nsq, 0);
+    const double norm = __dsqrt_rn(nsq);
+    uint32_t ncand = 0;
+    for (uint32_t c = lane; c < s; c += 32) ncand += fabs(fabs(li - sub_lam[c]) - bd) < eps ? 1u : 0u;
+    ncand = warp_sum_u(ncand);
+    uint32_t best = bi;
+    if (ncand > 1) {
+        double best_cos = -INFINITY; uint32_t best_sc = 0xFFFFFFFFu;
+        for (uint32_t c0 = 0; c0 < s; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const bool cand = c < s && fabs(fabs(li - sub_lam[c]) - bd) < eps;
+            if (!__any_sync(FULL, cand)) continue;
+            double cosv = -INFINITY;
+            if (cand) {
+                const double* y = subc + (uint64_t)c * f;
+                double dot = 0.0, cn = 0.0;
+                for (uint32_t t = 0; t < f; ++t) { dot = __dadd_rn(dot, __dmul_rn(xi[t], y[t])); cn = __dadd_rn(cn, __dmul_rn(y[t], y[t])); }
+                const double cnorm = __dsqrt_rn(cn);
+                cosv = (norm > 0.0 && cnorm > 0.0) ? __ddiv_rn(dot, __dmul_rn(norm, cnorm)) : 0.0;
+            }
+            // strictly-greater in ascending candidate order == lexicographic max of (cosine, -index)
+            double mc = cosv; uint32_t mi = cand ? c : 0xFFFFFFFFu;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                double oc = __shfl_xor_sync(FULL, mc, o); uint32_t oi = __shfl_xor_sync(FULL, mi, o);
+                if (oc > mc || (oc == mc && oi < mi)) { mc = oc; mi = oi; }
+            }
+            if (mi != 0xFFFFFFFFu && mc > best_cos) { best_cos = mc; best_sc = mi; }
+        }
+        if (best_sc != 0xFFFFFFFFu) best = best_sc;
+    }
+    if (lane == 0) { out_idx[i] = best; out_lam[i] = sub_lam[best]; out_norm[i] = norm; }
+}
+}  // namespace
+
+extern "C" int32_t sfb_map_items_to_subcentroids(sfb_ctx* ctx, const sfb_mat* items, const double* item_lambdas, const sfb_mat* sub_centroids,
+                                                 const double* sub_lambdas, double epsilon, uint32_t* out_idx, double* out_lambda,
+                                                 double* out_norm) {
+    if (!ctx || !items || !item_lambdas || !sub_centroids || !sub_lambdas || !out_idx) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (items->cols != sub_centroids->cols) return sfb_fail(ctx, SFB_EINVAL, "items have %u features, sub-centroids %u", items->cols, sub_centroids->cols);
+    if (sub_centroids->rows == 0 || sub_centroids->rows > 0xFFFFFFFEull) return sfb_fail(ctx, SFB_EINVAL, "bad sub-centroid count");
+    const uint64_t n = items->rows; const uint32_t s = (uint32_t)sub_centroids->rows;
+    StageTimer t(ctx, &ctx->times.ms_lambda);
+    DevBuf il, sl, oi, ol, on;
+    SFB_CUDA(ctx, il.alloc(sizeof(double) * n)); SFB_CUDA(ctx, sl.alloc(sizeof(double) * s));
+    SFB_CUDA(ctx, oi.alloc(sizeof(uint32_t) * n)); SFB_CUDA(ctx, ol.alloc(sizeof(double) * n)); SFB_CUDA(ctx, on.alloc(sizeof(double) * n));
+    SFB_CUDA(ctx, cudaMemcpyAsync(il.p, item_lambdas, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    SFB_CUDA(ctx, cudaMemcpyAsync(sl.p, sub_lambdas, sizeof(double) * s, cudaMemcpyHostToDevice, ctx->stream));
+    map_items_kernel<<<div_up(n * 32, 256), 256, 0, ctx->stream>>>(items->d, n, items->cols, il.as<double>(), sub_centroids->d, s, sl.as<double>(), epsilon,
+                                                                   oi.as<uint32_t>(), ol.as<double>(), on.as<double>());
+    SFB_LAUNCH_CHECK(ctx);
+    SFB_CUDA(ctx, cudaMemcpyAsync(out_idx, oi.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_lambda) SFB_CUDA(ctx, cudaMemcpyAsync(out_lambda, ol.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_norm) SFB_CUDA(ctx, cudaMemcpyAsync(out_norm, on.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFB_OK;
+}
+
 extern "C" int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, double eta, uint32_t steps) {
     if (!ctx || !L || !x) return sfb_fail(ctx, SFB_EINVAL, "null argument");
     if (L->rows != x->cols) return sfb_fail(ctx, SFB_EINVAL, "Laplacian rows %llu must match feature count %u", (unsigned long long)L->rows, x->cols);  // energymaps.rs:507-512

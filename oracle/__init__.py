@@ -72,6 +72,7 @@ def lib():
                               _c.c_uint32]
     L.orc_transpose.argtypes = [_dp, _c.c_uint64, _c.c_uint64, _dp]
     _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    L.orc_map_items.argtypes = [_dp, _c.c_uint64, _c.c_uint32, _dp, _dp, _c.c_uint32, _dp, _c.c_double, _u32p, _dp, _dp]
     L.orc_bc.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_float]
     L.orc_bc.restype = _c.c_float
     L.orc_bc_matrix.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_float, _fp]
@@ -246,3 +247,15 @@ def bc_knn(means, variances, k, reg=1e-6, thr=1e-9):
     cnt = np.empty(f, np.uint32)
     lib().orc_bc_knn(m, v, m.shape[0], f, k, reg, thr, idx, w, cnt)
     return idx, w, cnt
+
+
+def map_items(items, item_lambdas, sub_centroids, sub_lambdas, epsilon=1e-11):
+    """Item -> sub-centroid mapping by |delta lambda| with cosine tie-break (energymaps.rs:1246-1342)."""
+    x = np.ascontiguousarray(items, dtype=np.float64)
+    sc = np.ascontiguousarray(sub_centroids, dtype=np.float64)
+    il = np.ascontiguousarray(item_lambdas, dtype=np.float64)
+    sl = np.ascontiguousarray(sub_lambdas, dtype=np.float64)
+    n, f = x.shape
+    idx = np.empty(n, np.uint32); lam = np.empty(n, np.float64); norm = np.empty(n, np.float64)
+    lib().orc_map_items(x, n, f, il, sc, sc.shape[0], sl, float(epsilon), idx, lam, norm)
+    return idx, lam, norm

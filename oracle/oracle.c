@@ -872,3 +872,41 @@ void orc_bc_knn(const float* means, const float* vars, uint32_t c, uint32_t f, u
         free(sc);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Energy pipeline, item -> sub-centroid mapping (src_legacy/energymaps.rs:1246-1342):
+ *   best = first s minimising |lambda_item - lambda_s| (strict <, ascending s);
+ *   candidates = { s : | |lambda_item - lambda_s| - best_dist | < epsilon } (epsilon = 1e-11 in the reference);
+ *   more than one: the candidate with the strictly largest cosine to the item (ascending s; cosine = 0 when either
+ *   norm is 0; dot and |centroid|^2 are left folds over the features);
+ *   returns (index, lambda of the chosen sub-centroid, |item| as sqrt of the left-fold sum of squares).
+ * ------------------------------------------------------------------------------------------ */
+void orc_map_items(const double* items, uint64_t n, uint32_t f, const double* item_lambdas, const double* subc, uint32_t s,
+                   const double* sub_lambdas, double epsilon, uint32_t* out_idx, double* out_lambda, double* out_norm) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        const double* x = items + (size_t)i * f;
+        const double li = item_lambdas[i];
+        uint32_t best = 0; double best_d = INFINITY;
+        for (uint32_t c = 0; c < s; ++c) { double d = fabs(li - sub_lambdas[c]); if (d < best_d) { best_d = d; best = c; } }
+        double nsq = 0.0;
+        for (uint32_t t = 0; t < f; ++t) nsq += x[t] * x[t];
+        const double norm = sqrt(nsq);
+        uint32_t ncand = 0;
+        for (uint32_t c = 0; c < s; ++c) if (fabs(fabs(li - sub_lambdas[c]) - best_d) < epsilon) ++ncand;
+        if (ncand > 1) {
+            double best_cos = -INFINITY; uint32_t best_sc = best;
+            for (uint32_t c = 0; c < s; ++c) {
+                if (!(fabs(fabs(li - sub_lambdas[c]) - best_d) < epsilon)) continue;
+                const double* y = subc + (size_t)c * f;
+                double dot = 0.0, cn = 0.0;
+                for (uint32_t t = 0; t < f; ++t) { dot += x[t] * y[t]; cn += y[t] * y[t]; }
+                double cnorm = sqrt(cn);
+                double cosv = (norm > 0.0 && cnorm > 0.0) ? dot / (norm * cnorm) : 0.0;
+                if (cosv > best_cos) { best_cos = cosv; best_sc = c; }
+            }
+            best = best_sc;
+        }
+        out_idx[i] = best; out_lambda[i] = sub_lambdas[best]; out_norm[i] = norm;
+    }
+}

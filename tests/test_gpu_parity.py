@@ -404,3 +404,21 @@ def test_laplacian_stage_execute(sfb, oracle, ctx, normalize):
         x = np.random.default_rng(0).normal(size=90)
         r = out.matrix.rayleigh_quotient(x)
         assert -1e-6 <= r <= 2.0 + 1e-6
+
+
+# ---- energy pipeline: item -> sub-centroid mapping (energymaps.rs:1246-1342) ------------------------------------
+def test_map_items_to_subcentroids(sfb, oracle, ctx):
+    rng = np.random.default_rng(21)
+    n, f, s = 5000, 24, 67
+    x = rng.normal(size=(n, f)); x[11] = 0.0
+    sc = rng.normal(size=(s, f)); sc[5] = 0.0
+    sl = rng.uniform(0, 1, s)
+    sl[40] = sl[7]; sl[41] = sl[7]; sl[12] = sl[3]          # exact lambda ties -> cosine tie-break
+    il = rng.uniform(-0.1, 1.1, n)
+    il[:200] = sl[7]; il[200:300] = sl[3]; il[300:320] = (sl[3] + sl[12]) / 2 + 5e-12
+    sl[20] = 0.25; sl[21] = 0.75; il[320:340] = 0.5           # equidistant from two sub-centroids
+    want = oracle.map_items(x, il, sc, sl)
+    got = ctx.matrix(x).map_to_subcentroids(il, ctx.matrix(sc), sl)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    assert len(set(want[0][:200])) > 1                        # the tie-break really decided
