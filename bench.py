@@ -136,6 +136,9 @@ def build_once(sfb, ctx, X, wl, rank, world, out_lambda=None, keep=False):
     """One full build on device-resident X.  Returns (handles or None, stats)."""
     n, d = X.shape
     lo, hi = shard(n, rank, world)
+    # the feature graph (the reference's call shape: nodes = columns) is registered first and runs on a side stream
+    # beside the item graph's tensor-core screen; .end() joins it
+    pend = X.knn_columns_begin(min(wl["k"], d - 1), sfb.METRIC_COSINE, sharded=world > 1)
     g = _timed(ctx, "knn", lambda: X.knn(wl["k"], wl["metric"], q_begin=lo, q_end=hi))
     st = g.stats()
     if world > 1:
@@ -144,8 +147,8 @@ def build_once(sfb, ctx, X, wl, rank, world, out_lambda=None, keep=False):
         g = g_all
     adj = _timed(ctx, "adjacency", lambda: g.adjacency(P_WEIGHT, SIGMA))
     L = _timed(ctx, "laplacian", lambda: adj.laplacian())
-    # feature graph (the reference's call shape) + per-item lambda
-    gf = _timed(ctx, "knn_columns", lambda: X.knn_columns(min(wl["k"], d - 1), sfb.METRIC_COSINE, sharded=world > 1))
+    # feature Laplacian + per-item lambda
+    gf = _timed(ctx, "knn_columns", lambda: pend.end())
     adjf = _timed(ctx, "adjacency_f", lambda: gf.adjacency(P_WEIGHT, SIGMA))
     Lf = _timed(ctx, "laplacian_f", lambda: adjf.laplacian())
     xs = X.view_rows(lo, hi - lo)

@@ -136,6 +136,15 @@ int32_t sfb_knn_from_host(sfb_ctx* ctx, const uint32_t* idx, const double* dist,
                           uint64_t rows, uint32_t k, sfb_knn** out);
 void sfb_knn_free(sfb_knn* g);
 
+/* The feature graph hidden behind the item graph's screen: _begin registers the exact f64 pair sums of the
+ * columns of x (feature-graph shape only; anything else is computed in _end by the plain path); the next
+ * sfb_knn_build on this context launches them on a side stream beside its tensor-core kernel; _end joins
+ * (all-reduces when sharded != 0: collective, like sfb_knn_build_columns_sharded) and returns the graph.
+ * x must stay alive and unchanged until _end; one pending build per context. */
+typedef struct sfb_pending sfb_pending;
+int32_t sfb_knn_build_columns_begin(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* params, int32_t sharded, sfb_pending** out);
+int32_t sfb_knn_build_columns_end(sfb_ctx* ctx, sfb_pending* pending, sfb_knn** out);
+
 /* ---- kernel weights + sparsification -------------------------------------------------------
  * sfb_adjacency_build: src_legacy/laplacian.rs:231-290 -- w = 1/(1+(d/sigma)^p), keep w > 1e-12;
  *   inline sparsification when mean degree > 10: score = w*sqrt(deg_i*deg_j), rows with more than

@@ -196,6 +196,14 @@ class Matrix(_Handle):
         self.ctx.check(fn(self.ctx._h, self._h, C.byref(p), C.byref(h)))
         return KnnGraph(self.ctx, h)
 
+    def knn_columns_begin(self, k, metric=METRIC_COSINE, eps=math.inf, sharded=False):
+        """Registers the feature-graph build so that it runs beside the next knn() of this context (hidden behind the
+        tensor-core screen); call .end() on the result to get the graph.  This matrix must stay alive until then."""
+        p = _ffi.KnnParams(metric, k, float(eps), SCREEN_AUTO, 0, 0, 0, 1)
+        h = C.c_void_p()
+        self.ctx.check(lib().sfb_knn_build_columns_begin(self.ctx._h, self._h, C.byref(p), int(sharded), C.byref(h)))
+        return PendingKnn(self.ctx, h, self)
+
     def debug_screen_tile(self, metric=METRIC_COSINE, screen=SCREEN_F16, row0=0, col0=0):
         """Diagnostic: (tile 128x256 f32 accumulators, operands of the 128 rows, operands of the 256 columns, scale)."""
         r, c = self.shape
@@ -221,6 +229,21 @@ class Matrix(_Handle):
     def diffuse(self, L, eta, steps):
         self.ctx.check(lib().sfb_diffuse(self.ctx._h, L._h, self._h, float(eta), int(steps)))
         return self
+
+
+class PendingKnn:
+    """sfb_pending: a feature-graph build in flight (Matrix.knn_columns_begin)."""
+
+    def __init__(self, ctx, h, keep):
+        self.ctx, self._h, self._keep = ctx, h, keep
+
+    def end(self):
+        if not self._h:
+            raise ValueError("end() was already called")
+        out = C.c_void_p()
+        h, self._h = self._h, None
+        self.ctx.check(lib().sfb_knn_build_columns_end(self.ctx._h, h, C.byref(out)))
+        return KnnGraph(self.ctx, out)
 
 
 class KnnGraph(_Handle):

@@ -87,6 +87,8 @@ SYMBOLS = {
     "sfb_knn_build": (C.c_int32, [_P, _P, C.POINTER(KnnParams), _PP]),
     "sfb_knn_build_columns": (C.c_int32, [_P, _P, C.POINTER(KnnParams), _PP]),
     "sfb_knn_build_columns_sharded": (C.c_int32, [_P, _P, C.POINTER(KnnParams), _PP]),
+    "sfb_knn_build_columns_begin": (C.c_int32, [_P, _P, C.POINTER(KnnParams), C.c_int32, _PP]),
+    "sfb_knn_build_columns_end": (C.c_int32, [_P, _P, _PP]),
     "sfb_knn_shape": (C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "sfb_knn_copy": (C.c_int32, [_P, _P, _P, _P, _P]),
     "sfb_knn_stats_get": (C.c_int32, [_P, C.POINTER(KnnStats)]),

@@ -99,6 +99,7 @@ extern "C" void sfb_ctx_destroy(sfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     sfb_comm_destroy(ctx);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaEventDestroy(ctx->side_fork); cudaEventDestroy(ctx->side_done); cudaStreamDestroy(ctx->side); }
     cache_release_all(ctx);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     cudaStreamDestroy(ctx->stream);

@@ -25,6 +25,10 @@ struct sfb_ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> block_size;
     size_t cached_bytes = 0;
+    // side stream: work that hides behind the screen kernel (knn.cu: sfb_knn_build_columns_begin / _end)
+    cudaStream_t side = nullptr;
+    cudaEvent_t side_fork = nullptr, side_done = nullptr;
+    struct sfb_pending* side_job = nullptr;   // registered, not launched yet
     // NCCL (loaded lazily, comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -150,6 +154,9 @@ int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int m
                       const uint32_t* query_rows /* device, or null */, uint64_t nq, uint64_t q_begin,
                       uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);
 void sfb_comm_destroy(sfb_ctx* ctx);
+// launches the registered side job, if any (called right after the screen kernel is enqueued, so that the persistent
+// screen CTAs are placed first and the side kernel's small CTAs fill in beside them)
+void sfb_side_job_fire(sfb_ctx* ctx);
 int32_t sfb_row_norms(sfb_ctx* ctx, const sfb_mat* x, double* norms);
 int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const sfb_knn_params* p,
                          uint64_t q_begin, uint64_t q_end, sfb_knn* out);

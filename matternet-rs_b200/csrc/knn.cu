@@ -1,6 +1,8 @@
 // knn.cu -- sfb_knn_build: dispatch between the exact f64 path and the tensor-core screen.
 #include <math.h>
 
+#include <new>
+
 #include "common.cuh"
 
 int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out);
@@ -110,4 +112,104 @@ extern "C" int32_t sfb_knn_build_columns(sfb_ctx* ctx, const sfb_mat* x, const s
 
 extern "C" int32_t sfb_knn_build_columns_sharded(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, sfb_knn** out) {
     return knn_build_any(ctx, x, true, p, out, 1);
+}
+
+
+// ---- feature graph hidden behind the item screen ----------------------------------------------------------------
+// The Gram-tile kernel of the feature graph is latency-bound (one dependent f64 add chain per pair: ~27 ms at
+// N = 1M whatever the number of tiles, so it does not shrink with more GPUs) and needs almost nothing of an SM: 64
+// threads and 8 KB of shared memory.  _begin registers it; the screen launcher fires it on a side stream right after
+// the persistent screen kernel is enqueued, so its CTAs run beside the screen's; _end joins, all-reduces (sharded),
+// and selects.  If no screen runs before _end, the job simply runs there.
+int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uint32_t m, uint64_t kd, int metric, double* g,
+                        uint32_t t0, uint32_t t1, bool small_smem);
+void sfb_gram_tile_range(const sfb_ctx* ctx, uint32_t m, int collective, uint32_t* t0, uint32_t* t1);
+int32_t sfb_gram_finish(sfb_ctx* ctx, double* g, uint32_t m, int metric, uint32_t k, double eps, uint64_t q_begin, uint64_t nq,
+                        uint32_t* out_idx, double* out_dist, uint32_t* out_cnt, int collective);
+
+struct sfb_pending {
+    sfb_ctx* ctx = nullptr;
+    const sfb_mat* x = nullptr;
+    sfb_knn_params p{};
+    int collective = 0;
+    bool dense = false, launched = false;
+    double* g = nullptr;   // 2 * m * m doubles
+};
+
+void sfb_side_job_fire(sfb_ctx* ctx) {
+    sfb_pending* pd = ctx->side_job;
+    if (!pd) return;
+    ctx->side_job = nullptr;
+    if (!ctx->side) return;   // _begin could not create the side stream: _end runs the job inline
+    const uint32_t m = pd->x->cols;
+    uint32_t t0, t1;
+    sfb_gram_tile_range(ctx, m, pd->collective, &t0, &t1);
+    // side_fork was recorded by _begin (after the matrix upload and the memset of g) -- NOT here: an event recorded
+    // now would sit behind the screen kernel that was just enqueued
+    cudaStreamWaitEvent(ctx->side, ctx->side_fork, 0);
+    if (sfb_gram_launch(ctx, ctx->side, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, t0, t1, true) != SFB_OK) return;
+    cudaEventRecord(ctx->side_done, ctx->side);
+    pd->launched = true;
+}
+
+extern "C" int32_t sfb_knn_build_columns_begin(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, int32_t sharded, sfb_pending** out) {
+    if (!ctx || !x || !p || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    *out = nullptr;
+    if (ctx->side_job) return sfb_fail(ctx, SFB_EINVAL, "a feature-graph build is already pending on this context");
+    sfb_pending* pd = new (std::nothrow) sfb_pending();
+    if (!pd) return SFB_ENOMEM;
+    pd->ctx = ctx; pd->x = x; pd->p = *p; pd->collective = sharded ? 1 : 0;
+    const uint64_t nodes = x->cols, dims = x->rows;
+    pd->dense = nodes >= 2 && sfb_dense_shape(nodes, dims) && (p->screen == SFB_SCREEN_AUTO || p->screen == SFB_SCREEN_EXACT_F64) &&
+                p->k >= 1 && p->k <= 128 && p->metric >= SFB_METRIC_COSINE && p->metric <= SFB_METRIC_L2SQ;
+    if (pd->dense) {
+        const size_t bytes = sizeof(double) * 2 * (size_t)nodes * nodes;
+        if (sfb_dev_alloc(ctx, (void**)&pd->g, bytes) != cudaSuccess) { delete pd; return sfb_fail(ctx, SFB_ENOMEM, "Gram buffer"); }
+        if (pd->collective && ctx->world > 1) cudaMemsetAsync(pd->g, 0, bytes / 2, ctx->stream);
+        if (!ctx->side && cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess) {
+            cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming);
+        }
+        if (ctx->side) cudaEventRecord(ctx->side_fork, ctx->stream);
+        ctx->side_job = pd;   // fired by the next screen launch, or by _end
+    }
+    *out = pd;
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_knn_build_columns_end(sfb_ctx* ctx, sfb_pending* pd, sfb_knn** out) {
+    if (!ctx || !pd || !out || pd->ctx != ctx) return sfb_fail(ctx, SFB_EINVAL, "bad pending handle");
+    *out = nullptr;
+    int32_t st = SFB_OK;
+    if (!pd->dense) {
+        st = knn_build_any(ctx, pd->x, true, &pd->p, out, pd->collective);   // argument errors and non-feature shapes: the plain path
+    } else {
+        const uint32_t m = pd->x->cols;
+        const uint32_t kk = pd->p.k;
+        uint64_t q_begin = pd->p.q_begin, q_end = pd->p.q_end ? pd->p.q_end : m;
+        if (q_begin >= q_end || q_end > m || isnan(pd->p.eps)) st = sfb_fail(ctx, SFB_EINVAL, "bad query shard or eps");
+        if (ctx->side_job == pd || (!pd->launched && ctx->side_job == nullptr && !ctx->side)) {   // no screen ran in between (or no side stream): run the Gram tiles now, on the main stream
+            ctx->side_job = nullptr;
+            uint32_t t0, t1;
+            sfb_gram_tile_range(ctx, m, pd->collective, &t0, &t1);
+            if (st == SFB_OK) st = sfb_gram_launch(ctx, ctx->stream, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, t0, t1, false);
+        } else if (pd->launched) {
+            cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0);
+        } else if (st == SFB_OK) st = sfb_fail(ctx, SFB_ECUDA, "the side launch of the Gram tiles failed");
+        if (st == SFB_OK) st = sfb_knn_alloc(ctx, q_end - q_begin, kk, out);
+        if (st == SFB_OK) {
+            sfb_knn* g = *out;
+            g->q_begin = q_begin; g->total = m; g->stats = sfb_knn_stats{};
+            g->stats.rows = q_end - q_begin; g->stats.rows_fallback = g->stats.rows; g->stats.screen_used = SFB_SCREEN_EXACT_F64;
+            StageTimer t(ctx, &ctx->times.ms_knn);
+            st = sfb_gram_finish(ctx, pd->g, m, pd->p.metric, kk, pd->p.eps, q_begin, q_end - q_begin, g->idx, g->dist, g->cnt, pd->collective);
+            if (st == SFB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = sfb_fail(ctx, SFB_ECUDA, "feature-graph selection failed");
+            g->stats.ms_fallback = t.stop();
+            if (st != SFB_OK) { sfb_knn_free(g); *out = nullptr; }
+        }
+        if (ctx->side) cudaStreamSynchronize(ctx->side);
+        sfb_dev_free(ctx, pd->g);
+    }
+    delete pd;
+    return st;
 }

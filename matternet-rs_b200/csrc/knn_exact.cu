@@ -217,7 +217,8 @@ __global__ void knn_merge_kernel(const uint32_t* __restrict__ pidx, const double
 // and writes the raw sums G[i][j] (= G[j][i]: products commute) for tiles on or above the diagonal.
 // The diagonal G[i][i] is the squared norm, the same left fold as row_norms_kernel.
 // FP64-pipe bound: m^2/2 * N multiply + add pairs; at m = 384 the 300 tiles fill 148 SMs.
-constexpr int GT = 16, GCH = 64;
+constexpr int GT = 16;   // pair tile edge; GCH (template) = dimensions per staged chunk: 64 standalone (32 KB of shared memory),
+                        // 16 when the kernel runs beside a resident screen CTA (8 KB fit next to its 216 of 227 KB)
 
 __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, int bytes, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -226,12 +227,15 @@ __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc,
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 
-template <bool COS, int VEC>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
-__global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G, uint32_t tile0) {
+template <bool COS, int VEC, int GCH>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
+__global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G, uint32_t tile0,
+                                                       uint32_t n_tiles) {
     __shared__ __align__(16) double sa[2][GCH][GT], sb[2][GCH][GT];
-    // decode the upper-triangular tile index
     const uint32_t T = (m + GT - 1) / GT;
-    uint32_t ti = 0, rem = blockIdx.x + tile0;
+    // a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: beside the screen kernel the grid is capped at one CTA per SM
+    for (uint32_t tt = blockIdx.x; tt < n_tiles; tt += gridDim.x) {
+    // decode the upper-triangular tile index
+    uint32_t ti = 0, rem = tt + tile0;
     while (rem >= T - ti) { rem -= T - ti; ++ti; }
     const uint32_t tj = ti + rem;
     const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
@@ -287,6 +291,8 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
             const uint32_t i = i0 + di, j = j0 + dj;
             if (i < m && j < m) { G[(uint64_t)i * m + j] = acc[di][dj]; G[(uint64_t)j * m + i] = acc[di][dj]; }
         }
+    __syncthreads();
+    }
 }
 
 // raw sums G -> distance keys, written behind G (cosine: the norms are the square roots of the diagonal)
@@ -366,6 +372,51 @@ bool sfb_dense_shape(uint64_t nodes, uint64_t dims) { return nodes <= 4096 && di
 // kNN over few nodes with very long rows, from the DIMS-MAJOR matrix xd[kd][m] (see gram_tile_kernel).
 int32_t sfb_comm_allreduce_sum_f64(sfb_ctx* ctx, double* buf, size_t n);
 
+// raw pair sums of tiles [t0, t1) into g (m x m doubles) on `stream`; small_smem: the 8 KB variant that co-resides
+// with the screen kernel
+int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uint32_t m, uint64_t kd, int metric, double* g,
+                        uint32_t t0, uint32_t t1, bool small_smem) {
+    if (t1 <= t0) return SFB_OK;
+    const uint32_t nt = t1 - t0;
+    const bool cos = metric == SFB_METRIC_COSINE, even = (m & 1u) == 0 && (reinterpret_cast<uintptr_t>(xd) & 15u) == 0;
+    // beside the screen kernel: at most one CTA per SM, so that a CTA placed before the screen's never keeps the
+    // screen's 216 KB from fitting (two of them would)
+    const uint32_t grid = small_smem && nt > (uint32_t)ctx->sm_count ? (uint32_t)ctx->sm_count : nt;
+#define SFB_GRAM(C_, V_, G_) gram_tile_kernel<C_, V_, G_><<<grid, 64, 0, stream>>>(xd, m, kd, g, t0, nt)
+    if (small_smem) {
+        if (cos) { if (even) SFB_GRAM(true, 2, 16); else SFB_GRAM(true, 1, 16); }
+        else { if (even) SFB_GRAM(false, 2, 16); else SFB_GRAM(false, 1, 16); }
+    } else {
+        if (cos) { if (even) SFB_GRAM(true, 2, 64); else SFB_GRAM(true, 1, 64); }
+        else { if (even) SFB_GRAM(false, 2, 64); else SFB_GRAM(false, 1, 64); }
+    }
+#undef SFB_GRAM
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
+void sfb_gram_tile_range(const sfb_ctx* ctx, uint32_t m, int collective, uint32_t* t0, uint32_t* t1) {
+    const uint32_t T = (m + GT - 1) / GT, tiles = T * (T + 1) / 2;
+    *t0 = 0; *t1 = tiles;
+    if (collective && ctx->world > 1) {
+        const uint32_t per = (tiles + (uint32_t)ctx->world - 1) / (uint32_t)ctx->world;
+        *t0 = (uint32_t)ctx->rank * per; if (*t0 > tiles) *t0 = tiles;
+        *t1 = *t0 + per < tiles ? *t0 + per : tiles;
+    }
+}
+
+// g: [0, m*m) raw sums (complete on this rank, or this rank's tile share when `collective`), [m*m, 2*m*m) scratch for
+// the keys.  All-reduces the sums if needed, turns them into distance keys and selects the top-k of the query rows.
+int32_t sfb_gram_finish(sfb_ctx* ctx, double* g, uint32_t m, int metric, uint32_t k, double eps, uint64_t q_begin, uint64_t nq,
+                        uint32_t* out_idx, double* out_dist, uint32_t* out_cnt, int collective) {
+    if (collective && ctx->world > 1) SFB_TRY(sfb_comm_allreduce_sum_f64(ctx, g, (size_t)m * m));
+    dim3 kgrid(div_up(m, 128), m);
+    if (metric == SFB_METRIC_COSINE) gram_keys_kernel<true><<<kgrid, 128, 0, ctx->stream>>>(g, m, metric, nullptr);
+    else gram_keys_kernel<false><<<kgrid, 128, 0, ctx->stream>>>(g, m, metric, nullptr);
+    SFB_LAUNCH_CHECK(ctx);
+    return sfb_dense_select(ctx, g + (size_t)m * m, m, q_begin, nq, k, eps, out_idx, out_dist, out_cnt);
+}
+
 // `collective` != 0: every rank of the communicator calls this with the same matrix; the pair tiles are split
 // across the ranks and the raw sums all-reduced (each entry is non-zero on exactly one rank: x + 0 is exact).
 int32_t sfb_knn_dense(sfb_ctx* ctx, const double* xd, uint32_t m, uint64_t kd, int metric, uint32_t k, double eps,
@@ -374,32 +425,11 @@ int32_t sfb_knn_dense(sfb_ctx* ctx, const double* xd, uint32_t m, uint64_t kd, i
     if (k == 0 || k > 128) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k must be in 1..128 (got %u)", k);
     DevBuf g;  // [0, m*m): raw sums, [m*m, 2*m*m): keys
     SFB_CUDA(ctx, g.alloc(sizeof(double) * 2 * (size_t)m * m));
-    const uint32_t T = (m + GT - 1) / GT, tiles = T * (T + 1) / 2;
-    uint32_t t0 = 0, t1 = tiles;
-    const bool split = collective && ctx->world > 1;
-    if (split) {
-        const uint32_t per = (tiles + (uint32_t)ctx->world - 1) / (uint32_t)ctx->world;
-        t0 = (uint32_t)ctx->rank * per; if (t0 > tiles) t0 = tiles;
-        t1 = t0 + per < tiles ? t0 + per : tiles;
-        SFB_CUDA(ctx, cudaMemsetAsync(g.p, 0, sizeof(double) * (size_t)m * m, ctx->stream));
-    }
-    const bool cos = metric == SFB_METRIC_COSINE, even = (m & 1u) == 0 && (reinterpret_cast<uintptr_t>(xd) & 15u) == 0;
-    if (t1 > t0) {
-        const uint32_t nt = t1 - t0;
-        if (cos) { if (even) gram_tile_kernel<true, 2><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); else gram_tile_kernel<true, 1><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); }
-        else { if (even) gram_tile_kernel<false, 2><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); else gram_tile_kernel<false, 1><<<nt, 64, 0, ctx->stream>>>(xd, m, kd, g.as<double>(), t0); }
-        SFB_LAUNCH_CHECK(ctx);
-    }
-    if (split) SFB_TRY(sfb_comm_allreduce_sum_f64(ctx, g.as<double>(), (size_t)m * m));
-    dim3 kgrid(div_up(m, 128), m);
-    if (cos) gram_keys_kernel<true><<<kgrid, 128, 0, ctx->stream>>>(g.as<double>(), m, metric, nullptr);
-    else gram_keys_kernel<false><<<kgrid, 128, 0, ctx->stream>>>(g.as<double>(), m, metric, nullptr);
-    SFB_LAUNCH_CHECK(ctx);
-    const int wpb = 4;
-    size_t ssm = (size_t)wpb * k * (sizeof(double) + sizeof(uint32_t));
-    knn_dense_select_kernel<<<div_up(nq, wpb), wpb * 32, ssm, ctx->stream>>>(g.as<double>() + (size_t)m * m, m, q_begin, nq, k, eps, out_idx, out_dist, out_cnt);
-    SFB_LAUNCH_CHECK(ctx);
-    return SFB_OK;
+    uint32_t t0, t1;
+    sfb_gram_tile_range(ctx, m, collective, &t0, &t1);
+    if (collective && ctx->world > 1) SFB_CUDA(ctx, cudaMemsetAsync(g.p, 0, sizeof(double) * (size_t)m * m, ctx->stream));
+    SFB_TRY(sfb_gram_launch(ctx, ctx->stream, xd, m, kd, metric, g.as<double>(), t0, t1, false));
+    return sfb_gram_finish(ctx, g.as<double>(), m, metric, k, eps, q_begin, nq, out_idx, out_dist, out_cnt, collective);
 }
 
 int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int metric, uint32_t k, double eps,

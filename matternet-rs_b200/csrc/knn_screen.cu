@@ -1092,6 +1092,7 @@ int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2A
         knn_screen_pair_kernel<true><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, tmA, sa);
     }
     SFB_LAUNCH_CHECK(ctx);
+    sfb_side_job_fire(ctx);   // a pending feature-graph Gram rides beside the resident screen CTAs
     return SFB_OK;
 }
 

@@ -422,3 +422,33 @@ def test_map_items_to_subcentroids(sfb, oracle, ctx):
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
     assert len(set(want[0][:200])) > 1                        # the tie-break really decided
+
+
+# ---- feature graph hidden behind the item screen (sfb_knn_build_columns_begin / _end) --------------------------
+def test_knn_columns_begin_end(sfb, oracle, ctx):
+    x = np.random.default_rng(31).normal(size=(6000, 40))
+    x[:, 9] = x[:, 2]
+    want_f = oracle.knn(oracle.transpose(x), 7, 0)
+    want_i = oracle.knn(x, 5, 1)
+    m = ctx.matrix(x)
+    # a tensor-core screen runs between begin and end: the Gram tiles ride on the side stream beside it
+    pend = m.knn_columns_begin(7, 0)
+    g = m.knn(5, 1)
+    assert g.stats()["screen_used"] == sfb.SCREEN_F16
+    assert_knn_equal(pend.end().to_host(), want_f)
+    assert_knn_equal(g.to_host(), want_i)
+    # nothing in between: end() runs the job itself
+    assert_knn_equal(m.knn_columns_begin(7, 0).end().to_host(), want_f)
+    # an exact (no screen) kNN in between, other metric for the columns
+    pend = m.knn_columns_begin(3, 2)
+    g2 = m.knn(5, 1, screen=sfb.SCREEN_EXACT_F64, q_begin=0, q_end=300)
+    assert_knn_equal(pend.end().to_host(), oracle.knn(oracle.transpose(x), 3, 2))
+    assert_knn_equal(g2.to_host(), oracle.knn(x, 5, 1, query_rows=np.arange(300)))
+    # not the feature-graph shape: end() takes the plain path
+    y = np.random.default_rng(32).normal(size=(30, 500))
+    assert_knn_equal(ctx.matrix(y).knn_columns_begin(4, 0).end().to_host(), oracle.knn(oracle.transpose(y), 4, 0))
+    # one pending build per context
+    p1 = m.knn_columns_begin(7, 0)
+    with pytest.raises(sfb.SfbError):
+        m.knn_columns_begin(7, 0)
+    p1.end().free()
