@@ -9,7 +9,7 @@ One "step" = one full build over one synthetic embedding matrix (BASELINE.json c
     item graph     kNN (tcgen05 screen + exact f64 rescore) -> kernel weights / sparsification
                    -> symmetrise + CSR Laplacian                       (src_legacy/laplacian.rs:122-419)
     feature graph  the reference's own call shape: kNN over the D feature nodes (the columns), Laplacian
-                   (src_legacy/graph.rs:193-255)
+                   (src_legacy/graph.rs:193-255); its exact f64 pair sums run on a side stream beside the screen
     lambda         per-item taumode lambda against the D x D feature Laplacian, min-max normalised
                    (src_legacy/taumode.rs:117-318, core.rs:1341-1355)
 `value`  = rows / device time with the f64 matrix already resident in HBM.

@@ -816,10 +816,8 @@ float orc_bc(const float* means, const float* vars, uint32_t c, uint32_t f, uint
     float db = 0.0f;
     for (uint32_t cc = 0; cc < c; ++cc) {
         float vi = vars[(size_t)cc * f + i], vj = vars[(size_t)cc * f + j];
-        vi = vi > reg ? vi : reg;                       /* f32::max: NaN-ignoring, like fmaxf */
+        vi = vi > reg ? vi : reg;                       /* f32::max ignores a NaN operand: NaN > reg is false */
         vj = vj > reg ? vj : reg;
-        if (vars[(size_t)cc * f + i] != vars[(size_t)cc * f + i]) vi = reg;
-        if (vars[(size_t)cc * f + j] != vars[(size_t)cc * f + j]) vj = reg;
         float v_sum = vi + vj;
         float dm = means[(size_t)cc * f + i] - means[(size_t)cc * f + j];
         float mean_term = (dm * dm) / (4.0f * v_sum);
