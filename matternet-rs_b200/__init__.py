@@ -499,7 +499,8 @@ def build_laplacian_matrix(transposed, params: GraphParams, n_items=None, energy
                            int(params.sparsity_check))
     h = C.c_void_p()
     ctx.check(lib().sfb_build_laplacian_matrix(ctx._h, _ffi.ptr(x), n, d, C.byref(gp), screen, C.byref(h)))
-    return GraphLaplacian(matrix=Csr(ctx, h), nnodes=n if n_items is None else n_items, graph_params=params,
+    # `let (d, n) = transposed.shape(); ... nnodes: n_items.unwrap_or(n)` (laplacian.rs:129,166-169): the COLUMN count
+    return GraphLaplacian(matrix=Csr(ctx, h), nnodes=d if n_items is None else n_items, graph_params=params,
                           init_data=x, energy=energy)
 
 
