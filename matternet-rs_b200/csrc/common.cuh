@@ -69,6 +69,7 @@ struct sfb_csr {
     uint32_t* indices = nullptr;
     double* data = nullptr;
     uint64_t rows = 0, nnz = 0;
+    mutable int symmetric = -1;  // -1 unknown, 1: structure and values symmetric bit for bit (checked once, lambda.cu), 0: not
 };
 
 int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...);

@@ -225,6 +225,217 @@ __global__ void lambda_kernel(LambdaArgs a) {
     }
 }
 
+// ---- symmetric fast path -----------------------------------------------------------------------------------
+// When L is symmetric bit for bit (every Laplacian this library builds; checked once for matrices from the host) the
+// off-diagonal half below the diagonal repeats the half above it: x^T L x = sum_r L_rr x_r^2 + 2 sum_{r<c} L_rc x_r x_c
+// and the dispersion terms of (r, c) and (c, r) are equal.  Moreover x^T L x = sum_r (L_rr + sum_{c != r} L_rc) x_r^2
+// - sum_{r<c} L_rc (x_r - x_c)^2: with the row-sum defect precomputed (exactly 0 for L = D - W) the Rayleigh numerator is
+// the same edge sum as the dispersion's S -- no cancellation (a constant vector gives exactly 0, as the reference's
+// clamped value does) and no second product per edge.  The strict upper triangle is packed once per call
+// ((r << 16 | c) u32 + value f64, CSR order: deterministic) and kept in shared memory with the diagonal; a warp owns
+// an item, its lanes stride over the packed edges (coalesced shared-memory reads, two gathers of the item row per
+// edge) -- half the edges of the row-wise kernel above and no per-row loop overhead.  tau's median / percentile is a
+// quantised selection: min / max of the candidates, 256 bins, an 8-step binary search on counts for the bin that
+// holds the rank, recurse into that bin (usually <= 2 rounds for a few hundred entries), exact extraction at the end.
+// Sums are reordered with respect to the reference's left folds (as in the kernel above): within 1e-12 relative.
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// value of 0-based rank `rank` among the finite entries of xs[0..f); *n_le = number of finite entries <= that value
+__device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, int lane, uint32_t* n_le) {
+    double lo = -INFINITY, hi = INFINITY;   // candidates: finite v with lo <= v <= hi
+    uint32_t below = 0;                     // finite entries < lo
+    double mn = INFINITY, mx = -INFINITY;
+    uint32_t cnt = 0;
+    for (uint32_t t = lane; t < f; t += 32) { const double v = xs[t]; if (isfinite(v)) { mn = fmin(mn, v); mx = fmax(mx, v); ++cnt; } }
+    mn = warp_min_d(mn); mx = warp_max_d(mx); cnt = warp_sum_u(cnt);
+    for (int iter = 0; iter < 40; ++iter) {
+        lo = mn; hi = mx;
+        const uint32_t target = rank - below;
+        if (mn == mx) { *n_le = below + cnt; return mn; }
+        const double scale = 256.0 / (mx - mn);
+        if (cnt <= 8 || !(scale < 1e300) || iter == 39) break;
+        uint32_t cut = 0, below_cut = 0;
+#pragma unroll 1
+        for (int b = 7; b >= 0; --b) {
+            const uint32_t trial = cut | (1u << b);
+            uint32_t c = 0;
+            for (uint32_t t = lane; t < f; t += 32) {
+                const double v = xs[t];
+                if (isfinite(v) && v >= lo && v <= hi) { int q = (int)((v - lo) * scale); q = q > 255 ? 255 : q; c += (uint32_t)q < trial ? 1u : 0u; }
+            }
+            c = warp_sum_u(c);
+            if (c <= target) { cut = trial; below_cut = c; }
+        }
+        // recurse into bin `cut`: its min, max and population
+        double nmn = INFINITY, nmx = -INFINITY; uint32_t ncnt = 0;
+        for (uint32_t t = lane; t < f; t += 32) {
+            const double v = xs[t];
+            if (isfinite(v) && v >= lo && v <= hi) {
+                int q = (int)((v - lo) * scale); q = q > 255 ? 255 : q;
+                if ((uint32_t)q == cut) { nmn = fmin(nmn, v); nmx = fmax(nmx, v); ++ncnt; }
+            }
+        }
+        mn = warp_min_d(nmn); mx = warp_max_d(nmx); cnt = warp_sum_u(ncnt);
+        below += below_cut;
+    }
+    // exact tail: walk the distinct candidate values upwards
+    const uint32_t target = rank - below;
+    uint32_t seen = 0;
+    double last = -INFINITY;
+    bool first = true;
+    for (;;) {
+        double cand = INFINITY;
+        for (uint32_t t = lane; t < f; t += 32) { const double v = xs[t]; if (isfinite(v) && v >= lo && v <= hi && (first || v > last)) cand = fmin(cand, v); }
+        cand = warp_min_d(cand);
+        uint32_t mult = 0;
+        for (uint32_t t = lane; t < f; t += 32) mult += xs[t] == cand ? 1u : 0u;
+        mult = warp_sum_u(mult);
+        if (target < seen + mult || !(cand < INFINITY)) { *n_le = below + seen + mult; return cand; }
+        seen += mult; last = cand; first = false;
+    }
+}
+
+// TauMode::select_tau (taumode.rs:29-70) with the quantised selection
+__device__ double warp_select_tau_fast(const double* xs, uint32_t f, int mode, double value, int lane) {
+    const double FLOOR = 1e-10;
+    if (mode == SFB_TAU_FIXED) return (isfinite(value) && value > 0.0) ? value : FLOOR;
+    uint32_t n = 0; double s = 0.0;
+    for (uint32_t t = lane; t < f; t += 32) { double v = xs[t]; if (isfinite(v)) { ++n; s += v; } }
+    n = warp_sum_u(n);
+    if (n == 0) return FLOOR;
+    if (mode == SFB_TAU_MEAN) { double mean = warp_sum(s) / (double)n; return mean > FLOOR ? mean : FLOOR; }
+    uint32_t n_le;
+    double r;
+    if (mode == SFB_TAU_PERCENTILE) {
+        double pp = value < 0.0 ? 0.0 : (value > 1.0 ? 1.0 : value);
+        r = warp_kth_finite(xs, f, (uint32_t)round((double)(n - 1) * pp), lane, &n_le);
+    } else if (n & 1u) {
+        r = warp_kth_finite(xs, f, n / 2, lane, &n_le);
+    } else {
+        const double a = warp_kth_finite(xs, f, n / 2 - 1, lane, &n_le);
+        double b = a;
+        if (n_le <= n / 2) {   // rank n/2 is the next larger value
+            b = INFINITY;
+            for (uint32_t t = lane; t < f; t += 32) { double v = xs[t]; if (isfinite(v) && v > a) b = fmin(b, v); }
+            b = warp_min_d(b);
+        }
+        r = 0.5 * (a + b);
+    }
+    return r > FLOOR ? r : FLOOR;
+}
+
+// strict upper triangle of a symmetric CSR, packed in CSR order (deterministic), + the diagonal
+__global__ void upper_count_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, uint32_t f, uint32_t* __restrict__ cnt) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= f) return;
+    uint32_t c = 0;
+    for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) c += indices[e] > r ? 1u : 0u;
+    cnt[r] = c;
+}
+__global__ void upper_pack_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const double* __restrict__ data,
+                                  uint32_t f, const uint64_t* __restrict__ offs, uint32_t* __restrict__ rc, double* __restrict__ val,
+                                  double* __restrict__ diag) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= f) return;
+    uint64_t o = offs[r];
+    double d = 0.0, fold = 0.0;
+    for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+        const uint32_t c = indices[e];
+        if (c > r) { rc[o] = (r << 16) | c; val[o] = data[e]; ++o; }
+        if (c == r) d = data[e];
+        else fold = __dadd_rn(fold, -data[e]);   // the fold that produced L_rr in the builder (ascending column, from 0.0)
+    }
+    diag[r] = __dadd_rn(d, -fold);   // row-sum defect: exactly 0 for a Laplacian assembled as D - W
+}
+// symmetric bit for bit?  every stored (r, c) must have a stored (c, r) with the same bits
+__global__ void csr_symmetric_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const double* __restrict__ data,
+                                     uint64_t rows, int* __restrict__ bad) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+        const uint32_t c = indices[e];
+        if (c == r) continue;
+        if (c >= rows) { *bad = 1; return; }
+        uint64_t a = indptr[c], b = indptr[c + 1];
+        while (a < b) { uint64_t mid = (a + b) >> 1; if (indices[mid] < r) a = mid + 1; else b = mid; }
+        if (a >= indptr[c + 1] || indices[a] != r || __double_as_longlong(data[a]) != __double_as_longlong(data[e])) { *bad = 1; return; }
+    }
+}
+
+struct LambdaSymArgs {
+    const uint32_t* rc; const double* val; const double* diag; uint32_t ne, f;
+    const double* x; uint64_t n;
+    int tau_mode; double tau_value;
+    double* out_lambda; double* out_disp;
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* s_val = reinterpret_cast<double*>(smem_raw);                 // [ne]
+    double* s_diag = s_val + a.ne;                                       // [f]
+    double* xs = s_diag + a.f + (size_t)w * a.f;                         // [wpb][f]
+    uint32_t* s_rc = reinterpret_cast<uint32_t*>(s_diag + a.f + (size_t)wpb * a.f);   // [ne]
+    for (uint32_t e = threadIdx.x; e < a.ne; e += blockDim.x) { s_val[e] = a.val[e]; s_rc[e] = a.rc[e]; }
+    for (uint32_t r = threadIdx.x; r < a.f; r += blockDim.x) s_diag[r] = a.diag[r];
+    __syncthreads();
+    const uint32_t f = a.f;
+    for (uint64_t i = (uint64_t)blockIdx.x * wpb + w; i < a.n; i += (uint64_t)gridDim.x * wpb) {
+        const double* xr = a.x + i * f;
+        __syncwarp();
+        bool zero = true;
+        double den = 0.0, num = 0.0;
+        for (uint32_t t = lane; t < f; t += 32) {
+            const double v = xr[t];
+            xs[t] = v;
+            zero = zero && (fabs(v) <= 1e-10);
+            den += v * v;
+            num += (v * s_diag[t]) * v;   // row-sum defect term
+        }
+        __syncwarp();
+        zero = __all_sync(FULL, zero);
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE && zero) {  // taumode.rs:268-274
+            if (lane == 0) { a.out_lambda[i] = 0.0; if (a.out_disp) a.out_disp[i] = 0.0; }
+            continue;
+        }
+        double sall = 0.0, ssum = 0.0, qsum = 0.0;
+        for (uint32_t e = lane; e < a.ne; e += 32) {
+            const uint32_t rc = s_rc[e];
+            const double xa = xs[rc >> 16], xb = xs[rc & 0xFFFFu], wv = -s_val[e];
+            const double d = xa - xb;
+            const double contrib = (wv * d) * d;
+            sall += contrib;
+            if (wv > 0.0) {
+                ssum += contrib;
+                qsum = fma(contrib, contrib, qsum);
+            }
+        }
+        den = warp_sum(den); num = warp_sum(num) + warp_sum(sall);
+        ssum = warp_sum(ssum); qsum = warp_sum(qsum);
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) { ssum *= 2.0; qsum *= 2.0; }   // both triangles (taumode.rs:371-383)
+        double e_raw = 0.0;
+        if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
+        double g = 0.0;
+        if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
+        double lam;
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
+            const double tau = warp_select_tau_fast(xs, f, a.tau_mode, a.tau_value, lane);
+            lam = tau * (e_raw / (e_raw + tau)) + (1.0 - tau) * g;  // taumode.rs:306-310
+        } else lam = e_raw;
+        if (lane == 0) { a.out_lambda[i] = lam; if (a.out_disp) a.out_disp[i] = g; }
+    }
+}
+
 // CORE_F32SEM second pass: G_i = clamp(e_i / (sum e + 1e-12), 0, 1); lambda = R + G (f32)
 __global__ void core_sum_energy_kernel(const float* __restrict__ e, uint64_t n, float* __restrict__ total) {
     // single block, ascending chunks: deterministic
@@ -302,6 +513,57 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
     if (L->rows != f) return sfb_fail(ctx, SFB_EINVAL, "Matrix rows %llu must match vector length %u", (unsigned long long)L->rows, f);  // taumode.rs:330-337
     if (prm->variant < 0 || prm->variant > 2) return sfb_fail(ctx, SFB_EINVAL, "unknown lambda variant %d", prm->variant);
     if (prm->tau_mode < 0 || prm->tau_mode > 3) return sfb_fail(ctx, SFB_EINVAL, "unknown tau mode %d", prm->tau_mode);
+    // symmetric fast path (LEGACY_TAUMODE / ENERGY_NODE): L symmetric bit for bit, packed upper triangle in shared memory
+    if (prm->variant != SFB_LAMBDA_CORE_F32SEM && f <= 65535 && !getenv("SFB_LAMBDA_ROWWISE")) {
+        if (L->symmetric < 0) {
+            DevBuf bad;
+            SFB_CUDA(ctx, bad.alloc(sizeof(int)));
+            SFB_CUDA(ctx, cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+            csr_symmetric_kernel<<<div_up(L->rows, 128), 128, 0, ctx->stream>>>(L->indptr, L->indices, L->data, L->rows, bad.as<int>());
+            SFB_LAUNCH_CHECK(ctx);
+            int hb = 0;
+            SFB_CUDA(ctx, cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            L->symmetric = hb ? 0 : 1;
+        }
+        if (L->symmetric == 1) {
+            DevBuf cnt, offs, rc, val, diag;
+            SFB_CUDA(ctx, cnt.alloc(sizeof(uint32_t) * f));
+            SFB_CUDA(ctx, offs.alloc(sizeof(uint64_t) * ((size_t)f + 1)));
+            upper_count_kernel<<<div_up(f, 128), 128, 0, ctx->stream>>>(L->indptr, L->indices, f, cnt.as<uint32_t>());
+            SFB_LAUNCH_CHECK(ctx);
+            SFB_TRY(sfb_scan_exclusive_u64(ctx, cnt.as<uint32_t>(), f, offs.as<uint64_t>()));
+            uint64_t ne64 = 0;
+            SFB_CUDA(ctx, cudaMemcpyAsync(&ne64, offs.as<uint64_t>() + f, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const int wpb_s = 8;
+            const size_t smem_s = (size_t)ne64 * (sizeof(double) + sizeof(uint32_t)) + (size_t)f * sizeof(double) * (1 + wpb_s) + 16;
+            if (smem_s <= 112 * 1024) {   // two CTAs per SM
+                const uint32_t ne = (uint32_t)ne64;
+                SFB_CUDA(ctx, rc.alloc(sizeof(uint32_t) * (ne ? ne : 1)));
+                SFB_CUDA(ctx, val.alloc(sizeof(double) * (ne ? ne : 1)));
+                SFB_CUDA(ctx, diag.alloc(sizeof(double) * f));
+                upper_pack_kernel<<<div_up(f, 128), 128, 0, ctx->stream>>>(L->indptr, L->indices, L->data, f, offs.as<uint64_t>(), rc.as<uint32_t>(),
+                                                                         val.as<double>(), diag.as<double>());
+                SFB_LAUNCH_CHECK(ctx);
+                LambdaSymArgs sa{rc.as<uint32_t>(), val.as<double>(), diag.as<double>(), ne, f, x_dev, n, prm->tau_mode, prm->tau_value, d_lambda, d_disp};
+                const int per_sm = (int)((ctx->smem_optin ? ctx->smem_optin : 232448) / (smem_s + 1024));
+                uint64_t want = (n + wpb_s - 1) / wpb_s;
+                const uint64_t cap_grid = (uint64_t)ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+                const unsigned grid = (unsigned)(want < cap_grid ? want : cap_grid);
+                if (prm->variant == SFB_LAMBDA_LEGACY_TAUMODE) {
+                    SFB_CUDA(ctx, cudaFuncSetAttribute(lambda_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                    lambda_sym_kernel<0><<<grid, wpb_s * 32, smem_s, ctx->stream>>>(sa);
+                } else {
+                    SFB_CUDA(ctx, cudaFuncSetAttribute(lambda_sym_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                    lambda_sym_kernel<1><<<grid, wpb_s * 32, smem_s, ctx->stream>>>(sa);
+                }
+                SFB_LAUNCH_CHECK(ctx);
+                SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                return SFB_OK;
+            }
+        }
+    }
     size_t per_warp = (size_t)f * sizeof(double) + 256 * sizeof(uint32_t);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
