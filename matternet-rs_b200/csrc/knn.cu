@@ -133,6 +133,7 @@ struct sfb_pending {
     sfb_knn_params p{};
     int collective = 0;
     bool dense = false, launched = false;
+    bool deferred = false;   // not worth hiding: _end runs the tiles stand-alone
     double* g = nullptr;   // 2 * m * m doubles
 };
 
@@ -170,8 +171,17 @@ extern "C" int32_t sfb_knn_build_columns_begin(sfb_ctx* ctx, const sfb_mat* x, c
             cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming);
         }
-        if (ctx->side) cudaEventRecord(ctx->side_fork, ctx->stream);
-        ctx->side_job = pd;   // fired by the next screen launch, or by _end
+        // Hide it only if it can finish behind the screen that is about to run on this matrix: beside the screen the kernel
+        // gets one CTA per SM and ~45 ns per fold step; otherwise _end runs it stand-alone on every SM (C4, 3072
+        // features x 100k items: 18.5k tiles would take 0.5 s co-resident against a 60 ms screen, 0.11 s alone).
+        uint32_t t0, t1;
+        sfb_gram_tile_range(ctx, (uint32_t)nodes, pd->collective, &t0, &t1);
+        const double tiles_per_cta = ceil((double)(t1 - t0) / (double)ctx->sm_count);
+        const double gram_s = tiles_per_cta * (double)dims * 45e-9;
+        const double screen_s = 2.0 * (double)dims * (double)dims * (double)nodes / (double)(ctx->world > 0 ? ctx->world : 1) / 1.1e15;
+        const bool hide = gram_s < 0.8 * screen_s && dims >= 4096 && !getenv("SFB_NO_SIDE_STREAM");
+        if (hide && ctx->side) { cudaEventRecord(ctx->side_fork, ctx->stream); ctx->side_job = pd; }   // fired by the next screen launch, or by _end
+        pd->deferred = !(hide && ctx->side);
     }
     *out = pd;
     return SFB_OK;
@@ -188,7 +198,7 @@ extern "C" int32_t sfb_knn_build_columns_end(sfb_ctx* ctx, sfb_pending* pd, sfb_
         const uint32_t kk = pd->p.k;
         uint64_t q_begin = pd->p.q_begin, q_end = pd->p.q_end ? pd->p.q_end : m;
         if (q_begin >= q_end || q_end > m || isnan(pd->p.eps)) st = sfb_fail(ctx, SFB_EINVAL, "bad query shard or eps");
-        if (ctx->side_job == pd || (!pd->launched && ctx->side_job == nullptr && !ctx->side)) {   // no screen ran in between (or no side stream): run the Gram tiles now, on the main stream
+        if (ctx->side_job == pd || pd->deferred) {   // no screen ran in between, or not worth hiding: run the Gram tiles now, on the main stream
             ctx->side_job = nullptr;
             uint32_t t0, t1;
             sfb_gram_tile_range(ctx, m, pd->collective, &t0, &t1);

@@ -447,8 +447,16 @@ def test_knn_columns_begin_end(sfb, oracle, ctx):
     # not the feature-graph shape: end() takes the plain path
     y = np.random.default_rng(32).normal(size=(30, 500))
     assert_knn_equal(ctx.matrix(y).knn_columns_begin(4, 0).end().to_host(), oracle.knn(oracle.transpose(y), 4, 0))
-    # one pending build per context
+    # a build that is worth hiding (long rows: the Gram fits behind the screen of the same matrix) occupies the context's
+    # single side slot until its end(); small ones are simply deferred to end() and may be stacked
     p1 = m.knn_columns_begin(7, 0)
+    p2 = m.knn_columns_begin(7, 0)
+    assert_knn_equal(p2.end().to_host(), want_f)
+    assert_knn_equal(p1.end().to_host(), want_f)
+    big = ctx.generate(sfb.SYNTH_GAUSSIAN, 5, 700000, 48)
+    q1 = big.knn_columns_begin(5, 0)
     with pytest.raises(sfb.SfbError):
-        m.knn_columns_begin(7, 0)
-    p1.end().free()
+        big.knn_columns_begin(5, 0)
+    gq = big.knn(4, 0, q_begin=0, q_end=3000)
+    assert_knn_equal(q1.end().to_host(), oracle.knn(oracle.transpose(oracle.generate_rows(0, 5, 0, 700000, 48)), 5, 0))
+    gq.free()
