@@ -235,7 +235,7 @@ __global__ void lambda_kernel(LambdaArgs a) {
 // ((r << 16 | c) u32 + value f64, CSR order: deterministic) and kept in shared memory with the diagonal; a warp owns
 // an item, its lanes stride over the packed edges (coalesced shared-memory reads, two gathers of the item row per
 // edge) -- half the edges of the row-wise kernel above and no per-row loop overhead.  tau's median / percentile is a
-// quantised selection: min / max of the candidates, 256 bins, an 8-step binary search on counts for the bin that
+// quantised selection: min / max of the candidates, a 256-bin shared-memory histogram and a scan for the bin that
 // holds the rank, recurse into that bin (usually <= 2 rounds for a few hundred entries), exact extraction at the end.
 // Sums are reordered with respect to the reference's left folds (as in the kernel above): within 1e-12 relative.
 __device__ __forceinline__ double warp_min_d(double v) {
@@ -250,7 +250,7 @@ __device__ __forceinline__ double warp_max_d(double v) {
 }
 
 // value of 0-based rank `rank` among the finite entries of xs[0..f); *n_le = number of finite entries <= that value
-__device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, int lane, uint32_t* n_le) {
+__device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, int lane, uint32_t* n_le, uint32_t* hist /* 256 u32 of this warp */) {
     double lo = -INFINITY, hi = INFINITY;   // candidates: finite v with lo <= v <= hi
     uint32_t below = 0;                     // finite entries < lo
     double mn = INFINITY, mx = -INFINITY;
@@ -263,18 +263,29 @@ __device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, i
         if (mn == mx) { *n_le = below + cnt; return mn; }
         const double scale = 256.0 / (mx - mn);
         if (cnt <= 8 || !(scale < 1e300) || iter == 39) break;
-        uint32_t cut = 0, below_cut = 0;
-#pragma unroll 1
-        for (int b = 7; b >= 0; --b) {
-            const uint32_t trial = cut | (1u << b);
-            uint32_t c = 0;
-            for (uint32_t t = lane; t < f; t += 32) {
-                const double v = xs[t];
-                if (isfinite(v) && v >= lo && v <= hi) { int q = (int)((v - lo) * scale); q = q > 255 ? 255 : q; c += (uint32_t)q < trial ? 1u : 0u; }
-            }
-            c = warp_sum_u(c);
-            if (c <= target) { cut = trial; below_cut = c; }
+        // 256-bin histogram of the candidates in this warp's shared scratch, then a scan for the bin that holds `target`
+        for (int b = lane; b < 256; b += 32) hist[b] = 0;
+        __syncwarp();
+        for (uint32_t t = lane; t < f; t += 32) {
+            const double v = xs[t];
+            if (isfinite(v) && v >= lo && v <= hi) { int q = (int)((v - lo) * scale); q = q > 255 ? 255 : q; atomicAdd(&hist[q], 1u); }
         }
+        __syncwarp();
+        uint32_t c8[8], sum8 = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { c8[b] = hist[lane * 8 + b]; sum8 += c8[b]; }
+        uint32_t inc = sum8;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        uint32_t run = inc - sum8;   // candidates in the bins of lower lanes
+        int my_cut = -1; uint32_t my_below = 0;
+        if (target >= run && target < run + sum8) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { if (my_cut < 0 && target < run + c8[b]) { my_cut = lane * 8 + b; my_below = run; } run += c8[b]; }
+        }
+        const int src = __ffs(__ballot_sync(FULL, my_cut >= 0)) - 1;
+        const uint32_t cut = (uint32_t)__shfl_sync(FULL, my_cut, src), below_cut = __shfl_sync(FULL, my_below, src);
+        __syncwarp();
         // recurse into bin `cut`: its min, max and population
         double nmn = INFINITY, nmx = -INFINITY; uint32_t ncnt = 0;
         for (uint32_t t = lane; t < f; t += 32) {
@@ -305,7 +316,7 @@ __device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, i
 }
 
 // TauMode::select_tau (taumode.rs:29-70) with the quantised selection
-__device__ double warp_select_tau_fast(const double* xs, uint32_t f, int mode, double value, int lane) {
+__device__ double warp_select_tau_fast(const double* xs, uint32_t f, int mode, double value, int lane, uint32_t* hist) {
     const double FLOOR = 1e-10;
     if (mode == SFB_TAU_FIXED) return (isfinite(value) && value > 0.0) ? value : FLOOR;
     uint32_t n = 0; double s = 0.0;
@@ -317,11 +328,11 @@ __device__ double warp_select_tau_fast(const double* xs, uint32_t f, int mode, d
     double r;
     if (mode == SFB_TAU_PERCENTILE) {
         double pp = value < 0.0 ? 0.0 : (value > 1.0 ? 1.0 : value);
-        r = warp_kth_finite(xs, f, (uint32_t)round((double)(n - 1) * pp), lane, &n_le);
+        r = warp_kth_finite(xs, f, (uint32_t)round((double)(n - 1) * pp), lane, &n_le, hist);
     } else if (n & 1u) {
-        r = warp_kth_finite(xs, f, n / 2, lane, &n_le);
+        r = warp_kth_finite(xs, f, n / 2, lane, &n_le, hist);
     } else {
-        const double a = warp_kth_finite(xs, f, n / 2 - 1, lane, &n_le);
+        const double a = warp_kth_finite(xs, f, n / 2 - 1, lane, &n_le, hist);
         double b = a;
         if (n_le <= n / 2) {   // rank n/2 is the next larger value
             b = INFINITY;
@@ -386,6 +397,7 @@ __global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
     double* s_diag = s_val + a.ne;                                       // [f]
     double* xs = s_diag + a.f + (size_t)w * a.f;                         // [wpb][f]
     uint32_t* s_rc = reinterpret_cast<uint32_t*>(s_diag + a.f + (size_t)wpb * a.f);   // [ne]
+    uint32_t* hist = s_rc + a.ne + (size_t)w * 256;                                   // [wpb][256]
     for (uint32_t e = threadIdx.x; e < a.ne; e += blockDim.x) { s_val[e] = a.val[e]; s_rc[e] = a.rc[e]; }
     for (uint32_t r = threadIdx.x; r < a.f; r += blockDim.x) s_diag[r] = a.diag[r];
     __syncthreads();
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
         if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
         double lam;
         if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
-            const double tau = warp_select_tau_fast(xs, f, a.tau_mode, a.tau_value, lane);
+            const double tau = warp_select_tau_fast(xs, f, a.tau_mode, a.tau_value, lane, hist);
             lam = tau * (e_raw / (e_raw + tau)) + (1.0 - tau) * g;  // taumode.rs:306-310
         } else lam = e_raw;
         if (lane == 0) { a.out_lambda[i] = lam; if (a.out_disp) a.out_disp[i] = g; }
@@ -537,7 +549,7 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
             SFB_CUDA(ctx, cudaMemcpyAsync(&ne64, offs.as<uint64_t>() + f, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
             SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             const int wpb_s = 8;
-            const size_t smem_s = (size_t)ne64 * (sizeof(double) + sizeof(uint32_t)) + (size_t)f * sizeof(double) * (1 + wpb_s) + 16;
+            const size_t smem_s = (size_t)ne64 * (sizeof(double) + sizeof(uint32_t)) + (size_t)f * sizeof(double) * (1 + wpb_s) + (size_t)wpb_s * 256 * sizeof(uint32_t) + 16;
             if (smem_s <= 112 * 1024) {   // two CTAs per SM
                 const uint32_t ne = (uint32_t)ne64;
                 SFB_CUDA(ctx, rc.alloc(sizeof(uint32_t) * (ne ? ne : 1)));
