@@ -305,7 +305,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (fp16 tensor-core screen, exact f64 rescore)",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "dtype_note": "results are the exact f64 values of the reference arithmetic; the tensor-core screen that proposes candidates runs in fp16 with fp32 accumulation",
             "data": "synthetic (counter-based Philox + Box-Muller, generated on device)",
             "config": {"workload": wl["name"], "rows": n, "cols": d, "k": k, "metric": ["cosine", "l2", "l2sq"][wl["metric"]],
                        "p": P_WEIGHT, "sigma": SIGMA, "sharding": f"query rows / {world}, corpus replicated" if world > 1 else "single GPU",
