@@ -54,3 +54,10 @@ def test_product_does_not_reference_oracle():
                     if re.search(r"liboracle|import\s+oracle|from\s+oracle|oracle\.c|orc_[a-z]", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """The shipped-as-source Rust -sys crate (no Rust toolchain here) stays in sync with the header."""
+    rs = open(os.path.join(ROOT, "matternet-rs_b200", "rust", "surfface-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (sfb_[a-z0-9_]+)\(", rs))
+    assert declared == set(declared_symbols())
