@@ -223,6 +223,31 @@ int32_t sfb_map_items_to_subcentroids(sfb_ctx* ctx, const sfb_mat* items, const 
                                       const sfb_mat* sub_centroids, const double* sub_lambdas, double epsilon,
                                       uint32_t* out_idx, double* out_lambda, double* out_norm);
 
+/* ---- JL projection of the items ahead of lambda ---------------------------------------------
+ * sfb_project_rows = project_matrix / ImplicitProjection::project (src_legacy/reduction.rs:175-242), the step
+ *   compute_synthetic_lambda applies to an unprojected item before the Rayleigh quotient (taumode.rs:277-297).
+ *   The reference re-draws its ChaCha8 StandardNormal stream for every item; here the caller draws it ONCE
+ *   (the Rust wrapper does, with the same rand crates, matternet-rs_b200/rust/) and hands the samples in:
+ *     SFB_PROJECT_LEGACY    samples[i * r + j] (original_dim x reduced_dim, the reference's draw order);
+ *                           out_j = fold over i of  acc + (x_i * s_ij) * scale,  scale = 1/sqrt(r), f64
+ *     SFB_PROJECT_CORE_F32  samples[j * f + i] (reduced x original: surfface-core/src/clustering.rs:84-109 draws
+ *                           reduced-major); out_j = (fold over i of acc + x_i * s_ji) * scale in f32, carried in f64
+ *   Every output is a left fold in the reference's order: bit-exact.  out: x.rows x reduced_dim, on the device.
+ * sfb_compute_jl_dimension = compute_jl_dimension (reduction.rs:117-171; core != 0: clustering.rs:113-123). */
+typedef enum { SFB_PROJECT_LEGACY = 0, SFB_PROJECT_CORE_F32 = 1 } sfb_project_order;
+int32_t sfb_project_rows(sfb_ctx* ctx, const sfb_mat* x, const double* samples, uint32_t reduced_dim, int32_t order,
+                         sfb_mat** out);
+int32_t sfb_compute_jl_dimension(uint64_t n_points, uint64_t original_dim, double epsilon, int32_t core, uint64_t* out);
+
+/* ---- SortedLambdas ---------------------------------------------------------------------------
+ * sfb_sorted_lambdas_build = SortedLambdas::build_from + to_vec (src_legacy/sorted_index.rs:22-57), the index
+ *   ArrowSpace::build_lambdas_sorted fills after the lambdas (core.rs:937-940): lambdas ascending in OrderedFloat's
+ *   order (-0 == +0, NaN last), equal lambdas ordered by the DECIMAL STRING of the item index (zadd sorts buckets
+ *   by idx.to_string()), each bucket reporting the key first inserted.  out_std_dev = std_deviation(lambdas)
+ *   (laplacian.rs:421-448: sequential f64 sum, then f32).  lambdas, out_lambda: n doubles, out_idx: n (host). */
+int32_t sfb_sorted_lambdas_build(sfb_ctx* ctx, const double* lambdas, uint64_t n, double* out_lambda, uint32_t* out_idx,
+                                 double* out_std_dev);
+
 /* ---- reference-shaped one-shot entry points (host buffers in, host buffers out) ------------
  * sfb_build_laplacian_matrix = build_laplacian_matrix(transposed, &GraphParams, ..)
  *   (src_legacy/laplacian.rs:122-180): `items` is the already-transposed matrix, nodes = rows.

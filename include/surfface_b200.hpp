@@ -9,9 +9,12 @@
 //   TauMode, TauMode::compute_taumode_lambdas_parallel            src_legacy/taumode.rs:16-23,117-214 (+ core.rs:1427-1443)
 //   SfGrassSparsifier::sparsify_graph                             src_legacy/sparsification.rs:14-113
 //   LaplacianConfig, LaplacianOutput, LaplacianStage::execute     surfface-core/src/laplacian.rs:49-219
+//   compute_jl_dimension, ImplicitProjection, project_matrix      src_legacy/reduction.rs:117-248
+//   SortedLambdas::{build_from, to_vec, range_bylambda}           src_legacy/sorted_index.rs:8-79
 // The reference panics (assert! / panic!) on bad input; the mirror throws surfface_b200::Error carrying the status
 // and the library's message.  Everything computes on the GPU; there is no CPU fallback.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <memory>
 #include <optional>
@@ -237,6 +240,78 @@ public:
         return out;
     }
     LaplacianConfig config;
+};
+
+// ---- JL projection ahead of lambda (src_legacy/reduction.rs) -----------------------------------------------------
+inline size_t compute_jl_dimension(size_t n_points, size_t original_dim, double epsilon) {
+    uint64_t out = 0;
+    int st = sfb_compute_jl_dimension(n_points, original_dim, epsilon, 0, &out);
+    if (st != SFB_OK) throw Error(st, "sfb_compute_jl_dimension");
+    return (size_t)out;
+}
+
+// reduction.rs:202-248.  The reference keeps the seed and re-draws its ChaCha8 StandardNormal stream for every item;
+// the device wants the draws once: `samples[i * reduced_dim + j]` in the reference's draw order (the Rust wrapper
+// fills them with the reference's own rand crates; a C++ host supplies its own N(0,1) matrix).
+struct ImplicitProjection {
+    size_t original_dim = 0, reduced_dim = 0;
+    std::vector<double> samples;
+    ImplicitProjection(size_t original, size_t reduced, std::vector<double> draws) : original_dim(original), reduced_dim(reduced), samples(std::move(draws)) {
+        if (samples.size() != original_dim * reduced_dim) throw Error(SFB_EINVAL, "samples must be original_dim x reduced_dim");
+    }
+    size_t get_reduced_dim() const { return reduced_dim; }
+    std::vector<double> project(const std::vector<double>& query) const;
+};
+
+// reduction.rs:175-200: row-major n_rows x original_dim in, n_rows x reduced_dim out
+inline std::vector<double> project_matrix(const std::vector<double>& data, size_t n_rows, const ImplicitProjection& projection) {
+    if (data.size() != n_rows * projection.original_dim) throw Error(SFB_EINVAL, "data must be n_rows x original_dim");
+    Context& c = Context::thread_default();
+    sfb_mat *x = nullptr, *y = nullptr;
+    c.check(sfb_mat_from_host(c.get(), data.data(), n_rows, (uint32_t)projection.original_dim, &x));
+    int st = sfb_project_rows(c.get(), x, projection.samples.data(), (uint32_t)projection.reduced_dim, SFB_PROJECT_LEGACY, &y);
+    sfb_mat_free(x);
+    c.check(st);
+    std::vector<double> out(n_rows * projection.reduced_dim);
+    st = sfb_mat_copy_rows(c.get(), y, 0, n_rows, out.data());
+    sfb_mat_free(y);
+    c.check(st);
+    return out;
+}
+inline std::vector<double> ImplicitProjection::project(const std::vector<double>& query) const {
+    return project_matrix(std::vector<double>(query.begin(), query.begin() + (std::ptrdiff_t)original_dim), 1, *this);   // `.take(original_dim)`, :233
+}
+
+// ---- SortedLambdas (src_legacy/sorted_index.rs:8-79) ----------------------------------------------------------------
+class SortedLambdas {
+public:
+    // build_from (:32-46): throws where the reference panics (no lambdas)
+    void build_from(const std::vector<double>& lambdas) {
+        Context& c = Context::thread_default();
+        lambdas_.assign(lambdas.size(), 0.0);
+        indices_.assign(lambdas.size(), 0u);
+        c.check(sfb_sorted_lambdas_build(c.get(), lambdas.data(), lambdas.size(), lambdas_.data(), indices_.data(), &std_dev_));
+    }
+    // to_vec (:48-57): (lambda, idx) in map order
+    std::vector<std::pair<double, size_t>> to_vec() const {
+        std::vector<std::pair<double, size_t>> out(lambdas_.size());
+        for (size_t i = 0; i < out.size(); ++i) out[i] = {lambdas_[i], indices_[i]};
+        return out;
+    }
+    // range_bylambda (:60-79): the first k items with lambda in [q - band, q + band], band = std_dev / 2^p
+    std::vector<std::pair<size_t, double>> range_bylambda(double lambda_q, size_t k, double p) const {
+        const double band = std_dev_ / std::pow(2.0, p), lo = lambda_q - band, hi = lambda_q + band;
+        std::vector<std::pair<size_t, double>> out;
+        size_t a = 0, b = lambdas_.size();
+        while (a < b) { size_t m = (a + b) / 2; if (lambdas_[m] < lo) a = m + 1; else b = m; }
+        for (size_t i = a; i < lambdas_.size() && lambdas_[i] <= hi && out.size() < k; ++i) out.emplace_back(indices_[i], lambdas_[i]);
+        return out;
+    }
+    double std_dev() const { return std_dev_; }
+private:
+    std::vector<double> lambdas_;
+    std::vector<uint32_t> indices_;
+    double std_dev_ = 0.0;
 };
 
 }  // namespace surfface_b200

@@ -26,6 +26,7 @@ SCREEN_AUTO, SCREEN_EXACT_F64, SCREEN_F16, SCREEN_BF16 = 0, 1, 2, 3
 LAMBDA_LEGACY_TAUMODE, LAMBDA_ENERGY_NODE, LAMBDA_CORE_F32SEM = 0, 1, 2
 TAU_FIXED, TAU_MEDIAN, TAU_MEAN, TAU_PERCENTILE = 0, 1, 2, 3
 SYNTH_GAUSSIAN, SYNTH_CLUSTERED, SYNTH_ANISOTROPIC = 0, 1, 2
+PROJECT_LEGACY, PROJECT_CORE_F32 = 0, 1
 
 
 _PINNED = {}  # page-locked buffers stay alive for the life of the process
@@ -229,6 +230,18 @@ class Matrix(_Handle):
     def diffuse(self, L, eta, steps):
         self.ctx.check(lib().sfb_diffuse(self.ctx._h, L._h, self._h, float(eta), int(steps)))
         return self
+
+    def project(self, samples, order=PROJECT_LEGACY):
+        """project_matrix (reduction.rs:175-242): `samples` are the StandardNormal draws, original_dim x reduced_dim
+        (PROJECT_LEGACY) or reduced_dim x original_dim (PROJECT_CORE_F32, clustering.rs:84-109).  Stays on the device."""
+        s = _ffi.f64(samples)
+        f = self.shape[1]
+        if s.ndim != 2 or s.shape[0 if order == PROJECT_LEGACY else 1] != f:
+            raise ValueError(f"samples {s.shape} do not match {f} original dimensions")
+        r = s.shape[1 if order == PROJECT_LEGACY else 0]
+        out = C.c_void_p()
+        self.ctx.check(lib().sfb_project_rows(self.ctx._h, self._h, _ffi.ptr(s), r, int(order), C.byref(out)))
+        return Matrix(self.ctx, out)
 
 
 class PendingKnn:
@@ -638,3 +651,69 @@ class LaplacianStage:
         L = Csr(ctx, h)
         nnz = L.shape[1]
         return LaplacianOutput(matrix=L, n_features=f, nnz=nnz, degrees=deg, sparsity=1.0 - nnz / float(f * f))
+
+
+def compute_jl_dimension(n_points, original_dim, epsilon, core=False):
+    """reduction.rs:117-171 (core=True: surfface-core/src/clustering.rs:113-123)."""
+    out = C.c_uint64()
+    if lib().sfb_compute_jl_dimension(int(n_points), int(original_dim), float(epsilon), int(bool(core)), C.byref(out)) != 0:
+        raise SfbError("sfb_compute_jl_dimension")
+    return int(out.value)
+
+
+class ImplicitProjection:
+    """reduction.rs:202-248.  The reference keeps only the seed and re-draws the ChaCha8 StandardNormal stream per
+    item; the device path wants the draws once, so the mirror carries them (`samples`: original_dim x reduced_dim in
+    the reference's draw order -- the Rust wrapper fills them with the reference's own rand crates)."""
+
+    def __init__(self, original_dim, reduced_dim, samples):
+        self.original_dim, self.reduced_dim = int(original_dim), int(reduced_dim)
+        self.samples = _ffi.f64(samples)
+        if self.samples.shape != (self.original_dim, self.reduced_dim):
+            raise ValueError("samples must be original_dim x reduced_dim")
+
+    def get_reduced_dim(self):
+        return self.reduced_dim
+
+    def project(self, query, ctx=None):
+        q = _ffi.f64(query).reshape(1, -1)
+        ctx = ctx or default_context()
+        return ctx.matrix(q[:, :self.original_dim]).project(self.samples).rows()[0]
+
+
+def project_matrix(data, projection: ImplicitProjection, ctx=None) -> Matrix:
+    """reduction.rs:175-200; `data` is a host array or a device Matrix; the result stays on the device."""
+    ctx = ctx or default_context()
+    m = data if isinstance(data, Matrix) else ctx.matrix(data)
+    return m.project(projection.samples)
+
+
+class SortedLambdas:
+    """sorted_index.rs:8-57,59-79: items ordered by lambda (ties by the decimal string of the index); built by a
+    device radix sort instead of N BTreeMap insertions."""
+
+    def __init__(self):
+        self.lambdas = np.empty(0)
+        self.indices = np.empty(0, np.uint32)
+        self.std_dev = 0.0
+
+    def build_from(self, lambdas, ctx=None):
+        ctx = ctx or default_context()
+        lam = _ffi.f64(lambdas)
+        n = lam.shape[0]
+        self.lambdas, self.indices = np.empty(n, np.float64), np.empty(n, np.uint32)
+        sd = C.c_double()
+        ctx.check(lib().sfb_sorted_lambdas_build(ctx._h, _ffi.ptr(lam), n, _ffi.ptr(self.lambdas), _ffi.ptr(self.indices), C.byref(sd)))
+        self.std_dev = sd.value
+        return self
+
+    def to_vec(self):
+        return list(zip(self.lambdas.tolist(), self.indices.tolist()))
+
+    def range_bylambda(self, lambda_q, k, p):
+        """(idx, lambda) of the first k items with lambda in [q - band, q + band], band = std_dev / 2^p (:60-79)."""
+        band = self.std_dev / 2.0 ** p
+        lo = int(np.searchsorted(self.lambdas, lambda_q - band, "left"))
+        hi = int(np.searchsorted(self.lambdas, lambda_q + band, "right"))
+        hi = min(hi, lo + k)
+        return list(zip(self.indices[lo:hi].tolist(), self.lambdas[lo:hi].tolist()))

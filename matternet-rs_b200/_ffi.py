@@ -116,6 +116,9 @@ SYMBOLS = {
     "sfb_bc_adjacency_build": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _PP]),
     "sfb_laplacian_stage_execute": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(LaplacianConfigC), _PP, _P]),
     "sfb_map_items_to_subcentroids": (C.c_int32, [_P, _P, _P, _P, _P, C.c_double, _P, _P, _P]),
+    "sfb_project_rows": (C.c_int32, [_P, _P, _P, C.c_uint32, C.c_int32, _PP]),
+    "sfb_compute_jl_dimension": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_double, C.c_int32, C.POINTER(C.c_uint64)]),
+    "sfb_sorted_lambdas_build": (C.c_int32, [_P, _P, C.c_uint64, _P, _P, C.POINTER(C.c_double)]),
     "sfb_timings": (C.c_int32, [_P, C.POINTER(StageTimes)]),
     "sfb_timings_reset": (C.c_int32, [_P]),
     "sfb_timer_start": (C.c_int32, [_P]),

@@ -162,7 +162,7 @@ extern "C" int32_t sfb_timings_reset(sfb_ctx* ctx) {
 }
 
 // ---- matrices ---------------------------------------------------------------------------------
-static int32_t mat_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t cols, sfb_mat** out) {
+int32_t sfb_mat_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t cols, sfb_mat** out) {
     if (!ctx || !out || rows == 0 || cols == 0) return sfb_fail(ctx, SFB_EINVAL, "matrix must be non-empty");
     if (rows > 0xFFFFFFFEull) return sfb_fail(ctx, SFB_EINVAL, "rows must fit u32 node indices");
     sfb_mat* m = new (std::nothrow) sfb_mat();
@@ -176,7 +176,7 @@ static int32_t mat_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t cols, sfb_mat** o
 
 extern "C" int32_t sfb_mat_from_host(sfb_ctx* ctx, const double* x, uint64_t rows, uint32_t cols, sfb_mat** out) {
     if (!x) return sfb_fail(ctx, SFB_EINVAL, "null host pointer");
-    SFB_TRY(mat_alloc(ctx, rows, cols, out));
+    SFB_TRY(sfb_mat_alloc(ctx, rows, cols, out));
     StageTimer t(ctx, &ctx->times.ms_h2d);
     cudaError_t e = cudaMemcpyAsync((*out)->d, x, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, ctx->stream);
     t.stop();
@@ -201,7 +201,7 @@ extern "C" int32_t sfb_mat_generate(sfb_ctx* ctx, int32_t kind, uint64_t seed, u
                                     uint32_t n_centres, double noise, sfb_mat** out) {
     if (kind < 0 || kind > 2) return sfb_fail(ctx, SFB_EINVAL, "unknown synthetic kind %d", kind);
     if (kind == 1 && n_centres == 0) return sfb_fail(ctx, SFB_EINVAL, "clustered rows need n_centres > 0");
-    SFB_TRY(mat_alloc(ctx, rows, cols, out));
+    SFB_TRY(sfb_mat_alloc(ctx, rows, cols, out));
     uint64_t total = rows * ((cols + 3) / 4);
     generate_rows_kernel<<<div_up(total, 256), 256, 0, ctx->stream>>>((*out)->d, kind, seed, rows, cols, n_centres, noise);
     SFB_LAUNCH_CHECK(ctx);
@@ -237,7 +237,7 @@ int32_t sfb_transpose_device(sfb_ctx* ctx, const double* a, uint64_t rows, uint6
 extern "C" int32_t sfb_mat_transpose(sfb_ctx* ctx, const sfb_mat* a, sfb_mat** out) {
     if (!a) return sfb_fail(ctx, SFB_EINVAL, "null matrix");
     if (a->rows > 0xFFFFFFFFull) return sfb_fail(ctx, SFB_EINVAL, "too many rows to transpose");
-    SFB_TRY(mat_alloc(ctx, a->cols, (uint32_t)a->rows, out));
+    SFB_TRY(sfb_mat_alloc(ctx, a->cols, (uint32_t)a->rows, out));
     return sfb_transpose_device(ctx, a->d, a->rows, a->cols, (*out)->d);
 }
 

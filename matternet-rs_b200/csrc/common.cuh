@@ -155,6 +155,7 @@ int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int m
                       const uint32_t* query_rows /* device, or null */, uint64_t nq, uint64_t q_begin,
                       uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);
 void sfb_comm_destroy(sfb_ctx* ctx);
+int32_t sfb_mat_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t cols, sfb_mat** out);  // api.cu: uninitialised rows x cols f64
 // launches the registered side job, if any (called right after the screen kernel is enqueued, so that the persistent
 // screen CTAs are placed first and the side kernel's small CTAs fill in beside them)
 void sfb_side_job_fire(sfb_ctx* ctx);

@@ -3,7 +3,7 @@
 fn main() {
     let csrc = std::env::var("SURFFACE_B200_CSRC").unwrap_or_else(|_| "../../csrc".to_string());
     let include = std::env::var("SURFFACE_B200_INCLUDE").unwrap_or_else(|_| "../../../include".to_string());
-    let files = ["api.cu", "knn.cu", "knn_exact.cu", "knn_screen.cu", "laplacian.cu", "lambda.cu", "pipeline.cu", "comm.cu", "bc.cu"];
+    let files = ["api.cu", "knn.cu", "knn_exact.cu", "knn_screen.cu", "laplacian.cu", "lambda.cu", "pipeline.cu", "comm.cu", "bc.cu", "project.cu"];
     let mut b = cc::Build::new();
     b.cuda(true)
         .flag("-gencode").flag("arch=compute_100a,code=sm_100a")

@@ -69,6 +69,9 @@ extern "C" {
     pub fn sfb_lambda(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *const sfb_mat, params: *const sfb_lambda_params, out_lambda: *mut f64, out_dispersion: *mut f64, stats: *mut f64) -> i32;
     pub fn sfb_diffuse(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *mut sfb_mat, eta: f64, steps: u32) -> i32;
     pub fn sfb_map_items_to_subcentroids(ctx: *mut sfb_ctx, items: *const sfb_mat, item_lambdas: *const f64, sub_centroids: *const sfb_mat, sub_lambdas: *const f64, epsilon: f64, out_idx: *mut u32, out_lambda: *mut f64, out_norm: *mut f64) -> i32;
+    pub fn sfb_project_rows(ctx: *mut sfb_ctx, x: *const sfb_mat, samples: *const f64, reduced_dim: u32, order: i32, out: *mut *mut sfb_mat) -> i32;
+    pub fn sfb_compute_jl_dimension(n_points: u64, original_dim: u64, epsilon: f64, core: i32, out: *mut u64) -> i32;
+    pub fn sfb_sorted_lambdas_build(ctx: *mut sfb_ctx, lambdas: *const f64, n: u64, out_lambda: *mut f64, out_idx: *mut u32, out_std_dev: *mut f64) -> i32;
     pub fn sfb_build_laplacian_matrix(ctx: *mut sfb_ctx, items: *const f64, nodes: u64, dims: u32, params: *const sfb_graph_params, screen: i32, out: *mut *mut sfb_csr) -> i32;
     pub fn sfb_compute_taumode_lambdas(ctx: *mut sfb_ctx, L: *const sfb_csr, items: *const f64, n_items: u64, n_features: u32, tau_mode: i32, tau_value: f64, out_lambdas: *mut f64) -> i32;
     pub fn sfb_bc_adjacency_build(ctx: *mut sfb_ctx, means: *const f32, variances: *const f32, n_centroids: u32, n_features: u32, k: u32, variance_regularizer: f32, weight_threshold: f32, out: *mut *mut sfb_adj) -> i32;

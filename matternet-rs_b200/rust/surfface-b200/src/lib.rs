@@ -176,3 +176,78 @@ impl LaplacianStage {
         })
     }
 }
+
+// ---- JL projection ahead of lambda (src_legacy/reduction.rs:175-248) --------------------------------------------
+use rand::SeedableRng;
+use rand_chacha::ChaCha8Rng;
+use rand_distr::{Distribution, StandardNormal};
+
+/// `compute_jl_dimension` (`reduction.rs:117-171`)
+pub fn compute_jl_dimension(n_points: usize, original_dim: usize, epsilon: f64) -> usize {
+    let mut out = 0u64;
+    let st = unsafe { sys::sfb_compute_jl_dimension(n_points as u64, original_dim as u64, epsilon, 0, &mut out) };
+    assert!(st == sys::SFB_OK);
+    out as usize
+}
+
+/// `ImplicitProjection` (`reduction.rs:202-248`): still seed-only.
+#[derive(Clone, Debug, PartialEq, Eq)]
+pub struct ImplicitProjection {
+    pub original_dim: usize,
+    pub reduced_dim: usize,
+    pub seed: u64,
+}
+impl ImplicitProjection {
+    pub fn new(original_dim: usize, reduced_dim: usize, seed: Option<u64>) -> Self {
+        Self { original_dim, reduced_dim, seed: seed.unwrap_or_else(rand::random) }
+    }
+    /// The draws `project` makes, once: `samples[i * r + j]` is the StandardNormal drawn for (original i, reduced j)
+    /// -- the reference restarts `ChaCha8Rng::seed_from_u64(seed)` for every item and consumes it in exactly this
+    /// order (`reduction.rs:228-239`), so every item sees the same F x r matrix.
+    pub fn materialise(&self) -> Vec<f64> {
+        let mut rng = ChaCha8Rng::seed_from_u64(self.seed);
+        (0..self.original_dim * self.reduced_dim).map(|_| StandardNormal.sample(&mut rng)).collect()
+    }
+    pub fn get_reduced_dim(&self) -> usize {
+        self.reduced_dim
+    }
+}
+
+/// `project_matrix(data, projection)` (`reduction.rs:175-200`): row-major `n x original_dim` in, `n x reduced_dim` out.
+pub fn project_matrix(data: &[f64], n_rows: usize, projection: &ImplicitProjection) -> Vec<f64> {
+    assert_eq!(data.len(), n_rows * projection.original_dim);
+    let samples = projection.materialise();
+    let r = projection.reduced_dim;
+    let mut out = vec![0f64; n_rows * r];
+    with_ctx(|ctx| unsafe {
+        let (mut x, mut y) = (std::ptr::null_mut(), std::ptr::null_mut());
+        check(ctx, sys::sfb_mat_from_host(ctx, data.as_ptr(), n_rows as u64, projection.original_dim as u32, &mut x));
+        let st = sys::sfb_project_rows(ctx, x, samples.as_ptr(), r as u32, 0, &mut y);
+        sys::sfb_mat_free(x);
+        check(ctx, st);
+        let st = sys::sfb_mat_copy_rows(ctx, y, 0, n_rows as u64, out.as_mut_ptr());
+        sys::sfb_mat_free(y);
+        check(ctx, st);
+    });
+    out
+}
+
+// ---- SortedLambdas (src_legacy/sorted_index.rs) ------------------------------------------------------------------
+use ordered_float::OrderedFloat;
+use std::collections::BTreeMap;
+
+/// `SortedLambdas::build_from` (`sorted_index.rs:32-46`): the device returns the items already in map order, so the
+/// BTreeMap is bulk-built from a sorted run (O(N)) instead of N `zadd` calls that each re-sort a bucket of strings.
+pub fn build_sorted_lambdas(lambdas: &[f64]) -> (BTreeMap<OrderedFloat<f64>, Vec<(usize, String)>>, f64) {
+    let n = lambdas.len();
+    let (mut sorted, mut idx, mut std_dev) = (vec![0f64; n], vec![0u32; n], 0f64);
+    with_ctx(|ctx| check(ctx, unsafe { sys::sfb_sorted_lambdas_build(ctx, lambdas.as_ptr(), n as u64, sorted.as_mut_ptr(), idx.as_mut_ptr(), &mut std_dev) }));
+    let mut runs: Vec<(OrderedFloat<f64>, Vec<(usize, String)>)> = Vec::new();
+    for (lam, i) in sorted.into_iter().zip(idx) {
+        match runs.last_mut() {
+            Some((k, bucket)) if *k == OrderedFloat(lam) => bucket.push((i as usize, i.to_string())),
+            _ => runs.push((OrderedFloat(lam), vec![(i as usize, i.to_string())])),
+        }
+    }
+    (runs.into_iter().collect(), std_dev)
+}

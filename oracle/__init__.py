@@ -77,6 +77,14 @@ def lib():
     L.orc_bc.restype = _c.c_float
     L.orc_bc_matrix.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_float, _fp]
     L.orc_bc_knn.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_float, _c.c_float, _u32p, _fp, _u32p]
+    L.orc_jl_dimension.argtypes = [_c.c_uint64, _c.c_uint64, _c.c_double]
+    L.orc_jl_dimension.restype = _c.c_uint64
+    L.orc_jl_dimension_core.argtypes = [_c.c_uint64, _c.c_uint64, _c.c_float]
+    L.orc_jl_dimension_core.restype = _c.c_uint64
+    L.orc_project_rows.argtypes = [_dp, _c.c_uint64, _c.c_uint32, _dp, _c.c_uint32, _dp]
+    L.orc_project_rows_core.argtypes = [_fp, _c.c_uint64, _c.c_uint32, _fp, _c.c_uint32, _fp]
+    L.orc_sorted_lambdas.argtypes = [_dp, _c.c_uint64, _dp, _u32p, _c.POINTER(_c.c_double)]
+    L.orc_sorted_lambdas.restype = _c.c_int
     _lib = L
     return L
 
@@ -259,3 +267,41 @@ def map_items(items, item_lambdas, sub_centroids, sub_lambdas, epsilon=1e-11):
     idx = np.empty(n, np.uint32); lam = np.empty(n, np.float64); norm = np.empty(n, np.float64)
     lib().orc_map_items(x, n, f, il, sc, sc.shape[0], sl, float(epsilon), idx, lam, norm)
     return idx, lam, norm
+
+
+def jl_dimension(n_points, original_dim, epsilon, core=False):
+    """compute_jl_dimension: reduction.rs:117-171 (f64) / surfface-core clustering.rs:113-123 (f32)."""
+    if core:
+        return int(lib().orc_jl_dimension_core(n_points, original_dim, float(epsilon)))
+    return int(lib().orc_jl_dimension(n_points, original_dim, float(epsilon)))
+
+
+def project_rows(x, samples):
+    """project_matrix (reduction.rs:175-242): samples is original_dim x reduced_dim (draw order of the reference)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    s = np.ascontiguousarray(samples, dtype=np.float64)
+    assert s.shape[0] == x.shape[1]
+    out = np.empty((x.shape[0], s.shape[1]), np.float64)
+    lib().orc_project_rows(x, x.shape[0], x.shape[1], s, s.shape[1], out)
+    return out
+
+
+def project_rows_core(x, samples):
+    """surfface-core clustering.rs:84-109 (f32): samples is reduced_dim x original_dim (its draw order)."""
+    x = _f32(x)
+    s = _f32(samples)
+    assert s.shape[1] == x.shape[1]
+    out = np.empty((x.shape[0], s.shape[0]), np.float32)
+    lib().orc_project_rows_core(x, x.shape[0], x.shape[1], s, s.shape[0], out)
+    return out
+
+
+def sorted_lambdas(lam):
+    """SortedLambdas::build_from + to_vec (sorted_index.rs:22-57): (lambda_sorted, idx, std_dev)."""
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    out = np.empty(lam.shape[0], np.float64)
+    idx = np.empty(lam.shape[0], np.uint32)
+    sd = _c.c_double()
+    if lib().orc_sorted_lambdas(lam, lam.shape[0], out, idx, _c.byref(sd)) != 0:
+        raise ValueError("empty lambdas: the reference panics")
+    return out, idx, sd.value

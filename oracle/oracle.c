@@ -25,6 +25,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -907,4 +908,106 @@ void orc_map_items(const double* items, uint64_t n, uint32_t f, const double* it
         }
         out_idx[i] = best; out_lambda[i] = sub_lambdas[best]; out_norm[i] = norm;
     }
+}
+
+/* ---- JL projection of items ahead of lambda ("next" row 3) --------------------------------------
+ * compute_jl_dimension: src_legacy/reduction.rs:117-171 (f64) and surfface-core/src/clustering.rs:113-123 (f32).
+ * Pinned by the exact values in src_legacy/tests/test_reduction.rs:193-345 (tests/test_oracle_kat.py).
+ * Rust's `as usize` saturates (negative and NaN -> 0). */
+static uint64_t sat_usize(double v) { return (v != v || v <= 0.0) ? 0 : (v >= 1.8446744073709552e19 ? UINT64_MAX : (uint64_t)v); }
+static uint64_t clamp_u64(uint64_t v, uint64_t lo, uint64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+uint64_t orc_jl_dimension(uint64_t n_points, uint64_t original_dim, double epsilon) {
+    if (original_dim < 32) return original_dim;
+    double log_n = log((double)n_points);
+    double eps_sq = pow(epsilon, 2.0);
+    uint64_t jl_bound = sat_usize(ceil(8.0 * log_n / eps_sq));
+    if (original_dim > 2048) {
+        double ratio = (double)original_dim / (double)jl_bound;
+        double buffer = ratio < 10.0 ? 1.2 : (ratio < 100.0 ? 1.5 : 2.0);
+        return clamp_u64(sat_usize(ceil((double)jl_bound * buffer)), 32, original_dim);
+    }
+    return clamp_u64(jl_bound, 32, original_dim);
+}
+
+uint64_t orc_jl_dimension_core(uint64_t n_points, uint64_t original_dim, float epsilon) {
+    if (original_dim < 32) return original_dim;
+    float log_n = logf((float)n_points);
+    float eps_sq = epsilon * epsilon; /* powi(2) */
+    return clamp_u64(sat_usize((double)ceilf(8.0f * log_n / eps_sq)), 32, original_dim);
+}
+
+/* ImplicitProjection::project (src_legacy/reduction.rs:225-242) with the StandardNormal samples handed in as a
+ * matrix: samples[i*r + j] is the draw made for (original i, reduced j), the order the reference's nested loop
+ * consumes its ChaCha8 stream in.  out[j] = fold over i of  acc + (x_i * s_ij) * scale,  scale = 1/sqrt(r).
+ * project_matrix (reduction.rs:175-200) applies it to every row. */
+void orc_project_rows(const double* x, uint64_t n, uint32_t f, const double* samples, uint32_t r, double* out) {
+    const double scale = 1.0 / sqrt((double)r);
+#pragma omp parallel for schedule(static)
+    for (int64_t row = 0; row < (int64_t)n; row++) {
+        double* o = out + (uint64_t)row * r;
+        for (uint32_t j = 0; j < r; j++) o[j] = 0.0;
+        for (uint32_t i = 0; i < f; i++) {
+            double xi = x[(uint64_t)row * f + i];
+            for (uint32_t j = 0; j < r; j++) o[j] = o[j] + (xi * samples[(uint64_t)i * r + j]) * scale;
+        }
+    }
+}
+
+/* successor: surfface-core/src/clustering.rs:84-109, f32; samples[j*f + i] (the draw order there is j-major):
+ * out[j] = (fold over i of acc + x_i * s_ji) * scale. */
+void orc_project_rows_core(const float* x, uint64_t n, uint32_t f, const float* samples, uint32_t r, float* out) {
+    const float scale = 1.0f / sqrtf((float)r);
+#pragma omp parallel for schedule(static)
+    for (int64_t row = 0; row < (int64_t)n; row++)
+        for (uint32_t j = 0; j < r; j++) {
+            float sum = 0.0f;
+            for (uint32_t i = 0; i < f; i++) sum = sum + x[(uint64_t)row * f + i] * samples[(uint64_t)j * f + i];
+            out[(uint64_t)row * r + j] = sum * scale;
+        }
+}
+
+/* ---- SortedLambdas::build_from ("next" row 4; src_legacy/sorted_index.rs:22-46, laplacian.rs:421-448) ----------
+ * BTreeMap<OrderedFloat<f64>, Vec<(idx, idx.to_string())>>: keys ascending in OrderedFloat's total order (-0 == +0,
+ * NaN == NaN and greater than everything); inside a bucket the items are ordered by their DECIMAL STRING id
+ * ("10" < "2"); the key a bucket reports is the one first inserted (lowest idx).  to_vec() flattens that.
+ * std_dev: f32 arithmetic on a sequential f64 sum, as laplacian.rs:421-448 writes it. */
+static const double* g_sl_lam;
+static int of_cmp(double a, double b) {
+    int an = a != a, bn = b != b;
+    if (an || bn) return an - bn; /* NaN greatest, NaN == NaN */
+    return (a > b) - (a < b);     /* -0 == +0 */
+}
+static int sl_cmp(const void* pa, const void* pb) {
+    uint32_t a = *(const uint32_t*)pa, b = *(const uint32_t*)pb;
+    int c = of_cmp(g_sl_lam[a], g_sl_lam[b]);
+    if (c) return c;
+    char sa[24], sb[24];
+    snprintf(sa, sizeof sa, "%u", a);
+    snprintf(sb, sizeof sb, "%u", b);
+    return strcmp(sa, sb);
+}
+int orc_sorted_lambdas(const double* lam, uint64_t n, double* out_lambda, uint32_t* out_idx, double* out_std_dev) {
+    if (n == 0) return -1; /* mean() is None -> build_from panics */
+    double sum = 0.0;
+    for (uint64_t i = 0; i < n; i++) sum = sum + lam[i];
+    float mean = (float)sum / (float)n;
+    float var = 0.0f;
+    for (uint64_t i = 0; i < n; i++) {
+        float diff = mean - (float)lam[i];
+        var = var + diff * diff;
+    }
+    var = var / (float)n;
+    *out_std_dev = (double)sqrtf(var);
+    for (uint64_t i = 0; i < n; i++) out_idx[i] = (uint32_t)i;
+    g_sl_lam = lam;
+    qsort(out_idx, n, sizeof(uint32_t), sl_cmp);
+    for (uint64_t a = 0; a < n;) {
+        uint64_t b = a;
+        uint32_t first = out_idx[a];
+        while (b < n && of_cmp(lam[out_idx[b]], lam[out_idx[a]]) == 0) { if (out_idx[b] < first) first = out_idx[b]; b++; }
+        for (uint64_t t = a; t < b; t++) out_lambda[t] = lam[first];
+        a = b;
+    }
+    return 0;
 }

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <tuple>
 #include <vector>
 
 #include "surfface_b200.hpp"
@@ -27,6 +28,9 @@ void orc_csr_free(void* h);
 void orc_lambda(const uint64_t* indptr, const uint32_t* indices, const double* data, uint64_t f, const double* x, uint64_t n, int variant,
                 int tau_mode, double tau_value, double* lam, double* e, double* g);
 void orc_normalise_lambdas(double* lam, uint64_t n, double* stats);
+uint64_t orc_jl_dimension(uint64_t n_points, uint64_t original_dim, double epsilon);
+void orc_project_rows(const double* x, uint64_t n, uint32_t f, const double* samples, uint32_t r, double* out);
+int orc_sorted_lambdas(const double* lam, uint64_t n, double* out_lambda, uint32_t* out_idx, double* out_std_dev);
 }
 
 static int failures = 0;
@@ -174,6 +178,46 @@ static void test_sfgrass_and_stage() {
     for (size_t i = 0; i < 20; ++i) if (lo.degrees[i] > 1e-9f) CHECK(lo.matrix.get(i, i) && std::fabs(*lo.matrix.get(i, i) - 1.0) <= 1e-6, "L_sym diagonal");
 }
 
+// the reference's own reduction tests (src_legacy/tests/test_reduction.rs) + SortedLambdas, against the oracle
+static void test_projection_and_sorted_lambdas() {
+    CHECK(compute_jl_dimension(100, 16, 0.3) == 16 && compute_jl_dimension(10, 100, 0.3) == 100, "jl: low dims / never expands");   // :193-210
+    CHECK(compute_jl_dimension(2, 1000, 0.9) == 32 && compute_jl_dimension(1000, 512, 0.1) == 512, "jl: clamp");                      // :219-243
+    CHECK(compute_jl_dimension(1, 100, 0.1) == 32 && compute_jl_dimension(1, 10, 0.1) == 10, "jl: single point");                      // :468-475
+    for (auto [n, d, e] : {std::tuple<size_t, size_t, double>{10000, 5000, 0.3}, {100, 2049, 0.3}, {100, 100000, 0.3}})
+        CHECK(compute_jl_dimension(n, d, e) == orc_jl_dimension(n, d, e), "jl(%zu, %zu, %g)", n, d, e);
+    std::mt19937_64 rng(42);
+    std::normal_distribution<double> nd;
+    const size_t n = 333, f = 40, r = 10;
+    std::vector<double> draws(f * r), data(n * f);
+    for (double& v : draws) v = nd(rng);
+    for (double& v : data) v = nd(rng);
+    ImplicitProjection proj(f, r, draws);
+    std::vector<double> zero = proj.project(std::vector<double>(f, 0.0));                                                              // :60-69
+    for (double v : zero) CHECK(v == 0.0, "zero vector must project to zeros");
+    std::vector<double> ones(f, 1.0), twos(f, 2.0);
+    std::vector<double> p1 = proj.project(ones), p2 = proj.project(twos);                                                              // :72-93
+    for (size_t j = 0; j < r; ++j) CHECK(p2[j] == 2.0 * p1[j], "linearity at %zu", j);
+    std::vector<double> got = project_matrix(data, n, proj), want(n * r);                                                              // :128-148
+    orc_project_rows(data.data(), n, (uint32_t)f, draws.data(), (uint32_t)r, want.data());
+    CHECK(got == want, "projected matrix differs from the oracle's left folds");
+    std::vector<double> lam(5000);
+    for (size_t i = 0; i < lam.size(); ++i) lam[i] = std::floor(100.0 * std::fabs(std::sin(0.1 * (double)i))) / 100.0;              // heavy ties
+    SortedLambdas sl;
+    sl.build_from(lam);
+    std::vector<double> wl(lam.size()); std::vector<uint32_t> wi(lam.size()); double wsd = 0.0;
+    orc_sorted_lambdas(lam.data(), lam.size(), wl.data(), wi.data(), &wsd);
+    auto v = sl.to_vec();
+    bool same = v.size() == lam.size() && sl.std_dev() == wsd;
+    for (size_t i = 0; same && i < v.size(); ++i) same = v[i].first == wl[i] && v[i].second == wi[i];
+    CHECK(same, "SortedLambdas order / std_dev differ from the oracle");
+    auto hits = sl.range_bylambda(0.5, 7, 2.0);
+    CHECK(hits.size() == 7, "range_bylambda returns the first k in the band");
+    for (auto& h : hits) CHECK(std::fabs(h.second - 0.5) <= sl.std_dev() / 4.0, "range_bylambda band");
+    bool threw = false;
+    try { SortedLambdas().build_from({}); } catch (const Error& e) { threw = e.status == SFB_EINVAL; }                                 // sorted_index.rs:36-40 panics
+    CHECK(threw, "empty lambdas must be refused");
+}
+
 int main() {
     test_basic_laplacian_construction();
     test_laplacian_mathematical_properties();
@@ -182,6 +226,7 @@ int main() {
     test_oracle_parity();
     test_errors_are_exceptions();
     test_sfgrass_and_stage();
+    test_projection_and_sorted_lambdas();
     std::printf(failures ? "%d FAILED\n" : "all C++ mirror tests passed\n", failures);
     return failures ? 1 : 0;
 }

@@ -460,3 +460,91 @@ def test_knn_columns_begin_end(sfb, oracle, ctx):
     gq = big.knn(4, 0, q_begin=0, q_end=3000)
     assert_knn_equal(q1.end().to_host(), oracle.knn(oracle.transpose(oracle.generate_rows(0, 5, 0, 700000, 48)), 5, 0))
     gq.free()
+
+
+# ---- JL projection ahead of lambda, SortedLambdas after it ---------------------------
+@pytest.mark.parametrize("n,f,r", [(1000, 384, 91), (777, 50, 64), (130, 33, 1), (5, 700, 200), (2049, 128, 32)])
+def test_project_rows_bit_exact(sfb, oracle, ctx, n, f, r):
+    """Every projected entry is the reference's left fold ((x_i * s_ij) * scale added in i order): identical bits."""
+    rng = np.random.default_rng(n + f + r)
+    x = rng.standard_normal((n, f))
+    x[0] = 0.0                                            # zero vector -> zeros (test_reduction.rs:60-69)
+    s = rng.standard_normal((f, r))
+    got = ctx.matrix(x).project(s).rows()
+    want = oracle.project_rows(x, s)
+    assert got.shape == (n, r) and np.array_equal(got, want)
+    assert np.all(got[0] == 0.0)
+    # linearity by an exact factor (test_reduction.rs:72-93)
+    assert np.array_equal(ctx.matrix(2.0 * x).project(s).rows(), 2.0 * want)
+
+
+def test_project_rows_core_f32(sfb, oracle, ctx):
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((300, 96)).astype(np.float32)
+    s = rng.standard_normal((40, 96)).astype(np.float32)  # reduced-major, as clustering.rs:94-105 draws
+    got = ctx.matrix(x.astype(np.float64)).project(s.astype(np.float64), order=sfb.PROJECT_CORE_F32).rows()
+    assert np.array_equal(got.astype(np.float32), oracle.project_rows_core(x, s)) and np.array_equal(got, got.astype(np.float32))
+    with pytest.raises(ValueError):
+        ctx.matrix(x.astype(np.float64)).project(np.zeros((95, 40)))
+
+
+def test_projected_lambdas_match_reference_pipeline(sfb, oracle, ctx):
+    """compute_synthetic_lambda on unprojected items (taumode.rs:277-297): project, then lambda against the r x r
+    Laplacian -- device pipeline against the oracle's, <= 1e-9 relative."""
+    rng = np.random.default_rng(21)
+    n, f, r = 3000, 128, sfb.compute_jl_dimension(40, 128, 0.5)
+    assert r == oracle.jl_dimension(40, 128, 0.5) and 32 <= r < 128
+    x = rng.standard_normal((n, f))
+    s = rng.standard_normal((f, r))
+    proj = sfb.ImplicitProjection(f, r, s)
+    y = sfb.project_matrix(x, proj, ctx=ctx)
+    L = y.knn_columns(6, 0).adjacency(2.0, 1.0).laplacian()
+    got = L.lambdas(y, tau_mode=sfb.TAU_MEDIAN, normalise=True)[0]
+    yo = oracle.project_rows(x, s)
+    idx, dist, cnt = oracle.knn(oracle.transpose(yo), 6, 0)
+    a = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0)
+    ip, ind, dat = oracle.laplacian(a[0], a[1], a[2])
+    want = oracle.normalise_lambdas(oracle.lambdas(ip, ind, dat, yo, tau_mode=oracle.TAU_MEDIAN))[0]
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+    assert np.array_equal(proj.project(x[3], ctx=ctx), yo[3])
+
+
+def test_jl_dimension_matches_oracle(sfb, oracle):
+    for n, d, e in [(100, 16, 0.3), (10, 100, 0.3), (2, 1000, 0.9), (1000, 512, 0.1), (100, 2000, 0.2), (10_000, 5_000, 0.3),
+                    (5_000, 3_000, 0.3), (100, 100_000, 0.3), (1, 100, 0.1), (0, 64, 0.3), (100, 2048, 0.3), (100, 2049, 0.3)]:
+        assert sfb.compute_jl_dimension(n, d, e) == oracle.jl_dimension(n, d, e)
+        assert sfb.compute_jl_dimension(n, d, e, core=True) == oracle.jl_dimension(n, d, e, core=True)
+
+
+@pytest.mark.parametrize("n", [1, 13, 2048, 2049, 100_003, 1_000_000])
+def test_sorted_lambdas_parity(sfb, oracle, ctx, n):
+    """Order (lambda, decimal string of idx), bucket keys and the f32 std_dev, identical to the oracle's BTreeMap
+    restatement; heavy ties (quantised lambdas, the zero bucket with both signs) exercise the string order."""
+    rng = np.random.default_rng(n)
+    lam = np.round(rng.random(n), 3 if n > 100 else 1)
+    lam[rng.random(n) < 0.05] = 0.0
+    lam[rng.random(n) < 0.01] = -0.0
+    if n > 12:
+        lam[7], lam[11] = 1.0, -0.25
+    sl = sfb.SortedLambdas().build_from(lam, ctx=ctx)
+    want, widx, wsd = oracle.sorted_lambdas(lam)
+    assert np.array_equal(sl.indices, widx)
+    assert np.array_equal(sl.lambdas.view(np.uint64), want.view(np.uint64))
+    assert sl.std_dev == wsd
+    assert sl.to_vec()[:3] == list(zip(want[:3].tolist(), widx[:3].tolist()))
+
+
+def test_sorted_lambdas_nan_and_range(sfb, oracle, ctx):
+    lam = np.array([math.nan, 0.3, math.nan, math.inf, 0.3, -1.0])
+    sl = sfb.SortedLambdas().build_from(lam, ctx=ctx)
+    want, widx, _ = oracle.sorted_lambdas(lam)
+    assert np.array_equal(sl.indices, widx) and list(widx) == [5, 1, 4, 3, 0, 2]
+    assert np.array_equal(np.isnan(sl.lambdas), np.isnan(want))
+    with pytest.raises(sfb.SfbError):
+        sfb.SortedLambdas().build_from(np.zeros(0), ctx=ctx)
+    # range_bylambda (sorted_index.rs:60-79): first k inside [q - std/2^p, q + std/2^p] in index order of the map
+    lam = np.random.default_rng(4).random(5000)
+    sl = sfb.SortedLambdas().build_from(lam, ctx=ctx)
+    band = sl.std_dev / 2.0 ** 2.0
+    inside = [(int(i), float(lam[i])) for i in np.argsort(lam, kind="stable") if 0.5 - band <= lam[i] <= 0.5 + band]
+    assert sl.range_bylambda(0.5, 10, 2.0) == inside[:10]

@@ -329,3 +329,104 @@ def test_bhattacharyya_knn_order_and_threshold(oracle):
     assert cnt[3] == 0 and np.all(idx[3] == oracle.IDX_NONE)  # BC(3, .) ~ exp(-200) underflows below the threshold
     idx, w, cnt = oracle.bc_knn(m, v, 10)
     assert cnt[0] == 3 and idx.shape == (5, 10)               # feature 3 is out of reach of everyone
+
+
+# ---- JL projection ahead of lambda: src_legacy/tests/test_reduction.rs -------------------------------------------
+def test_jl_dimension_table(oracle):
+    """Every exact value the reference asserts (test_reduction.rs:193-229,233-243,317-357,453-475,525-539,556-562)."""
+    jl = oracle.jl_dimension
+    assert [jl(100, 16, 0.3), jl(1000, 8, 0.1), jl(50, 31, 0.2), jl(10, 1, 0.5)] == [16, 8, 31, 1]
+    assert jl(10, 100, 0.3) == 100 and jl(10, 50, 0.3) == 50
+    assert 148 <= jl(100, 200, 0.5) <= 149
+    assert jl(2, 1000, 0.9) == 32 and jl(2, 20, 0.9) == 20
+    assert jl(1000, 512, 0.1) == 512
+    assert 921 <= jl(100, 2000, 0.2) <= 923
+    bound = lambda n, e: math.ceil(8.0 * math.log(n) / (e * e))
+    assert jl(10_000, 5_000, 0.3) == math.ceil(bound(10_000, 0.3) * 1.2)
+    assert jl(5_000, 3_000, 0.3) == min(math.ceil(bound(5_000, 0.3) * 1.2), 3_000)
+    assert jl(1000, 1500, 0.15) == min(max(bound(1000, 0.15), 32), 1500)
+    assert jl(1, 100, 0.1) == 32 and jl(1, 10, 0.1) == 10
+    assert jl(100, 2048, 0.3) == min(max(bound(100, 0.3), 32), 2048)
+    assert jl(100, 2049, 0.3) == min(max(math.ceil(bound(100, 0.3) * 1.2), 32), 2049)
+    assert 800 <= jl(100, 100_000, 0.3) <= 850                      # 2.0x buffer tier
+    for n, d, e in ((500, 3000, 0.3), (100, 100_000, 0.3), (10, 50_000, 0.3)):   # :255-315, within +-2 of the tier
+        tier = 1.2 if d / bound(n, e) < 10 else (1.5 if d / bound(n, e) < 100 else 2.0)
+        assert abs(jl(n, d, e) - math.ceil(bound(n, e) * tier)) <= 2
+    assert jl(10, 10_000, 0.3) < jl(100, 10_000, 0.3)
+    # successor (surfface-core/src/clustering.rs:113-123): plain clamp, f32
+    assert oracle.jl_dimension(100, 16, 0.3, core=True) == 16
+    assert oracle.jl_dimension(1000, 4096, 0.3, core=True) == math.ceil(np.float32(8.0) * np.log(np.float32(1000)) / (np.float32(0.3) * np.float32(0.3)))
+
+
+def test_projection_kats(oracle):
+    """Zero vector -> zeros (test_reduction.rs:60-69), project(2x) = 2 project(x) (:72-93), norm roughly preserved
+    (:96-109), rows of a matrix project independently (:139-148); and the fold order itself on a hand case."""
+    rng = np.random.default_rng(42)
+    s = rng.standard_normal((40, 10))
+    assert np.all(oracle.project_rows(np.zeros((1, 40)), s) == 0.0)
+    s = rng.standard_normal((25, 6))
+    p1 = oracle.project_rows(np.ones((1, 25)), s)
+    p2 = oracle.project_rows(2.0 * np.ones((1, 25)), s)
+    assert np.array_equal(p2, 2.0 * p1)               # doubling is exact in binary floating point
+    s = rng.standard_normal((50, 15))
+    ratio = np.linalg.norm(oracle.project_rows(np.ones((1, 50)), s)) / math.sqrt(50.0)
+    assert 0.5 < ratio < 2.0
+    x = rng.standard_normal((7, 50))
+    whole = oracle.project_rows(x, s)
+    for i in range(7):
+        assert np.array_equal(whole[i:i + 1], oracle.project_rows(x[i:i + 1], s))
+    # ((x_i * s_ij) * scale) added left to right: a case where any other association differs in the last bit
+    x = np.array([[0.1, 0.2, 0.3]])
+    s = np.array([[0.7], [1.1], [-0.3]])
+    want = 0.0
+    for i in range(3):
+        want = want + (x[0, i] * s[i, 0]) * (1.0 / math.sqrt(1.0))
+    assert oracle.project_rows(x, s)[0, 0] == want
+    s3 = rng.standard_normal((3, 3))
+    scale = 1.0 / math.sqrt(3.0)
+    want = [0.0] * 3
+    for i in range(3):
+        for j in range(3):
+            want[j] = want[j] + (x[0, i] * s3[i, j]) * scale
+    assert list(oracle.project_rows(x, s3)[0]) == want
+    # successor, f32: (sum_i x_i s_ji) * scale
+    xs = rng.standard_normal((2, 9)).astype(np.float32)
+    sc = rng.standard_normal((4, 9)).astype(np.float32)
+    got = oracle.project_rows_core(xs, sc)
+    for r in range(2):
+        for j in range(4):
+            acc = np.float32(0)
+            for i in range(9):
+                acc = np.float32(acc + np.float32(xs[r, i] * sc[j, i]))
+            assert got[r, j] == np.float32(acc * np.float32(np.float32(1.0) / np.sqrt(np.float32(4.0))))
+
+
+# ---- SortedLambdas (src_legacy/sorted_index.rs:22-57) ------------------------------------------------------------
+def test_sorted_lambdas_semantics(oracle):
+    """Keys ascending, equal keys in one bucket ordered by the DECIMAL STRING of the index (zadd sorts by id), the
+    key of a +-0 bucket is the first one inserted; std_dev in f32 as laplacian.rs:421-448 computes it."""
+    lam = np.array([0.5, 0.1, 0.5, 0.0, -0.0, 0.1, 1.0, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5])
+    srt, idx, sd = oracle.sorted_lambdas(lam)
+    # the reference's structure, restated with Python's own containers
+    buckets = {}
+    for i, v in enumerate(lam):
+        buckets.setdefault(float(v) + 0.0 if v != 0 else 0.0, []).append(i)
+    want_idx = []
+    for key in sorted(buckets):
+        want_idx += sorted(buckets[key], key=str)
+    assert list(idx) == want_idx == [3, 4, 1, 5, 0, 10, 11, 12, 2, 7, 8, 9, 6]
+    assert np.array_equal(srt, np.sort(lam)) and not np.signbit(srt[0]) and not np.signbit(srt[1])
+    lam2 = lam.copy(); lam2[3], lam2[4] = -0.0, 0.0
+    srt2, idx2, _ = oracle.sorted_lambdas(lam2)
+    assert list(idx2) == want_idx and np.signbit(srt2[0]) and np.signbit(srt2[1])
+    mean = np.float32(np.float32(np.sum(lam)) / np.float32(len(lam)))
+    var = np.float32(0)
+    for v in lam:
+        d = np.float32(mean - np.float32(v))
+        var = np.float32(var + np.float32(d * d))
+    assert sd == float(np.sqrt(np.float32(var / np.float32(len(lam)))))
+    with pytest.raises(ValueError):
+        oracle.sorted_lambdas(np.zeros(0))
+    # NaN keys sort last and share one bucket (OrderedFloat)
+    srt3, idx3, _ = oracle.sorted_lambdas(np.array([math.nan, 0.3, math.nan, math.inf]))
+    assert list(idx3) == [1, 3, 0, 2] and np.isnan(srt3[2]) and np.isnan(srt3[3])
