@@ -77,6 +77,22 @@ struct GraphParams {
     }
 };
 
+// The lambda-graph half of the reference's builder (surfface-pipeline/src/builder.rs): defaults :105-111,
+// with_lambda_graph :629-657, define_result_k :785-793 (run first thing by every build, :839,1096).
+struct LambdaGraphBuilder {
+    double lambda_eps = 1e-3;
+    size_t lambda_k = 6, lambda_topk = 3;
+    double lambda_p = 2.0;
+    std::optional<double> lambda_sigma;
+    bool normalise = false, sparsity_check = false;
+    LambdaGraphBuilder& with_lambda_graph(double eps, size_t k, size_t topk, double p, std::optional<double> sigma_override = std::nullopt) {
+        lambda_eps = eps; lambda_k = k; lambda_topk = topk; lambda_p = p; lambda_sigma = sigma_override;
+        return *this;
+    }
+    void define_result_k() { if (lambda_k <= 5) lambda_topk = 3; else if (lambda_k < 10) lambda_topk = 4; }
+    GraphParams graph_params() { define_result_k(); return GraphParams{lambda_eps, lambda_k, lambda_topk, lambda_p, lambda_sigma, normalise, sparsity_check}; }
+};
+
 // src_legacy/graph.rs:127-136
 struct GraphLaplacian {
     std::vector<double> init_data;   // the matrix the graph was built from (row-major, one row per graph node)

@@ -439,6 +439,35 @@ class GraphParams:
 
 
 @dataclass
+class LambdaGraphBuilder:
+    """The lambda-graph half of the reference's builder (surfface-pipeline/src/builder.rs): defaults :105-111,
+    `with_lambda_graph` :629-657, `define_result_k` :785-793 (run first thing by every build, :839,1096), and the
+    GraphParams the build hands to the Laplacian stage (`GraphFactory::build_laplacian_matrix_from_k_cluster`)."""
+    lambda_eps: float = 1e-3
+    lambda_k: int = 6
+    lambda_topk: int = 3
+    lambda_p: float = 2.0
+    lambda_sigma: Optional[float] = None
+    normalise: bool = False
+    sparsity_check: bool = False
+
+    def with_lambda_graph(self, eps, k, topk, p, sigma_override=None):
+        self.lambda_eps, self.lambda_k, self.lambda_topk, self.lambda_p, self.lambda_sigma = float(eps), int(k), int(topk), float(p), sigma_override
+        return self
+
+    def define_result_k(self):
+        if self.lambda_k <= 5:
+            self.lambda_topk = 3
+        elif self.lambda_k < 10:
+            self.lambda_topk = 4
+        return self
+
+    def graph_params(self) -> "GraphParams":
+        self.define_result_k()
+        return GraphParams(self.lambda_eps, self.lambda_k, self.lambda_topk, self.lambda_p, self.lambda_sigma, self.normalise, self.sparsity_check)
+
+
+@dataclass
 class GraphLaplacian:
     """src_legacy/graph.rs:127-136: `matrix` is the CSR Laplacian (here: a device handle plus lazily
     fetched host arrays), `nnodes` the item count of the original data, `init_data` the matrix the
