@@ -211,6 +211,12 @@ typedef struct {
 /* out_lambda: R (host); out_dispersion: R or NULL; stats: 3 or NULL */
 int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_lambda_params* params,
                    double* out_lambda, double* out_dispersion, double* stats);
+/* Items that are JL-projected before the Rayleigh quotient (compute_synthetic_lambda with a projection,
+ * src_legacy/taumode.rs:261-318): tau (select_tau on the item, :174-175) and the zero-vector test (:268-274) are taken
+ * from the UNPROJECTED row of x_original, energy and dispersion from the row of x_projected (= sfb_project_rows of it);
+ * L is reduced_dim x reduced_dim.  LEGACY_TAUMODE only. */
+int32_t sfb_lambda_projected(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x_original, const sfb_mat* x_projected,
+                             const sfb_lambda_params* params, double* out_lambda, double* out_dispersion, double* stats);
 /* diffusion step of diffuse_and_split_subcentroids (src_legacy/energymaps.rs:520-546):
  * X <- X - eta * X L^T, `steps` times, in place on the device matrix. */
 int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, double eta, uint32_t steps);

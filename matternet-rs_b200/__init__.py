@@ -401,6 +401,17 @@ class Csr(_Handle):
         self.ctx.synchronize()
         return (lam, disp, stats) if with_dispersion else (lam, stats)
 
+    def lambdas_projected(self, x_original: Matrix, x_projected: Matrix, tau_mode=TAU_MEDIAN, tau_value=0.0, normalise=False):
+        """Taumode lambda of JL-projected items (taumode.rs:261-318): tau and the zero test from the unprojected rows."""
+        n = x_projected.shape[0]
+        prm = _ffi.LambdaParams(LAMBDA_LEGACY_TAUMODE, tau_mode, float(tau_value), int(normalise))
+        lam = np.empty(n, np.float64)
+        stats = np.empty(3, np.float64)
+        self.ctx.check(lib().sfb_lambda_projected(self.ctx._h, self._h, x_original._h, x_projected._h, C.byref(prm), _ffi.ptr(lam), None,
+                                                  _ffi.ptr(stats)))
+        self.ctx.synchronize()
+        return lam, stats
+
     def lambdas_allgather(self, x_shard: Matrix, row0, total_rows, variant=LAMBDA_LEGACY_TAUMODE,
                           tau_mode=TAU_MEDIAN, tau_value=0.0, normalise=True):
         prm = _ffi.LambdaParams(variant, tau_mode, float(tau_value), int(normalise))

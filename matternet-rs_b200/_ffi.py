@@ -108,6 +108,7 @@ SYMBOLS = {
     "sfb_spmv": (C.c_int32, [_P, _P, _P, _P]),
     "sfb_rayleigh_quotient": (C.c_int32, [_P, _P, _P, C.POINTER(C.c_double)]),
     "sfb_lambda": (C.c_int32, [_P, _P, _P, C.POINTER(LambdaParams), _P, _P, _P]),
+    "sfb_lambda_projected": (C.c_int32, [_P, _P, _P, _P, C.POINTER(LambdaParams), _P, _P, _P]),
     "sfb_diffuse": (C.c_int32, [_P, _P, _P, C.c_double, C.c_uint32]),
     "sfb_build_laplacian_matrix": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, C.POINTER(GraphParamsC), C.c_int32, _PP]),
     "sfb_compute_taumode_lambdas": (C.c_int32, [_P, _P, _P, C.c_uint64, C.c_uint32, C.c_int32, C.c_double, _P]),

@@ -17,7 +17,7 @@
 
 int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out);
 int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, uint64_t n, uint32_t f,
-                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp);
+                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp, const double* tau_in);
 int32_t sfb_minmax_device(sfb_ctx* ctx, const double* d_lambda, uint64_t n, double* mn, double* mx);
 int32_t sfb_normalise_device(sfb_ctx* ctx, double* d_lambda, uint64_t n, double mn, double mx, double* stats);
 
@@ -191,7 +191,7 @@ extern "C" int32_t sfb_lambda_allgather(sfb_ctx* ctx, const sfb_csr* L, const sf
     SFB_CUDA(ctx, mm.alloc(sizeof(double) * 2));
     double* mine = all.as<double>() + lo;
     SFB_CUDA(ctx, cudaMemsetAsync(mine, 0, sizeof(double) * S, ctx->stream));
-    SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, mine, nullptr));
+    SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, mine, nullptr, nullptr));
     double mn = INFINITY, mx = 0.0;
     SFB_TRY(sfb_minmax_device(ctx, mine, x->rows, &mn, &mx));
     if (world > 1) {

@@ -138,6 +138,7 @@ struct LambdaArgs {
     const double* x; uint64_t n;
     int variant, tau_mode; double tau_value;
     double* out_lambda; double* out_disp; float* out_energy_f32;
+    const double* tau_in;   // per item: tau chosen upstream (< 0: the item is a zero vector); null: select it from the row
 };
 
 // shared memory: per warp f doubles (the item row) + 256 u32 (select histogram)
@@ -160,7 +161,7 @@ __global__ void lambda_kernel(LambdaArgs a) {
             den += v * v;
         }
         __syncwarp();
-        zero = __all_sync(FULL, zero);
+        zero = a.tau_in ? a.tau_in[i] < 0.0 : __all_sync(FULL, zero);   // projected items: the test was made on the unprojected vector
         if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE && zero) {  // taumode.rs:268-274
             if (lane == 0) { a.out_lambda[i] = 0.0; if (a.out_disp) a.out_disp[i] = 0.0; }
             continue;
@@ -216,7 +217,7 @@ __global__ void lambda_kernel(LambdaArgs a) {
         if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
         double lam;
         if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
-            double tau = warp_select_tau(xs, f, a.tau_mode, a.tau_value, hist, lane);
+            const double tau = a.tau_in ? a.tau_in[i] : warp_select_tau(xs, f, a.tau_mode, a.tau_value, hist, lane);
             lam = tau * (e_raw / (e_raw + tau)) + (1.0 - tau) * g;  // taumode.rs:306-310
         } else {
             lam = e_raw;
@@ -387,6 +388,7 @@ struct LambdaSymArgs {
     const double* x; uint64_t n;
     int tau_mode; double tau_value;
     double* out_lambda; double* out_disp;
+    const double* tau_in;   // as in LambdaArgs
 };
 
 template <int VARIANT>
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
             num += (v * s_diag[t]) * v;   // row-sum defect term
         }
         __syncwarp();
-        zero = __all_sync(FULL, zero);
+        zero = a.tau_in ? a.tau_in[i] < 0.0 : __all_sync(FULL, zero);   // projected items: the test was made on the unprojected vector
         if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE && zero) {  // taumode.rs:268-274
             if (lane == 0) { a.out_lambda[i] = 0.0; if (a.out_disp) a.out_disp[i] = 0.0; }
             continue;
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
         if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
         double lam;
         if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
-            const double tau = warp_select_tau_fast(xs, f, a.tau_mode, a.tau_value, lane, hist);
+            const double tau = a.tau_in ? a.tau_in[i] : warp_select_tau_fast(xs, f, a.tau_mode, a.tau_value, lane, hist);
             lam = tau * (e_raw / (e_raw + tau)) + (1.0 - tau) * g;  // taumode.rs:306-310
         } else lam = e_raw;
         if (lane == 0) { a.out_lambda[i] = lam; if (a.out_disp) a.out_disp[i] = g; }
@@ -517,11 +519,30 @@ __global__ void diffuse_kernel(const uint64_t* __restrict__ indptr, const uint32
     }
 }
 
+// tau and the zero-vector test of every row (select_tau on the item, taumode.rs:174-175, and :268-274), for items that are
+// projected before the Rayleigh quotient: both are taken from the UNPROJECTED vector.  One warp per row; -1 marks a zero vector.
+__global__ void tau_rows_kernel(const double* __restrict__ x, uint64_t n, uint32_t f, int tau_mode, double tau_value, double* __restrict__ tau_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* xs = reinterpret_cast<double*>(smem_raw) + (size_t)w * f;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)wpb * f) + w * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * wpb + w; i < n; i += (uint64_t)gridDim.x * wpb) {
+        const double* xr = x + i * f;
+        __syncwarp();
+        bool zero = true;
+        for (uint32_t t = lane; t < f; t += 32) { const double v = xr[t]; xs[t] = v; zero = zero && (fabs(v) <= 1e-10); }
+        __syncwarp();
+        zero = __all_sync(FULL, zero);
+        const double tau = zero ? -1.0 : warp_select_tau_fast(xs, f, tau_mode, tau_value, lane, hist);
+        if (lane == 0) tau_out[i] = tau;
+    }
+}
+
 }  // namespace
 
 // lambdas of rows [0, n) of a device matrix into a device array; shared by the single- and multi-GPU paths
 int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, uint64_t n, uint32_t f,
-                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp) {
+                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp, const double* tau_in) {
     if (L->rows != f) return sfb_fail(ctx, SFB_EINVAL, "Matrix rows %llu must match vector length %u", (unsigned long long)L->rows, f);  // taumode.rs:330-337
     if (prm->variant < 0 || prm->variant > 2) return sfb_fail(ctx, SFB_EINVAL, "unknown lambda variant %d", prm->variant);
     if (prm->tau_mode < 0 || prm->tau_mode > 3) return sfb_fail(ctx, SFB_EINVAL, "unknown tau mode %d", prm->tau_mode);
@@ -558,7 +579,7 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
                 upper_pack_kernel<<<div_up(f, 128), 128, 0, ctx->stream>>>(L->indptr, L->indices, L->data, f, offs.as<uint64_t>(), rc.as<uint32_t>(),
                                                                          val.as<double>(), diag.as<double>());
                 SFB_LAUNCH_CHECK(ctx);
-                LambdaSymArgs sa{rc.as<uint32_t>(), val.as<double>(), diag.as<double>(), ne, f, x_dev, n, prm->tau_mode, prm->tau_value, d_lambda, d_disp};
+                LambdaSymArgs sa{rc.as<uint32_t>(), val.as<double>(), diag.as<double>(), ne, f, x_dev, n, prm->tau_mode, prm->tau_value, d_lambda, d_disp, tau_in};
                 const int per_sm = (int)((ctx->smem_optin ? ctx->smem_optin : 232448) / (smem_s + 1024));
                 uint64_t want = (n + wpb_s - 1) / wpb_s;
                 const uint64_t cap_grid = (uint64_t)ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
@@ -582,7 +603,7 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
     if (per_warp * wpb > ctx->smem_optin) return sfb_fail(ctx, SFB_EUNSUPPORTED, "feature count %u too large for the shared-memory row staging", f);
     size_t smem = per_warp * wpb;
     DevBuf e32, tot;
-    LambdaArgs a{L->indptr, L->indices, L->data, f, x_dev, n, prm->variant, prm->tau_mode, prm->tau_value, d_lambda, d_disp, nullptr};
+    LambdaArgs a{L->indptr, L->indices, L->data, f, x_dev, n, prm->variant, prm->tau_mode, prm->tau_value, d_lambda, d_disp, nullptr, tau_in};
     // enough resident warps to cover HBM latency; grid = multiple of the SM count
     int blocks_per_sm = (int)((ctx->smem_optin) / (smem + 1024));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -636,14 +657,28 @@ int32_t sfb_normalise_device(sfb_ctx* ctx, double* d_lambda, uint64_t n, double 
     return SFB_OK;
 }
 
-extern "C" int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_lambda_params* prm,
+// x_tau != null: tau and the zero-vector test come from its rows (the unprojected items), energy and dispersion from x
+static int32_t lambda_to_host(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_mat* x_tau, const sfb_lambda_params* prm,
                               double* out_lambda, double* out_disp, double* stats) {
-    if (!ctx || !L || !x || !prm || !out_lambda) return sfb_fail(ctx, SFB_EINVAL, "null argument");
     StageTimer t(ctx, &ctx->times.ms_lambda);
-    DevBuf lam, disp;
+    DevBuf lam, disp, tau;
     SFB_CUDA(ctx, lam.alloc(sizeof(double) * x->rows));
     if (out_disp) SFB_CUDA(ctx, disp.alloc(sizeof(double) * x->rows));
-    SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, lam.as<double>(), out_disp ? disp.as<double>() : nullptr));
+    if (x_tau) {
+        const uint32_t ft = x_tau->cols;
+        const size_t per_warp = (size_t)ft * sizeof(double) + 256 * sizeof(uint32_t);
+        int wpb = 8;
+        while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
+        if (per_warp * wpb > ctx->smem_optin) return sfb_fail(ctx, SFB_EUNSUPPORTED, "feature count %u too large for the shared-memory row staging", ft);
+        SFB_CUDA(ctx, tau.alloc(sizeof(double) * x->rows));
+        SFB_CUDA(ctx, cudaFuncSetAttribute(tau_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
+        const uint64_t want = (x->rows + wpb - 1) / wpb;
+        const unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 8 ? want : (uint64_t)ctx->sm_count * 8);
+        tau_rows_kernel<<<grid, wpb * 32, per_warp * wpb, ctx->stream>>>(x_tau->d, x->rows, ft, prm->tau_mode, prm->tau_value, tau.as<double>());
+        SFB_LAUNCH_CHECK(ctx);
+    }
+    SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, lam.as<double>(), out_disp ? disp.as<double>() : nullptr,
+                              x_tau ? tau.as<double>() : nullptr));
     if (prm->normalise_minmax || stats) {
         double mn, mx;
         SFB_TRY(sfb_minmax_device(ctx, lam.as<double>(), x->rows, &mn, &mx));
@@ -656,6 +691,22 @@ extern "C" int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, 
     if (out_disp) SFB_CUDA(ctx, cudaMemcpyAsync(out_disp, disp.p, sizeof(double) * x->rows, cudaMemcpyDeviceToHost, ctx->stream));
     t2.stop();
     return SFB_OK;
+}
+
+extern "C" int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_lambda_params* prm,
+                              double* out_lambda, double* out_disp, double* stats) {
+    if (!ctx || !L || !x || !prm || !out_lambda) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    return lambda_to_host(ctx, L, x, nullptr, prm, out_lambda, out_disp, stats);
+}
+
+extern "C" int32_t sfb_lambda_projected(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x_original, const sfb_mat* x_projected,
+                                        const sfb_lambda_params* prm, double* out_lambda, double* out_disp, double* stats) {
+    if (!ctx || !L || !x_original || !x_projected || !prm || !out_lambda) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (prm->variant != SFB_LAMBDA_LEGACY_TAUMODE) return sfb_fail(ctx, SFB_EINVAL, "only the taumode lambda projects its items (taumode.rs:261-318)");
+    if (x_original->rows != x_projected->rows) return sfb_fail(ctx, SFB_EINVAL, "original and projected items differ in count");
+    // taumode.rs:287-297: the projected length must be the Laplacian's ("item seems neither projected nor unprojected" otherwise)
+    if (L->rows != x_projected->cols) return sfb_fail(ctx, SFB_EINVAL, "projected items have %u dimensions, the Laplacian %llu rows", x_projected->cols, (unsigned long long)L->rows);
+    return lambda_to_host(ctx, L, x_projected, x_original, prm, out_lambda, out_disp, stats);
 }
 
 // ---- energy pipeline: item -> sub-centroid mapping (src_legacy/energymaps.rs:1246-1342) ----------------------

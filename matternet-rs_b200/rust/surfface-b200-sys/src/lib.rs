@@ -67,6 +67,7 @@ extern "C" {
     pub fn sfb_spmv(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *const f64, y: *mut f64) -> i32;
     pub fn sfb_rayleigh_quotient(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *const f64, out: *mut f64) -> i32;
     pub fn sfb_lambda(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *const sfb_mat, params: *const sfb_lambda_params, out_lambda: *mut f64, out_dispersion: *mut f64, stats: *mut f64) -> i32;
+    pub fn sfb_lambda_projected(ctx: *mut sfb_ctx, L: *const sfb_csr, x_original: *const sfb_mat, x_projected: *const sfb_mat, params: *const sfb_lambda_params, out_lambda: *mut f64, out_dispersion: *mut f64, stats: *mut f64) -> i32;
     pub fn sfb_diffuse(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *mut sfb_mat, eta: f64, steps: u32) -> i32;
     pub fn sfb_map_items_to_subcentroids(ctx: *mut sfb_ctx, items: *const sfb_mat, item_lambdas: *const f64, sub_centroids: *const sfb_mat, sub_lambdas: *const f64, epsilon: f64, out_idx: *mut u32, out_lambda: *mut f64, out_norm: *mut f64) -> i32;
     pub fn sfb_project_rows(ctx: *mut sfb_ctx, x: *const sfb_mat, samples: *const f64, reduced_dim: u32, order: i32, out: *mut *mut sfb_mat) -> i32;

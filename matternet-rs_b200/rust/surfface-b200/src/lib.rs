@@ -232,6 +232,35 @@ pub fn project_matrix(data: &[f64], n_rows: usize, projection: &ImplicitProjecti
     out
 }
 
+/// `TauMode::compute_taumode_lambdas_parallel` for an ArrowSpace that carries a projection (`taumode.rs:117-214` with
+/// `aspace.projection_matrix = Some(..)`): items are `n_items x original_dim`, `gl` is `reduced_dim x reduced_dim`;
+/// tau and the zero-vector test come from the unprojected item, energy and dispersion from the projected one.
+pub fn compute_taumode_lambdas_projected(items: &[f64], n_items: usize, projection: &ImplicitProjection, gl: &DeviceLaplacian, taumode: TauMode) -> Vec<f64> {
+    assert_eq!(items.len(), n_items * projection.original_dim);
+    let (mode, value) = match taumode {
+        TauMode::Fixed(t) => (0, t),
+        TauMode::Median => (1, 0.0),
+        TauMode::Mean => (2, 0.0),
+        TauMode::Percentile(p) => (3, p),
+    };
+    let samples = projection.materialise();
+    let mut out = vec![0f64; n_items];
+    with_ctx(|ctx| unsafe {
+        let (mut x, mut y) = (std::ptr::null_mut(), std::ptr::null_mut());
+        check(ctx, sys::sfb_mat_from_host(ctx, items.as_ptr(), n_items as u64, projection.original_dim as u32, &mut x));
+        let st = sys::sfb_project_rows(ctx, x, samples.as_ptr(), projection.reduced_dim as u32, 0, &mut y);
+        if st != sys::SFB_OK { sys::sfb_mat_free(x); }
+        check(ctx, st);
+        let prm = sys::sfb_lambda_params { variant: 0, tau_mode: mode, tau_value: value, normalise_minmax: 1 };   // update_lambdas normalises
+        let st = sys::sfb_lambda_projected(ctx, gl.handle, x, y, &prm, out.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut());
+        sys::sfb_mat_free(x);
+        sys::sfb_mat_free(y);
+        check(ctx, st);
+        check(ctx, sys::sfb_synchronize(ctx));
+    });
+    out
+}
+
 // ---- SortedLambdas (src_legacy/sorted_index.rs) ------------------------------------------------------------------
 use ordered_float::OrderedFloat;
 use std::collections::BTreeMap;

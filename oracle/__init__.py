@@ -85,6 +85,7 @@ def lib():
     L.orc_project_rows_core.argtypes = [_fp, _c.c_uint64, _c.c_uint32, _fp, _c.c_uint32, _fp]
     L.orc_sorted_lambdas.argtypes = [_dp, _c.c_uint64, _dp, _u32p, _c.POINTER(_c.c_double)]
     L.orc_sorted_lambdas.restype = _c.c_int
+    L.orc_lambda_projected.argtypes = [_u64p, _u32p, _dp, _c.c_uint64, _dp, _c.c_uint64, _dp, _c.c_uint64, _c.c_int, _c.c_double, _dp]
     _lib = L
     return L
 
@@ -305,3 +306,15 @@ def sorted_lambdas(lam):
     if lib().orc_sorted_lambdas(lam, lam.shape[0], out, idx, _c.byref(sd)) != 0:
         raise ValueError("empty lambdas: the reference panics")
     return out, idx, sd.value
+
+
+def lambdas_projected(indptr, indices, data, x_projected, x_original, tau_mode=TAU_MEDIAN, tau_value=0.0):
+    """compute_synthetic_lambda with a projection (taumode.rs:261-318): tau and the zero test from the unprojected
+    item, energy and dispersion from the projected one."""
+    ip, ix, dv = _csr_args(indptr, indices, data)
+    xp = np.ascontiguousarray(x_projected, dtype=np.float64)
+    xo = np.ascontiguousarray(x_original, dtype=np.float64)
+    assert xp.shape[0] == xo.shape[0] and xp.shape[1] == len(ip) - 1
+    lam = np.empty(xp.shape[0], dtype=np.float64)
+    lib().orc_lambda_projected(ip, ix, dv, xp.shape[1], xp, xp.shape[0], xo, xo.shape[1], tau_mode, float(tau_value), lam)
+    return lam

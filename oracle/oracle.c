@@ -611,13 +611,15 @@ double orc_select_tau(const double* e, uint64_t n, int mode, double value) {
  *     R = clamp(num/(den+1e-9), +-1e6); e_i = sum_f max(deg_f x_f^2 - 2 x_f (Wx)_f + (W x^2)_f, 0);
  *     G_i = clamp(e_i/(sum_i e_i + 1e-12), 0, 1); lambda = R + G.
  * ------------------------------------------------------------------------------------------ */
+/* xt / ft: the vector the zero test and tau are taken from -- the item itself, or its UNPROJECTED form when the item
+ * is JL-projected before the Rayleigh quotient (taumode.rs:174-175 select_tau(&item.item), :268-297). */
 static double lambda_legacy_row(const uint64_t* indptr, const uint32_t* indices, const double* data,
-                                uint64_t f, const double* x, int tau_mode, double tau_value,
+                                uint64_t f, const double* x, const double* xt, uint64_t ft, int tau_mode, double tau_value,
                                 double* out_e, double* out_g) {
     int all_zero = 1;
-    for (uint64_t r = 0; r < f; ++r) if (!(fabs(x[r]) <= 1e-10)) { all_zero = 0; break; }
+    for (uint64_t r = 0; r < ft; ++r) if (!(fabs(xt[r]) <= 1e-10)) { all_zero = 0; break; }
     if (all_zero) { if (out_e) *out_e = 0.0; if (out_g) *out_g = 0.0; return 0.0; }
-    double tau = orc_select_tau(x, f, tau_mode, tau_value);
+    double tau = orc_select_tau(xt, ft, tau_mode, tau_value);
     double num = 0.0, den = 0.0;
     for (uint64_t r = 0; r < f; ++r) {
         double xi = x[r], rs = 0.0;
@@ -756,7 +758,7 @@ void orc_lambda(const uint64_t* indptr, const uint32_t* indices, const double* d
             const double* xi = x + (size_t)i * f;
             double e = 0.0, g = 0.0, lam;
             if (variant == ORC_LAMBDA_LEGACY_TAUMODE) {
-                lam = lambda_legacy_row(indptr, indices, data, f, xi, tau_mode, tau_value, &e, &g);
+                lam = lambda_legacy_row(indptr, indices, data, f, xi, xi, f, tau_mode, tau_value, &e, &g);
             } else {
                 lam = lambda_energy_row(indptr, indices, data, f, xi, lx, out_g ? &g : NULL);
                 e = lam;
@@ -767,6 +769,16 @@ void orc_lambda(const uint64_t* indptr, const uint32_t* indices, const double* d
         }
         free(lx);
     }
+}
+
+/* taumode lambda of JL-projected items: x_proj n x f (f = rows of L), x_orig n x f_orig (tau and zero test). */
+void orc_lambda_projected(const uint64_t* indptr, const uint32_t* indices, const double* data, uint64_t f,
+                          const double* x_proj, uint64_t n, const double* x_orig, uint64_t f_orig, int tau_mode, double tau_value,
+                          double* out_lambda) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)n; ++i)
+        out_lambda[i] = lambda_legacy_row(indptr, indices, data, f, x_proj + (size_t)i * f, x_orig + (size_t)i * f_orig, f_orig,
+                                          tau_mode, tau_value, NULL, NULL);
 }
 
 /* min-max normalisation: src_legacy/core.rs:1341-1355 (max fold starts at 0.0). stats = {min,max,range}. */

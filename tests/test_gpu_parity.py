@@ -489,24 +489,44 @@ def test_project_rows_core_f32(sfb, oracle, ctx):
 
 
 def test_projected_lambdas_match_reference_pipeline(sfb, oracle, ctx):
-    """compute_synthetic_lambda on unprojected items (taumode.rs:277-297): project, then lambda against the r x r
+    """compute_synthetic_lambda on unprojected items (taumode.rs:261-318): tau = select_tau(item) and the zero-vector
+    test use the UNPROJECTED item, the Rayleigh quotient and the dispersion the projected one, against the r x r
     Laplacian -- device pipeline against the oracle's, <= 1e-9 relative."""
     rng = np.random.default_rng(21)
     n, f, r = 3000, 128, sfb.compute_jl_dimension(40, 128, 0.5)
     assert r == oracle.jl_dimension(40, 128, 0.5) and 32 <= r < 128
-    x = rng.standard_normal((n, f))
+    x = np.abs(rng.standard_normal((n, f)))          # positive entries: the median tau is well above the floor
+    x[5] = 0.0                                        # zero vector -> lambda 0 without touching the graph
+    x[6] = 1e-11                                      # |v| <= 1e-10 everywhere: also "zero" (taumode.rs:268-274)
+    x[7, 1:] = 0.0                                    # one live entry: tau from the unprojected row's median (floor)
     s = rng.standard_normal((f, r))
     proj = sfb.ImplicitProjection(f, r, s)
-    y = sfb.project_matrix(x, proj, ctx=ctx)
+    xm = ctx.matrix(x)
+    y = sfb.project_matrix(xm, proj, ctx=ctx)
     L = y.knn_columns(6, 0).adjacency(2.0, 1.0).laplacian()
-    got = L.lambdas(y, tau_mode=sfb.TAU_MEDIAN, normalise=True)[0]
     yo = oracle.project_rows(x, s)
     idx, dist, cnt = oracle.knn(oracle.transpose(yo), 6, 0)
     a = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0)
     ip, ind, dat = oracle.laplacian(a[0], a[1], a[2])
-    want = oracle.normalise_lambdas(oracle.lambdas(ip, ind, dat, yo, tau_mode=oracle.TAU_MEDIAN))[0]
-    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+    for mode, val in ((sfb.TAU_MEDIAN, 0.0), (sfb.TAU_MEAN, 0.0), (sfb.TAU_FIXED, 0.4), (sfb.TAU_PERCENTILE, 0.9)):
+        got, stats = L.lambdas_projected(xm, y, tau_mode=mode, tau_value=val)
+        want = oracle.lambdas_projected(ip, ind, dat, yo, x, tau_mode=mode, tau_value=val)
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-14)
+        assert got[5] == 0.0 and got[6] == 0.0 and want[5] == 0.0
+        # tau really comes from the unprojected rows: taking it from the projected ones gives different lambdas
+        if mode != sfb.TAU_FIXED:
+            assert not np.allclose(got, oracle.lambdas(ip, ind, dat, yo, tau_mode=mode, tau_value=val), rtol=1e-6)
+    got_n, stats = L.lambdas_projected(xm, y, normalise=True)
+    want_n, wstats = oracle.normalise_lambdas(oracle.lambdas_projected(ip, ind, dat, yo, x))
+    np.testing.assert_allclose(got_n, want_n, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(stats, wstats, rtol=1e-9)
     assert np.array_equal(proj.project(x[3], ctx=ctx), yo[3])
+    # already-projected items (len == reduced_dim) go through the plain call; a mismatched length is refused
+    # like the reference's panic ("item seems neither projected nor unprojected", taumode.rs:287-297)
+    with pytest.raises(sfb.SfbError):
+        L.lambdas_projected(xm, xm)
+    with pytest.raises(sfb.SfbError):
+        L.lambdas_projected(ctx.matrix(x[:10]), y)
 
 
 def test_jl_dimension_matches_oracle(sfb, oracle):

@@ -430,3 +430,24 @@ def test_sorted_lambdas_semantics(oracle):
     # NaN keys sort last and share one bucket (OrderedFloat)
     srt3, idx3, _ = oracle.sorted_lambdas(np.array([math.nan, 0.3, math.nan, math.inf]))
     assert list(idx3) == [1, 3, 0, 2] and np.isnan(srt3[2]) and np.isnan(srt3[3])
+
+
+def test_projected_lambda_uses_the_unprojected_item_for_tau(oracle):
+    """taumode.rs:174-175,261-318: tau = select_tau(&item.item) and the zero test see the UNPROJECTED item; E and G the
+    projected one.  Same vector on both sides == the plain lambda; otherwise the blend of (tau(original), E, G(projected))."""
+    rng = np.random.default_rng(8)
+    ip = np.array([0, 2, 5, 7], np.uint64)
+    ind = np.array([0, 1, 0, 1, 2, 1, 2], np.uint32)
+    dat = np.array([1.0, -1.0, -1.0, 2.0, -1.0, -1.0, 1.0])       # chain graph (test_spectral.rs:187-251)
+    xp = rng.standard_normal((6, 3))
+    xo = np.abs(rng.standard_normal((6, 5)))
+    xo[2] = 0.0
+    assert np.array_equal(oracle.lambdas_projected(ip, ind, dat, xp, xp), oracle.lambdas(ip, ind, dat, xp))
+    got = oracle.lambdas_projected(ip, ind, dat, xp, xo, tau_mode=oracle.TAU_MEAN)
+    _, e, g = oracle.lambdas(ip, ind, dat, xp, tau_mode=oracle.TAU_MEAN, with_parts=True)
+    for i in range(6):
+        if i == 2:
+            assert got[i] == 0.0                                    # zero ORIGINAL vector, whatever the projected one holds
+            continue
+        tau = oracle.select_tau(xo[i], oracle.TAU_MEAN)
+        assert got[i] == tau * (e[i] / (e[i] + tau)) + (1.0 - tau) * min(max(g[i], 0.0), 1.0)
