@@ -298,6 +298,27 @@ inline std::vector<double> ImplicitProjection::project(const std::vector<double>
     return project_matrix(std::vector<double>(query.begin(), query.begin() + (std::ptrdiff_t)original_dim), 1, *this);   // `.take(original_dim)`, :233
 }
 
+// TauMode::compute_taumode_lambdas_parallel for an ArrowSpace that carries a projection (taumode.rs:117-214 with
+// aspace.projection_matrix = Some(..)): items n_items x original_dim, gl over the reduced_dim projected features; tau and
+// the zero-vector test come from the unprojected item (:174-175,268-274), energy and dispersion from the projected one.
+inline std::vector<double> compute_taumode_lambdas_projected(const std::vector<double>& items, size_t n_items, const ImplicitProjection& projection,
+                                                             const GraphLaplacian& gl, TauMode mode) {
+    if (items.size() != n_items * projection.original_dim) throw Error(SFB_EINVAL, "items must be n_items x original_dim");
+    Context& c = Context::thread_default();
+    sfb_mat *x = nullptr, *y = nullptr;
+    c.check(sfb_mat_from_host(c.get(), items.data(), n_items, (uint32_t)projection.original_dim, &x));
+    int st = sfb_project_rows(c.get(), x, projection.samples.data(), (uint32_t)projection.reduced_dim, SFB_PROJECT_LEGACY, &y);
+    if (st != SFB_OK) { sfb_mat_free(x); c.check(st); }
+    std::vector<double> out(n_items);
+    sfb_lambda_params prm{SFB_LAMBDA_LEGACY_TAUMODE, (int)mode.kind, mode.value, 1};   // update_lambdas normalises (core.rs:1427-1443)
+    st = sfb_lambda_projected(c.get(), gl.device.get(), x, y, &prm, out.data(), nullptr, nullptr);
+    if (st == SFB_OK) st = sfb_synchronize(c.get());
+    sfb_mat_free(x);
+    sfb_mat_free(y);
+    c.check(st);
+    return out;
+}
+
 // ---- SortedLambdas (src_legacy/sorted_index.rs:8-79) ----------------------------------------------------------------
 class SortedLambdas {
 public:

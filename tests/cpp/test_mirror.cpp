@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <algorithm>
 #include <tuple>
 #include <vector>
 
@@ -200,6 +201,18 @@ static void test_projection_and_sorted_lambdas() {
     std::vector<double> got = project_matrix(data, n, proj), want(n * r);                                                              // :128-148
     orc_project_rows(data.data(), n, (uint32_t)f, draws.data(), (uint32_t)r, want.data());
     CHECK(got == want, "projected matrix differs from the oracle's left folds");
+    // lambdas of unprojected items against the Laplacian of the projected features: normalised, the zero item at the minimum
+    {
+        std::vector<double> pos(data);
+        for (double& v : pos) v = std::fabs(v);
+        for (size_t j = 0; j < f; ++j) pos[7 * f + j] = 0.0;
+        std::vector<double> y = project_matrix(pos, n, proj);
+        GraphLaplacian glp = GraphFactory::build_laplacian_matrix_from_k_cluster(y, n, r, INFINITY, 6, 3, 2.0, 1.0, false, false, n);
+        std::vector<double> lp = compute_taumode_lambdas_projected(pos, n, proj, glp, TauMode::Median());
+        CHECK(lp.size() == n && lp[7] == 0.0, "zero unprojected item must sit at the normalised minimum, got %g", lp[7]);
+        double mx = 0.0; for (double v : lp) { CHECK(v >= 0.0 && v <= 1.0, "normalised lambda out of [0,1]"); mx = std::max(mx, v); }
+        CHECK(mx == 1.0, "normalised maximum");
+    }
     std::vector<double> lam(5000);
     for (size_t i = 0; i < lam.size(); ++i) lam[i] = std::floor(100.0 * std::fabs(std::sin(0.1 * (double)i))) / 100.0;              // heavy ties
     SortedLambdas sl;
