@@ -721,7 +721,7 @@ struct RescoreArgs {
 // One warp per query row.
 //   filter   the screen hands over k' .. cap candidates per row, but only those whose screen key is within
 //            the error margin of the k-th best key can be among the exact k nearest: with S_k the k-th
-//            largest key (self excluded) every candidate below S_k - 3 * margin (cosine; the L2 form goes
+//            largest key (self excluded) every candidate below S_k - 2 * margin (cosine; the L2 form goes
 //            through the distance bounds) is provably farther than k others.  That cuts the rows gathered
 //            in f64 -- the cost of this kernel -- from ~100 to ~k + a few.  Excluded candidates join the
 //            screen's dropped set: the certificate below is evaluated against the larger threshold.
@@ -803,7 +803,10 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
             }
             const double sk = (double)sortable_f32(prefix);   // k-th largest screen key among the other rows
             double tf;
-            if (COS) tf = sk - 3.0 * cos_margin;
+            // The k rows with key >= sk have exact keys >= sk - margin, so the exact k-th key is >= sk - margin; a candidate
+            // below sk - 2 margin has an exact key below sk - margin: it is farther than those k, and -- joining the dropped
+            // set with its key + margin <= sk - margin -- it can never be what keeps the row from certifying.
+            if (COS) tf = sk - 2.0 * (1.0 + 1e-6) * cos_margin;
             else {
                 // the k rows with key >= sk are within T of row i (scaled units); exclude what is provably farther
                 const double eta_k = eta_base + 2.4e-7 * (fabs(sk) + q2);
