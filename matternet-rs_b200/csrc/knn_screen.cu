@@ -183,7 +183,7 @@ struct ScreenArgs {
     uint32_t idesc;
     uint32_t kprime, cap;
     const float* nq32;      // |q_j|^2 as f32 (L2 keys)
-    float* buf_key; uint32_t* buf_idx;  // [(row_local * n_splits + split) * cap]
+    uint2* buf;  // candidates as (key bits, corpus row) pairs: [(row_local * n_splits + split) * cap]
     uint32_t* out_cnt; float* out_thr;  // [row_local * n_splits + split]
     float* dump;            // DUMP mode: 128 x 256 accumulators of the CTA's first tile
 };
@@ -196,13 +196,12 @@ struct ScreenArgs {
 //   exact path MSB-first radix select of the k'-th largest key (32 steps); taken when the fast cut would
 //              drop nothing (all keys equal, or one outlier stretching the range).
 template <int E>
-__device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_t* my_idx, uint32_t& cnt, float& thr,
+__device__ __forceinline__ void prune_rows(uint32_t need, uint2* my_buf, uint32_t& cnt, float& thr,
                                            uint32_t kprime, int lane) {
     while (need) {
         const int L = __ffs(need) - 1;
         need &= need - 1;
-        float* kp = reinterpret_cast<float*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(my_key), L));
-        uint32_t* ip = reinterpret_cast<uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(my_idx), L));
+        uint2* bp = reinterpret_cast<uint2*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(my_buf), L));
         const uint32_t n = __shfl_sync(FULL, cnt, L);
         float kf[E];
         uint32_t idx[E];
@@ -211,8 +210,9 @@ __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_
         for (int u = 0; u < E; ++u) {
             const uint32_t e = lane + 32 * u;
             const bool v = e < n;
-            kf[u] = v ? __ldcg(kp + e) : -INFINITY;
-            idx[u] = v ? __ldcg(ip + e) : 0u;
+            const uint2 ent = v ? __ldcg(bp + e) : make_uint2(0xFF800000u, 0u);   // -inf
+            kf[u] = __uint_as_float(ent.x);
+            idx[u] = ent.y;
             if (v) mn = fminf(mn, kf[u]);
             mx = fmaxf(mx, kf[u]);
         }
@@ -286,7 +286,7 @@ __device__ __forceinline__ void prune_rows(uint32_t need, float* my_key, uint32_
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < E; ++u)
-            if (keep[u]) { __stcg(kp + pos[u], kf[u]); __stcg(ip + pos[u], idx[u]); }
+            if (keep[u]) __stcg(bp + pos[u], make_uint2(__float_as_uint(kf[u]), idx[u]));
         __syncwarp();
         if (lane == L) { cnt = base; thr = fmaxf(thr, new_thr); }
     }
@@ -309,7 +309,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // (20 instructions) and one warp vote; per-element compares run only inside groups of 4 whose max passes.
 template <bool L2>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const float* __restrict__ nqv, uint32_t col0, uint64_t n_rows,
-                                             bool row_valid, float* my_key, uint32_t* my_idx, uint32_t& cnt, float& thr,
+                                             bool row_valid, uint2* my_buf, uint32_t& cnt, float& thr,
                                              uint32_t cap, uint32_t kprime, int lane) {
     float key[32];
 #pragma unroll
@@ -333,6 +333,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
     if (hit && row_valid) {
         // The mask of groups that hold a hit is built branch-free; per set bit ONE dispatch picks that group's four
         // keys (lanes with different groups diverge only over four moves) and one shared body appends the hits.
+        const uint32_t n_rows32 = (uint32_t)n_rows;   // node indices are 32-bit
         uint32_t gm = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) gm |= (g[q] > thr ? 1u : 0u) << q;
@@ -351,10 +352,10 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
                 case 6: k0 = key[24]; k1 = key[25]; k2 = key[26]; k3 = key[27]; break;
                 default: k0 = key[28]; k1 = key[29]; k2 = key[30]; k3 = key[31]; break;
             }
-            if (k0 > thr && jb < n_rows) { __stcg(my_key + cnt, k0); __stcg(my_idx + cnt, jb); ++cnt; }
-            if (k1 > thr && jb + 1 < n_rows) { __stcg(my_key + cnt, k1); __stcg(my_idx + cnt, jb + 1); ++cnt; }
-            if (k2 > thr && jb + 2 < n_rows) { __stcg(my_key + cnt, k2); __stcg(my_idx + cnt, jb + 2); ++cnt; }
-            if (k3 > thr && jb + 3 < n_rows) { __stcg(my_key + cnt, k3); __stcg(my_idx + cnt, jb + 3); ++cnt; }
+            if (k0 > thr && jb < n_rows32) { __stcg(my_buf + cnt, make_uint2(__float_as_uint(k0), jb)); ++cnt; }
+            if (k1 > thr && jb + 1 < n_rows32) { __stcg(my_buf + cnt, make_uint2(__float_as_uint(k1), jb + 1)); ++cnt; }
+            if (k2 > thr && jb + 2 < n_rows32) { __stcg(my_buf + cnt, make_uint2(__float_as_uint(k2), jb + 2)); ++cnt; }
+            if (k3 > thr && jb + 3 < n_rows32) { __stcg(my_buf + cnt, make_uint2(__float_as_uint(k3), jb + 3)); ++cnt; }
         } while (gm);
     }
     // a chunk appends at most 32 entries: prune whenever fewer than 32 slots remain
@@ -365,8 +366,8 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
         long long t_p = 0;
         if (prof) t_p = clock64();
 #endif
-        if (cap <= 128) prune_rows<4>(need, my_key, my_idx, cnt, thr, kprime, lane);
-        else prune_rows<8>(need, my_key, my_idx, cnt, thr, kprime, lane);
+        if (cap <= 128) prune_rows<4>(need, my_buf, cnt, thr, kprime, lane);
+        else prune_rows<8>(need, my_buf, cnt, thr, kprime, lane);
 #ifdef SFB_SCREEN_PROFILE
         if (prof) { atomicAdd(&g_screen_dbg[2], (unsigned long long)(clock64() - t_p)); atomicAdd(&g_screen_dbg[3], 1ull); atomicAdd(&g_screen_dbg[4], (unsigned long long)__popc(need)); }
 #endif
@@ -457,8 +458,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint64_t row_local = (uint64_t)mb * BM + row_in_tile;
         const bool row_valid = row_local < a.nq;
         const size_t slot = (size_t)(row_valid ? row_local : 0) * a.n_splits + split;
-        float* my_key = a.buf_key + slot * a.cap;
-        uint32_t* my_idx = a.buf_idx + slot * a.cap;
+        uint2* my_buf = a.buf + slot * a.cap;
         uint32_t cnt = 0;
         float thr = -INFINITY;
         const int etid = threadIdx.x - 64;            // 0..127 among the epilogue threads
@@ -484,7 +484,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int c = 0; c < 32; ++c) a.dump[(size_t)row_in_tile * BN + ch * 32 + c] = __uint_as_float(v[c]);
                     continue;
                 }
-                filter_chunk<L2>(v, s_nq + as * BN + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
+                filter_chunk<L2>(v, s_nq + as * BN + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_buf, cnt, thr, a.cap, a.kprime, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -523,7 +523,7 @@ struct Screen2Args {
     uint32_t idesc;
     uint32_t kprime, cap;
     const float* nq32;
-    float* buf_key; uint32_t* buf_idx;
+    uint2* buf;
     uint32_t* out_cnt; float* out_thr;
     uint32_t dbg;           // SFB_SCREEN_DBG (timing experiments, results invalid): 1 = tcgen05.ld only, 2 = no epilogue work
 };
@@ -651,8 +651,7 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
             const uint64_t row_local = (uint64_t)mb2 * 256 + rank * P_BM + row_in_tile;
             const bool row_valid = row_local < a.nq;
             const size_t slot = (size_t)(row_valid ? row_local : 0) * a.n_splits + split;
-            float* my_key = a.buf_key + slot * a.cap;
-            uint32_t* my_idx = a.buf_idx + slot * a.cap;
+            uint2* my_buf = a.buf + slot * a.cap;
             uint32_t cnt = 0;
             float thr = -INFINITY;
             if (chunk != 0 && row_valid) { cnt = a.out_cnt[slot]; thr = a.out_thr[slot]; }
@@ -684,10 +683,10 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
                     for (int ch = 0; ch < BN / 32; ch += 2) {
                         tmem_ld_wait();
                         tmem_ld32(taddr + (ch + 1) * 32, vb);   // in flight while chunk ch is filtered
-                        filter_chunk<L2>(va, nqt + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
+                        filter_chunk<L2>(va, nqt + ch * 32, n0 + ch * 32, a.n_rows, row_valid, my_buf, cnt, thr, a.cap, a.kprime, lane);
                         tmem_ld_wait();
                         if (ch + 2 < BN / 32) tmem_ld32(taddr + (ch + 2) * 32, va);
-                        filter_chunk<L2>(vb, nqt + (ch + 1) * 32, n0 + (ch + 1) * 32, a.n_rows, row_valid, my_key, my_idx, cnt, thr, a.cap, a.kprime, lane);
+                        filter_chunk<L2>(vb, nqt + (ch + 1) * 32, n0 + (ch + 1) * 32, a.n_rows, row_valid, my_buf, cnt, thr, a.cap, a.kprime, lane);
                     }
                 } else if (a.dbg == 1) {
                     uint32_t acc = 0;
@@ -723,7 +722,7 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
 struct RescoreArgs {
     const double* x; const double* norms; uint64_t m; uint32_t kd; int metric; uint32_t k; double eps;
     uint64_t q_begin, nq; uint32_t n_splits, cap;
-    const float* buf_key; const uint32_t* buf_idx; const uint32_t* cnt; const float* thr;
+    const uint2* buf; const uint32_t* cnt; const float* thr;
     const double* aux;      // |q|, |delta|, |q|^2
     double nmax, dmax, gamma, scale;
     uint32_t* out_idx; double* out_dist; uint32_t* out_cnt;
@@ -794,8 +793,9 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
             const uint32_t n = a.cnt[slot];
             for (uint32_t b = 0; b < n; b += 32) {
                 const bool v = b + lane < n;
-                const uint32_t j = v ? __ldcg(a.buf_idx + slot * a.cap + b + lane) : SFB_IDX_NONE;
-                const float kf = v ? __ldcg(a.buf_key + slot * a.cap + b + lane) : -INFINITY;
+                const uint2 ent = v ? __ldcg(a.buf + slot * a.cap + b + lane) : make_uint2(0xFF800000u, SFB_IDX_NONE);
+                const uint32_t j = ent.y;
+                const float kf = __uint_as_float(ent.x);
                 const bool keep = v && j != gi;
                 const uint32_t bal = __ballot_sync(FULL, keep);
                 if (keep) { const uint32_t pos = n_list + __popc(bal & ((1u << lane) - 1u)); skey[pos] = kf; sidx[pos] = j; }
@@ -915,8 +915,8 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
         for (uint32_t s = 0; s < a.n_splits; ++s) {
             const size_t slot = (size_t)rl * a.n_splits + s;
             const uint32_t n = a.cnt[slot];
-            const uint32_t* cand = a.buf_idx + slot * a.cap;
-            for (uint32_t b = 0; b < n; b += 32) run_batch(b + lane < n ? cand[b + lane] : SFB_IDX_NONE, n - b < 32 ? n - b : 32);
+            const uint2* cand = a.buf + slot * a.cap;
+            for (uint32_t b = 0; b < n; b += 32) run_batch(b + lane < n ? cand[b + lane].y : SFB_IDX_NONE, n - b < 32 ? n - b : 32);
         }
     }
 
@@ -1181,13 +1181,12 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
     }
 
     const size_t slots = (size_t)nq * n_splits_used;
-    DevBuf buf_key, buf_idx, cnt, thr;
-    SFB_CUDA(ctx, buf_key.alloc(slots * cap * sizeof(float)));
-    SFB_CUDA(ctx, buf_idx.alloc(slots * cap * sizeof(uint32_t)));
+    DevBuf buf, cnt, thr;
+    SFB_CUDA(ctx, buf.alloc(slots * cap * sizeof(uint2)));
     SFB_CUDA(ctx, cnt.alloc(slots * sizeof(uint32_t)));
     SFB_CUDA(ctx, thr.alloc(slots * sizeof(float)));
     SFB_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, slots * sizeof(uint32_t), ctx->stream));
-    sa.buf_key = s2.buf_key = buf_key.as<float>(); sa.buf_idx = s2.buf_idx = buf_idx.as<uint32_t>();
+    sa.buf = s2.buf = buf.as<uint2>();
     sa.out_cnt = s2.out_cnt = cnt.as<uint32_t>(); sa.out_thr = s2.out_thr = thr.as<float>();
     sa.n_splits = n_splits_used;
     {
@@ -1213,7 +1212,7 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
     // tensor-core fp32 accumulation: K products, each partial sum off by at most 2 ulp of the running bound
     const double gamma = ((double)P.kpad + 64.0) * ldexp(1.0, -23);
     RescoreArgs ra{x->d, norms, m, x->cols, p->metric, p->k, p->eps, a_row0, nq, sa.n_splits, cap,
-                   sa.buf_key, sa.buf_idx, sa.out_cnt, sa.out_thr, P.aux.as<double>(), P.nmax, P.dmax, gamma, P.scale,
+                   sa.buf, sa.out_cnt, sa.out_thr, P.aux.as<double>(), P.nmax, P.dmax, gamma, P.scale,
                    out->idx, out->dist, out->cnt, fb_rows, reinterpret_cast<uint32_t*>(fb_count),
                    reinterpret_cast<double*>(fb_count + 1), qlist, out_base};
     {
