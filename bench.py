@@ -293,7 +293,7 @@ def run_ours(args):
         ach = flops / (scr_ms * 1e-3) / 1e12
         peak = pk["tc_sustained"] if scr_ms > 100 else pk["tc_burst"]
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01b_screen_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01e_screen_traffic.json")
         if args.config == "c2" and not args.rows and world == 1 and os.path.exists(tpath):
             tj = json.load(open(tpath))   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
