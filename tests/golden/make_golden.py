@@ -49,7 +49,36 @@ def build(case):
     return out
 
 
+def build_post():
+    """The steps either side of lambda: JL projection, taumode lambda of projected items (tau and
+    the zero test from the unprojected rows), SortedLambdas.  The projection draws are Philox Gaussians here (the
+    reference's ChaCha8 + ziggurat stream is made by the Rust wrapper)."""
+    n, f, r = 150, 48, 12
+    x = np.abs(oracle.generate_rows(1, 23, 0, n, f, 6, 0.4))
+    x[11] = 0.0
+    samples = oracle.generate_rows(0, 99, 0, f, r)
+    y = oracle.project_rows(x, samples)
+    out = {"x": x, "samples": samples, "projected": y,
+           "jl": np.array([oracle.jl_dimension(a, b, c) for a, b, c in POST_JL], np.uint64)}
+    idx, dist, cnt = oracle.knn(oracle.transpose(y), 3, oracle.METRIC_COSINE)
+    a = oracle.build_adjacency(idx, dist, cnt, 2.0, 1.0)
+    ptr, ind, dat = oracle.laplacian(a[0], a[1], a[2])
+    out.update(plap_indptr=ptr, plap_indices=ind, plap_data=dat)
+    lam = oracle.lambdas_projected(ptr, ind, dat, y, x, oracle.TAU_MEDIAN)
+    out["lambda_projected"] = lam
+    lam_n, _ = oracle.normalise_lambdas(lam)
+    q = np.round(lam_n, 2)                      # quantised: many equal lambdas, ordered by the decimal string of the index
+    srt, order, sd = oracle.sorted_lambdas(q)
+    out.update(lambda_quantised=q, sorted_lambda=srt, sorted_idx=order, std_dev=np.array([sd]))
+    return out
+
+
+POST_JL = [(100, 16, 0.3), (10, 100, 0.3), (2, 1000, 0.9), (1000, 512, 0.1), (100, 2000, 0.2), (10000, 5000, 0.3), (100, 100000, 0.3)]
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "post_steps.npz"), **build_post())
+    print("wrote post_steps")
     for name, case in CASES.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **build(case))
         print("wrote", name)

@@ -70,3 +70,33 @@ def test_cuda_path_reproduces_golden(sfb, name, screen):
     x.diffuse(Lf, 0.1, 4)
     np.testing.assert_allclose(x.rows(), g["diffused"], rtol=RTOL, atol=1e-15)
     ctx.close()
+
+
+def test_oracle_reproduces_post_steps_golden(oracle):
+    want = load("post_steps")
+    got = make_golden.build_post()
+    assert sorted(got) == sorted(want)
+    for key in want:
+        assert np.array_equal(np.asarray(got[key]), want[key]), key
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_post_steps_golden(sfb):
+    """JL projection (bit-exact), lambda of the projected items, SortedLambdas order / keys / std_dev against the fixture."""
+    g = load("post_steps")
+    ctx = sfb.Context(0)
+    x = ctx.matrix(g["x"])
+    y = x.project(g["samples"])
+    assert np.array_equal(y.rows(), g["projected"])
+    assert [sfb.compute_jl_dimension(a, b, c) for a, b, c in make_golden.POST_JL] == g["jl"].tolist()
+    L = y.knn_columns(3, sfb.METRIC_COSINE).adjacency(2.0, 1.0).laplacian()
+    ptr, ind, dat = L.to_host()
+    assert np.array_equal(ptr, g["plap_indptr"]) and np.array_equal(ind, g["plap_indices"])
+    np.testing.assert_allclose(dat, g["plap_data"], rtol=RTOL, atol=1e-300)
+    lam, _ = L.lambdas_projected(x, y, tau_mode=sfb.TAU_MEDIAN)
+    np.testing.assert_allclose(lam, g["lambda_projected"], rtol=RTOL, atol=1e-15)
+    assert lam[11] == 0.0
+    sl = sfb.SortedLambdas().build_from(g["lambda_quantised"], ctx=ctx)
+    assert np.array_equal(sl.indices, g["sorted_idx"]) and np.array_equal(sl.lambdas, g["sorted_lambda"])
+    assert sl.std_dev == float(g["std_dev"][0])
+    ctx.close()
