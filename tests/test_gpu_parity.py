@@ -157,6 +157,27 @@ def test_sfgrass_reference_layer(sfb, oracle, ctx):
     assert [j for j, _ in out[7]] == list(want[0][7, :want[2][7]])
 
 
+def test_sfgrass_reference_cases(sfb, oracle, ctx):
+    """The reference's own SF-GRASS tests (src_legacy/tests/test_sparsification.rs:3-46), ragged rows through the mirror."""
+    basic = [[(1, 1.0), (2, 0.5)], [(0, 1.0), (2, 0.8)], [(0, 0.5), (1, 0.8)]]
+    out = sfb.SfGrassSparsifier().sparsify_graph(basic, 3, ctx=ctx)
+    assert len(out) == 3 and all(len(r) > 0 for r in out) and [j for j, _ in out[0]] == [1, 2]
+    n = 50
+    rows = [[(j, 1.0 / (1.0 + abs(i - j))) for j in range(n) if i != j and (i + j) % 3 == 0] for i in range(n)]
+    out = sfb.SfGrassSparsifier().sparsify_graph(rows, n, ctx=ctx)
+    assert len(out) == n and sum(len(r) for r in out) < sum(len(r) for r in rows)
+    k = max(len(r) for r in rows)
+    idx = np.full((n, k), 0xFFFFFFFF, np.uint32); w = np.zeros((n, k)); cnt = np.zeros(n, np.uint32)
+    for i, r in enumerate(rows):
+        cnt[i] = len(r)
+        for t, (j, v) in enumerate(r):
+            idx[i, t], w[i, t] = j, v
+    want = oracle.sfgrass(idx, w, cnt)
+    for i in range(n):
+        assert [j for j, _ in out[i]] == want[0][i, :want[2][i]].tolist()
+        assert [v for _, v in out[i]] == want[1][i, :want[2][i]].tolist()
+
+
 # ---- symmetrise + Laplacian -------------------------------------------------------------------
 def assert_csr_equal(got, want, data_exact=False):
     assert np.array_equal(got[0], want[0]), "indptr differs"
@@ -398,8 +419,11 @@ def test_laplacian_stage_execute(sfb, oracle, ctx, normalize):
     u_ptr, u_ind, u_dat = oracle.laplacian(o_idx, o_w.astype(np.float64), o_cnt, normalised=False)
     deg = np.array([u_dat[s:e][u_ind[s:e] == r][0] for r, (s, e) in enumerate(zip(u_ptr[:-1].astype(int), u_ptr[1:].astype(int)))])
     np.testing.assert_allclose(out.degrees, deg, rtol=1e-5)
+    row_of = np.repeat(np.arange(90), np.diff(indptr.astype(np.int64)))
+    assert np.all(data[indices != row_of] <= 0.0)   # off-diagonals <= 0 (tests/test_laplacian.rs:41-62)
+    if not normalize:   # L = D - W: every row sums to 0 (tests/test_laplacian.rs:221-250, |sum| < 1e-4 in f32)
+        assert np.all(np.abs(np.bincount(row_of, weights=data, minlength=90)) < 1e-4)
     if normalize:   # diag = 1, Rayleigh quotients in [0, 2] (tests/test_laplacian.rs:16-114)
-        row_of = np.repeat(np.arange(90), np.diff(indptr.astype(np.int64)))
         assert np.allclose(data[indices == row_of], 1.0)
         x = np.random.default_rng(0).normal(size=90)
         r = out.matrix.rayleigh_quotient(x)

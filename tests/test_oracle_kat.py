@@ -274,6 +274,35 @@ def test_sparsify_rules(oracle):
     assert not sparse[3]  # mean degree 5 < 10: skipped
 
 
+def _ragged(rows, k):
+    m = len(rows)
+    idx = np.full((m, k), 0xFFFFFFFF, np.uint32); w = np.zeros((m, k)); cnt = np.zeros(m, np.uint32)
+    for i, r in enumerate(rows):
+        cnt[i] = len(r)
+        for t, (j, v) in enumerate(r):
+            idx[i, t], w[i, t] = j, v
+    return idx, w, cnt
+
+
+def test_sfgrass_reference_cases(oracle):
+    """src_legacy/tests/test_sparsification.rs:3-46 on ragged rows: the 3-node graph is below the mean-degree
+    gate (every row survives, non-empty); the 50-node (i + j) % 3 == 0 graph loses edges, each row keeping
+    clamp(ceil(len * 0.5), 1, len) of them."""
+    basic = [[(1, 1.0), (2, 0.5)], [(0, 1.0), (2, 0.8)], [(0, 0.5), (1, 0.8)]]
+    idx, w, cnt, applied = oracle.sfgrass(*_ragged(basic, 2))
+    assert not applied and list(cnt) == [2, 2, 2] and idx[0].tolist() == [1, 2]
+    n = 50
+    rows = [[(j, 1.0 / (1.0 + abs(i - j))) for j in range(n) if i != j and (i + j) % 3 == 0] for i in range(n)]
+    k = max(len(r) for r in rows)
+    idx, w, cnt, applied = oracle.sfgrass(*_ragged(rows, k))
+    assert applied and int(cnt.sum()) < sum(len(r) for r in rows)
+    assert list(cnt) == [min(max(math.ceil(len(r) * 0.5), 1), len(r)) for r in rows]
+    # the survivors of row 4 are its best (w * sqrt(len_i * len_j)) scores, ties by index
+    i = 4
+    sc = sorted((-v * math.sqrt(float(len(rows[i]) * len(rows[j]))), j) for j, v in rows[i])
+    assert [j for _, j in sc[:cnt[i]]] == idx[i, :cnt[i]].tolist()
+
+
 # ---- diffusion: energymaps.rs:520-546 ---------------------------------------------------------
 def test_diffusion(oracle):
     L = csr_from_dense([[1, -1, 0], [-1, 2, -1], [0, -1, 1]])
