@@ -193,8 +193,10 @@ struct ScreenArgs {
 //   fast path  the keys are quantised to 8 bits over the buffer's [min, max] and the cut is found by an
 //              8-step binary search on ballot counts: keeps k' plus the few entries sharing the cut's bin.
 //              Quantisation is monotone, so every kept key is strictly greater than every dropped key.
-//   exact path MSB-first radix select of the k'-th largest key (32 steps); taken when the fast cut would
-//              drop nothing (all keys equal, or one outlier stretching the range).
+//   exact path MSB-first radix select of the k'-th largest key (32 steps), keeps exactly k'; taken when the fast cut
+//              would drop nothing (all keys equal, or one outlier stretching the range) or would keep more than
+//              k' + 16 (many equal keys in the cut's bin, e.g. exact duplicates: cap >= k' + 64 guarantees 32 free
+//              slots after every prune only if the prune keeps at most k' + 32).
 template <int E>
 __device__ __forceinline__ void prune_rows(uint32_t need, uint2* my_buf, uint32_t& cnt, float& thr,
                                            uint32_t kprime, int lane) {
@@ -249,8 +251,9 @@ __device__ __forceinline__ void prune_rows(uint32_t need, uint2* my_buf, uint32_
             dropped_max = sortable_f32(__reduce_max_sync(FULL, f32_sortable(dropped_max)));
             new_thr = dropped_max;
         }
-        if (kept == n) {
-            // exact path: k'-th largest key by MSB-first radix select
+        if (kept == n || kept > kprime + 16) {
+            // exact path: k'-th largest key by MSB-first radix select.  Also taken when many keys share the cut's bin
+            // (a cluster of exact duplicates): the buffer must come out of a prune with room for a full chunk of appends.
             uint32_t key[E];
 #pragma unroll
             for (int u = 0; u < E; ++u) key[u] = (uint32_t)(lane + 32 * u) < n ? f32_sortable(kf[u]) : 0u;  // 0 sorts below every real key

@@ -152,3 +152,18 @@ def test_knn_three_levels(sfb, oracle, ctx):
     assert st["rows_certified"] + st["rows_fallback"] == 30000
     assert_knn_equal(g.to_host(), oracle.knn(x, 8, 0))
     print(st)
+
+
+def test_knn_screen_many_exact_duplicates(sfb, oracle, ctx):
+    """A cluster of exact duplicates puts more equal keys into a row's candidate buffer than the quantised prune can
+    separate: the prune must still leave room for the next chunk's appends (it switches to the exact select), and the
+    result is the oracle's -- ties by index -- for the duplicates, their neighbours and every other row."""
+    rng = np.random.default_rng(15)
+    base = rng.normal(size=(4500, 48))
+    hot = base[7] + 0.01 * rng.normal(size=48)
+    x = np.concatenate([base[:2000], np.tile(hot, (150, 1)), base[2000:], np.tile(base[11], (90, 1))])
+    for metric in (0, 1):
+        g = ctx.matrix(x).knn(16, metric, screen=sfb.SCREEN_F16)
+        assert_knn_equal(g.to_host(), oracle.knn(x, 16, metric))
+        st = g.stats()
+        assert st["rows_certified"] + st["rows_fallback"] == x.shape[0]
