@@ -11,14 +11,19 @@ One "step" = one full build over one synthetic embedding matrix (BASELINE.json c
     feature graph  the reference's own call shape: kNN over the D feature nodes (the columns), Laplacian
                    (src_legacy/graph.rs:193-255); its exact f64 pair sums run on a side stream beside the screen
     lambda         per-item taumode lambda against the D x D feature Laplacian, min-max normalised
-                   (src_legacy/taumode.rs:117-318, core.rs:1341-1355)
+                   (src_legacy/taumode.rs:117-318, core.rs:1341-1355); config c5: the energy pipeline's node
+                   energies (energymaps.rs:923-1045) after SF-GRASS (sparsification.rs:32-113), diffusion timed apart
 `value`  = rows / device time with the f64 matrix already resident in HBM.
 `e2e`    = the same build through the public API with the matrix in pinned HOST memory: H2D upload,
            build, D2H of the item Laplacian (CSR) and the lambda vector inside the timed region.
+`verify` = parity of the build just timed, at the size just timed, against the CPU oracle (always on; --no-verify skips):
+           kNN lists of sampled rows bit-exact against brute force over the FULL corpus, item Laplacian against the
+           oracle's assembly, feature graph, lambdas within 1e-9.
 N > 1: one process per GPU (torchrun); query rows are sharded, the f64 corpus is replicated, the kNN
 lists and lambdas are all-gathered with NCCL (strong scaling: the matrix is the same at every N).
 The reference arm times the CPU oracle (a C restatement of the reference; Rust cannot be built here)
-on a bounded sample of the same workload and extrapolates per stage -- see `cpu_baseline.sample`.
+on a bounded sample of the same workload and extrapolates per stage -- see `cpu_baseline.sample`; config c1 runs
+on the CPU in full.
 """
 import argparse
 import json
@@ -44,10 +49,21 @@ WORKLOADS = {
                centres=4096, noise=0.3, metric=1, k=16),
     "c4": dict(name="C4 100k x 3072 anisotropic, cosine k=32", rows=100_000, cols=3072, kind=2, seed=13, centres=0,
                noise=0.1, metric=0, k=32),
-    "c5": dict(name="C5 5M x 128 clustered, L2 k=64", rows=5_000_000, cols=128, kind=1, seed=17, centres=2048, noise=0.5,
-               metric=1, k=64),
+    "c5": dict(name="C5 5M x 128 clustered, L2 k=64 + SF-GRASS 0.5 + energymaps lambda", rows=5_000_000, cols=128, kind=1, seed=17,
+               centres=2048, noise=0.5, metric=1, k=64, sparsify="sfgrass", ratio=0.5, variant=1, diffuse_steps=4, eta=0.1, feature_k=4),
 }
 P_WEIGHT, SIGMA = 2.0, 1.0
+LAMBDA_ENERGY_NODE = 1
+
+
+def config_dict(wl):
+    """The `config` object of the JSON line: identical for both arms."""
+    c = {"workload": wl["name"], "rows": wl["rows"], "cols": wl["cols"], "k": wl["k"], "metric": ["cosine", "l2", "l2sq"][wl["metric"]],
+         "p": P_WEIGHT, "sigma": SIGMA}
+    if wl.get("sparsify") == "sfgrass":
+        c["sparsify"] = f"sfgrass({wl['ratio']})"
+        c["lambda"] = "energy_node"
+    return c
 
 
 def peaks():
@@ -132,40 +148,52 @@ def _timed(ctx, name, f):
     return r
 
 
+def feature_k(wl):
+    """Neighbours per node of the FEATURE graph.  The taumode build uses the same k as the item graph (round-1 definition
+    of the step); the energy pipeline bootstraps its Laplacian with topk = lambda_topk.min(4) (energymaps.rs:463-466)."""
+    return min(wl.get("feature_k", wl["k"]), wl["cols"] - 1)
+
+
 def build_once(sfb, ctx, X, wl, rank, world, out_lambda=None, keep=False):
-    """One full build on device-resident X.  Returns (handles or None, stats)."""
+    """One full build on device-resident X.  Returns (handles or None, knn stats, lambda stats)."""
     n, d = X.shape
     lo, hi = shard(n, rank, world)
+    sfgrass = wl.get("sparsify") == "sfgrass"
+    variant = wl.get("variant", 0)
     # the feature graph (the reference's call shape: nodes = columns) is registered first and runs on a side stream
     # beside the item graph's tensor-core screen; .end() joins it
-    pend = X.knn_columns_begin(min(wl["k"], d - 1), sfb.METRIC_COSINE, sharded=world > 1)
+    pend = X.knn_columns_begin(feature_k(wl), sfb.METRIC_COSINE, sharded=world > 1)
     g = _timed(ctx, "knn", lambda: X.knn(wl["k"], wl["metric"], q_begin=lo, q_end=hi))
     st = g.stats()
     if world > 1:
         g_all = _timed(ctx, "allgather", lambda: g.allgather(n))
         g.free()
         g = g_all
-    adj = _timed(ctx, "adjacency", lambda: g.adjacency(P_WEIGHT, SIGMA))
+    # config c5: SfGrassSparsifier on the weighted lists instead of the builder's inline rule (sparsification.rs:32-113)
+    adj = _timed(ctx, "adjacency", lambda: g.adjacency(P_WEIGHT, SIGMA, sparsify=0 if sfgrass else -1))
+    if sfgrass:
+        _timed(ctx, "sfgrass", lambda: adj.sfgrass(wl["ratio"]))
     L = _timed(ctx, "laplacian", lambda: adj.laplacian())
+    st["nnz_item"] = L.shape[1]
     # feature Laplacian + per-item lambda
     gf = _timed(ctx, "knn_columns", lambda: pend.end())
     adjf = _timed(ctx, "adjacency_f", lambda: gf.adjacency(P_WEIGHT, SIGMA))
     Lf = _timed(ctx, "laplacian_f", lambda: adjf.laplacian())
     xs = X.view_rows(lo, hi - lo)
-    lam, lstats = _timed(ctx, "lambda", lambda: Lf.lambdas_allgather(xs, lo, n, normalise=True))
+    lam, lstats = _timed(ctx, "lambda", lambda: Lf.lambdas_allgather(xs, lo, n, variant=variant, normalise=True))
     if out_lambda is not None:
         out_lambda[:] = lam
     if keep == "all":
-        for h in (xs, adjf, gf, adj):
+        for h in (xs, adjf, adj):
             h.free()
-        return (L, Lf, lam, g), st
+        return (L, Lf, lam, g, gf), st, lstats
     _timed(ctx, "free", lambda: [h.free() for h in (xs, adjf, gf, adj, g)])
     if keep:
-        return (L, Lf, lam), st
+        return (L, Lf, lam), st, lstats
     L.free(); Lf.free()
     if _TRACE:
         sys.stderr.write(f"  knn stats: prepare {st['ms_prepare']:.2f} screen {st['ms_screen']:.2f} rescore {st['ms_rescore']:.2f} fallback {st['ms_fallback']:.2f}\n")
-    return None, st
+    return None, st, lstats
 
 
 def run_ours(args):
@@ -181,7 +209,8 @@ def run_ours(args):
             raise SystemExit("--gpus N > 1 must be launched with torchrun (one process per GPU)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=30))
     ctx = sfb.Context(local)
     if world > 1:
         ids = [sfb.comm_unique_id() if rank == 0 else None]
@@ -216,7 +245,7 @@ def run_ours(args):
     step_wall = []
     for _ in range(args.steps):
         t_s = time.perf_counter()
-        _, st = build_once(sfb, ctx, X, wl, rank, world)
+        _, st, _ = build_once(sfb, ctx, X, wl, rank, world)
         stats.append(st)
         step_wall.append((time.perf_counter() - t_s) * 1e3)  # every step ends with a synchronising D2H of lambda
     ms = ctx.timer_stop()
@@ -231,35 +260,45 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3)
 
-    # ---- parity at full size (--verify): sampled rows against the CPU oracle, structural invariants ---
+    # ---- the energy pipeline's diffusion pass (config c5), timed apart from the build ----------
+    diffusion = None
+    if wl.get("diffuse_steps"):
+        diffusion = time_diffusion(sfb, ctx, X, wl, rank, world, torch, dist)
+
+    # ---- parity at the size just timed: sampled rows against the CPU oracle --------------------
     verify = None
-    if args.verify:
-        verify = verify_build(sfb, ctx, X, wl, rank, world)
+    if not args.no_verify:
+        verify = verify_build(sfb, ctx, X, wl, rank, world, args.verify_rows, full=args.verify_full)
+        barrier()
 
     # ---- end to end: pinned host matrix in, CSR + lambda out ----------------------------------
     e2e = None
     if not args.no_e2e:
-        xh = ctx.pinned_empty((n, d))
+        xh = ctx.pinned_empty((hi - lo, d))          # this rank's rows only
         step_rows = 1 << 16
-        for r0 in range(0, n, step_rows):
-            xh[r0:r0 + step_rows] = X.rows(r0, min(step_rows, n - r0))
+        for r0 in range(lo, hi, step_rows):
+            nb = min(step_rows, hi - r0)
+            xh[r0 - lo:r0 - lo + nb] = X.rows(r0, nb)
         X.free()
         nnz_cap = n * (2 * k + 1)
-        out_csr = (ctx.pinned_empty(n + 1, np.uint64), ctx.pinned_empty(nnz_cap, np.uint32), ctx.pinned_empty(nnz_cap, np.float64))
+        fetch_csr = rank == 0                         # the result is read back once, by rank 0
+        out_csr = (ctx.pinned_empty(n + 1, np.uint64), ctx.pinned_empty(nnz_cap, np.uint32), ctx.pinned_empty(nnz_cap, np.float64)) if fetch_csr else None
         out_lam = ctx.pinned_empty(n, np.float64)
         d2h = 0
 
         def e2e_step():
             nonlocal d2h
             if world > 1:   # upload this rank's rows only; the corpus is replicated over NVLink, not PCIe
-                xs_ = ctx.matrix(xh[lo:hi])
+                xs_ = ctx.matrix(xh)
                 Xd = xs_.allgather_rows(n)
                 xs_.free()
             else:
                 Xd = ctx.matrix(xh)
-            (L, Lf, lam), _ = build_once(sfb, ctx, Xd, wl, rank, world, out_lambda=out_lam, keep=True)
-            indptr, indices, data = L.to_host(out_csr)
-            d2h = indptr.nbytes + indices.nbytes + data.nbytes + out_lam.nbytes
+            (L, Lf, lam), _, _ = build_once(sfb, ctx, Xd, wl, rank, world, out_lambda=out_lam, keep=True)
+            d2h = out_lam.nbytes
+            if fetch_csr:
+                indptr, indices, data = L.to_host(out_csr)
+                d2h += indptr.nbytes + indices.nbytes + data.nbytes
             L.free(); Lf.free(); Xd.free()
 
         e2e_steps = max(1, min(args.steps, 3))
@@ -272,18 +311,23 @@ def run_ours(args):
         ms_e = ctx.timer_stop()
         barrier()
         wall_e = (time.perf_counter() - t0) * 1e3
-        te = torch.tensor([max(ms_e, wall_e)], device="cuda", dtype=torch.float64)
+        te = torch.tensor([max(ms_e, wall_e), float(d2h)], device="cuda", dtype=torch.float64)
         if world > 1:
+            tsum = te.clone()
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            d2h_total = int(tsum[1])
+        else:
+            d2h_total = int(d2h)
         ms_e_step = float(te[0]) / e2e_steps
         e2e = {"value": n / (ms_e_step * 1e-3), "unit": UNIT, "ms_per_step": ms_e_step, "steps": e2e_steps,
-               "h2d_bytes_per_step": int(hi - lo) * d * 8 * world, "d2h_bytes_per_step": int(d2h) * world,
-               "api": "Context.matrix(host f64 rows of this rank) [-> Matrix.allgather_rows] -> Matrix.knn -> adjacency -> laplacian -> Csr.to_host; "
-                      "Csr.lambdas_allgather -> host (every rank fetches the full CSR and lambda)"}
+               "h2d_bytes_per_step": int(n) * d * 8, "d2h_bytes_per_step": d2h_total,
+               "api": "Context.matrix(host f64 rows of this rank) [-> Matrix.allgather_rows] -> Matrix.knn -> adjacency -> laplacian -> Csr.to_host "
+                      "(rank 0); Csr.lambdas_allgather -> host (every rank)"}
     else:
         X.free()
 
-    # ---- roofline of the dominant kernel (tcgen05 distance screen) ----------------------------
+    # ---- rooflines: the dominant kernel (tcgen05 distance screen) and the HBM-bound stages -------
     pk = peaks()
     scr_ms = sum(s["ms_screen"] for s in stats) / len(stats)
     screened = stats[0]["screen_used"] in (sfb.SCREEN_F16, sfb.SCREEN_BF16)
@@ -293,7 +337,7 @@ def run_ours(args):
         ach = flops / (scr_ms * 1e-3) / 1e12
         peak = pk["tc_sustained"] if scr_ms > 100 else pk["tc_burst"]
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01e_screen_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "screen_traffic.json")
         if args.config == "c2" and not args.rows and world == 1 and os.path.exists(tpath):
             tj = json.load(open(tpath))   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
@@ -301,6 +345,23 @@ def run_ours(args):
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "ms_per_launch": scr_ms, "flops_per_launch": flops,
                 "peak_source": pk["source"] + (", sustained" if scr_ms > 100 else ", burst")}
+    # HBM-bound stages: algorithmic bytes / device time of the stage's kernels on this rank
+    lam_bytes = (hi - lo) * d * 8.0 + (hi - lo) * 8.0                       # X read once + lambda written
+    lam_ms = tm.get("ms_lambda_kernel", 0.0) / args.steps
+    nnz_item = float(stats[-1].get("nnz_item", 0))
+    lap_bytes = n * k * 12.0 + n * 4.0 + (n + 1) * 8.0 + nnz_item * 12.0
+    lap_ms = tm["ms_laplacian"] / args.steps
+    stages = {}
+    if lam_ms > 0:
+        stages["lambda"] = {"kernel": "lambda_tile_kernel", "bound": "hbm", "bytes": lam_bytes, "ms": lam_ms,
+                            "achieved": lam_bytes / (lam_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": lam_bytes / (lam_ms * 1e-3) / 1e9 / pk["hbm"],
+                            "note": "R*F*8 + R*8 bytes per launch; at this graph density the kernel is bound by the FP64 pipe, not HBM (DESIGN.md 3.5)"}
+    if lap_ms > 0 and nnz_item:
+        stages["laplacian"] = {"kernels": "rev_count/scan/rev_scatter/merge/emit", "bound": "hbm", "bytes": lap_bytes, "ms": lap_ms,
+                               "achieved": lap_bytes / (lap_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": lap_bytes / (lap_ms * 1e-3) / 1e9 / pk["hbm"],
+                               "note": "lists N*k*12 + N*4 read, (N+1)*8 + nnz*12 written; ms covers both Laplacians of a step"}
 
     if rank == 0:
         line = {
@@ -308,17 +369,19 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "dtype_note": "results are the exact f64 values of the reference arithmetic; the tensor-core screen that proposes candidates runs in fp16 with fp32 accumulation",
             "data": "synthetic (counter-based Philox + Box-Muller, generated on device)",
-            "config": {"workload": wl["name"], "rows": n, "cols": d, "k": k, "metric": ["cosine", "l2", "l2sq"][wl["metric"]],
-                       "p": P_WEIGHT, "sigma": SIGMA, "sharding": f"query rows / {world}, corpus replicated" if world > 1 else "single GPU",
-                       "l2_policy": f"inputs larger than L2 ({n * d * 8 / 1e9:.2f} GB f64 matrix streamed every step)"},
+            "config": config_dict(wl),
+            "run": {"sharding": f"query rows / {world}, corpus replicated" if world > 1 else "single GPU",
+                    "l2_policy": f"inputs larger than L2 ({n * d * 8 / 1e9:.2f} GB f64 matrix streamed every step)"},
             "impl": "surfface_b200", "wall_ms_per_step": wall_ms / args.steps, "wall_ms_steps": [round(v, 2) for v in step_wall],
             "knn_ms_steps": [[round(s_[k_], 2) for k_ in ("ms_prepare", "ms_screen", "ms_rescore")] for s_ in stats],
-            "stages_ms_per_step": {kk: tm[kk] / args.steps for kk in ("ms_knn", "ms_adjacency", "ms_laplacian", "ms_lambda")},
+            "stages_ms_per_step": {kk: tm[kk] / args.steps for kk in ("ms_knn", "ms_adjacency", "ms_laplacian", "ms_lambda") if kk in tm},
             "knn": {kk: stats[-1][kk] for kk in ("rows", "rows_certified", "rows_fallback", "k_prime", "screen_used", "ms_prepare",
                                                  "ms_screen", "ms_rescore", "ms_fallback", "max_margin", "rows_rescreened", "ms_rescreen")},
             "gpu_launches": int(tm["kernel_launches"]),
-            "clocks": clocks, "roofline": roof, "e2e": e2e,
+            "clocks": clocks, "roofline": roof, "roofline_stages": stages, "e2e": e2e,
         }
+        if diffusion is not None:
+            line["diffusion"] = diffusion
         if verify is not None:
             line["verify"] = verify
         if world == 1 and not args.no_cpu:
@@ -329,26 +392,107 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def verify_build(sfb, ctx, X, wl, rank, world, n_sample=48):
-    """Full-size parity (every rank runs the build; rank 0 checks): kNN lists of sampled rows bit-exact against
-    the oracle's brute force over the FULL corpus; CSR invariants of the item Laplacian (sorted columns, stored
-    diagonal, row sums 0, symmetry on sampled entries); feature Laplacian and sampled lambdas against the oracle."""
+def time_diffusion(sfb, ctx, X, wl, rank, world, torch, dist):
+    """diffuse_and_split_subcentroids' diffusion (energymaps.rs:520-546): X <- X - eta * X L^T, `steps` times, over this
+    rank's rows of a COPY of X (one read + one write of the rows per call: the steps stay in shared memory)."""
     import numpy as np
-    import oracle
-    oracle.build()
-    oracle.use_all_threads()
-    n, d, k = wl["rows"], wl["cols"], wl["k"]
-    (L, Lf, lam, g), _ = build_once(sfb, ctx, X, wl, rank, world, keep="all")
-    out = None
+    n, d = X.shape
+    lo, hi = shard(n, rank, world)
+    gf = X.knn_columns(feature_k(wl), sfb.METRIC_COSINE, sharded=world > 1)
+    adjf = gf.adjacency(P_WEIGHT, SIGMA)
+    Lf = adjf.laplacian()
+    rows = np.unique(np.random.default_rng(3).integers(lo, hi, 32))
+    before = np.stack([X.rows(int(r), 1)[0] for r in rows])
+    ms_all = []
+    xc = None
+    for it in range(3):
+        xc = ctx.matrix_copy(X.view_rows(lo, hi - lo))
+        ctx.synchronize()
+        ctx.timer_start()
+        xc.diffuse(Lf, wl["eta"], wl["diffuse_steps"])
+        ms_all.append(ctx.timer_stop())
+        if it < 2:
+            xc.free()
+    after = np.stack([xc.rows(int(r - lo), 1)[0] for r in rows])
+    xc.free()
+    ms = min(ms_all)
+    tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt[0])
+    out = {"steps": wl["diffuse_steps"], "eta": wl["eta"], "ms": ms, "bytes": 2.0 * n * d * 8,
+           "achieved_gbs": 2.0 * n * d * 8 / (ms * 1e-3) / 1e9 / world, "note": "read + write of the item matrix once; per GPU"}
     if rank == 0:
-        xh = np.empty((n, d))
-        step = 1 << 16
-        for r0 in range(0, n, step):
-            xh[r0:r0 + step] = X.rows(r0, min(step, n - r0))
-        rows = np.unique(np.random.default_rng(1).integers(0, n, n_sample))
+        import oracle
+        oracle.build()
+        fl = Lf.to_host()
+        want = oracle.diffuse(*fl, before, wl["eta"], wl["diffuse_steps"])
+        out["sampled_rows_bit_exact"] = bool(np.array_equal(want, after))
+    for h in (Lf, adjf, gf):
+        h.free()
+    return out
+
+
+def verify_build(sfb, ctx, X, wl, rank, world, n_sample=256, full=False):
+    """Parity at the size just timed (every rank runs the build; rank 0 checks):
+      kNN       lists of sampled rows bit-exact (indices, distances, counts) against the oracle's brute force over the FULL corpus
+      item L    CSR invariants (sorted columns, stored diagonal, zero row sums, symmetry); equal to the oracle's assembly of
+                the gathered lists (whole matrix when it fits the host comfortably, else the sampled rows)
+      feature   graph over the columns against the oracle (all nodes when affordable, else a sample), feature Laplacian
+                against the oracle's assembly
+      lambda    within 1e-9 of the oracle (all rows when affordable, else the sampled rows)
+    Matrices that cannot sit on the host (C3: 61 GB) are streamed from the device in row blocks through the oracle's
+    block forms.  full=True additionally compares the screened kNN of ALL rows with the exact f64 kernel on the GPU."""
+    import numpy as np
+    n, d, k = wl["rows"], wl["cols"], wl["k"]
+    variant = wl.get("variant", 0)
+    t_start = time.perf_counter()
+    (L, Lf, lam, g, gf), _, lstats = build_once(sfb, ctx, X, wl, rank, world, keep="all")
+    out = None
+    full_out = None
+    if full:
+        full_out = verify_full_knn(sfb, ctx, X, wl, g, rank, world)
+    if rank == 0:
+        import oracle
+        oracle.build()
+        oracle.use_all_threads()
+        kf = feature_k(wl)
+        small = n * d * 8 <= 8e9
+        rows = np.unique(np.random.default_rng(1).integers(0, n, n_sample if small else min(n_sample, 64)))
         idx, dist_, cnt = g.to_host()
-        o_idx, o_dist, o_cnt = oracle.knn(xh, k, wl["metric"], query_rows=rows)
+        f_idx, f_dist, f_cnt = gf.to_host()
+        feat_all = 2.0 * d * d * n <= 4e11
+        if small:
+            xh = np.empty((n, d))
+            step = 1 << 16
+            for r0 in range(0, n, step):
+                xh[r0:r0 + step] = X.rows(r0, min(step, n - r0))
+            o_idx, o_dist, o_cnt = oracle.knn(xh, k, wl["metric"], query_rows=rows)
+            if feat_all:
+                fo = oracle.knn(oracle.transpose(xh), kf, oracle.METRIC_COSINE)
+                fcols = np.arange(d, dtype=np.uint32)
+            else:
+                fcols = np.unique(np.random.default_rng(2).integers(0, d, 32)).astype(np.uint32)
+                cg = oracle.ColsGramStream(d, fcols, kf)
+                cg.feed(xh)
+                fo = cg.finish()
+        else:
+            xq = np.stack([X.rows(int(r), 1)[0] for r in rows])
+            ks = oracle.KnnStream(xq, rows, k, wl["metric"])
+            fcols = np.unique(np.random.default_rng(2).integers(0, d, 16)).astype(np.uint32)
+            cg = oracle.ColsGramStream(d, fcols, kf)
+            step = 1 << 18
+            for r0 in range(0, n, step):
+                xb = X.rows(r0, min(step, n - r0))
+                ks.feed(xb, r0)
+                cg.feed(xb)
+            o_idx, o_dist, o_cnt = ks.finish()
+            fo = cg.finish()
+            xh = None
         knn_ok = bool(np.array_equal(idx[rows], o_idx) and np.array_equal(dist_[rows], o_dist) and np.array_equal(cnt[rows], o_cnt))
+        feat_ok = bool(np.array_equal(f_idx[fcols], fo[0]) and np.array_equal(f_dist[fcols], fo[1]) and np.array_equal(f_cnt[fcols], fo[2]))
+
+        # item Laplacian: invariants over the whole CSR
         indptr, indices, data = L.to_host()
         ip = indptr.astype(np.int64)
         deg = np.diff(ip)
@@ -358,30 +502,99 @@ def verify_build(sfb, ctx, X, wl, rank, world, n_sample=48):
         rs = np.add.reduceat(data, ip[:-1])
         scale = np.add.reduceat(np.abs(data), ip[:-1]) + 1e-300
         rowsum_ok = bool(np.max(np.abs(rs) / scale) < 1e-12)
+        del row_of
         sym_ok = True
-        for r in rows[:16]:
+        for r in rows[:64]:
             for e in range(ip[r], ip[r + 1]):
                 c = int(indices[e])
                 pos = ip[c] + np.searchsorted(indices[ip[c]:ip[c + 1]], r)
                 sym_ok = sym_ok and pos < ip[c + 1] and indices[pos] == r and data[pos] == data[e]
-        # the item graph from the gathered lists == the oracle's assembly of the same lists
-        a = oracle.build_adjacency(idx, dist_, cnt, P_WEIGHT, SIGMA)
-        o_ptr, o_ind, o_dat = oracle.laplacian(*a[:3])
-        lap_ok = bool(np.array_equal(indptr, o_ptr) and np.array_equal(indices, o_ind) and np.allclose(data, o_dat, rtol=1e-9, atol=0))
-        # feature graph + lambda
-        f = oracle.knn(oracle.transpose(xh), min(k, d - 1), oracle.METRIC_COSINE)
-        fl = oracle.laplacian(*oracle.build_adjacency(*f, P_WEIGHT, SIGMA)[:3])
+        # ... and equality with the oracle's assembly of the gathered lists
+        sfg = wl.get("sparsify") == "sfgrass"
+        a = oracle.build_adjacency(idx, dist_, cnt, P_WEIGHT, SIGMA, force_sparsify=0 if sfg else -1)
+        if sfg:
+            a = oracle.sfgrass(a[0], a[1], a[2], wl["ratio"])
+        if n <= 2_000_000:
+            o_ptr, o_ind, o_dat = oracle.laplacian(*a[:3])
+            lap_ok = bool(np.array_equal(indptr, o_ptr) and np.array_equal(indices, o_ind) and np.allclose(data, o_dat, rtol=1e-9, atol=0))
+            lap_how = "all rows"
+        else:
+            lap_ok = True
+            a_idx, a_w, a_cnt = a[:3]
+            for r in rows:
+                nb = {}
+                for t in range(int(a_cnt[r])):
+                    nb[int(a_idx[r, t])] = float(a_w[r, t])
+                rr, tt = np.nonzero(a_idx == r)
+                for j, t in zip(rr, tt):
+                    if t < a_cnt[j] and j != r:
+                        nb[int(j)] = max(nb.get(int(j), -np.inf), float(a_w[j, t]))
+                nb.pop(int(r), None)
+                cols = sorted(nb)
+                dsum = 0.0
+                for c in cols:
+                    dsum += nb[c]
+                want_c = sorted(cols + [int(r)])
+                want_v = [dsum if c == r else -nb[c] for c in want_c]
+                got_c = indices[ip[r]:ip[r + 1]]; got_v = data[ip[r]:ip[r + 1]]
+                lap_ok = lap_ok and len(got_c) == len(want_c) and bool(np.array_equal(got_c, np.array(want_c, np.uint32))) and \
+                    bool(np.allclose(got_v, np.array(want_v), rtol=1e-9, atol=0))
+            lap_how = f"{len(rows)} sampled rows (+ invariants over all rows)"
+
+        # feature Laplacian: the oracle's assembly of the (verified) feature lists; lambda against it
+        fl = oracle.laplacian(*oracle.build_adjacency(f_idx, f_dist, f_cnt, P_WEIGHT, SIGMA)[:3])
         fptr, find, fdat = Lf.to_host()
         flap_ok = bool(np.array_equal(fptr, fl[0]) and np.array_equal(find, fl[1]) and np.allclose(fdat, fl[2], rtol=1e-9, atol=0))
-        o_lam, _ = oracle.normalise_lambdas(oracle.lambdas(*fl, xh))
-        lam_ok = bool(np.allclose(lam, o_lam, rtol=1e-9, atol=1e-12))
+        o_variant = oracle.LAMBDA_ENERGY_NODE if variant == LAMBDA_ENERGY_NODE else oracle.LAMBDA_LEGACY_TAUMODE
+        if small and n <= 2_000_000:
+            o_lam, _ = oracle.normalise_lambdas(oracle.lambdas(*fl, xh, o_variant, oracle.TAU_MEDIAN))
+            lam_ok = bool(np.allclose(lam, o_lam, rtol=1e-9, atol=1e-12))
+            lam_how = "all rows"
+        else:
+            # sampled rows + one contiguous block; normalised with the build's own global min / range
+            blk0 = int(rows[len(rows) // 2]) // 4096 * 4096
+            sel = np.unique(np.concatenate([rows, np.arange(blk0, min(blk0 + 4096, n))]))
+            xsel = np.concatenate([X.rows(blk0, min(4096, n - blk0))] + [X.rows(int(r), 1) for r in rows if not (blk0 <= r < blk0 + 4096)])
+            order = np.concatenate([np.arange(blk0, min(blk0 + 4096, n)), [r for r in rows if not (blk0 <= r < blk0 + 4096)]]).astype(np.int64)
+            raw = oracle.lambdas(*fl, xsel, o_variant, oracle.TAU_MEDIAN)
+            want = (raw - lstats[0]) / lstats[2]
+            lam_ok = bool(np.allclose(lam[order], want, rtol=1e-9, atol=1e-12)) and bool(lam.min() >= 0.0 and lam.max() <= 1.0 + 1e-12)
+            lam_how = f"{len(order)} rows (a 4096-row block + the sampled rows), normalised with the build's global min / range"
+            del sel
         out = {"knn_rows_checked": int(len(rows)), "knn_bit_exact": knn_ok, "csr_sorted": sorted_ok, "csr_diagonal_stored": diag_ok,
                "csr_row_sums_zero": rowsum_ok, "csr_symmetric_sample": bool(sym_ok), "item_laplacian_matches_oracle": lap_ok,
-               "feature_laplacian_matches_oracle": flap_ok, "lambda_all_rows_within_1e-9": lam_ok}
-        out["ok"] = all(v for kk, v in out.items() if kk != "knn_rows_checked")
-    for h in (L, Lf, g):
+               "item_laplacian_checked": lap_how, "feature_nodes_checked": int(len(fcols)), "feature_knn_bit_exact": feat_ok,
+               "feature_laplacian_matches_oracle": flap_ok, "lambda_within_1e-9": lam_ok, "lambda_checked": lam_how,
+               "host_matrix": "full copy" if small else "streamed from the device in 262144-row blocks"}
+        if full_out is not None:
+            out["full_knn"] = full_out
+        out["ok"] = all(v for kk, v in out.items() if isinstance(v, bool)) and (full_out is None or full_out["ok"])
+        out["seconds"] = round(time.perf_counter() - t_start, 1)
+    for h in (L, Lf, g, gf):
         h.free()
     return out
+
+
+def verify_full_knn(sfb, ctx, X, wl, g, rank, world):
+    """Every row of the screened kNN (tensor-core candidates + f64 rescore + certificates) against the exact f64
+    brute-force kernel on the GPU (knn_exact_kernel, itself oracle-verified in tests/): indices, distances, counts."""
+    import numpy as np
+    n, k = wl["rows"], wl["k"]
+    lo, hi = shard(n, rank, world)
+    idx, dist_, cnt = g.to_host()
+    bad_rows, checked = 0, 0
+    t0 = time.perf_counter()
+    step = 50_000
+    for r0 in range(lo, hi, step):
+        r1 = min(r0 + step, hi)
+        e = X.knn(k, wl["metric"], screen=sfb.SCREEN_EXACT_F64, q_begin=r0, q_end=r1)
+        e_idx, e_dist, e_cnt = e.to_host()
+        e.free()
+        same = np.all(idx[r0:r1] == e_idx, axis=1) & np.all(dist_[r0:r1] == e_dist, axis=1) & (cnt[r0:r1] == e_cnt)
+        bad_rows += int(np.count_nonzero(~same))
+        checked += r1 - r0
+    return {"rows_checked": checked, "rows_differing": bad_rows, "ok": bad_rows == 0, "seconds": round(time.perf_counter() - t0, 1),
+            "how": "screened lists of every row of this rank == SFB_SCREEN_EXACT_F64 lists (indices, distances, counts bit for bit)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -408,6 +621,38 @@ def cpu_setup(wl):
     return _CPU_CACHE[key]
 
 
+def cpu_rest(wl, x, lists):
+    """Everything after the item kNN, on the rows of `x`, from their lists."""
+    import oracle
+    d, k = wl["cols"], wl["k"]
+    sfg = wl.get("sparsify") == "sfgrass"
+    a = oracle.build_adjacency(*lists, P_WEIGHT, SIGMA, force_sparsify=0 if sfg else -1)
+    if sfg:
+        a = oracle.sfgrass(a[0], a[1], a[2], wl["ratio"])
+    oracle.laplacian(*a[:3])
+    xt = oracle.transpose(x)
+    f = oracle.knn(xt, feature_k(wl), oracle.METRIC_COSINE)
+    fa = oracle.build_adjacency(*f, P_WEIGHT, SIGMA)
+    fl = oracle.laplacian(*fa[:3])
+    variant = oracle.LAMBDA_ENERGY_NODE if wl.get("variant", 0) == LAMBDA_ENERGY_NODE else oracle.LAMBDA_LEGACY_TAUMODE
+    lam = oracle.lambdas(*fl, x, variant, oracle.TAU_MEDIAN)
+    oracle.normalise_lambdas(lam)
+
+
+def cpu_full(wl):
+    """The whole build on the CPU, nothing sampled (config c1).  Returns (vectors/s, detail)."""
+    import oracle
+    x, _, _ = cpu_setup(wl)
+    n = wl["rows"]
+    t0 = time.perf_counter()
+    lists = oracle.knn(x, wl["k"], wl["metric"])
+    t_knn = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cpu_rest(wl, x, lists)
+    t_rest = time.perf_counter() - t0
+    return n / (t_knn + t_rest), {"t_knn_s": t_knn, "nq": n, "t_rest_s": t_rest, "rest_rows": n, "full": True}
+
+
 def cpu_step(wl, nq):
     """One sampled pass.  Returns (vectors/s extrapolated, detail)."""
     import numpy as np
@@ -420,30 +665,40 @@ def cpu_step(wl, nq):
     oracle.knn(x, k, wl["metric"], query_rows=q)           # nq query rows against the FULL corpus
     t_knn = time.perf_counter() - t0
     t0 = time.perf_counter()
-    a = oracle.build_adjacency(*lists, P_WEIGHT, SIGMA)
-    L = oracle.laplacian(*a[:3])
-    xt = oracle.transpose(xb)
-    f = oracle.knn(xt, min(k, d - 1), oracle.METRIC_COSINE)
-    fa = oracle.build_adjacency(*f, P_WEIGHT, SIGMA)
-    fl = oracle.laplacian(*fa[:3])
-    lam = oracle.lambdas(*fl, xb, oracle.LAMBDA_LEGACY_TAUMODE, oracle.TAU_MEDIAN)
-    oracle.normalise_lambdas(lam)
+    cpu_rest(wl, xb, lists)
     t_rest = time.perf_counter() - t0
     per_row = t_knn / nq + t_rest / nb
-    return 1.0 / per_row, {"t_knn_s": t_knn, "nq": nq, "t_rest_s": t_rest, "rest_rows": nb}
+    return 1.0 / per_row, {"t_knn_s": t_knn, "nq": nq, "t_rest_s": t_rest, "rest_rows": nb, "full": False}
+
+
+def cpu_is_full(wl):
+    return wl["rows"] <= 20_000
+
+
+def sample_text(wl, det):
+    n, d = wl["rows"], wl["cols"]
+    if det.get("full"):
+        return (f"oracle (C restatement of the reference, OpenMP), the WHOLE build, nothing sampled or extrapolated: kNN of all {n} rows "
+                f"in {det['t_knn_s']:.2f} s; weights + Laplacian + feature graph + lambda in {det['t_rest_s']:.2f} s")
+    return (f"oracle (C restatement of the reference, OpenMP): kNN of {det['nq']} query rows against the full {n} x {d} "
+            f"corpus in {det['t_knn_s']:.2f} s, scaled by rows; weights + Laplacian + feature graph + lambda on a "
+            f"{det['rest_rows']}-row block in {det['t_rest_s']:.2f} s, scaled by rows")
+
+
+def pick_nq(wl, seconds):
+    _, probe = cpu_step(wl, 16)
+    return int(max(16, min(4096, seconds / max(probe["t_knn_s"] / 16, 1e-9))))
 
 
 def cpu_sample(wl, seconds):
     import oracle
     cpu_setup(wl)
-    n, d = wl["rows"], wl["cols"]
-    _, probe = cpu_step(wl, 16)
-    nq = int(max(16, min(4096, seconds / max(probe["t_knn_s"] / 16, 1e-9))))
-    v, det = cpu_step(wl, nq)
-    return {"value": v, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-            "sample": (f"oracle (C restatement of the reference, OpenMP): kNN of {det['nq']} query rows against the full {n} x {d} "
-                       f"corpus in {det['t_knn_s']:.2f} s, scaled by rows; weights + Laplacian + feature graph + lambda on a "
-                       f"{det['rest_rows']}-row block in {det['t_rest_s']:.2f} s, scaled by rows")}
+    if cpu_is_full(wl):
+        v, det = cpu_full(wl)
+    else:
+        v, det = cpu_step(wl, pick_nq(wl, seconds))
+    return {"value": v, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample_text(wl, det),
+            "build": "gcc -O2 -march=x86-64-v3 -ffp-contract=off -fopenmp (oracle/Makefile)"}
 
 
 def run_reference(args):
@@ -454,29 +709,31 @@ def run_reference(args):
     wl = dict(WORKLOADS[args.config])
     if args.rows:
         wl["rows"] = args.rows
+        wl["name"] += f" (rows overridden to {args.rows})"
     cpu_setup(wl)
-    n, d = wl["rows"], wl["cols"]
-    _, probe = cpu_step(wl, 16)
-    nq = int(max(16, min(4096, args.cpu_seconds / max(probe["t_knn_s"] / 16, 1e-9))))
+    full = cpu_is_full(wl)
+    nq = 0 if full else pick_nq(wl, args.ref_seconds)
     for _ in range(args.warmup):
-        cpu_step(wl, max(16, nq // 8))
+        if full:
+            cpu_full(wl)
+        else:
+            cpu_step(wl, max(16, nq // 8))
     vals, t0 = [], time.perf_counter()
     for _ in range(args.steps):
-        v, det = cpu_step(wl, nq)
+        v, det = cpu_full(wl) if full else cpu_step(wl, nq)
         vals.append(1.0 / v)
     wall = time.perf_counter() - t0
     value = 1.0 / (sum(vals) / len(vals))
-    sample = (f"per step: kNN of {nq} query rows against the full {n} x {d} corpus, scaled by rows; weights + Laplacian + "
-              f"feature graph + lambda on a {det['rest_rows']}-row block, scaled by rows")
+    sample = "per step: " + sample_text(wl, det)
     line = {"impl": "reference", "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (same counter-based generator, on the host)",
-            "config": {"workload": wl["name"], "rows": n, "cols": d, "k": wl["k"], "metric": ["cosine", "l2", "l2sq"][wl["metric"]],
-                       "p": P_WEIGHT, "sigma": SIGMA},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+            "config": config_dict(wl),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample,
+                             "build": "gcc -O2 -march=x86-64-v3 -ffp-contract=off -fopenmp (oracle/Makefile)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference is a Rust workspace that cannot be compiled in this image (no cargo/rustc); the CPU arm is the "
-                    "oracle port of its algorithm, all host threads"}
+                    "oracle port of its algorithm, all host threads" + ("" if full else "; ms_per_step is the time of the SAMPLE, value the throughput it implies")}
     print(json.dumps(line), flush=True)
 
 
@@ -488,9 +745,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the row count (development only)")
-    ap.add_argument("--cpu-seconds", type=float, default=25.0, help="CPU time budget of one sampled kNN pass")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline leg's sampled kNN pass")
+    ap.add_argument("--ref-seconds", type=float, default=50.0, help="--impl reference: CPU time budget of one step's sampled kNN pass (about 2000 query rows at C2 on 16 threads)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--verify", action="store_true", help="after timing, check the full-size build against the CPU oracle (adds ~1 min)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity check of the timed build against the CPU oracle")
+    ap.add_argument("--verify", action="store_true", help="(default; kept for compatibility)")
+    ap.add_argument("--verify-rows", type=int, default=256, help="sampled rows whose kNN lists are checked against brute force over the full corpus")
+    ap.add_argument("--verify-full", action="store_true", help="also compare the screened kNN of ALL rows with the exact f64 kernel (about 100 s at C2)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (diagnosis)")
     args = ap.parse_args()

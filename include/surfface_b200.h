@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 2
+#define SFB_ABI_VERSION 3
 #define SFB_IDX_NONE 0xFFFFFFFFu
 
 typedef enum {
@@ -65,6 +65,11 @@ void sfb_pinned_free(void* p);
  * The reference moves whole flat Vec copies host<->device (surfface-core/src/laplacian.rs:157-158,
  * spectral/mod.rs:39-51,170-171).  sfb_mat_from_host is that upload. */
 int32_t sfb_mat_from_host(sfb_ctx* ctx, const double* x, uint64_t rows, uint32_t cols, sfb_mat** out);
+/* The successor's item matrices are f32 (compute_tau_mode_gpu(&LaplacianOutput, data: &[f32], ..),
+ * surfface-core/src/spectral/bridge.rs:27-32): 4 bytes per value cross PCIe, widened to f64 on the device (exact). */
+int32_t sfb_mat_from_host_f32(sfb_ctx* ctx, const float* x, uint64_t rows, uint32_t cols, sfb_mat** out);
+/* device copy (sfb_diffuse works in place; the reference's diffusion clones its matrix first, energymaps.rs:520-524) */
+int32_t sfb_mat_clone(sfb_ctx* ctx, const sfb_mat* a, sfb_mat** out);
 /* Synthetic rows generated on the device: counter-based Philox4x32-10 +
  * Box-Muller with reproducible arithmetic, so any row can be regenerated on the CPU.
  * kind 0: N(0,1) iid; 1: clustered (n_centres centres ~ N(0,I), x = c + noise*N(0,I));
@@ -217,6 +222,15 @@ int32_t sfb_lambda(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_l
  * L is reduced_dim x reduced_dim.  LEGACY_TAUMODE only. */
 int32_t sfb_lambda_projected(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x_original, const sfb_mat* x_projected,
                              const sfb_lambda_params* params, double* out_lambda, double* out_dispersion, double* stats);
+/* compute_tau_mode_gpu (surfface-core/src/spectral/bridge.rs:27-32) = compute_lambdas_gpu (spectral/mod.rs:158-181) widened
+ * to f64: data is N x F f32 on the host, L the F x F Laplacian of Stage C; lambda = Rayleigh + Dirichlet in f32 semantics
+ * (SFB_LAMBDA_CORE_F32SEM), not normalised.  out_lambdas: n_items doubles. */
+int32_t sfb_compute_tau_mode_lambdas(sfb_ctx* ctx, const sfb_csr* L, const float* data, uint64_t n_items, uint32_t n_features,
+                                     double* out_lambdas);
+/* compute_tau (surfface-core/src/taumode.rs:37-65): ONE f32 tau resolved from the lambda DISTRIBUTION (host array): finite
+ * entries only, TAU_FLOOR = 1e-9; Fixed(t) / Mean (f32 left fold) / Median = sorted[len / 2] / Percentile(p) =
+ * sorted[round((len - 1) * clamp(p, 0, 1))].  The selection runs on the device (radix select on the f32 keys). */
+int32_t sfb_compute_tau(sfb_ctx* ctx, const float* lambdas, uint64_t n, int32_t tau_mode, float tau_value, float* out_tau);
 /* diffusion step of diffuse_and_split_subcentroids (src_legacy/energymaps.rs:520-546):
  * X <- X - eta * X L^T, `steps` times, in place on the device matrix. */
 int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, double eta, uint32_t steps);
@@ -311,6 +325,8 @@ int32_t sfb_debug_screen_tile(sfb_ctx* ctx, const sfb_mat* x, int32_t metric, in
 typedef struct {
     double ms_h2d, ms_knn, ms_adjacency, ms_laplacian, ms_lambda, ms_d2h;
     uint64_t kernel_launches; /* kernels of this library launched since ctx creation */
+    double ms_lambda_kernel;  /* the per-item lambda kernel alone (inside ms_lambda)         */
+    double ms_diffuse;        /* sfb_diffuse                                                  */
 } sfb_stage_times;
 int32_t sfb_timings(const sfb_ctx* ctx, sfb_stage_times* out);
 /* device stopwatch on the context's stream (CUDA events): start, run any calls, stop -> ms */

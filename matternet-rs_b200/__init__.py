@@ -107,6 +107,28 @@ class Context:
         self.synchronize()
         return Matrix(self, h)
 
+    def matrix_f32(self, x):
+        """Upload an f32 host matrix (4 bytes per value over PCIe), widened to f64 on the device."""
+        x = _ffi.f32(x)
+        if x.ndim != 2:
+            raise ValueError("matrix must be 2-D")
+        h = C.c_void_p()
+        self.check(lib().sfb_mat_from_host_f32(self._h, _ffi.ptr(x), x.shape[0], x.shape[1], C.byref(h)))
+        return Matrix(self, h)
+
+    def matrix_copy(self, m):
+        """Device copy of a Matrix (or of a row view)."""
+        h = C.c_void_p()
+        self.check(lib().sfb_mat_clone(self._h, m._h, C.byref(h)))
+        return Matrix(self, h)
+
+    def compute_tau(self, lambdas, mode=TAU_MEDIAN, value=0.0):
+        """compute_tau (surfface-core/src/taumode.rs:37-65): one f32 tau from the lambda distribution."""
+        v = _ffi.f32(lambdas).ravel()
+        out = C.c_float()
+        self.check(lib().sfb_compute_tau(self._h, _ffi.ptr(v) if v.size else None, v.size, int(mode), float(value), C.byref(out)))
+        return out.value
+
     def generate(self, kind, seed, rows, cols, n_centres=0, noise=0.0):
         h = C.c_void_p()
         self.check(lib().sfb_mat_generate(self._h, kind, seed, rows, cols, n_centres, float(noise), C.byref(h)))
@@ -691,6 +713,38 @@ class LaplacianStage:
         L = Csr(ctx, h)
         nnz = L.shape[1]
         return LaplacianOutput(matrix=L, n_features=f, nnz=nnz, degrees=deg, sparsity=1.0 - nnz / float(f * f))
+
+
+def compute_tau_mode_gpu(laplacian: LaplacianOutput, data, n_items, n_features, ctx=None):
+    """Stage D seam of the successor, compute_tau_mode_gpu(&LaplacianOutput, data: &[f32], n_items, n_features) -> Vec<f64>
+    (surfface-core/src/spectral/bridge.rs:27-32): Rayleigh + Dirichlet per item in f32 semantics, widened to f64,
+    not normalised.  `data` is the flat row-major f32 item matrix; it crosses PCIe as f32."""
+    ctx = ctx or laplacian.matrix.ctx
+    x = _ffi.f32(data).reshape(-1)
+    if x.size != n_items * n_features:
+        raise ValueError(f"data has {x.size} values, expected {n_items} x {n_features}")
+    out = np.empty(n_items, np.float64)
+    ctx.check(lib().sfb_compute_tau_mode_lambdas(ctx._h, laplacian.matrix._h, _ffi.ptr(x), n_items, n_features, _ffi.ptr(out)))
+    return out
+
+
+class CoreTauMode:
+    """TauMode of the successor (surfface-core/src/taumode.rs:12-23): tau is resolved from the lambda DISTRIBUTION."""
+    Median, Mean = (TAU_MEDIAN, 0.0), (TAU_MEAN, 0.0)
+
+    @staticmethod
+    def Fixed(t):
+        return (TAU_FIXED, float(t))
+
+    @staticmethod
+    def Percentile(p):
+        return (TAU_PERCENTILE, float(p))
+
+
+def compute_tau(lambdas, mode=CoreTauMode.Median, ctx=None):
+    """compute_tau(lambdas: &[f32], mode) -> f32 (surfface-core/src/taumode.rs:37-65)."""
+    ctx = ctx or default_context()
+    return ctx.compute_tau(lambdas, mode[0], mode[1])
 
 
 def compute_jl_dimension(n_points, original_dim, epsilon, core=False):

@@ -61,7 +61,7 @@ class LaplacianConfigC(C.Structure):
 class StageTimes(C.Structure):
     _fields_ = [("ms_h2d", C.c_double), ("ms_knn", C.c_double), ("ms_adjacency", C.c_double),
                 ("ms_laplacian", C.c_double), ("ms_lambda", C.c_double), ("ms_d2h", C.c_double),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("ms_lambda_kernel", C.c_double), ("ms_diffuse", C.c_double)]
 
 
 # every symbol include/surfface_b200.h declares: name -> (restype, argtypes)
@@ -77,6 +77,8 @@ SYMBOLS = {
     "sfb_pinned_alloc": (C.c_int32, [_P, C.c_uint64, _PP]),
     "sfb_pinned_free": (None, [_P]),
     "sfb_mat_from_host": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, _PP]),
+    "sfb_mat_from_host_f32": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, _PP]),
+    "sfb_mat_clone": (C.c_int32, [_P, _P, _PP]),
     "sfb_mat_generate": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, _PP]),
     "sfb_mat_transpose": (C.c_int32, [_P, _P, _PP]),
     "sfb_mat_view_rows": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, _PP]),
@@ -109,6 +111,8 @@ SYMBOLS = {
     "sfb_rayleigh_quotient": (C.c_int32, [_P, _P, _P, C.POINTER(C.c_double)]),
     "sfb_lambda": (C.c_int32, [_P, _P, _P, C.POINTER(LambdaParams), _P, _P, _P]),
     "sfb_lambda_projected": (C.c_int32, [_P, _P, _P, _P, C.POINTER(LambdaParams), _P, _P, _P]),
+    "sfb_compute_tau_mode_lambdas": (C.c_int32, [_P, _P, _P, C.c_uint64, C.c_uint32, _P]),
+    "sfb_compute_tau": (C.c_int32, [_P, _P, C.c_uint64, C.c_int32, C.c_float, C.POINTER(C.c_float)]),
     "sfb_diffuse": (C.c_int32, [_P, _P, _P, C.c_double, C.c_uint32]),
     "sfb_build_laplacian_matrix": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint32, C.POINTER(GraphParamsC), C.c_int32, _PP]),
     "sfb_compute_taumode_lambdas": (C.c_int32, [_P, _P, _P, C.c_uint64, C.c_uint32, C.c_int32, C.c_double, _P]),
@@ -160,6 +164,10 @@ def f64(a):
 
 def u32(a):
     return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
 
 
 def u64(a):

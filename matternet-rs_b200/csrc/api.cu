@@ -184,6 +184,38 @@ extern "C" int32_t sfb_mat_from_host(sfb_ctx* ctx, const double* x, uint64_t row
     return SFB_OK;
 }
 
+__global__ void widen_f32_kernel(const float* __restrict__ in, uint64_t n, double* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+extern "C" int32_t sfb_mat_from_host_f32(sfb_ctx* ctx, const float* x, uint64_t rows, uint32_t cols, sfb_mat** out) {
+    if (!x) return sfb_fail(ctx, SFB_EINVAL, "null host pointer");
+    SFB_TRY(sfb_mat_alloc(ctx, rows, cols, out));
+    const uint64_t n = rows * cols;
+    DevBuf stage;
+    cudaError_t e = (sfb_tls_ctx = ctx, stage.alloc(sizeof(float) * n));
+    if (e == cudaSuccess) {
+        StageTimer t(ctx, &ctx->times.ms_h2d);
+        e = cudaMemcpyAsync(stage.p, x, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            widen_f32_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(stage.as<float>(), n, (*out)->d);
+            ctx->times.kernel_launches++;
+            e = cudaGetLastError();
+        }
+        t.stop();   // synchronises: the staging buffer may be released
+    }
+    if (e != cudaSuccess) { sfb_mat_free(*out); *out = nullptr; return sfb_fail(ctx, SFB_ECUDA, "f32 upload: %s", cudaGetErrorString(e)); }
+    return SFB_OK;
+}
+
+extern "C" int32_t sfb_mat_clone(sfb_ctx* ctx, const sfb_mat* a, sfb_mat** out) {
+    if (!a) return sfb_fail(ctx, SFB_EINVAL, "null matrix");
+    SFB_TRY(sfb_mat_alloc(ctx, a->rows, a->cols, out));
+    cudaError_t e = cudaMemcpyAsync((*out)->d, a->d, sizeof(double) * a->rows * a->cols, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { sfb_mat_free(*out); *out = nullptr; return sfb_fail(ctx, SFB_ECUDA, "device copy: %s", cudaGetErrorString(e)); }
+    return SFB_OK;
+}
+
 __global__ void generate_rows_kernel(double* __restrict__ out, int kind, uint64_t seed, uint64_t rows, uint32_t cols,
                                      uint32_t n_centres, double noise) {
     const uint32_t quads = (cols + 3) / 4;
@@ -271,6 +303,17 @@ extern "C" void sfb_mat_free(sfb_mat* a) {
 }
 
 // ---- kNN / adjacency / CSR handles ------------------------------------------------------------
+// Lists from the host index device arrays downstream (adjacency_kernel reads in_cnt[j], the reverse-edge kernels count into
+// rev_cnt[j]): a bad index would corrupt neighbouring blocks silently where the reference panics on an out-of-bounds index.
+static int32_t sfb_check_lists(sfb_ctx* ctx, const uint32_t* idx, const uint32_t* cnt, uint64_t rows, uint32_t k) {
+    for (uint64_t i = 0; i < rows; ++i) {
+        if (cnt[i] > k) return sfb_fail(ctx, SFB_EINVAL, "row %llu: count %u exceeds k = %u", (unsigned long long)i, cnt[i], k);
+        for (uint32_t t = 0; t < cnt[i]; ++t)
+            if (idx[i * k + t] >= rows)
+                return sfb_fail(ctx, SFB_EINVAL, "row %llu: neighbour %u is index %u, not below %llu rows", (unsigned long long)i, t, idx[i * k + t], (unsigned long long)rows);
+    }
+    return SFB_OK;
+}
 extern "C" int32_t sfb_knn_shape(const sfb_knn* g, uint64_t* rows, uint32_t* k, uint64_t* q_begin) {
     if (!g) return SFB_EINVAL;
     if (rows) *rows = g->rows;
@@ -308,6 +351,7 @@ int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out) {
 extern "C" int32_t sfb_knn_from_host(sfb_ctx* ctx, const uint32_t* idx, const double* dist, const uint32_t* cnt,
                                      uint64_t rows, uint32_t k, sfb_knn** out) {
     if (!ctx || !idx || !dist || !cnt || !out || rows == 0 || k == 0) return sfb_fail(ctx, SFB_EINVAL, "bad kNN arrays");
+    SFB_TRY(sfb_check_lists(ctx, idx, cnt, rows, k));
     SFB_TRY(sfb_knn_alloc(ctx, rows, k, out));
     sfb_knn* g = *out;
     SFB_CUDA(ctx, cudaMemcpyAsync(g->idx, idx, sizeof(uint32_t) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -352,6 +396,7 @@ int32_t sfb_adj_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_adj** out) {
 extern "C" int32_t sfb_adj_from_host(sfb_ctx* ctx, const uint32_t* idx, const double* w, const uint32_t* cnt,
                                      uint64_t rows, uint32_t k, sfb_adj** out) {
     if (!ctx || !idx || !w || !cnt || !out || rows == 0 || k == 0) return sfb_fail(ctx, SFB_EINVAL, "bad adjacency arrays");
+    SFB_TRY(sfb_check_lists(ctx, idx, cnt, rows, k));
     SFB_TRY(sfb_adj_alloc(ctx, rows, k, out));
     sfb_adj* a = *out;
     SFB_CUDA(ctx, cudaMemcpyAsync(a->idx, idx, sizeof(uint32_t) * rows * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -413,6 +458,7 @@ extern "C" int32_t sfb_csr_from_host(sfb_ctx* ctx, uint64_t rows, const uint64_t
 extern "C" void sfb_csr_free(sfb_csr* L) {
     if (!L) return;
     sfb_dev_free(L->ctx, L->indptr); sfb_dev_free(L->ctx, L->indices); sfb_dev_free(L->ctx, L->data);
+    sfb_dev_free(L->ctx, L->lt_recs); sfb_dev_free(L->ctx, L->lt_defect); sfb_dev_free(L->ctx, L->lt_meta);
     delete L;
 }
 

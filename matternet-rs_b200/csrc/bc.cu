@@ -8,17 +8,46 @@
 // centroids in f32 with separately rounded operations.  BC is not GEMM-form (a log and a ratio per centroid and
 // pair), so this stays on the FP32 / SFU pipes: F^2 * C evaluations.  The top-k (BC desc, j asc) reuses the
 // dense-key selection of knn_exact.cu; max-symmetrisation and the normalised Laplacian reuse laplacian.cu.
-// libm: logf / expf differ in the last bit between CUDA and the host; the reference's own tests compare at 1e-5.
+// log / exp: CUDA's logf / expf and the host libm's differ in the last bit, which would let a transcendental decide a
+// neighbour ORDER differently on the two sides.  Both are therefore evaluated here in f64 with + - * / only, in a fixed
+// order (the atanh series of synth.cuh; Taylor after a k*ln2 reduction), and rounded to f32 -- the same sequence as the
+// CPU restatement the tests check against, so indices and weights agree with it bit for bit; against glibc (the reference on
+// Linux) the values agree except for < 0.1 % of arguments that land 1 ulp apart (tests/test_oracle_kat.py).
 #include <float.h>
 #include <math.h>
 
 #include "common.cuh"
+#include "synth.cuh"
 
 int32_t sfb_adj_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_adj** out);
 int32_t sfb_dense_select(sfb_ctx* ctx, const double* keys, uint32_t m, uint64_t q_begin, uint64_t nq, uint32_t k, double eps,
                          uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);
 
 namespace {
+
+__device__ __forceinline__ float det_logf(float a) {
+    if (a != a || a < 0.0f) return __int_as_float(0x7FC00000);
+    if (a == 0.0f) return -INFINITY;
+    if (isinf(a)) return INFINITY;
+    return __double2float_rn(synth_log((double)a));   // every positive f32, subnormals included, is a normal f64
+}
+__device__ __forceinline__ float det_expf(float xf) {
+    if (xf != xf) return xf;
+    const double x = (double)xf;
+    if (x > 100.0) return INFINITY;
+    if (x < -120.0) return 0.0f;
+    const double kf = rint(__dmul_rn(x, 1.4426950408889634));
+    const double r = __dadd_rn(__dadd_rn(x, -__dmul_rn(kf, 6.93147180369123816490e-01)), -__dmul_rn(kf, 1.90821492927058770002e-10));
+    double p = 1.0 / 87178291200.0;
+    p = __dadd_rn(__dmul_rn(p, r), 1.0 / 6227020800.0);  p = __dadd_rn(__dmul_rn(p, r), 1.0 / 479001600.0); p = __dadd_rn(__dmul_rn(p, r), 1.0 / 39916800.0);
+    p = __dadd_rn(__dmul_rn(p, r), 1.0 / 3628800.0);     p = __dadd_rn(__dmul_rn(p, r), 1.0 / 362880.0);    p = __dadd_rn(__dmul_rn(p, r), 1.0 / 40320.0);
+    p = __dadd_rn(__dmul_rn(p, r), 1.0 / 5040.0);        p = __dadd_rn(__dmul_rn(p, r), 1.0 / 720.0);       p = __dadd_rn(__dmul_rn(p, r), 1.0 / 120.0);
+    p = __dadd_rn(__dmul_rn(p, r), 1.0 / 24.0);          p = __dadd_rn(__dmul_rn(p, r), 1.0 / 6.0);         p = __dadd_rn(__dmul_rn(p, r), 0.5);
+    p = __dadd_rn(__dmul_rn(p, r), 1.0);                 p = __dadd_rn(__dmul_rn(p, r), 1.0);
+    const long long k = (long long)kf;
+    const double sc = __longlong_as_double((k + 1023) << 52);
+    return __double2float_rn(__dmul_rn(p, sc));
+}
 
 // keys[i][j] = -BC(i, j) (ascending key = descending affinity), +inf where j == i or BC <= thr
 __global__ void __launch_bounds__(128) bc_keys_kernel(const float* __restrict__ means, const float* __restrict__ vars, uint32_t c,
@@ -41,10 +70,10 @@ __global__ void __launch_bounds__(128) bc_keys_kernel(const float* __restrict__ 
                 const float v_sum = __fadd_rn(vi, vj);
                 const float dm = __fadd_rn(mu_i[cc], -__ldg(means + (size_t)cc * f + j));
                 const float mean_term = __fdiv_rn(__fmul_rn(dm, dm), __fmul_rn(4.0f, v_sum));
-                const float log_term = __fmul_rn(0.5f, logf(__fdiv_rn(v_sum, __fmul_rn(2.0f, __fsqrt_rn(__fmul_rn(vi, vj))))));
+                const float log_term = __fmul_rn(0.5f, det_logf(__fdiv_rn(v_sum, __fmul_rn(2.0f, __fsqrt_rn(__fmul_rn(vi, vj))))));
                 db = __fadd_rn(db, __fadd_rn(mean_term, log_term));
             }
-            float bc = expf(-db);
+            float bc = det_expf(-db);
             bc = bc < 0.0f ? 0.0f : (bc > 1.0f ? 1.0f : bc);
             if (bc > thr) key = -(double)bc;
         }

@@ -17,9 +17,8 @@
 
 int32_t sfb_knn_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t k, sfb_knn** out);
 int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, uint64_t n, uint32_t f,
-                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp, const double* tau_in);
-int32_t sfb_minmax_device(sfb_ctx* ctx, const double* d_lambda, uint64_t n, double* mn, double* mx);
-int32_t sfb_normalise_device(sfb_ctx* ctx, double* d_lambda, uint64_t n, double mn, double mx, double* stats);
+                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp, const double* tau_in, double* d_mm);
+int32_t sfb_normalise_device(sfb_ctx* ctx, double* d_lambda, uint64_t n, const double* d_mm);
 
 namespace {
 
@@ -30,6 +29,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -47,7 +48,9 @@ NcclApi* nccl() {
             api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
             api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-            if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.GetErrorString) api.handle = h;
+            api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+            if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.GetErrorString && api.GroupStart && api.GroupEnd) api.handle = h;
         }
     }
     return api.handle ? &api : nullptr;
@@ -98,6 +101,13 @@ int32_t sfb_comm_allreduce_sum_f64(sfb_ctx* ctx, double* buf, size_t n) {
     return SFB_OK;
 }
 
+int32_t sfb_comm_allreduce_sum_f32(sfb_ctx* ctx, float* buf, size_t n) {
+    if (ctx->world == 1) return SFB_OK;
+    if (!ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    SFB_NCCL(ctx, nccl()->AllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return SFB_OK;
+}
+
 extern "C" int32_t sfb_comm_barrier(sfb_ctx* ctx) {
     if (!ctx) return SFB_EINVAL;
     if (ctx->world == 1) { SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return SFB_OK; }
@@ -140,9 +150,13 @@ extern "C" int32_t sfb_knn_allgather(sfb_ctx* ctx, const sfb_knn* shard, uint64_
     SFB_CUDA(ctx, cudaMemcpyAsync(my_dist, shard->dist, sizeof(double) * shard->rows * k, cudaMemcpyDeviceToDevice, ctx->stream));
     SFB_CUDA(ctx, cudaMemcpyAsync(my_cnt, shard->cnt, sizeof(uint32_t) * shard->rows, cudaMemcpyDeviceToDevice, ctx->stream));
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-    SFB_NCCL(ctx, nccl()->AllGather(my_idx, g->idx, S * k, ncclUint32, comm, ctx->stream));
-    SFB_NCCL(ctx, nccl()->AllGather(my_dist, g->dist, S * k, ncclFloat64, comm, ctx->stream));
-    SFB_NCCL(ctx, nccl()->AllGather(my_cnt, g->cnt, S, ncclUint32, comm, ctx->stream));
+    // the three lists in one grouped call: one launch, one pass over the NVLink rings
+    SFB_NCCL(ctx, nccl()->GroupStart());
+    ncclResult_t r1 = nccl()->AllGather(my_idx, g->idx, S * k, ncclUint32, comm, ctx->stream);
+    ncclResult_t r2 = nccl()->AllGather(my_dist, g->dist, S * k, ncclFloat64, comm, ctx->stream);
+    ncclResult_t r3 = nccl()->AllGather(my_cnt, g->cnt, S, ncclUint32, comm, ctx->stream);
+    SFB_NCCL(ctx, nccl()->GroupEnd());
+    if (r1 != ncclSuccess || r2 != ncclSuccess || r3 != ncclSuccess) return sfb_fail(ctx, SFB_ENCCL, "ncclAllGather of the kNN lists failed");
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SFB_OK;
 }
@@ -185,31 +199,33 @@ extern "C" int32_t sfb_lambda_allgather(sfb_ctx* ctx, const sfb_csr* L, const sf
     const uint64_t lo = (uint64_t)ctx->rank * S, hi = lo + S < total_rows ? lo + S : total_rows;
     if (row0 != lo || x->rows != hi - lo) return sfb_fail(ctx, SFB_EINVAL, "rank %d must hold rows [%llu, %llu)", ctx->rank, (unsigned long long)lo, (unsigned long long)hi);
     if (world > 1 && !ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    double h_mm[2] = {0.0, 0.0};
     StageTimer t(ctx, &ctx->times.ms_lambda);
     DevBuf all, mm;
     SFB_CUDA(ctx, all.alloc(sizeof(double) * world * S));
     SFB_CUDA(ctx, mm.alloc(sizeof(double) * 2));
     double* mine = all.as<double>() + lo;
-    SFB_CUDA(ctx, cudaMemsetAsync(mine, 0, sizeof(double) * S, ctx->stream));
-    SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, mine, nullptr, nullptr));
-    double mn = INFINITY, mx = 0.0;
-    SFB_TRY(sfb_minmax_device(ctx, mine, x->rows, &mn, &mx));
-    if (world > 1) {
+    if (x->rows < S) SFB_CUDA(ctx, cudaMemsetAsync(mine + x->rows, 0, sizeof(double) * (S - x->rows), ctx->stream));
+    ctx->lambda_sharded = true;    // CORE_F32SEM: the energy total is all-reduced inside (every rank makes the same calls)
+    int32_t st = sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, mine, nullptr, nullptr, mm.as<double>());
+    ctx->lambda_sharded = false;
+    SFB_TRY(st);
+    if (world > 1) {   // global min / max(0, .) (core.rs:1345-1346), on the device values: no host round trip
         ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-        double h[2] = {mn, mx};
-        SFB_CUDA(ctx, cudaMemcpyAsync(mm.p, h, 16, cudaMemcpyHostToDevice, ctx->stream));
-        SFB_NCCL(ctx, nccl()->AllReduce(mm.p, mm.p, 1, ncclFloat64, ncclMin, comm, ctx->stream));
-        SFB_NCCL(ctx, nccl()->AllReduce(mm.as<double>() + 1, mm.as<double>() + 1, 1, ncclFloat64, ncclMax, comm, ctx->stream));
-        SFB_CUDA(ctx, cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
-        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        mn = h[0]; mx = h[1];
+        SFB_NCCL(ctx, nccl()->GroupStart());
+        ncclResult_t r1 = nccl()->AllReduce(mm.p, mm.p, 1, ncclFloat64, ncclMin, comm, ctx->stream);
+        ncclResult_t r2 = nccl()->AllReduce(mm.as<double>() + 1, mm.as<double>() + 1, 1, ncclFloat64, ncclMax, comm, ctx->stream);
+        SFB_NCCL(ctx, nccl()->GroupEnd());
+        if (r1 != ncclSuccess || r2 != ncclSuccess) return sfb_fail(ctx, SFB_ENCCL, "min / max all-reduce failed");
     }
-    if (prm->normalise_minmax) SFB_TRY(sfb_normalise_device(ctx, mine, x->rows, mn, mx, stats));
-    else if (stats) { stats[0] = mn; stats[1] = mx; stats[2] = (mx - mn) > 1e-9 ? (mx - mn) : 1e-9; }
+    if (prm->normalise_minmax) SFB_TRY(sfb_normalise_device(ctx, mine, x->rows, mm.as<double>()));
     if (world > 1) SFB_NCCL(ctx, nccl()->AllGather(mine, all.p, S, ncclFloat64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     t.stop();
     StageTimer t2(ctx, &ctx->times.ms_d2h);
     SFB_CUDA(ctx, cudaMemcpyAsync(out_lambda, all.p, sizeof(double) * total_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    SFB_CUDA(ctx, cudaMemcpyAsync(h_mm, mm.p, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
+    t2.stop();
+    if (stats) { stats[0] = h_mm[0]; stats[1] = h_mm[1]; stats[2] = (h_mm[1] - h_mm[0]) > 1e-9 ? (h_mm[1] - h_mm[0]) : 1e-9; }
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SFB_OK;
 }

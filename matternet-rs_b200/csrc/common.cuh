@@ -32,6 +32,7 @@ struct sfb_ctx {
     // NCCL (loaded lazily, comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    bool lambda_sharded = false;   // inside sfb_lambda_allgather: per-rank totals of CORE_F32SEM are all-reduced (lambda.cu)
 };
 
 struct sfb_mat {
@@ -69,7 +70,9 @@ struct sfb_csr {
     uint32_t* indices = nullptr;
     double* data = nullptr;
     uint64_t rows = 0, nnz = 0;
-    mutable int symmetric = -1;  // -1 unknown, 1: structure and values symmetric bit for bit (checked once, lambda.cu), 0: not
+    mutable int symmetric = -1;  // -1 unknown, 1: structure and values symmetric bit for bit (set by the builder, else checked once in lambda.cu), 0: not
+    // packed strict upper triangle for the lambda tile kernel (lambda.cu: lt_pack), built on first use, released by sfb_csr_free
+    mutable void* lt_recs = nullptr; mutable void* lt_defect = nullptr; mutable void* lt_meta = nullptr;
 };
 
 int32_t sfb_fail(sfb_ctx* ctx, int32_t code, const char* fmt, ...);

@@ -16,6 +16,8 @@
 
 #include "common.cuh"
 
+int32_t sfb_comm_allreduce_sum_f32(sfb_ctx* ctx, float* buf, size_t n);
+
 namespace {
 
 constexpr uint32_t FULL = 0xffffffffu;
@@ -450,6 +452,361 @@ __global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
     }
 }
 
+// ---- tile kernel: lane = item -------------------------------------------------------------------------------
+// The warp-per-item kernels above gather x[r], x[c] from shared memory with one lane per EDGE: 28 bytes of shared-memory
+// traffic per item-edge and multi-way bank conflicts on the gathers (ncu, C2: 2.3e8 conflicts, issue slots 71 %, DRAM 5 %
+// of peak).  Here a CTA stages a TILE of 32 items transposed (xs[feature][item], row stride 33 doubles) and the edge loop
+// runs with lane = ITEM: the edge record (weight, offsets) is the same for the whole warp (one broadcast load), x[c] of
+// 32 items is one conflict-free 256-byte read, and x[r] stays in a register across the run of edges that share row r:
+// 9 bytes of shared-memory traffic per item-edge and 5 FP64 instructions (d, w*d, (w*d)*d, two accumulations).  The
+// eight warps of a CTA split the packed upper-triangle edge list evenly; partial sums meet in shared memory in warp
+// order (deterministic).  At C2 (F = 384, ~3k upper edges) the kernel is bound by the FP64 pipe: 1.5e10 DP instructions
+// = 0.8 ms at full rate against 0.47 ms of HBM time for the 3.07 GB it reads.
+//
+// Phase 1 (one warp per item, coalesced 256-byte loads, the row in REGISTERS, E = ceil(F / 32) values per lane): zero
+// test, |x|^2, row-sum-defect term, tau (median / percentile by one 256-bin quantised histogram + an exact ranking of
+// the two bins that hold the wanted ranks), then the transposed store.  Phase 2: the edge loop.  Phase 3: warp 0
+// combines, blends and writes 32 consecutive lambdas; the running min / max feed the normalisation without a second pass.
+constexpr int LT_TS = 33;          // tile row stride in doubles (odd: the transposing store is conflict-free)
+
+struct __align__(16) EdgeRec { double w; uint32_t coff; uint32_t roff; };   // w = -L_rc; offsets = index * LT_TS; roff bit 31: first edge of its row
+
+struct PackMeta { uint32_t ne; uint32_t any_defect; uint32_t any_nonpos; uint32_t pad; };
+
+// one CTA, thread = row (F <= 1024): strict upper triangle in CSR order -> EdgeRec list, row-sum defects, flags
+__global__ void __launch_bounds__(1024) lambda_pack_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                                           const double* __restrict__ data, uint32_t f, EdgeRec* __restrict__ recs,
+                                                           double* __restrict__ defect, PackMeta* __restrict__ meta) {
+    __shared__ uint32_t s_scan[1024];
+    __shared__ uint32_t s_flags[2];
+    const uint32_t r = threadIdx.x;
+    if (r < 2) s_flags[r] = 0;
+    uint32_t c_up = 0;
+    if (r < f) for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) c_up += indices[e] > r ? 1u : 0u;
+    s_scan[r] = c_up;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+        uint32_t v = r >= o ? s_scan[r - o] : 0u;
+        __syncthreads();
+        s_scan[r] += v;
+        __syncthreads();
+    }
+    if (r < f) {
+        uint32_t o = s_scan[r] - c_up;
+        double d = 0.0, fold = 0.0;
+        bool first = true, nonpos = false;
+        for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+            const uint32_t c = indices[e];
+            if (c > r) {
+                EdgeRec rec; rec.w = -data[e]; rec.coff = c * LT_TS; rec.roff = r * LT_TS | (first ? 0x80000000u : 0u);
+                recs[o++] = rec; first = false;
+                nonpos = nonpos || !(rec.w > 0.0);
+            }
+            if (c == r) d = data[e];
+            else fold = __dadd_rn(fold, -data[e]);   // the fold that produced L_rr in the builder (ascending column, from 0.0)
+        }
+        const double df = __dadd_rn(d, -fold);       // row-sum defect: exactly 0 for a Laplacian assembled as D - W
+        defect[r] = df;
+        if (df != 0.0) s_flags[0] = 1;
+        if (nonpos) s_flags[1] = 1;
+    }
+    __syncthreads();
+    if (r == 0) { meta->ne = s_scan[1023]; meta->any_defect = s_flags[0]; meta->any_nonpos = s_flags[1]; meta->pad = 0; }
+}
+
+__device__ __forceinline__ uint32_t f32_key(float v) { uint32_t u = __float_as_uint(v); return (u >> 31) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float key_f32(uint32_t k) { return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k); }
+
+// Values of 0-based ranks k1 <= k2 <= k1 + 1 among the finite entries of v[] (E per lane, entry u of lane l is element
+// l + 32u, valid while < f).  scratch: 128 u32 of this warp.  Falls back (returns false) when the quantised histogram cannot
+// separate the candidates (all equal in f32, overflowing range, more than 64 values in the target bins).
+template <int E>
+__device__ __forceinline__ bool regs_select2(const double (&v)[E], uint32_t f, int lane, uint32_t k1, uint32_t k2, uint32_t* scratch,
+                                             double* out1, double* out2) {
+    float a[E];
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+    for (int u = 0; u < E; ++u) {
+        const bool ok = (uint32_t)(lane + 32 * u) < f && isfinite(v[u]);
+        a[u] = fminf(fmaxf(__double2float_rn(v[u]), -3.4028234e38f), 3.4028234e38f);
+        if (ok) { const uint32_t kk = f32_key(a[u]); kmin = min(kmin, kk); kmax = max(kmax, kk); }
+    }
+    kmin = __reduce_min_sync(FULL, kmin); kmax = __reduce_max_sync(FULL, kmax);
+    const float lo = key_f32(kmin), hi = key_f32(kmax);
+    const float scale = 255.0f / (hi - lo);
+    if (!(scale > 0.0f) || !(scale < 3.0e38f)) return false;
+    // 256 bins, 16-bit counters packed two to a word
+#pragma unroll
+    for (int b = 0; b < 4; ++b) scratch[lane * 4 + b] = 0u;
+    __syncwarp();
+    uint32_t q[E];
+#pragma unroll
+    for (int u = 0; u < E; ++u) {
+        const bool ok = (uint32_t)(lane + 32 * u) < f && isfinite(v[u]);
+        q[u] = 0xFFFFu;
+        if (ok) {
+            int qq = (int)((a[u] - lo) * scale); qq = qq < 0 ? 0 : (qq > 255 ? 255 : qq);
+            q[u] = (uint32_t)qq;
+            atomicAdd(&scratch[qq >> 1], 1u << ((qq & 1) * 16));
+        }
+    }
+    __syncwarp();
+    const uint4 wv = *reinterpret_cast<const uint4*>(&scratch[lane * 4]);   // bins 8*lane .. 8*lane + 7
+    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+    uint32_t c8[8], s8 = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { c8[b] = (ww[b >> 1] >> ((b & 1) * 16)) & 0xFFFFu; s8 += c8[b]; }
+    uint32_t inc = s8;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    const uint32_t ex = inc - s8;
+    // the bin of rank k1 (and of rank k2), with the number of entries in lower bins
+    int bin1 = -1, bin2 = -1; uint32_t below1 = 0, cnt1 = 0, cnt2 = 0;
+    {
+        uint32_t run = ex;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (bin1 < 0 && k1 >= run && k1 < run + c8[b]) { bin1 = lane * 8 + b; below1 = run; cnt1 = c8[b]; }
+            if (bin2 < 0 && k2 >= run && k2 < run + c8[b]) { bin2 = lane * 8 + b; cnt2 = c8[b]; }
+            run += c8[b];
+        }
+    }
+    const uint32_t m1 = __ballot_sync(FULL, bin1 >= 0), m2 = __ballot_sync(FULL, bin2 >= 0);
+    if (!m1 || !m2) return false;   // rank beyond the population (cannot happen for k < n)
+    const int l1 = __ffs(m1) - 1, l2 = __ffs(m2) - 1;
+    bin1 = __shfl_sync(FULL, bin1, l1); below1 = __shfl_sync(FULL, below1, l1); cnt1 = __shfl_sync(FULL, cnt1, l1);
+    bin2 = __shfl_sync(FULL, bin2, l2); cnt2 = __shfl_sync(FULL, cnt2, l2);
+    const uint32_t nc = cnt1 + (bin2 != bin1 ? cnt2 : 0u);
+    if (nc > 62) return false;
+    __syncwarp();
+    // candidates of the two bins -> scratch as doubles [0, 62), slot counter in word 126
+    double* cand = reinterpret_cast<double*>(scratch);
+    if (lane == 0) scratch[126] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < E; ++u)
+        if (q[u] == (uint32_t)bin1 || q[u] == (uint32_t)bin2) cand[atomicAdd(&scratch[126], 1u)] = v[u];
+    __syncwarp();
+    // exact rank of every candidate (ties by slot: equal values are interchangeable)
+    const uint32_t t1 = k1 - below1, t2 = k2 - below1;
+    double r1 = 0.0, r2 = 0.0; bool h1 = false, h2 = false;
+    for (uint32_t j = lane; j < nc; j += 32) {
+        const double cj = cand[j];
+        uint32_t rk = 0;
+        for (uint32_t i = 0; i < nc; ++i) { const double ci = cand[i]; rk += (ci < cj || (ci == cj && i < j)) ? 1u : 0u; }
+        if (rk == t1) { r1 = cj; h1 = true; }
+        if (rk == t2) { r2 = cj; h2 = true; }
+    }
+    const uint32_t b1 = __ballot_sync(FULL, h1), b2 = __ballot_sync(FULL, h2);
+    if (!b1 || !b2) return false;
+    *out1 = __shfl_sync(FULL, r1, __ffs(b1) - 1);
+    *out2 = __shfl_sync(FULL, r2, __ffs(b2) - 1);
+    __syncwarp();
+    return true;
+}
+
+// exact selection of rank k among the finite register entries by bisection on the order-preserving 64-bit image (rare path)
+template <int E>
+__device__ double regs_select_exact(const double (&v)[E], uint32_t f, int lane, uint32_t k) {
+    uint64_t prefix = 0;
+    for (int b = 63; b >= 0; --b) {
+        const uint64_t trial = prefix | (1ull << b);
+        uint32_t c = 0;   // entries with key < trial
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+            const bool ok = (uint32_t)(lane + 32 * u) < f && isfinite(v[u]);
+            c += (ok && sort_key(v[u]) < trial) ? 1u : 0u;
+        }
+        c = __reduce_add_sync(FULL, c);
+        if (c <= k) prefix = trial;   // at most k entries lie below trial: the rank-k key is >= trial
+    }
+    return key_value(prefix);
+}
+
+// TauMode::select_tau (taumode.rs:29-70) on a row held in registers
+template <int E>
+__device__ __forceinline__ double regs_select_tau(const double (&v)[E], uint32_t f, int lane, int mode, double value, uint32_t* scratch) {
+    const double FLOOR = 1e-10;
+    if (mode == SFB_TAU_FIXED) return (isfinite(value) && value > 0.0) ? value : FLOOR;
+    uint32_t n = 0; double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < E; ++u) if ((uint32_t)(lane + 32 * u) < f && isfinite(v[u])) { ++n; s += v[u]; }
+    n = __reduce_add_sync(FULL, n);
+    if (n == 0) return FLOOR;
+    if (mode == SFB_TAU_MEAN) { const double mean = warp_sum(s) / (double)n; return mean > FLOOR ? mean : FLOOR; }
+    uint32_t k1, k2;
+    if (mode == SFB_TAU_PERCENTILE) {
+        const double pp = value < 0.0 ? 0.0 : (value > 1.0 ? 1.0 : value);
+        k1 = k2 = (uint32_t)round((double)(n - 1) * pp);
+    } else if (n & 1u) k1 = k2 = n / 2;
+    else { k1 = n / 2 - 1; k2 = n / 2; }
+    double a, b;
+    if (!regs_select2<E>(v, f, lane, k1, k2, scratch, &a, &b)) {
+        a = regs_select_exact<E>(v, f, lane, k1);
+        b = k2 == k1 ? a : regs_select_exact<E>(v, f, lane, k2);
+    }
+    const double r = k1 == k2 ? a : 0.5 * (a + b);
+    return r > FLOOR ? r : FLOOR;
+}
+
+struct LambdaTileArgs {
+    const EdgeRec* recs; const double* defect; const PackMeta* meta; uint32_t f;
+    const double* x; uint64_t n;
+    int tau_mode; double tau_value;
+    double* out_lambda; double* out_disp;
+    const double* tau_in;
+    unsigned long long* minmax;   // [0]: min of lambda, [1]: max(0, lambda), as order-preserving keys (atomicMin / atomicMax); may be null
+};
+
+template <int VARIANT, int E, int LT_WARPS>
+__global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_tile_kernel(LambdaTileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t f = a.f;
+    double* xs = reinterpret_cast<double*>(smem_raw);                         // [f][LT_TS]
+    double* s_den = xs + (size_t)f * LT_TS;                                   // [32]
+    double* s_dfc = s_den + 32;                                               // [32]
+    double* s_tau = s_dfc + 32;                                               // [32]  < 0: zero vector
+    double* s_part = s_tau + 32;                                              // [LT_WARPS][3][32]
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(s_part + LT_WARPS * 3 * 32) + w * 128;   // [LT_WARPS][128]
+    const uint32_t ne = a.meta->ne;
+    const bool has_defect = a.meta->any_defect != 0, nonpos = a.meta->any_nonpos != 0;
+    const uint32_t e_lo = (uint32_t)((uint64_t)ne * w / LT_WARPS), e_hi = (uint32_t)((uint64_t)ne * (w + 1) / LT_WARPS);
+    const double* xs_lane = xs + lane;
+    double run_mn = INFINITY, run_mx = 0.0;
+    const uint64_t n_tiles = (a.n + 31) / 32;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t i0 = tile * 32;
+        // ---- phase 1: this warp's four items
+#pragma unroll 1
+        for (int qi = 0; qi < 32 / LT_WARPS; ++qi) {
+            const int it = w * (32 / LT_WARPS) + qi;
+            const uint64_t i = i0 + it;
+            double v[E];
+            if (i < a.n) {
+                const double* xr = a.x + i * f;
+#pragma unroll
+                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; v[u] = t < f ? __ldcs(xr + t) : 0.0; }
+            } else {
+#pragma unroll
+                for (int u = 0; u < E; ++u) v[u] = 0.0;
+            }
+            bool zero = true;
+            double den = 0.0, dfc = 0.0;
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+                const uint32_t t = lane + 32 * u;
+                if (t < f) {
+                    xs[(size_t)t * LT_TS + it] = v[u];
+                    zero = zero && (fabs(v[u]) <= 1e-10);
+                    den = fma(v[u], v[u], den);
+                }
+            }
+            if (has_defect) {
+#pragma unroll
+                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; if (t < f) dfc += (v[u] * a.defect[t]) * v[u]; }
+                dfc = warp_sum(dfc);
+            }
+            den = warp_sum(den);
+            double tau = 0.0;
+            if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
+                if (a.tau_in) tau = i < a.n ? a.tau_in[i] : -1.0;           // projected items: tau and the zero test come from the unprojected rows
+                else if (__all_sync(FULL, zero)) tau = -1.0;                // taumode.rs:268-274
+                else tau = regs_select_tau<E>(v, f, lane, a.tau_mode, a.tau_value, scratch);
+            }
+            if (lane == 0) { s_den[it] = den; s_dfc[it] = dfc; s_tau[it] = tau; }
+        }
+        __syncthreads();
+        // ---- phase 2: lane = item, this warp's slice of the edge list
+        double s0 = 0.0, q0 = 0.0, sa = 0.0;
+        if (e_lo < e_hi) {
+            double xa = xs_lane[a.recs[e_lo].roff & 0x7FFFFFFFu];
+            if (!nonpos) {
+                double s1 = 0.0, q1 = 0.0;
+                uint32_t e = e_lo;
+                for (; e + 2 <= e_hi; e += 2) {
+                    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.recs + e));
+                    const uint4 rb = __ldg(reinterpret_cast<const uint4*>(a.recs + e + 1));
+                    if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
+                    const double xb0 = xs_lane[ra.z];
+                    const double d0 = xa - xb0;
+                    if (rb.w & 0x80000000u) xa = xs_lane[rb.w & 0x7FFFFFFFu];
+                    const double xb1 = xs_lane[rb.z];
+                    const double d1 = xa - xb1;
+                    const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
+                    const double c1 = (__hiloint2double((int)rb.y, (int)rb.x) * d1) * d1;
+                    s0 += c0; q0 = fma(c0, c0, q0);
+                    s1 += c1; q1 = fma(c1, c1, q1);
+                }
+                if (e < e_hi) {
+                    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.recs + e));
+                    if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
+                    const double d0 = xa - xs_lane[ra.z];
+                    const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
+                    s0 += c0; q0 = fma(c0, c0, q0);
+                }
+                s0 += s1; q0 += q1; sa = s0;
+            } else {
+                for (uint32_t e = e_lo; e < e_hi; ++e) {
+                    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.recs + e));
+                    if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
+                    const double wv = __hiloint2double((int)ra.y, (int)ra.x);
+                    const double d0 = xa - xs_lane[ra.z];
+                    const double c0 = (wv * d0) * d0;
+                    sa += c0;
+                    if (wv > 0.0) { s0 += c0; q0 = fma(c0, c0, q0); }
+                }
+            }
+        }
+        s_part[(w * 3 + 0) * 32 + lane] = s0; s_part[(w * 3 + 1) * 32 + lane] = q0; s_part[(w * 3 + 2) * 32 + lane] = sa;
+        __syncthreads();
+        // ---- phase 3: combine, blend, write
+        if (w == 0) {
+            const uint64_t i = i0 + lane;
+            double ssum = 0.0, qsum = 0.0, sall = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < LT_WARPS; ++ww) { ssum += s_part[(ww * 3 + 0) * 32 + lane]; qsum += s_part[(ww * 3 + 1) * 32 + lane]; sall += s_part[(ww * 3 + 2) * 32 + lane]; }
+            const double den = s_den[lane], num = s_dfc[lane] + sall, tau = s_tau[lane];
+            if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) { ssum *= 2.0; qsum *= 2.0; }   // both triangles (taumode.rs:371-383)
+            double e_raw = 0.0;
+            if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
+            double g = 0.0;
+            if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
+            double lam;
+            if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
+                if (tau < 0.0) { lam = 0.0; g = 0.0; }
+                else lam = tau * (e_raw / (e_raw + tau)) + (1.0 - tau) * g;       // taumode.rs:306-310
+            } else lam = e_raw;
+            if (i < a.n) {
+                a.out_lambda[i] = lam;
+                if (a.out_disp) a.out_disp[i] = g;
+                run_mn = fmin(run_mn, lam); run_mx = fmax(run_mx, lam);
+            }
+        }
+        __syncthreads();
+    }
+    if (w == 0 && a.minmax) {
+        run_mn = warp_min_d(run_mn); run_mx = warp_max_d(run_mx);
+        if (lane == 0) {
+            if (run_mn == run_mn) atomicMin(&a.minmax[0], (unsigned long long)sort_key(run_mn));
+            if (run_mx == run_mx) atomicMax(&a.minmax[1], (unsigned long long)sort_key(run_mx));
+        }
+    }
+}
+
+// minmax keys -> {min, max(0, .)} as doubles (the input of the NCCL min / max exchange and of the normalisation)
+__global__ void minmax_keys_kernel(const unsigned long long* __restrict__ keys, double* __restrict__ out) {
+    out[0] = key_value(keys[0]); out[1] = key_value(keys[1]);
+}
+// (lambda - min) / max(max - min, 1e-9) with min / max read from device memory (core.rs:1341-1355)
+__global__ void normalise_dev_kernel(double* __restrict__ v, uint64_t n, const double* __restrict__ mm) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double mn = mm[0];
+    double rng = __dadd_rn(mm[1], -mn);
+    if (!(rng > 1e-9)) rng = 1e-9;
+    if (i < n) v[i] = __ddiv_rn(__dadd_rn(v[i], -mn), rng);
+}
+
 // CORE_F32SEM second pass: G_i = clamp(e_i / (sum e + 1e-12), 0, 1); lambda = R + G (f32)
 __global__ void core_sum_energy_kernel(const float* __restrict__ e, uint64_t n, float* __restrict__ total) {
     // single block, ascending chunks: deterministic
@@ -540,25 +897,115 @@ __global__ void tau_rows_kernel(const double* __restrict__ x, uint64_t n, uint32
 
 }  // namespace
 
-// lambdas of rows [0, n) of a device matrix into a device array; shared by the single- and multi-GPU paths
+namespace {
+
+size_t lt_smem_bytes(uint32_t f, int nw) { return ((size_t)f * LT_TS + 96 + (size_t)nw * 96) * sizeof(double) + (size_t)nw * 128 * sizeof(uint32_t); }
+
+template <int VARIANT, int E, int NW>
+int32_t lt_launch(sfb_ctx* ctx, const LambdaTileArgs& a) {
+    const size_t smem = lt_smem_bytes(a.f, NW);
+    auto kern = lambda_tile_kernel<VARIANT, E, NW>;
+    SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    const uint64_t tiles = (a.n + 31) / 32, cap = (uint64_t)ctx->sm_count * per_sm;
+    kern<<<(unsigned)(tiles < cap ? tiles : cap), NW * 32, smem, ctx->stream>>>(a);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+template <int VARIANT>
+int32_t lt_dispatch(sfb_ctx* ctx, const LambdaTileArgs& a) {
+    const uint32_t e = (a.f + 31) / 32;
+    if (e <= 4) return lt_launch<VARIANT, 4, 8>(ctx, a);
+    if (e <= 8) return lt_launch<VARIANT, 8, 8>(ctx, a);
+    if (e <= 12) return lt_launch<VARIANT, 12, 8>(ctx, a);
+    if (e <= 16) return lt_launch<VARIANT, 16, 16>(ctx, a);
+    return lt_launch<VARIANT, 24, 16>(ctx, a);
+}
+
+__global__ void minmax_final_kernel(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    double mn = INFINITY, mx = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 32) { mn = fmin(mn, part[2 * i]); mx = fmax(mx, part[2 * i + 1]); }
+    mn = warp_min_d(mn); mx = warp_max_d(mx);
+    if (threadIdx.x == 0) { out[0] = mn; out[1] = mx; }
+}
+__global__ void init_minmax_keys_kernel(unsigned long long* keys) { keys[0] = sort_key(INFINITY); keys[1] = sort_key(0.0); }
+
+}  // namespace
+
+// The packed upper triangle of a symmetric L for the tile kernel, built once per handle (sfb_csr_free releases it).
+static int32_t lt_pack(sfb_ctx* ctx, const sfb_csr* L) {
+    if (L->lt_recs) return SFB_OK;
+    const uint32_t f = (uint32_t)L->rows;
+    void *recs = nullptr, *defect = nullptr, *meta = nullptr;
+    if (sfb_dev_alloc(ctx, &recs, sizeof(EdgeRec) * (L->nnz / 2 + 1)) != cudaSuccess || sfb_dev_alloc(ctx, &defect, sizeof(double) * f) != cudaSuccess ||
+        sfb_dev_alloc(ctx, &meta, sizeof(PackMeta)) != cudaSuccess) {
+        sfb_dev_free(ctx, recs); sfb_dev_free(ctx, defect); sfb_dev_free(ctx, meta);
+        return sfb_fail(ctx, SFB_ENOMEM, "packed Laplacian");
+    }
+    lambda_pack_kernel<<<1, 1024, 0, ctx->stream>>>(L->indptr, L->indices, L->data, f, (EdgeRec*)recs, (double*)defect, (PackMeta*)meta);
+    ctx->times.kernel_launches++;
+    if (cudaGetLastError() != cudaSuccess) { sfb_dev_free(ctx, recs); sfb_dev_free(ctx, defect); sfb_dev_free(ctx, meta); return sfb_fail(ctx, SFB_ECUDA, "lambda_pack_kernel launch failed"); }
+    L->lt_recs = recs; L->lt_defect = defect; L->lt_meta = meta;
+    return SFB_OK;
+}
+
+// lambdas of rows [0, n) of a device matrix into a device array; shared by the single- and multi-GPU paths.
+// d_mm (2 doubles on the device, may be null): receives {min lambda, max(0, max lambda)} of these rows (core.rs:1345-1346).
 int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, uint64_t n, uint32_t f,
-                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp, const double* tau_in) {
+                          const sfb_lambda_params* prm, double* d_lambda, double* d_disp, const double* tau_in, double* d_mm) {
     if (L->rows != f) return sfb_fail(ctx, SFB_EINVAL, "Matrix rows %llu must match vector length %u", (unsigned long long)L->rows, f);  // taumode.rs:330-337
     if (prm->variant < 0 || prm->variant > 2) return sfb_fail(ctx, SFB_EINVAL, "unknown lambda variant %d", prm->variant);
     if (prm->tau_mode < 0 || prm->tau_mode > 3) return sfb_fail(ctx, SFB_EINVAL, "unknown tau mode %d", prm->tau_mode);
-    // symmetric fast path (LEGACY_TAUMODE / ENERGY_NODE): L symmetric bit for bit, packed upper triangle in shared memory
-    if (prm->variant != SFB_LAMBDA_CORE_F32SEM && f <= 65535 && !getenv("SFB_LAMBDA_ROWWISE")) {
-        if (L->symmetric < 0) {
-            DevBuf bad;
-            SFB_CUDA(ctx, bad.alloc(sizeof(int)));
-            SFB_CUDA(ctx, cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
-            csr_symmetric_kernel<<<div_up(L->rows, 128), 128, 0, ctx->stream>>>(L->indptr, L->indices, L->data, L->rows, bad.as<int>());
+    auto minmax_generic = [&]() -> int32_t {
+        if (!d_mm) return SFB_OK;
+        const int nb = 128;
+        DevBuf part;
+        SFB_CUDA(ctx, part.alloc(sizeof(double) * 2 * nb));
+        minmax_kernel<<<nb, 256, 0, ctx->stream>>>(d_lambda, n, part.as<double>());
+        SFB_LAUNCH_CHECK(ctx);
+        minmax_final_kernel<<<1, 32, 0, ctx->stream>>>(part.as<double>(), nb, d_mm);
+        SFB_LAUNCH_CHECK(ctx);
+        return SFB_OK;   // part goes back to the context's cache; stream order keeps it valid
+    };
+    const bool sym_variant = prm->variant != SFB_LAMBDA_CORE_F32SEM;
+    if (sym_variant && f <= 65535 && L->symmetric < 0 && !getenv("SFB_LAMBDA_ROWWISE")) {
+        DevBuf bad;
+        SFB_CUDA(ctx, bad.alloc(sizeof(int)));
+        SFB_CUDA(ctx, cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+        csr_symmetric_kernel<<<div_up(L->rows, 128), 128, 0, ctx->stream>>>(L->indptr, L->indices, L->data, L->rows, bad.as<int>());
+        SFB_LAUNCH_CHECK(ctx);
+        int hb = 0;
+        SFB_CUDA(ctx, cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        L->symmetric = hb ? 0 : 1;
+    }
+    // tile kernel (lane = item): LEGACY_TAUMODE / ENERGY_NODE, symmetric L, F <= 768
+    if (sym_variant && L->symmetric == 1 && f <= 768 && L->nnz / 2 < 0x7FFFFFFFull / LT_TS && !getenv("SFB_LAMBDA_ROWWISE") && !getenv("SFB_LAMBDA_SYM")) {
+        SFB_TRY(lt_pack(ctx, L));
+        DevBuf keys;
+        if (d_mm) {
+            SFB_CUDA(ctx, keys.alloc(2 * sizeof(unsigned long long)));
+            init_minmax_keys_kernel<<<1, 1, 0, ctx->stream>>>(keys.as<unsigned long long>());
             SFB_LAUNCH_CHECK(ctx);
-            int hb = 0;
-            SFB_CUDA(ctx, cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            L->symmetric = hb ? 0 : 1;
         }
+        LambdaTileArgs ta{(const EdgeRec*)L->lt_recs, (const double*)L->lt_defect, (const PackMeta*)L->lt_meta, f, x_dev, n, prm->tau_mode, prm->tau_value,
+                          d_lambda, d_disp, tau_in, d_mm ? keys.as<unsigned long long>() : nullptr};
+        {
+            StageTimer tk(ctx, &ctx->times.ms_lambda_kernel);
+            if (prm->variant == SFB_LAMBDA_LEGACY_TAUMODE) SFB_TRY(lt_dispatch<0>(ctx, ta));
+            else SFB_TRY(lt_dispatch<1>(ctx, ta));
+        }
+        if (d_mm) {
+            minmax_keys_kernel<<<1, 1, 0, ctx->stream>>>(keys.as<unsigned long long>(), d_mm);
+            SFB_LAUNCH_CHECK(ctx);
+        }
+        return SFB_OK;
+    }
+    // symmetric fast path (LEGACY_TAUMODE / ENERGY_NODE): L symmetric bit for bit, packed upper triangle in shared memory
+    if (sym_variant && f <= 65535 && !getenv("SFB_LAMBDA_ROWWISE")) {
         if (L->symmetric == 1) {
             DevBuf cnt, offs, rc, val, diag;
             SFB_CUDA(ctx, cnt.alloc(sizeof(uint32_t) * f));
@@ -584,6 +1031,7 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
                 uint64_t want = (n + wpb_s - 1) / wpb_s;
                 const uint64_t cap_grid = (uint64_t)ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
                 const unsigned grid = (unsigned)(want < cap_grid ? want : cap_grid);
+                StageTimer tk(ctx, &ctx->times.ms_lambda_kernel);
                 if (prm->variant == SFB_LAMBDA_LEGACY_TAUMODE) {
                     SFB_CUDA(ctx, cudaFuncSetAttribute(lambda_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
                     lambda_sym_kernel<0><<<grid, wpb_s * 32, smem_s, ctx->stream>>>(sa);
@@ -592,8 +1040,8 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
                     lambda_sym_kernel<1><<<grid, wpb_s * 32, smem_s, ctx->stream>>>(sa);
                 }
                 SFB_LAUNCH_CHECK(ctx);
-                SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                return SFB_OK;
+                tk.stop();   // synchronises: the packed arrays may be released on return
+                return minmax_generic();
             }
         }
     }
@@ -610,6 +1058,7 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
     if (blocks_per_sm > 8) blocks_per_sm = 8;
     uint64_t want = (n + wpb - 1) / wpb;
     unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * blocks_per_sm ? want : (uint64_t)ctx->sm_count * blocks_per_sm);
+    StageTimer tk(ctx, &ctx->times.ms_lambda_kernel);
     if (prm->variant == SFB_LAMBDA_LEGACY_TAUMODE) {
         SFB_CUDA(ctx, cudaFuncSetAttribute(lambda_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lambda_kernel<0><<<grid, wpb * 32, smem, ctx->stream>>>(a);
@@ -625,71 +1074,64 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
         SFB_LAUNCH_CHECK(ctx);
         core_sum_energy_kernel<<<1, 256, 0, ctx->stream>>>(e32.as<float>(), n, tot.as<float>());
         SFB_LAUNCH_CHECK(ctx);
+        // sharded items (sfb_lambda_allgather): the dispersion is normalised by the energy of ALL items
+        // (dirichlet_dispersion_gpu "normalize by global total", spectral/mod.rs:140-145): sum the per-rank totals
+        if (ctx->world > 1 && ctx->lambda_sharded) SFB_TRY(sfb_comm_allreduce_sum_f32(ctx, tot.as<float>(), 1));
         core_finish_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(e32.as<float>(), tot.as<float>(), n, d_lambda, d_disp);
     }
     SFB_LAUNCH_CHECK(ctx);
-    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tk.stop();   // synchronises: e32 / tot may be released on return
+    return minmax_generic();
+}
+
+// (lambda - min) / max(max - min, 1e-9) with {min, max} in device memory (core.rs:1341-1355)
+int32_t sfb_normalise_device(sfb_ctx* ctx, double* d_lambda, uint64_t n, const double* d_mm) {
+    normalise_dev_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(d_lambda, n, d_mm);
+    SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
 }
 
-// local min / max(0,.) of a device lambda array
-int32_t sfb_minmax_device(sfb_ctx* ctx, const double* d_lambda, uint64_t n, double* mn, double* mx) {
-    const int nb = 128;
-    DevBuf part;
-    SFB_CUDA(ctx, part.alloc(sizeof(double) * 2 * nb));
-    minmax_kernel<<<nb, 256, 0, ctx->stream>>>(d_lambda, n, part.as<double>());
+// tau and the zero-vector test of every row of x_tau (the unprojected items) into a device array
+int32_t sfb_tau_rows_device(sfb_ctx* ctx, const sfb_mat* x_tau, uint64_t rows, const sfb_lambda_params* prm, double* d_tau) {
+    const uint32_t ft = x_tau->cols;
+    const size_t per_warp = (size_t)ft * sizeof(double) + 256 * sizeof(uint32_t);
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
+    if (per_warp * wpb > ctx->smem_optin) return sfb_fail(ctx, SFB_EUNSUPPORTED, "feature count %u too large for the shared-memory row staging", ft);
+    SFB_CUDA(ctx, cudaFuncSetAttribute(tau_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
+    const uint64_t want = (rows + wpb - 1) / wpb;
+    const unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 8 ? want : (uint64_t)ctx->sm_count * 8);
+    tau_rows_kernel<<<grid, wpb * 32, per_warp * wpb, ctx->stream>>>(x_tau->d, rows, ft, prm->tau_mode, prm->tau_value, d_tau);
     SFB_LAUNCH_CHECK(ctx);
-    double h[2 * nb];
-    SFB_CUDA(ctx, cudaMemcpyAsync(h, part.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    double a = INFINITY, b = 0.0;
-    for (int i = 0; i < nb; ++i) { a = fmin(a, h[2 * i]); b = fmax(b, h[2 * i + 1]); }
-    *mn = a; *mx = b;
-    return SFB_OK;
-}
-
-int32_t sfb_normalise_device(sfb_ctx* ctx, double* d_lambda, uint64_t n, double mn, double mx, double* stats) {
-    double rng = mx - mn;
-    if (!(rng > 1e-9)) rng = 1e-9;
-    normalise_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(d_lambda, n, mn, rng);
-    SFB_LAUNCH_CHECK(ctx);
-    if (stats) { stats[0] = mn; stats[1] = mx; stats[2] = rng; }
     return SFB_OK;
 }
 
 // x_tau != null: tau and the zero-vector test come from its rows (the unprojected items), energy and dispersion from x
 static int32_t lambda_to_host(sfb_ctx* ctx, const sfb_csr* L, const sfb_mat* x, const sfb_mat* x_tau, const sfb_lambda_params* prm,
                               double* out_lambda, double* out_disp, double* stats) {
-    StageTimer t(ctx, &ctx->times.ms_lambda);
-    DevBuf lam, disp, tau;
-    SFB_CUDA(ctx, lam.alloc(sizeof(double) * x->rows));
-    if (out_disp) SFB_CUDA(ctx, disp.alloc(sizeof(double) * x->rows));
-    if (x_tau) {
-        const uint32_t ft = x_tau->cols;
-        const size_t per_warp = (size_t)ft * sizeof(double) + 256 * sizeof(uint32_t);
-        int wpb = 8;
-        while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
-        if (per_warp * wpb > ctx->smem_optin) return sfb_fail(ctx, SFB_EUNSUPPORTED, "feature count %u too large for the shared-memory row staging", ft);
-        SFB_CUDA(ctx, tau.alloc(sizeof(double) * x->rows));
-        SFB_CUDA(ctx, cudaFuncSetAttribute(tau_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
-        const uint64_t want = (x->rows + wpb - 1) / wpb;
-        const unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 8 ? want : (uint64_t)ctx->sm_count * 8);
-        tau_rows_kernel<<<grid, wpb * 32, per_warp * wpb, ctx->stream>>>(x_tau->d, x->rows, ft, prm->tau_mode, prm->tau_value, tau.as<double>());
-        SFB_LAUNCH_CHECK(ctx);
+    double h_mm[2] = {0.0, 0.0};
+    {
+        StageTimer t(ctx, &ctx->times.ms_lambda);
+        DevBuf lam, disp, tau, mm;
+        SFB_CUDA(ctx, lam.alloc(sizeof(double) * x->rows));
+        SFB_CUDA(ctx, mm.alloc(sizeof(double) * 2));
+        if (out_disp) SFB_CUDA(ctx, disp.alloc(sizeof(double) * x->rows));
+        if (x_tau) {
+            SFB_CUDA(ctx, tau.alloc(sizeof(double) * x->rows));
+            SFB_TRY(sfb_tau_rows_device(ctx, x_tau, x->rows, prm, tau.as<double>()));
+        }
+        const bool want_mm = prm->normalise_minmax || stats;
+        SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, lam.as<double>(), out_disp ? disp.as<double>() : nullptr,
+                                  x_tau ? tau.as<double>() : nullptr, want_mm ? mm.as<double>() : nullptr));
+        if (prm->normalise_minmax) SFB_TRY(sfb_normalise_device(ctx, lam.as<double>(), x->rows, mm.as<double>()));
+        t.stop();
+        StageTimer t2(ctx, &ctx->times.ms_d2h);
+        SFB_CUDA(ctx, cudaMemcpyAsync(out_lambda, lam.p, sizeof(double) * x->rows, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_disp) SFB_CUDA(ctx, cudaMemcpyAsync(out_disp, disp.p, sizeof(double) * x->rows, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_mm) SFB_CUDA(ctx, cudaMemcpyAsync(h_mm, mm.p, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
+        t2.stop();   // synchronises: the results are on the host, the scratch may go back to the cache
     }
-    SFB_TRY(sfb_lambda_device(ctx, L, x->d, x->rows, x->cols, prm, lam.as<double>(), out_disp ? disp.as<double>() : nullptr,
-                              x_tau ? tau.as<double>() : nullptr));
-    if (prm->normalise_minmax || stats) {
-        double mn, mx;
-        SFB_TRY(sfb_minmax_device(ctx, lam.as<double>(), x->rows, &mn, &mx));
-        if (prm->normalise_minmax) SFB_TRY(sfb_normalise_device(ctx, lam.as<double>(), x->rows, mn, mx, stats));
-        else if (stats) { stats[0] = mn; stats[1] = mx; stats[2] = (mx - mn) > 1e-9 ? (mx - mn) : 1e-9; }
-    }
-    t.stop();
-    StageTimer t2(ctx, &ctx->times.ms_d2h);
-    SFB_CUDA(ctx, cudaMemcpyAsync(out_lambda, lam.p, sizeof(double) * x->rows, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_disp) SFB_CUDA(ctx, cudaMemcpyAsync(out_disp, disp.p, sizeof(double) * x->rows, cudaMemcpyDeviceToHost, ctx->stream));
-    t2.stop();
+    if (stats) { stats[0] = h_mm[0]; stats[1] = h_mm[1]; stats[2] = (h_mm[1] - h_mm[0]) > 1e-9 ? (h_mm[1] - h_mm[0]) : 1e-9; }
     return SFB_OK;
 }
 
@@ -707,6 +1149,120 @@ extern "C" int32_t sfb_lambda_projected(sfb_ctx* ctx, const sfb_csr* L, const sf
     // taumode.rs:287-297: the projected length must be the Laplacian's ("item seems neither projected nor unprojected" otherwise)
     if (L->rows != x_projected->cols) return sfb_fail(ctx, SFB_EINVAL, "projected items have %u dimensions, the Laplacian %llu rows", x_projected->cols, (unsigned long long)L->rows);
     return lambda_to_host(ctx, L, x_projected, x_original, prm, out_lambda, out_disp, stats);
+}
+
+// ---- the successor's Stage D seams ------------------------------------------------------------------------------
+// compute_tau_mode_gpu (surfface-core/src/spectral/bridge.rs:27-32): f32 items in, f64 lambdas out, CORE_F32SEM.
+extern "C" int32_t sfb_compute_tau_mode_lambdas(sfb_ctx* ctx, const sfb_csr* L, const float* data, uint64_t n_items, uint32_t n_features,
+                                                double* out_lambdas) {
+    if (!ctx || !L || !data || !out_lambdas) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    sfb_mat* x = nullptr;
+    SFB_TRY(sfb_mat_from_host_f32(ctx, data, n_items, n_features, &x));
+    sfb_lambda_params lp{SFB_LAMBDA_CORE_F32SEM, SFB_TAU_MEDIAN, 0.0, 0};
+    int32_t st = lambda_to_host(ctx, L, x, nullptr, &lp, out_lambdas, nullptr, nullptr);
+    sfb_mat_free(x);
+    return st;
+}
+
+// compute_tau (surfface-core/src/taumode.rs:37-65): one f32 tau from the lambda distribution.
+namespace {
+// pass over the finite entries whose key matches `prefix` under `mask`: 256-bin histogram of the next 8 bits
+__global__ void __launch_bounds__(256) tau_hist_kernel(const float* __restrict__ v, uint64_t n, uint32_t prefix, uint32_t mask, int shift,
+                                                       uint32_t* __restrict__ hist /* 256 + 1 (finite count) */) {
+    __shared__ uint32_t sh[257];
+    for (int b = threadIdx.x; b < 257; b += 256) sh[b] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = v[i];
+        if (!isfinite(x)) continue;
+        const uint32_t key = f32_key(x);
+        if ((key & mask) == prefix) { atomicAdd(&sh[(key >> shift) & 0xFFu], 1u); if (mask == 0u) atomicAdd(&sh[256], 1u); }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 257; b += 256) if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+// Rust's iter().sum::<f32>() over the finite entries: one strictly sequential f32 chain (thread 0), tiles staged by warps 1-3
+constexpr int TM_TILE = 4096;
+__global__ void __launch_bounds__(128) tau_mean_kernel(const float* __restrict__ v, uint64_t n, float* __restrict__ out /* sum, count */) {
+    __shared__ float buf[2][TM_TILE];
+    const int tid = threadIdx.x;
+    const uint64_t ntiles = (n + TM_TILE - 1) / TM_TILE;
+    for (int e = tid; e < TM_TILE; e += 128) buf[0][e] = (uint64_t)e < n ? v[e] : INFINITY;   // non-finite entries are skipped by the fold
+    __syncthreads();
+    float sum = 0.0f; uint32_t cnt = 0;
+    for (uint64_t t = 0; t < ntiles; t++) {
+        if (tid >= 32) {
+            const uint64_t base = (t + 1) * TM_TILE;
+            if (base < n) for (int e = tid - 32; e < TM_TILE; e += 96) buf[(t + 1) & 1][e] = base + e < n ? v[base + e] : INFINITY;
+        } else if (tid == 0) {
+            const float* b = buf[t & 1];
+#pragma unroll 16
+            for (int e = 0; e < TM_TILE; e++) { const float x = b[e]; if (isfinite(x)) { sum = __fadd_rn(sum, x); ++cnt; } }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { out[0] = sum; out[1] = __uint_as_float(cnt); }
+}
+}  // namespace
+
+extern "C" int32_t sfb_compute_tau(sfb_ctx* ctx, const float* lambdas, uint64_t n, int32_t tau_mode, float tau_value, float* out_tau) {
+    if (!ctx || !out_tau || (n && !lambdas)) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (tau_mode < 0 || tau_mode > 3) return sfb_fail(ctx, SFB_EINVAL, "unknown tau mode %d", tau_mode);
+    const float FLOOR = 1e-9f;
+    *out_tau = FLOOR;
+    if (n == 0) return SFB_OK;
+    DevBuf dv, hist;
+    SFB_CUDA(ctx, dv.alloc(sizeof(float) * n));
+    SFB_CUDA(ctx, hist.alloc(sizeof(uint32_t) * 257));
+    SFB_CUDA(ctx, cudaMemcpyAsync(dv.p, lambdas, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = (unsigned)(n / 256 + 1 < (uint64_t)ctx->sm_count * 8 ? n / 256 + 1 : (uint64_t)ctx->sm_count * 8);
+    uint32_t h[257];
+    auto pass = [&](uint32_t prefix, uint32_t mask, int shift) -> int32_t {
+        SFB_CUDA(ctx, cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 257, ctx->stream));
+        tau_hist_kernel<<<grid, 256, 0, ctx->stream>>>(dv.as<float>(), n, prefix, mask, shift, hist.as<uint32_t>());
+        SFB_LAUNCH_CHECK(ctx);
+        SFB_CUDA(ctx, cudaMemcpyAsync(h, hist.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SFB_OK;
+    };
+    SFB_TRY(pass(0u, 0u, 24));
+    const uint64_t c = h[256];                      // finite entries (n < 2^32: lambdas of u32-indexed items)
+    if (c == 0) return SFB_OK;                      // finite.is_empty() -> TAU_FLOOR
+    float r;
+    if (tau_mode == SFB_TAU_FIXED) r = isfinite(tau_value) ? tau_value : FLOOR;
+    else if (tau_mode == SFB_TAU_MEAN) {
+        DevBuf o;
+        SFB_CUDA(ctx, o.alloc(2 * sizeof(float)));
+        tau_mean_kernel<<<1, 128, 0, ctx->stream>>>(dv.as<float>(), n, o.as<float>());
+        SFB_LAUNCH_CHECK(ctx);
+        float ho[2];
+        SFB_CUDA(ctx, cudaMemcpyAsync(ho, o.p, sizeof(ho), cudaMemcpyDeviceToHost, ctx->stream));
+        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        r = ho[0] / (float)c;
+    } else {
+        uint64_t rank;
+        if (tau_mode == SFB_TAU_MEDIAN) rank = c / 2;
+        else {
+            float pp = tau_value;
+            if (pp < 0.0f) pp = 0.0f; else if (pp > 1.0f) pp = 1.0f;
+            const float fi = roundf(((float)c - 1.0f) * pp);
+            rank = fi != fi ? 0 : (uint64_t)fi;
+            if (rank >= c) rank = c - 1;
+        }
+        uint32_t prefix = 0, mask = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (shift != 24) SFB_TRY(pass(prefix, mask, shift));
+            uint64_t run = 0; uint32_t b = 0;
+            for (; b < 256; ++b) { if (rank < run + h[b]) break; run += h[b]; }
+            if (b == 256) return sfb_fail(ctx, SFB_ECUDA, "radix select lost its rank");
+            rank -= run;
+            prefix |= b << shift; mask |= 0xFFu << shift;
+        }
+        const uint32_t u = (prefix >> 31) ? (prefix & 0x7FFFFFFFu) : ~prefix;
+        memcpy(&r, &u, 4);
+    }
+    *out_tau = r > FLOOR ? r : FLOOR;   // f32::max(TAU_FLOOR)
+    return SFB_OK;
 }
 
 // ---- energy pipeline: item -> sub-centroid mapping (src_legacy/energymaps.rs:1246-1342) ----------------------

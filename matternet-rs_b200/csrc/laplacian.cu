@@ -524,6 +524,7 @@ extern "C" int32_t sfb_laplacian_build(sfb_ctx* ctx, const sfb_adj* a, const sfb
     sfb_csr* L = new (std::nothrow) sfb_csr();
     if (!L) return SFB_ENOMEM;
     L->ctx = ctx; L->rows = m;
+    L->symmetric = 1;   // union / max symmetrisation, L_ij and L_ji are the same expression of (w, d_i, d_j): symmetric bit for bit
     if (sfb_dev_alloc(ctx, (void**)&L->indptr, sizeof(uint64_t) * (m + 1)) != cudaSuccess) { sfb_csr_free(L); return sfb_fail(ctx, SFB_ENOMEM, "indptr"); }
     int32_t st = sfb_scan_exclusive_u64(ctx, row_nnz.as<uint32_t>(), m, L->indptr);
     if (st != SFB_OK) { sfb_csr_free(L); return st; }

@@ -26,7 +26,7 @@ pub struct sfb_graph_params { pub eps: f64, pub k: u32, pub topk: u32, pub p: f6
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct sfb_laplacian_config { pub k_neighbors: u32, pub variance_regularizer: f32, pub normalize: i32, pub weight_threshold: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct sfb_stage_times { pub ms_h2d: f64, pub ms_knn: f64, pub ms_adjacency: f64, pub ms_laplacian: f64, pub ms_lambda: f64, pub ms_d2h: f64, pub kernel_launches: u64 }
+pub struct sfb_stage_times { pub ms_h2d: f64, pub ms_knn: f64, pub ms_adjacency: f64, pub ms_laplacian: f64, pub ms_lambda: f64, pub ms_d2h: f64, pub kernel_launches: u64, pub ms_lambda_kernel: f64, pub ms_diffuse: f64 }
 
 extern "C" {
     pub fn sfb_abi_version() -> i32;
@@ -38,6 +38,8 @@ extern "C" {
     pub fn sfb_pinned_alloc(ctx: *mut sfb_ctx, bytes: u64, out: *mut *mut c_void) -> i32;
     pub fn sfb_pinned_free(p: *mut c_void);
     pub fn sfb_mat_from_host(ctx: *mut sfb_ctx, x: *const f64, rows: u64, cols: u32, out: *mut *mut sfb_mat) -> i32;
+    pub fn sfb_mat_from_host_f32(ctx: *mut sfb_ctx, x: *const f32, rows: u64, cols: u32, out: *mut *mut sfb_mat) -> i32;
+    pub fn sfb_mat_clone(ctx: *mut sfb_ctx, a: *const sfb_mat, out: *mut *mut sfb_mat) -> i32;
     pub fn sfb_mat_generate(ctx: *mut sfb_ctx, kind: i32, seed: u64, rows: u64, cols: u32, n_centres: u32, noise: f64, out: *mut *mut sfb_mat) -> i32;
     pub fn sfb_mat_transpose(ctx: *mut sfb_ctx, a: *const sfb_mat, out: *mut *mut sfb_mat) -> i32;
     pub fn sfb_mat_view_rows(ctx: *mut sfb_ctx, a: *const sfb_mat, row0: u64, nrows: u64, out: *mut *mut sfb_mat) -> i32;
@@ -68,6 +70,8 @@ extern "C" {
     pub fn sfb_rayleigh_quotient(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *const f64, out: *mut f64) -> i32;
     pub fn sfb_lambda(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *const sfb_mat, params: *const sfb_lambda_params, out_lambda: *mut f64, out_dispersion: *mut f64, stats: *mut f64) -> i32;
     pub fn sfb_lambda_projected(ctx: *mut sfb_ctx, L: *const sfb_csr, x_original: *const sfb_mat, x_projected: *const sfb_mat, params: *const sfb_lambda_params, out_lambda: *mut f64, out_dispersion: *mut f64, stats: *mut f64) -> i32;
+    pub fn sfb_compute_tau_mode_lambdas(ctx: *mut sfb_ctx, L: *const sfb_csr, data: *const f32, n_items: u64, n_features: u32, out_lambdas: *mut f64) -> i32;
+    pub fn sfb_compute_tau(ctx: *mut sfb_ctx, lambdas: *const f32, n: u64, tau_mode: i32, tau_value: f32, out_tau: *mut f32) -> i32;
     pub fn sfb_diffuse(ctx: *mut sfb_ctx, L: *const sfb_csr, x: *mut sfb_mat, eta: f64, steps: u32) -> i32;
     pub fn sfb_map_items_to_subcentroids(ctx: *mut sfb_ctx, items: *const sfb_mat, item_lambdas: *const f64, sub_centroids: *const sfb_mat, sub_lambdas: *const f64, epsilon: f64, out_idx: *mut u32, out_lambda: *mut f64, out_norm: *mut f64) -> i32;
     pub fn sfb_project_rows(ctx: *mut sfb_ctx, x: *const sfb_mat, samples: *const f64, reduced_dim: u32, order: i32, out: *mut *mut sfb_mat) -> i32;

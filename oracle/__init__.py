@@ -86,6 +86,21 @@ def lib():
     L.orc_sorted_lambdas.argtypes = [_dp, _c.c_uint64, _dp, _u32p, _c.POINTER(_c.c_double)]
     L.orc_sorted_lambdas.restype = _c.c_int
     L.orc_lambda_projected.argtypes = [_u64p, _u32p, _dp, _c.c_uint64, _dp, _c.c_uint64, _dp, _c.c_uint64, _c.c_int, _c.c_double, _dp]
+    L.orc_bc_det.argtypes = L.orc_bc.argtypes
+    L.orc_bc_det.restype = _c.c_float
+    L.orc_bc_matrix2.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_float, _c.c_int, _fp]
+    L.orc_bc_knn2.argtypes = [_fp, _fp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_float, _c.c_float, _c.c_int, _u32p, _fp, _u32p]
+    L.orc_det_logf.argtypes = [_c.c_float]
+    L.orc_det_logf.restype = _c.c_float
+    L.orc_det_expf.argtypes = [_c.c_float]
+    L.orc_det_expf.restype = _c.c_float
+    L.orc_knn_block.argtypes = [_dp, _dp, _u64p, _c.c_uint64, _dp, _c.c_uint64, _c.c_uint64, _c.c_uint32, _c.c_int, _c.c_uint32,
+                                _c.c_double, _u32p, _dp, _u32p]
+    L.orc_knn_block_finish.argtypes = [_c.c_uint64, _c.c_uint32, _u32p, _dp, _u32p]
+    L.orc_cols_gram_accumulate.argtypes = [_dp, _c.c_uint64, _c.c_uint32, _u32p, _c.c_uint32, _dp, _dp]
+    L.orc_cols_gram_finish.argtypes = [_dp, _dp, _c.c_uint32, _u32p, _c.c_uint32, _c.c_uint32, _c.c_double, _u32p, _dp, _u32p]
+    L.orc_compute_tau_core.argtypes = [_fp, _c.c_uint64, _c.c_int, _c.c_float]
+    L.orc_compute_tau_core.restype = _c.c_float
     _lib = L
     return L
 
@@ -234,28 +249,90 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def bc(means, variances, i, j, reg=1e-6):
-    """bhattacharyya_coefficient (surfface-core/src/distance.rs:260-290) of features i, j of a [C, F] state."""
+def bc(means, variances, i, j, reg=1e-6, det=False):
+    """bhattacharyya_coefficient (surfface-core/src/distance.rs:260-290) of features i, j of a [C, F] state.
+    det=False: glibc logf / expf (the reference on Linux); det=True: the portable log / exp the device evaluates."""
     m, v = _f32(means), _f32(variances)
-    return float(lib().orc_bc(m, v, m.shape[0], m.shape[1], i, j, reg))
+    fn = lib().orc_bc_det if det else lib().orc_bc
+    return float(fn(m, v, m.shape[0], m.shape[1], i, j, reg))
 
 
-def bc_matrix(means, variances, reg=1e-6):
+def bc_matrix(means, variances, reg=1e-6, det=False):
     m, v = _f32(means), _f32(variances)
     out = np.empty((m.shape[1], m.shape[1]), np.float32)
-    lib().orc_bc_matrix(m, v, m.shape[0], m.shape[1], reg, out)
+    lib().orc_bc_matrix2(m, v, m.shape[0], m.shape[1], reg, int(det), out)
     return out
 
 
-def bc_knn(means, variances, k, reg=1e-6, thr=1e-9):
+def bc_knn(means, variances, k, reg=1e-6, thr=1e-9, det=False):
     """compute_bhattacharyya_weights (surfface-core/src/laplacian.rs:254-298): (idx [F,k], w [F,k] f32, cnt [F])."""
     m, v = _f32(means), _f32(variances)
     f = m.shape[1]
     idx = np.empty((f, k), np.uint32)
     w = np.empty((f, k), np.float32)
     cnt = np.empty(f, np.uint32)
-    lib().orc_bc_knn(m, v, m.shape[0], f, k, reg, thr, idx, w, cnt)
+    lib().orc_bc_knn2(m, v, m.shape[0], f, k, reg, thr, int(det), idx, w, cnt)
     return idx, w, cnt
+
+
+def det_logf(a):
+    return float(lib().orc_det_logf(float(a)))
+
+
+def det_expf(a):
+    return float(lib().orc_det_expf(float(a)))
+
+
+def compute_tau_core(lambdas, mode, value=0.0):
+    """compute_tau (surfface-core/src/taumode.rs:37-65): one f32 tau from the lambda distribution."""
+    v = _f32(lambdas)
+    if v.size == 0:
+        return float(lib().orc_compute_tau_core(np.zeros(1, np.float32), 0, mode, float(value)))
+    return float(lib().orc_compute_tau_core(v, v.size, mode, float(value)))
+
+
+class KnnStream:
+    """orc_knn over a corpus fed in ascending row blocks (for matrices that never exist on the host in full)."""
+
+    def __init__(self, queries, query_rows, k, metric=METRIC_COSINE, eps=np.inf):
+        self.q = np.ascontiguousarray(queries, dtype=np.float64)
+        self.rows = np.ascontiguousarray(query_rows, dtype=np.uint64)
+        self.k, self.metric, self.eps = int(k), int(metric), float(eps)
+        nq = self.q.shape[0]
+        self.qn = row_norms(self.q) if metric == METRIC_COSINE else np.zeros(nq)
+        self.idx = np.zeros((nq, self.k), np.uint32)
+        self.dist = np.zeros((nq, self.k), np.float64)
+        self.cnt = np.zeros(nq, np.uint32)
+
+    def feed(self, block, row0):
+        b = np.ascontiguousarray(block, dtype=np.float64)
+        lib().orc_knn_block(self.q, self.qn, self.rows, self.q.shape[0], b, int(row0), b.shape[0], b.shape[1], self.metric,
+                            self.k, self.eps, self.idx, self.dist, self.cnt)
+
+    def finish(self):
+        lib().orc_knn_block_finish(self.q.shape[0], self.k, self.idx, self.dist, self.cnt)
+        return self.idx, self.dist, self.cnt
+
+
+class ColsGramStream:
+    """Rectified-cosine kNN lists of a SAMPLE of the feature nodes (columns) of a row-streamed item matrix: the sums
+    orc_knn(orc_transpose(x)) would form, carried across row blocks."""
+
+    def __init__(self, f, cols, k, eps=np.inf):
+        self.f, self.k, self.eps = int(f), int(k), float(eps)
+        self.cols = np.ascontiguousarray(cols, dtype=np.uint32)
+        self.acc = np.zeros((len(self.cols), self.f), np.float64)
+        self.nrm2 = np.zeros(self.f, np.float64)
+
+    def feed(self, block):
+        b = np.ascontiguousarray(block, dtype=np.float64)
+        lib().orc_cols_gram_accumulate(b, b.shape[0], self.f, self.cols, len(self.cols), self.acc, self.nrm2)
+
+    def finish(self):
+        ns = len(self.cols)
+        idx = np.empty((ns, self.k), np.uint32); dist = np.empty((ns, self.k), np.float64); cnt = np.empty(ns, np.uint32)
+        lib().orc_cols_gram_finish(self.acc, self.nrm2, self.f, self.cols, ns, self.k, self.eps, idx, dist, cnt)
+        return idx, dist, cnt
 
 
 def map_items(items, item_lambdas, sub_centroids, sub_lambdas, epsilon=1e-11):

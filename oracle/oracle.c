@@ -825,7 +825,38 @@ void orc_transpose(const double* x, uint64_t rows, uint64_t cols, double* out) {
  * The reference's sort is unstable with no tie-break; the contract is (BC desc, j asc).
  * libm: logf / expf here are glibc's, the reference's are the platform's -- its own tests compare at 1e-5.
  * ------------------------------------------------------------------------------------------ */
-float orc_bc(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t i, uint32_t j, float reg) {
+/* Portable f32 log / exp: evaluated in f64 with + - * / only, in a fixed order (no libm, no FMA), then rounded to
+ * f32 -- the f64 result is accurate to ~1e-16, so the f32 value is the correctly rounded one except when the exact
+ * result lies within ~1e-9 ulp of a rounding boundary.  csrc/bc.cu evaluates the SAME sequence on the device, so the
+ * device and this restatement agree bit for bit and a transcendental never decides a neighbour ORDER differently on
+ * the two sides.  glibc's logf / expf (what the reference's f32::ln / f32::exp call on Linux)
+ * differ from these in < 1 ulp; tests/test_oracle_kat.py measures how often. */
+float orc_det_logf(float a) {
+    if (a != a || a < 0.0f) return NAN;
+    if (a == 0.0f) return -INFINITY;
+    if (isinf(a)) return INFINITY;
+    return (float)det_log((double)a);   /* every positive f32, subnormals included, is a normal f64 */
+}
+float orc_det_expf(float xf) {
+    if (xf != xf) return NAN;
+    double x = (double)xf;
+    if (x > 100.0) return INFINITY;     /* expf overflows above 88.73 */
+    if (x < -120.0) return 0.0f;        /* below the smallest f32 subnormal (ln = -103.3) */
+    double kf = rint(x * 1.4426950408889634);
+    double r = (x - kf * 6.93147180369123816490e-01) - kf * 1.90821492927058770002e-10;
+    double p = 1.0 / 87178291200.0;                 /* 1/14! */
+    p = p * r + 1.0 / 6227020800.0;  p = p * r + 1.0 / 479001600.0; p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;     p = p * r + 1.0 / 362880.0;    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;        p = p * r + 1.0 / 720.0;       p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;          p = p * r + 1.0 / 6.0;         p = p * r + 0.5;
+    p = p * r + 1.0;                 p = p * r + 1.0;
+    int64_t k = (int64_t)kf;
+    uint64_t bits = (uint64_t)(k + 1023) << 52;     /* |k| <= 174: a normal f64 */
+    double sc; memcpy(&sc, &bits, 8);
+    return (float)(p * sc);
+}
+
+static inline float bc_pair(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t i, uint32_t j, float reg, int det) {
     float db = 0.0f;
     for (uint32_t cc = 0; cc < c; ++cc) {
         float vi = vars[(size_t)cc * f + i], vj = vars[(size_t)cc * f + j];
@@ -834,19 +865,30 @@ float orc_bc(const float* means, const float* vars, uint32_t c, uint32_t f, uint
         float v_sum = vi + vj;
         float dm = means[(size_t)cc * f + i] - means[(size_t)cc * f + j];
         float mean_term = (dm * dm) / (4.0f * v_sum);
-        float log_term = 0.5f * logf(v_sum / (2.0f * sqrtf(vi * vj)));
+        float arg = v_sum / (2.0f * sqrtf(vi * vj));
+        float log_term = 0.5f * (det ? orc_det_logf(arg) : logf(arg));
         db += mean_term + log_term;
     }
-    float bc = expf(-db);
+    float bc = det ? orc_det_expf(-db) : expf(-db);
     if (bc < 0.0f) bc = 0.0f;
     if (bc > 1.0f) bc = 1.0f;
     return bc;
 }
+/* libm form (glibc logf / expf: the reference on Linux) and portable form (what the device evaluates) */
+float orc_bc(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t i, uint32_t j, float reg) {
+    return bc_pair(means, vars, c, f, i, j, reg, 0);
+}
+float orc_bc_det(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t i, uint32_t j, float reg) {
+    return bc_pair(means, vars, c, f, i, j, reg, 1);
+}
 
-void orc_bc_matrix(const float* means, const float* vars, uint32_t c, uint32_t f, float reg, float* out /* f*f */) {
+void orc_bc_matrix2(const float* means, const float* vars, uint32_t c, uint32_t f, float reg, int det, float* out /* f*f */) {
 #pragma omp parallel for schedule(dynamic, 4)
     for (int64_t i = 0; i < (int64_t)f; ++i)
-        for (uint32_t j = 0; j < f; ++j) out[(size_t)i * f + j] = orc_bc(means, vars, c, f, (uint32_t)i, j, reg);
+        for (uint32_t j = 0; j < f; ++j) out[(size_t)i * f + j] = bc_pair(means, vars, c, f, (uint32_t)i, j, reg, det);
+}
+void orc_bc_matrix(const float* means, const float* vars, uint32_t c, uint32_t f, float reg, float* out /* f*f */) {
+    orc_bc_matrix2(means, vars, c, f, reg, 0, out);
 }
 
 typedef struct { float w; uint32_t j; } orc_bc_pair;
@@ -858,8 +900,8 @@ static int orc_bc_cmp(const void* a, const void* b) {
 }
 
 /* out_idx / out_w: f x k (padded with IDX_NONE / 0), out_cnt: f */
-void orc_bc_knn(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t k, float reg, float thr,
-                uint32_t* out_idx, float* out_w, uint32_t* out_cnt) {
+void orc_bc_knn2(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t k, float reg, float thr, int det,
+                 uint32_t* out_idx, float* out_w, uint32_t* out_cnt) {
     uint32_t kk = k < (f ? f - 1 : 0) ? k : (f ? f - 1 : 0);
 #pragma omp parallel
     {
@@ -869,7 +911,7 @@ void orc_bc_knn(const float* means, const float* vars, uint32_t c, uint32_t f, u
             uint32_t n = 0;
             for (uint32_t j = 0; j < f; ++j) {
                 if (j == (uint32_t)i) continue;
-                float w = orc_bc(means, vars, c, f, (uint32_t)i, j, reg);
+                float w = bc_pair(means, vars, c, f, (uint32_t)i, j, reg, det);
                 if (w > thr) { sc[n].w = w; sc[n].j = j; ++n; }
             }
             qsort(sc, n, sizeof(orc_bc_pair), orc_bc_cmp);
@@ -882,6 +924,11 @@ void orc_bc_knn(const float* means, const float* vars, uint32_t c, uint32_t f, u
         }
         free(sc);
     }
+}
+
+void orc_bc_knn(const float* means, const float* vars, uint32_t c, uint32_t f, uint32_t k, float reg, float thr,
+                uint32_t* out_idx, float* out_w, uint32_t* out_cnt) {
+    orc_bc_knn2(means, vars, c, f, k, reg, thr, 0, out_idx, out_w, out_cnt);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1022,4 +1069,129 @@ int orc_sorted_lambdas(const double* lam, uint64_t n, double* out_lambda, uint32
         a = b;
     }
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Streaming forms for corpora that never exist on the host in full (C3: 10M x 768 f64 = 61 GB).
+ * Same arithmetic and order as orc_knn; the caller feeds the corpus in ascending row blocks.
+ *   q: nq x kd query vectors, q_norms: their norms (orc_row_norms; unused for L2), q_global: their row indices;
+ *   io_idx / io_dist / io_cnt: running top-k lists (io_cnt zeroed before the first block).
+ * orc_knn_block_finish pads the lists like orc_knn.
+ * ------------------------------------------------------------------------------------------ */
+void orc_knn_block(const double* q, const double* q_norms, const uint64_t* q_global, uint64_t nq, const double* block,
+                   uint64_t block_row0, uint64_t block_rows, uint32_t kd, int metric, uint32_t k, double eps,
+                   uint32_t* io_idx, double* io_dist, uint32_t* io_cnt) {
+    double* norms = (double*)malloc(sizeof(double) * (size_t)(block_rows ? block_rows : 1));
+    if (metric == ORC_METRIC_COSINE) orc_row_norms(block, block_rows, kd, norms);
+    else memset(norms, 0, sizeof(double) * (size_t)block_rows);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t qq = 0; qq < (int64_t)nq; ++qq) {
+        const double* a = q + (size_t)qq * kd;
+        const double na = metric == ORC_METRIC_COSINE ? q_norms[qq] : 0.0;
+        double* bd = io_dist + (size_t)qq * k;
+        uint32_t* bi = io_idx + (size_t)qq * k;
+        uint32_t cnt = io_cnt[qq];
+        uint64_t j = 0;
+        for (; j + 8 <= block_rows; j += 8) {
+            const double* b[8]; double nb[8], key[8];
+            for (int t = 0; t < 8; ++t) { b[t] = block + (size_t)(j + t) * kd; nb[t] = norms[j + t]; }
+            pair_keys8(a, b, kd, metric, na, nb, key);
+            for (int t = 0; t < 8; ++t) {
+                if (block_row0 + j + t == q_global[qq]) continue;
+                if (key[t] <= eps) topk_insert(bd, bi, &cnt, k, key[t], (uint32_t)(block_row0 + j + t));
+            }
+        }
+        for (; j < block_rows; ++j) {
+            if (block_row0 + j == q_global[qq]) continue;
+            double key = pair_key(a, block + (size_t)j * kd, kd, metric, na, norms[j]);
+            if (key <= eps) topk_insert(bd, bi, &cnt, k, key, (uint32_t)(block_row0 + j));
+        }
+        io_cnt[qq] = cnt;
+    }
+    free(norms);
+}
+void orc_knn_block_finish(uint64_t nq, uint32_t k, uint32_t* io_idx, double* io_dist, const uint32_t* io_cnt) {
+    for (uint64_t qq = 0; qq < nq; ++qq)
+        for (uint32_t t = io_cnt[qq]; t < k; ++t) { io_dist[qq * k + t] = INFINITY; io_idx[qq * k + t] = ORC_IDX_NONE; }
+}
+
+/* Feature graph (nodes = columns) of a row-streamed item matrix, for a SAMPLE of the feature nodes: the dot
+ * products of the sampled columns with every column and every column's sum of squares, each a left fold over the
+ * item rows carried across blocks -- the sums orc_knn(orc_transpose(x)) forms (pair_key, orc_row_norms).
+ *   acc: ns x f, nrm2: f, both zeroed before the first block. */
+void orc_cols_gram_accumulate(const double* block, uint64_t rows, uint32_t f, const uint32_t* cols, uint32_t ns,
+                              double* acc, double* nrm2) {
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (int64_t)f; ++c) {
+        double n2 = nrm2[c];
+        for (uint64_t r = 0; r < rows; ++r) { double v = block[(size_t)r * f + c]; n2 += v * v; }
+        nrm2[c] = n2;
+        for (uint32_t s = 0; s < ns; ++s) {
+            double a = acc[(size_t)s * f + c];
+            const uint32_t cs = cols[s];
+            for (uint64_t r = 0; r < rows; ++r) a += block[(size_t)r * f + cs] * block[(size_t)r * f + c];
+            acc[(size_t)s * f + c] = a;
+        }
+    }
+}
+/* rectified-cosine kNN lists of the sampled feature nodes from those sums (pair_key's cosine branch) */
+void orc_cols_gram_finish(const double* acc, const double* nrm2, uint32_t f, const uint32_t* cols, uint32_t ns, uint32_t k,
+                          double eps, uint32_t* out_idx, double* out_dist, uint32_t* out_cnt) {
+    for (uint32_t s = 0; s < ns; ++s) {
+        const uint32_t i = cols[s];
+        const double na = sqrt(nrm2[i]);
+        double* bd = out_dist + (size_t)s * k; uint32_t* bi = out_idx + (size_t)s * k; uint32_t cnt = 0;
+        for (uint32_t j = 0; j < f; ++j) {
+            if (j == i) continue;
+            double denom = na * sqrt(nrm2[j]), cosv = 0.0;
+            if (denom > 1e-12) {
+                cosv = acc[(size_t)s * f + j] / denom;
+                if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0;
+            }
+            double key = 1.0 - ((cosv > 0.0) ? cosv : 0.0);
+            if (key <= eps) topk_insert(bd, bi, &cnt, k, key, j);
+        }
+        for (uint32_t t = cnt; t < k; ++t) { bd[t] = INFINITY; bi[t] = ORC_IDX_NONE; }
+        out_cnt[s] = cnt;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The successor's tau: compute_tau (surfface-core/src/taumode.rs:37-65) -- ONE tau resolved from the lambda
+ * DISTRIBUTION in f32 (TAU_FLOOR = 1e-9, :9): finite entries only; Fixed(t): t.max(floor) if finite else floor;
+ * Mean: left-fold f32 sum / len; Median: sorted[len / 2] (upper median, no averaging); Percentile(p):
+ * sorted[round((len - 1) as f32 * clamp(p, 0, 1))]; every result .max(floor).
+ * ------------------------------------------------------------------------------------------ */
+static int cmp_f32(const void* a, const void* b) {
+    float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+float orc_compute_tau_core(const float* lambdas, uint64_t n, int mode, float value) {
+    const float FLOOR = 1e-9f;
+    float* v = (float*)malloc(sizeof(float) * (size_t)(n ? n : 1));
+    uint64_t c = 0;
+    for (uint64_t i = 0; i < n; ++i) if (isfinite(lambdas[i])) v[c++] = lambdas[i];
+    float r = FLOOR;
+    if (c != 0) {
+        if (mode == ORC_TAU_FIXED) r = isfinite(value) ? (value > FLOOR ? value : FLOOR) : FLOOR;
+        else if (mode == ORC_TAU_MEAN) {
+            float s = 0.0f;
+            for (uint64_t i = 0; i < c; ++i) s += v[i];
+            r = s / (float)c;
+        } else {
+            qsort(v, (size_t)c, sizeof(float), cmp_f32);
+            if (mode == ORC_TAU_MEDIAN) r = v[c / 2];
+            else {
+                float pp = value;
+                if (pp < 0.0f) pp = 0.0f; else if (pp > 1.0f) pp = 1.0f;
+                float fi = roundf(((float)c - 1.0f) * pp);                 /* f32::round: half away from zero */
+                uint64_t idx = fi != fi ? 0 : (uint64_t)fi;                /* `as usize` maps NaN to 0 */
+                if (idx >= c) idx = c - 1;
+                r = v[idx];
+            }
+        }
+        if (!(r > FLOOR)) r = FLOOR;   /* f32::max(FLOOR): a NaN mean (inf - inf cannot occur: finite inputs; inf sum / c = inf) */
+    }
+    free(v);
+    return r;
 }

@@ -8,8 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_line(oracle):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "20000", "--steps", "1",
-                          "--warmup", "1", "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "30000", "--steps", "1",
+                          "--warmup", "1", "--ref-seconds", "0.5"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, "exactly one JSON line"
@@ -21,6 +21,22 @@ def test_reference_arm_line(oracle):
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "query rows" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None
+    # both arms print the same `config` object (the driver compares them): bench.config_dict is the only producer
+    import bench
+    wl = dict(bench.WORKLOADS["c2"], rows=30000)
+    wl["name"] += " (rows overridden to 30000)"
+    assert d["config"] == bench.config_dict(wl)
+
+
+def test_reference_arm_runs_small_configs_in_full(oracle):
+    """Config c1 is the one the CPU runs whole: nothing sampled, nothing extrapolated."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c1", "--rows", "1500",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert "WHOLE build" in d["cpu_baseline"]["sample"] and d["config"]["rows"] == 1500
+    # value is rows / wall time of the step: no extrapolation
+    assert abs(d["value"] - 1500 / (d["ms_per_step"] * 1e-3)) / d["value"] < 0.05
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

@@ -167,3 +167,62 @@ def test_knn_screen_many_exact_duplicates(sfb, oracle, ctx):
         assert_knn_equal(g.to_host(), oracle.knn(x, 16, metric))
         st = g.stats()
         assert st["rows_certified"] + st["rows_fallback"] == x.shape[0]
+
+
+# ---- the accumulation-error model of the certificate under adversarial operands -----------------------------------
+def _adversarial_rows(case, m, kd, rng):
+    """Rows that stress fp32 accumulation in the tensor core (cosine metric: the operands are the unit rows x 64).
+      cancel   products +c for the first half of the dimensions, -c for the second: partial sums reach K*c/2, the dot is ~0
+      range    every row spans 2^14 in magnitude (the widest spread fp16 operands keep after the x 64 scaling)
+      drop     one dominant coordinate A and K-1 coordinates t with t*t just under one ulp of A*A: an accumulator that
+               truncates each addend to the running sum's exponent loses every one of them (the worst case the model allows)
+      drop16   the same with t*t = 0.9 ulp / 16: sixteen products (one MMA instruction's worth) together stay under an ulp"""
+    if case == "cancel":
+        x = np.ones((m, kd)) + rng.normal(size=(m, kd)) * 1e-3
+        x[1::2, kd // 2:] *= -1.0
+        return x
+    if case == "range":
+        return np.sign(rng.normal(size=(m, kd))) * 2.0 ** rng.uniform(-7, 7, size=(m, kd))
+    t = math.sqrt(0.9 * 2.0 ** -23 / (16.0 if case == "drop16" else 1.0))
+    x = np.full((m, kd), t) * (1.0 + rng.uniform(0, 0.05, size=(m, kd)))
+    x[:, 0] = 1.0
+    x[2::3, 0] = -1.0   # negative dots too
+    return x
+
+
+@pytest.mark.parametrize("screen", [2, 3])
+@pytest.mark.parametrize("kd", [16, 384, 3072])
+@pytest.mark.parametrize("case", ["cancel", "range", "drop", "drop16"])
+def test_tile_accumulators_adversarial(sfb, ctx, screen, kd, case):
+    """|S~ - q_i.q_j| <= gamma |q_i||q_j| with gamma = (kpad + 64) 2^-23 (knn_screen.cu: screen_level) must hold for operands
+    built to maximise the accumulation error, not only for Gaussian rows; the worst err / bound is printed."""
+    rng = np.random.default_rng(kd + len(case))
+    x = _adversarial_rows(case, 512, kd, rng)
+    worst = 0.0
+    for row0, col0 in ((0, 0), (128, 256)):
+        tile, qr, qc, scale = ctx.matrix(x).debug_screen_tile(sfb.METRIC_COSINE, screen, row0, col0)
+        ref = qr.astype(np.float64) @ qc.astype(np.float64).T
+        nr = np.linalg.norm(qr.astype(np.float64), axis=1)
+        nc = np.linalg.norm(qc.astype(np.float64), axis=1)
+        gamma = (qr.shape[1] + 64) * 2.0 ** -23
+        bound = gamma * np.outer(nr, nc) + 1e-30
+        worst = max(worst, float(np.max(np.abs(tile.astype(np.float64) - ref) / bound)))
+    print(f"ACCUM case={case} screen={screen} kd={kd}: worst err/bound = {worst:.4f}")
+    assert worst <= 0.5, f"accumulation error reaches {worst:.3f} of the certificate's bound: widen gamma"
+
+
+@pytest.mark.parametrize("screen", [2, 3])
+@pytest.mark.parametrize("metric", [0, 1, 2])
+@pytest.mark.parametrize("case,kd", [("cancel", 384), ("range", 384), ("drop", 384), ("range", 16), ("drop", 3072), ("cancel", 1030)])
+def test_knn_screen_parity_adversarial(sfb, oracle, ctx, screen, metric, case, kd):
+    """End to end on the same operands: whatever the screen drops or mis-ranks, the certificate must notice (rows it
+    cannot certify go to the exact path), so the lists equal the brute-force oracle bit for bit."""
+    rng = np.random.default_rng(kd * 3 + metric)
+    m = 4300 if kd <= 1030 else 4100
+    x = _adversarial_rows(case, m, kd, rng)
+    x[:64] = x[64:128]                      # exact duplicates: ties by index
+    g = ctx.matrix(x).knn(8, metric, screen=screen)
+    assert_knn_equal(g.to_host(), oracle.knn(x, 8, metric))
+    st = g.stats()
+    assert st["rows_certified"] + st["rows_fallback"] == m
+    print(case, kd, metric, {k: st[k] for k in ("rows_certified", "rows_fallback", "rows_rescreened", "max_margin")})
