@@ -173,7 +173,8 @@ def build_once(sfb, ctx, X, wl, rank, world, out_lambda=None, keep=False):
     adj = _timed(ctx, "adjacency", lambda: g.adjacency(P_WEIGHT, SIGMA, sparsify=0 if sfgrass else -1))
     if sfgrass:
         _timed(ctx, "sfgrass", lambda: adj.sfgrass(wl["ratio"]))
-    L = _timed(ctx, "laplacian", lambda: adj.laplacian())
+    # sharded: every rank assembles the CSR rows it owns from the gathered lists
+    L = _timed(ctx, "laplacian", lambda: adj.laplacian(rows=(lo, hi)) if world > 1 else adj.laplacian())
     st["nnz_item"] = L.shape[1]
     # feature Laplacian + per-item lambda
     gf = _timed(ctx, "knn_columns", lambda: pend.end())
@@ -280,9 +281,9 @@ def run_ours(args):
             nb = min(step_rows, hi - r0)
             xh[r0 - lo:r0 - lo + nb] = X.rows(r0, nb)
         X.free()
-        nnz_cap = n * (2 * k + 1)
-        fetch_csr = rank == 0                         # the result is read back once, by rank 0
-        out_csr = (ctx.pinned_empty(n + 1, np.uint64), ctx.pinned_empty(nnz_cap, np.uint32), ctx.pinned_empty(nnz_cap, np.float64)) if fetch_csr else None
+        nnz_cap = (hi - lo) * (2 * k + 1)
+        # the result is read back once: every rank fetches the CSR rows it owns (as it uploaded the rows it owns)
+        out_csr = (ctx.pinned_empty(hi - lo + 1, np.uint64), ctx.pinned_empty(nnz_cap, np.uint32), ctx.pinned_empty(nnz_cap, np.float64))
         out_lam = ctx.pinned_empty(n, np.float64)
         d2h = 0
 
@@ -295,10 +296,8 @@ def run_ours(args):
             else:
                 Xd = ctx.matrix(xh)
             (L, Lf, lam), _, _ = build_once(sfb, ctx, Xd, wl, rank, world, out_lambda=out_lam, keep=True)
-            d2h = out_lam.nbytes
-            if fetch_csr:
-                indptr, indices, data = L.to_host(out_csr)
-                d2h += indptr.nbytes + indices.nbytes + data.nbytes
+            indptr, indices, data = L.to_host(out_csr)
+            d2h = out_lam.nbytes + indptr.nbytes + indices.nbytes + data.nbytes
             L.free(); Lf.free(); Xd.free()
 
         e2e_steps = max(1, min(args.steps, 3))
@@ -322,8 +321,8 @@ def run_ours(args):
         ms_e_step = float(te[0]) / e2e_steps
         e2e = {"value": n / (ms_e_step * 1e-3), "unit": UNIT, "ms_per_step": ms_e_step, "steps": e2e_steps,
                "h2d_bytes_per_step": int(n) * d * 8, "d2h_bytes_per_step": d2h_total,
-               "api": "Context.matrix(host f64 rows of this rank) [-> Matrix.allgather_rows] -> Matrix.knn -> adjacency -> laplacian -> Csr.to_host "
-                      "(rank 0); Csr.lambdas_allgather -> host (every rank)"}
+               "api": "Context.matrix(host f64 rows of this rank) [-> Matrix.allgather_rows] -> Matrix.knn -> adjacency -> laplacian(rows of this rank) "
+                      "-> Csr.to_host; Csr.lambdas_allgather -> host (every rank: the lambda vector is the all-gathered one)"}
     else:
         X.free()
 
@@ -452,12 +451,41 @@ def verify_build(sfb, ctx, X, wl, rank, world, n_sample=256, full=False):
     full_out = None
     if full:
         full_out = verify_full_knn(sfb, ctx, X, wl, g, rank, world)
+    lo, hi = shard(n, rank, world)
+    # the item Laplacian as the timed path leaves it: every rank holds the CSR rows it owns.  Structural invariants are
+    # checked by every rank on its own rows; the rows are gathered on rank 0 for the comparison with the oracle's assembly
+    # when the matrix is small enough to ship (else rank 0 compares sampled rows of its own shard).
+    indptr, indices, data = L.to_host()
+    ip = indptr.astype(np.int64)
+    row_of = np.repeat(np.arange(lo, hi), np.diff(ip))
+    sorted_ok = bool(np.all((np.diff(indices.astype(np.int64)) > 0) | (np.diff(row_of) > 0)))
+    diag_ok = bool(np.count_nonzero(indices == row_of) == hi - lo)
+    rs = np.add.reduceat(data, ip[:-1])
+    scale = np.add.reduceat(np.abs(data), ip[:-1]) + 1e-300
+    rowsum_ok = bool(np.max(np.abs(rs) / scale) < 1e-12)
+    del row_of
+    gather_csr = n <= 2_000_000
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        flags = torch.tensor([int(sorted_ok), int(diag_ok), int(rowsum_ok)], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        sorted_ok, diag_ok, rowsum_ok = (bool(v) for v in flags.tolist())
+        if gather_csr:
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object((indptr, indices, data), parts, dst=0)
+            if rank == 0:
+                offs = np.cumsum([0] + [int(p[0][-1]) for p in parts])
+                indptr = np.concatenate([parts[0][0]] + [p[0][1:] + np.uint64(o) for p, o in zip(parts[1:], offs[1:])])
+                indices = np.concatenate([p[1] for p in parts]); data = np.concatenate([p[2] for p in parts])
+                ip = indptr.astype(np.int64)
+                del parts
     if rank == 0:
         import oracle
         oracle.build()
         oracle.use_all_threads()
         kf = feature_k(wl)
-        small = n * d * 8 <= 8e9
+        small = n * d * 8 <= 8e9 and not os.environ.get("SFB_VERIFY_STREAM")   # SFB_VERIFY_STREAM=1: exercise the streamed form at a small size
         rows = np.unique(np.random.default_rng(1).integers(0, n, n_sample if small else min(n_sample, 64)))
         idx, dist_, cnt = g.to_host()
         f_idx, f_dist, f_cnt = gf.to_host()
@@ -492,36 +520,30 @@ def verify_build(sfb, ctx, X, wl, rank, world, n_sample=256, full=False):
         knn_ok = bool(np.array_equal(idx[rows], o_idx) and np.array_equal(dist_[rows], o_dist) and np.array_equal(cnt[rows], o_cnt))
         feat_ok = bool(np.array_equal(f_idx[fcols], fo[0]) and np.array_equal(f_dist[fcols], fo[1]) and np.array_equal(f_cnt[fcols], fo[2]))
 
-        # item Laplacian: invariants over the whole CSR
-        indptr, indices, data = L.to_host()
-        ip = indptr.astype(np.int64)
-        deg = np.diff(ip)
-        row_of = np.repeat(np.arange(n), deg)
-        sorted_ok = bool(np.all((np.diff(indices.astype(np.int64)) > 0) | (np.diff(row_of) > 0)))
-        diag_ok = bool(np.count_nonzero(indices == row_of) == n)
-        rs = np.add.reduceat(data, ip[:-1])
-        scale = np.add.reduceat(np.abs(data), ip[:-1]) + 1e-300
-        rowsum_ok = bool(np.max(np.abs(rs) / scale) < 1e-12)
-        del row_of
+        # item Laplacian: symmetry on sampled entries (needs both rows: whole matrix on this rank only)
+        have_all = world == 1 or gather_csr
+        r_lo, r_hi = (0, n) if have_all else (lo, hi)       # rows of the CSR arrays held here; ip is relative to r_lo
         sym_ok = True
-        for r in rows[:64]:
-            for e in range(ip[r], ip[r + 1]):
-                c = int(indices[e])
-                pos = ip[c] + np.searchsorted(indices[ip[c]:ip[c + 1]], r)
-                sym_ok = sym_ok and pos < ip[c + 1] and indices[pos] == r and data[pos] == data[e]
+        if have_all:
+            for r in rows[:64]:
+                for e in range(ip[r], ip[r + 1]):
+                    c = int(indices[e])
+                    pos = ip[c] + np.searchsorted(indices[ip[c]:ip[c + 1]], r)
+                    sym_ok = sym_ok and pos < ip[c + 1] and indices[pos] == r and data[pos] == data[e]
         # ... and equality with the oracle's assembly of the gathered lists
         sfg = wl.get("sparsify") == "sfgrass"
         a = oracle.build_adjacency(idx, dist_, cnt, P_WEIGHT, SIGMA, force_sparsify=0 if sfg else -1)
         if sfg:
             a = oracle.sfgrass(a[0], a[1], a[2], wl["ratio"])
-        if n <= 2_000_000:
+        if have_all and n <= 2_000_000 and not os.environ.get("SFB_VERIFY_STREAM"):
             o_ptr, o_ind, o_dat = oracle.laplacian(*a[:3])
             lap_ok = bool(np.array_equal(indptr, o_ptr) and np.array_equal(indices, o_ind) and np.allclose(data, o_dat, rtol=1e-9, atol=0))
-            lap_how = "all rows"
+            lap_how = "all rows" + (" (row shards gathered from every rank)" if world > 1 else "")
         else:
             lap_ok = True
             a_idx, a_w, a_cnt = a[:3]
-            for r in rows:
+            rows_l = np.unique(np.random.default_rng(4).integers(r_lo, r_hi, 48))
+            for r in rows_l:
                 nb = {}
                 for t in range(int(a_cnt[r])):
                     nb[int(a_idx[r, t])] = float(a_w[r, t])
@@ -536,10 +558,10 @@ def verify_build(sfb, ctx, X, wl, rank, world, n_sample=256, full=False):
                     dsum += nb[c]
                 want_c = sorted(cols + [int(r)])
                 want_v = [dsum if c == r else -nb[c] for c in want_c]
-                got_c = indices[ip[r]:ip[r + 1]]; got_v = data[ip[r]:ip[r + 1]]
+                got_c = indices[ip[r - r_lo]:ip[r - r_lo + 1]]; got_v = data[ip[r - r_lo]:ip[r - r_lo + 1]]
                 lap_ok = lap_ok and len(got_c) == len(want_c) and bool(np.array_equal(got_c, np.array(want_c, np.uint32))) and \
                     bool(np.allclose(got_v, np.array(want_v), rtol=1e-9, atol=0))
-            lap_how = f"{len(rows)} sampled rows (+ invariants over all rows)"
+            lap_how = f"{len(rows_l)} sampled rows of rank 0's shard (+ invariants over all rows of every rank)"
 
         # feature Laplacian: the oracle's assembly of the (verified) feature lists; lambda against it
         fl = oracle.laplacian(*oracle.build_adjacency(f_idx, f_dist, f_cnt, P_WEIGHT, SIGMA)[:3])

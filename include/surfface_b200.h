@@ -185,6 +185,12 @@ typedef struct {
 } sfb_lap_params;
 
 int32_t sfb_laplacian_build(sfb_ctx* ctx, const sfb_adj* adj, const sfb_lap_params* params, sfb_csr** out);
+/* Row-owned assembly of a sharded build ("each GPU builds the CSR rows it owns"): rows
+ * [row_begin, row_end) of the same Laplacian, from the all-gathered lists.  The handle holds row_end - row_begin rows,
+ * indptr starting at 0, GLOBAL column indices; sfb_csr_shape / sfb_csr_copy work on it, the square-matrix consumers
+ * (lambda, SpMV) refuse it.  Unnormalised form only (L_sym needs the degree of every neighbour). */
+int32_t sfb_laplacian_build_rows(sfb_ctx* ctx, const sfb_adj* adj, const sfb_lap_params* params, uint64_t row_begin, uint64_t row_end,
+                                 sfb_csr** out);
 int32_t sfb_csr_shape(const sfb_csr* L, uint64_t* rows, uint64_t* nnz);
 int32_t sfb_csr_copy(sfb_ctx* ctx, const sfb_csr* L, uint64_t* indptr, uint32_t* indices, double* data);
 int32_t sfb_csr_from_host(sfb_ctx* ctx, uint64_t rows, const uint64_t* indptr, const uint32_t* indices,

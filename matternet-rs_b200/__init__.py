@@ -363,10 +363,15 @@ class Adjacency(_Handle):
         self.ctx.check(lib().sfb_sparsify_sfgrass(self.ctx._h, self._h, float(ratio), C.byref(applied)))
         return bool(applied.value)
 
-    def laplacian(self, normalised=False, weight_threshold=1e-9):
+    def laplacian(self, normalised=False, weight_threshold=1e-9, rows=None):
+        """rows=(begin, end): only those rows of the Laplacian (row-owned assembly of a sharded build): a Csr of
+        end - begin rows with global column indices."""
         prm = _ffi.LapParams(int(normalised), float(weight_threshold))
         h = C.c_void_p()
-        self.ctx.check(lib().sfb_laplacian_build(self.ctx._h, self._h, C.byref(prm), C.byref(h)))
+        if rows is None:
+            self.ctx.check(lib().sfb_laplacian_build(self.ctx._h, self._h, C.byref(prm), C.byref(h)))
+        else:
+            self.ctx.check(lib().sfb_laplacian_build_rows(self.ctx._h, self._h, C.byref(prm), int(rows[0]), int(rows[1]), C.byref(h)))
         return Csr(self.ctx, h)
 
 

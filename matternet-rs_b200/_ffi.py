@@ -103,6 +103,7 @@ SYMBOLS = {
     "sfb_adj_from_host": (C.c_int32, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, _PP]),
     "sfb_adj_free": (None, [_P]),
     "sfb_laplacian_build": (C.c_int32, [_P, _P, C.POINTER(LapParams), _PP]),
+    "sfb_laplacian_build_rows": (C.c_int32, [_P, _P, C.POINTER(LapParams), C.c_uint64, C.c_uint64, _PP]),
     "sfb_csr_shape": (C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "sfb_csr_copy": (C.c_int32, [_P, _P, _P, _P, _P]),
     "sfb_csr_from_host": (C.c_int32, [_P, C.c_uint64, _P, _P, _P, _PP]),

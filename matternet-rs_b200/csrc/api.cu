@@ -462,8 +462,14 @@ extern "C" void sfb_csr_free(sfb_csr* L) {
     delete L;
 }
 
-// ---- exclusive scan u32 -> u64 (three kernels: block sums, scan of sums, block scan) ----------
+// ---- exclusive scan u32 -> u64: ONE pass, decoupled look-back ---------------------------------------
+// Tiles are taken in ticket order (atomic counter), each publishes its aggregate, then its inclusive prefix, in one
+// 64-bit word (flag in the top two bits); a tile resolves its exclusive prefix by walking back over its predecessors'
+// words until it meets an inclusive one.  One read and one write of the data, no block-sums array, no host round trip.
+// in_b (optional) is added element-wise and `add` to every element: the callers scan cnt[i] + rev_len[i] or ulen[i] + 1
+// without materialising them.
 static constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+static constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
 
 __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total) {
     __shared__ uint64_t warp_sums[SCAN_BLOCK / 32];
@@ -492,54 +498,56 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* t
     return inc - v + warp_sums[wid];
 }
 
-__global__ void scan_block_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ sums) {
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-    uint64_t s = 0;
-#pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t) if (base + t < n) s += in[base + t];
-    uint64_t total;
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-__global__ void scan_sums_serial(uint64_t* sums, uint64_t nb, uint64_t* out_total) {
-    // single block: nb is at most a few thousand
-    __shared__ uint64_t carry;
-    if (threadIdx.x == 0) carry = 0;
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_lookback_kernel(const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_b, uint32_t add,
+                                                                   uint64_t n, uint64_t* __restrict__ out, volatile unsigned long long* state /* [tiles] + ticket */,
+                                                                   uint64_t n_tiles) {
+    __shared__ uint64_t s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd((unsigned long long*)(state + n_tiles), 1ull);
     __syncthreads();
-    for (uint64_t b0 = 0; b0 < nb; b0 += SCAN_BLOCK) {
-        uint64_t i = b0 + threadIdx.x;
-        uint64_t v = i < nb ? sums[i] : 0, total;
-        uint64_t ex = block_exclusive_scan(v, &total);
-        if (i < nb) sums[i] = ex + carry;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *out_total = carry;
-}
-__global__ void scan_apply(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ sums,
-                           uint64_t* __restrict__ out) {
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    const uint64_t tile = s_tile;
+    const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint64_t s = 0;
 #pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t) { v[t] = base + t < n ? in[base + t] : 0; s += v[t]; }
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        v[t] = base + t < n ? in_a[base + t] + (in_b ? in_b[base + t] : 0u) + add : 0u;
+        s += v[t];
+    }
     uint64_t total;
-    uint64_t ex = block_exclusive_scan(s, &total) + sums[blockIdx.x];
+    const uint64_t ex_in_block = block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) {
+        uint64_t prefix = 0;
+        if (tile == 0) state[0] = LB_PREFIX | total;
+        else {
+            state[tile] = LB_AGG | total;
+            for (uint64_t j = tile; j-- > 0;) {
+                unsigned long long w;
+                do { w = state[j]; } while ((w >> 62) == 0);
+                prefix += w & LB_MASK;
+                if ((w >> 62) == 2) break;
+            }
+            state[tile] = LB_PREFIX | (prefix + total);
+        }
+        s_prefix = prefix;
+        if (tile == n_tiles - 1) out[n] = prefix + total;
+    }
+    __syncthreads();
+    uint64_t ex = s_prefix + ex_in_block;
 #pragma unroll
     for (int t = 0; t < SCAN_ITEMS; ++t) { if (base + t < n) out[base + t] = ex; ex += v[t]; }
 }
 
+// out: n + 1 entries (out[n] = the total).  Asynchronous on the context's stream.
+int32_t sfb_scan_exclusive_u64_ex(sfb_ctx* ctx, const uint32_t* in_a, const uint32_t* in_b, uint32_t add, uint64_t n, uint64_t* out) {
+    if (n == 0) { SFB_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(uint64_t), ctx->stream)); return SFB_OK; }
+    const uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    DevBuf state;
+    SFB_CUDA(ctx, state.alloc(sizeof(unsigned long long) * (nb + 1)));
+    SFB_CUDA(ctx, cudaMemsetAsync(state.p, 0, sizeof(unsigned long long) * (nb + 1), ctx->stream));
+    scan_lookback_kernel<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in_a, in_b, add, n, out, state.as<unsigned long long>(), nb);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;   // `state` returns to the context's cache; stream order keeps it valid until the kernel has run
+}
 int32_t sfb_scan_exclusive_u64(sfb_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out) {
-    uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    DevBuf sums;
-    SFB_CUDA(ctx, sums.alloc(sizeof(uint64_t) * nb));
-    scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, sums.as<uint64_t>());
-    SFB_LAUNCH_CHECK(ctx);
-    scan_sums_serial<<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums.as<uint64_t>(), nb, out + n);
-    SFB_LAUNCH_CHECK(ctx);
-    scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, n, sums.as<uint64_t>(), out);
-    SFB_LAUNCH_CHECK(ctx);
-    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SFB_OK;
+    return sfb_scan_exclusive_u64_ex(ctx, in, nullptr, 0u, n, out);
 }

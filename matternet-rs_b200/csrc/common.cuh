@@ -70,6 +70,7 @@ struct sfb_csr {
     uint32_t* indices = nullptr;
     double* data = nullptr;
     uint64_t rows = 0, nnz = 0;
+    uint64_t row0 = 0, cols = 0;  // a row shard of a larger matrix (sfb_laplacian_build_rows): global index of row 0, column count (0: square)
     mutable int symmetric = -1;  // -1 unknown, 1: structure and values symmetric bit for bit (set by the builder, else checked once in lambda.cu), 0: not
     // packed strict upper triangle for the lambda tile kernel (lambda.cu: lt_pack), built on first use, released by sfb_csr_free
     mutable void* lt_recs = nullptr; mutable void* lt_defect = nullptr; mutable void* lt_meta = nullptr;
@@ -153,7 +154,8 @@ struct HostTrace {
 static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- internal entry points between translation units -------------------------------------------
-int32_t sfb_scan_exclusive_u64(sfb_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out /* n+1 */);
+int32_t sfb_scan_exclusive_u64(sfb_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out /* n+1 */);   // asynchronous
+int32_t sfb_scan_exclusive_u64_ex(sfb_ctx* ctx, const uint32_t* in_a, const uint32_t* in_b /* or null */, uint32_t add, uint64_t n, uint64_t* out);
 int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int metric, uint32_t k, double eps,
                       const uint32_t* query_rows /* device, or null */, uint64_t nq, uint64_t q_begin,
                       uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);

@@ -658,38 +658,61 @@ struct LambdaTileArgs {
     unsigned long long* minmax;   // [0]: min of lambda, [1]: max(0, lambda), as order-preserving keys (atomicMin / atomicMax); may be null
 };
 
+__device__ __forceinline__ void lt_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// shared memory: xs [f][LT_TS] | den, defect term, tau [3][32] | one 1 KB region per warp: the tau selection's scratch in
+// phase 1, the ring of edge records in phase 2 (2 x 32 records, filled by cp.async one chunk ahead), the warp's partial sums
+// at the end of phase 2
 template <int VARIANT, int E, int LT_WARPS>
 __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_tile_kernel(LambdaTileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t f = a.f;
     double* xs = reinterpret_cast<double*>(smem_raw);                         // [f][LT_TS]
-    double* s_den = xs + (size_t)f * LT_TS;                                   // [32]
+    double* s_den = xs + (((size_t)f * LT_TS + 1) & ~(size_t)1);              // [32]   (16-byte aligned)
     double* s_dfc = s_den + 32;                                               // [32]
     double* s_tau = s_dfc + 32;                                               // [32]  < 0: zero vector
-    double* s_part = s_tau + 32;                                              // [LT_WARPS][3][32]
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(s_part + LT_WARPS * 3 * 32) + w * 128;   // [LT_WARPS][128]
+    unsigned char* region0 = reinterpret_cast<unsigned char*>(s_tau + 32);
+    unsigned char* region = region0 + (size_t)w * 1024;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(region);                  // phase 1
+    uint4* ring = reinterpret_cast<uint4*>(region);                           // phase 2: [2][32] records
+    double* part = reinterpret_cast<double*>(region);                         // end of phase 2: [3][32]
     const uint32_t ne = a.meta->ne;
     const bool has_defect = a.meta->any_defect != 0, nonpos = a.meta->any_nonpos != 0;
     const uint32_t e_lo = (uint32_t)((uint64_t)ne * w / LT_WARPS), e_hi = (uint32_t)((uint64_t)ne * (w + 1) / LT_WARPS);
+    const uint32_t n_chunks = (e_hi - e_lo + 31) / 32;
     const double* xs_lane = xs + lane;
     double run_mn = INFINITY, run_mx = 0.0;
     const uint64_t n_tiles = (a.n + 31) / 32;
+    constexpr int IPW = 32 / LT_WARPS;   // items per warp in phase 1
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t i0 = tile * 32;
-        // ---- phase 1: this warp's four items
+        // ---- phase 1: this warp's items, the next item's loads in flight while the current one is processed
+        constexpr bool PREFETCH = E <= 16;   // E = 24 runs 512 threads per CTA: 128 registers leave no room for a second row
+        double vn[PREFETCH ? E : 1];
+        if (PREFETCH) {
+            const uint64_t i = i0 + w * IPW;
+#pragma unroll
+            for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; vn[PREFETCH ? u : 0] = (i < a.n && t < f) ? __ldcs(a.x + i * f + t) : 0.0; }
+        }
 #pragma unroll 1
-        for (int qi = 0; qi < 32 / LT_WARPS; ++qi) {
-            const int it = w * (32 / LT_WARPS) + qi;
+        for (int qi = 0; qi < IPW; ++qi) {
+            const int it = w * IPW + qi;
             const uint64_t i = i0 + it;
             double v[E];
-            if (i < a.n) {
-                const double* xr = a.x + i * f;
+            if (PREFETCH) {
 #pragma unroll
-                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; v[u] = t < f ? __ldcs(xr + t) : 0.0; }
+                for (int u = 0; u < E; ++u) v[u] = vn[PREFETCH ? u : 0];
+                if (qi + 1 < IPW) {
+                    const uint64_t i2 = i + 1;
+#pragma unroll
+                    for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; vn[PREFETCH ? u : 0] = (i2 < a.n && t < f) ? __ldcs(a.x + i2 * f + t) : 0.0; }
+                }
             } else {
 #pragma unroll
-                for (int u = 0; u < E; ++u) v[u] = 0.0;
+                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; v[u] = (i < a.n && t < f) ? __ldcs(a.x + i * f + t) : 0.0; }
             }
             bool zero = true;
             double den = 0.0, dfc = 0.0;
@@ -717,55 +740,69 @@ __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_t
             if (lane == 0) { s_den[it] = den; s_dfc[it] = dfc; s_tau[it] = tau; }
         }
         __syncthreads();
-        // ---- phase 2: lane = item, this warp's slice of the edge list
-        double s0 = 0.0, q0 = 0.0, sa = 0.0;
-        if (e_lo < e_hi) {
-            double xa = xs_lane[a.recs[e_lo].roff & 0x7FFFFFFFu];
-            if (!nonpos) {
-                double s1 = 0.0, q1 = 0.0;
-                uint32_t e = e_lo;
-                for (; e + 2 <= e_hi; e += 2) {
-                    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.recs + e));
-                    const uint4 rb = __ldg(reinterpret_cast<const uint4*>(a.recs + e + 1));
-                    if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
-                    const double xb0 = xs_lane[ra.z];
-                    const double d0 = xa - xb0;
-                    if (rb.w & 0x80000000u) xa = xs_lane[rb.w & 0x7FFFFFFFu];
-                    const double xb1 = xs_lane[rb.z];
-                    const double d1 = xa - xb1;
-                    const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
-                    const double c1 = (__hiloint2double((int)rb.y, (int)rb.x) * d1) * d1;
-                    s0 += c0; q0 = fma(c0, c0, q0);
-                    s1 += c1; q1 = fma(c1, c1, q1);
+        // ---- phase 2: lane = item, this warp's slice of the edge list, records one chunk ahead in the ring
+        double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0, sa = 0.0;
+        if (n_chunks) {
+            { const uint32_t e = e_lo + lane; if (e < e_hi) lt_cp_async16(&ring[lane], a.recs + e); asm volatile("cp.async.commit_group;" ::: "memory"); }
+            { const uint32_t e = e_lo + 32 + lane; if (e < e_hi) lt_cp_async16(&ring[32 + lane], a.recs + e); asm volatile("cp.async.commit_group;" ::: "memory"); }
+            double xa = 0.0;
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+                const uint4* rr = ring + (c & 1) * 32;
+                const uint32_t cnt = min(32u, e_hi - e_lo - c * 32);
+                if (c == 0) xa = xs_lane[rr[0].w & 0x7FFFFFFFu];
+                if (!nonpos) {
+                    uint32_t j = 0;
+#pragma unroll 2
+                    for (; j + 2 <= cnt; j += 2) {
+                        const uint4 ra = rr[j], rb = rr[j + 1];
+                        if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
+                        const double d0 = xa - xs_lane[ra.z];
+                        if (rb.w & 0x80000000u) xa = xs_lane[rb.w & 0x7FFFFFFFu];
+                        const double d1 = xa - xs_lane[rb.z];
+                        const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
+                        const double c1 = (__hiloint2double((int)rb.y, (int)rb.x) * d1) * d1;
+                        s0 += c0; q0 = fma(c0, c0, q0);
+                        s1 += c1; q1 = fma(c1, c1, q1);
+                    }
+                    if (j < cnt) {
+                        const uint4 ra = rr[j];
+                        if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
+                        const double d0 = xa - xs_lane[ra.z];
+                        const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
+                        s0 += c0; q0 = fma(c0, c0, q0);
+                    }
+                } else {
+                    for (uint32_t j = 0; j < cnt; ++j) {
+                        const uint4 ra = rr[j];
+                        if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
+                        const double wv = __hiloint2double((int)ra.y, (int)ra.x);
+                        const double d0 = xa - xs_lane[ra.z];
+                        const double c0 = (wv * d0) * d0;
+                        sa += c0;
+                        if (wv > 0.0) { s0 += c0; q0 = fma(c0, c0, q0); }
+                    }
                 }
-                if (e < e_hi) {
-                    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.recs + e));
-                    if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
-                    const double d0 = xa - xs_lane[ra.z];
-                    const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
-                    s0 += c0; q0 = fma(c0, c0, q0);
-                }
-                s0 += s1; q0 += q1; sa = s0;
-            } else {
-                for (uint32_t e = e_lo; e < e_hi; ++e) {
-                    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(a.recs + e));
-                    if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
-                    const double wv = __hiloint2double((int)ra.y, (int)ra.x);
-                    const double d0 = xa - xs_lane[ra.z];
-                    const double c0 = (wv * d0) * d0;
-                    sa += c0;
-                    if (wv > 0.0) { s0 += c0; q0 = fma(c0, c0, q0); }
-                }
+                __syncwarp();
+                { const uint32_t e = e_lo + (c + 2) * 32 + lane; if (e < e_hi) lt_cp_async16(&ring[(c & 1) * 32 + lane], a.recs + e); asm volatile("cp.async.commit_group;" ::: "memory"); }
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
         }
-        s_part[(w * 3 + 0) * 32 + lane] = s0; s_part[(w * 3 + 1) * 32 + lane] = q0; s_part[(w * 3 + 2) * 32 + lane] = sa;
+        s0 += s1; q0 += q1;
+        if (!nonpos) sa = s0;
+        part[lane] = s0; part[32 + lane] = q0; part[64 + lane] = sa;
         __syncthreads();
         // ---- phase 3: combine, blend, write
         if (w == 0) {
             const uint64_t i = i0 + lane;
             double ssum = 0.0, qsum = 0.0, sall = 0.0;
 #pragma unroll
-            for (int ww = 0; ww < LT_WARPS; ++ww) { ssum += s_part[(ww * 3 + 0) * 32 + lane]; qsum += s_part[(ww * 3 + 1) * 32 + lane]; sall += s_part[(ww * 3 + 2) * 32 + lane]; }
+            for (int ww = 0; ww < LT_WARPS; ++ww) {
+                const double* pw = reinterpret_cast<const double*>(region0 + (size_t)ww * 1024);
+                ssum += pw[lane]; qsum += pw[32 + lane]; sall += pw[64 + lane];
+            }
             const double den = s_den[lane], num = s_dfc[lane] + sall, tau = s_tau[lane];
             if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) { ssum *= 2.0; qsum *= 2.0; }   // both triangles (taumode.rs:371-383)
             double e_raw = 0.0;
@@ -844,10 +881,6 @@ __global__ void minmax_kernel(const double* __restrict__ v, uint64_t n, double* 
     }
     if (threadIdx.x == 0) { out[2 * blockIdx.x] = smin[0]; out[2 * blockIdx.x + 1] = smax[0]; }
 }
-__global__ void normalise_kernel(double* __restrict__ v, uint64_t n, double mn, double rng) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = __ddiv_rn(__dadd_rn(v[i], -mn), rng);
-}
 
 // diffusion: x_r' = x_r - eta * (L x)_r, `steps` times, row resident in shared memory (two slots)
 __global__ void diffuse_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
@@ -899,7 +932,7 @@ __global__ void tau_rows_kernel(const double* __restrict__ x, uint64_t n, uint32
 
 namespace {
 
-size_t lt_smem_bytes(uint32_t f, int nw) { return ((size_t)f * LT_TS + 96 + (size_t)nw * 96) * sizeof(double) + (size_t)nw * 128 * sizeof(uint32_t); }
+size_t lt_smem_bytes(uint32_t f, int nw) { return ((((size_t)f * LT_TS + 1) & ~(size_t)1) + 96) * sizeof(double) + (size_t)nw * 1024; }
 
 template <int VARIANT, int E, int NW>
 int32_t lt_launch(sfb_ctx* ctx, const LambdaTileArgs& a) {
@@ -956,6 +989,7 @@ static int32_t lt_pack(sfb_ctx* ctx, const sfb_csr* L) {
 // d_mm (2 doubles on the device, may be null): receives {min lambda, max(0, max lambda)} of these rows (core.rs:1345-1346).
 int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, uint64_t n, uint32_t f,
                           const sfb_lambda_params* prm, double* d_lambda, double* d_disp, const double* tau_in, double* d_mm) {
+    if (L->cols && L->cols != L->rows) return sfb_fail(ctx, SFB_EINVAL, "a row shard of a Laplacian is not a square operator");
     if (L->rows != f) return sfb_fail(ctx, SFB_EINVAL, "Matrix rows %llu must match vector length %u", (unsigned long long)L->rows, f);  // taumode.rs:330-337
     if (prm->variant < 0 || prm->variant > 2) return sfb_fail(ctx, SFB_EINVAL, "unknown lambda variant %d", prm->variant);
     if (prm->tau_mode < 0 || prm->tau_mode > 3) return sfb_fail(ctx, SFB_EINVAL, "unknown tau mode %d", prm->tau_mode);
@@ -1349,6 +1383,7 @@ extern "C" int32_t sfb_map_items_to_subcentroids(sfb_ctx* ctx, const sfb_mat* it
 
 extern "C" int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, double eta, uint32_t steps) {
     if (!ctx || !L || !x) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (L->cols && L->cols != L->rows) return sfb_fail(ctx, SFB_EINVAL, "a row shard of a Laplacian is not a square operator");
     if (L->rows != x->cols) return sfb_fail(ctx, SFB_EINVAL, "Laplacian rows %llu must match feature count %u", (unsigned long long)L->rows, x->cols);  // energymaps.rs:507-512
     size_t per_warp = (size_t)x->cols * 2 * sizeof(double);
     int wpb = 8;

@@ -5,11 +5,13 @@
 // surfface-core/src/laplacian.rs:333-372,209-219 (normalised L_sym).
 //
 // The reference symmetrises with an O(M*E) DashMap scan and assembles through a sequential TriMat
-// fill.  Here: reverse edges are bucketed by destination with a counting sort (histogram, exclusive
-// scan, scatter), then each row is handled by one warp (one block for rows longer than 256): forward
-// and reverse entries are bitonic-sorted by column in shared memory, duplicates merged (max), the
-// degree is a left fold in ascending column order (same order as the reference), and the CSR row is
-// written with coalesced stores.  HBM-bound: reads M*k*12 B of lists, writes (M+1)*8 + nnz*12 B.
+// fill.  Here: reverse edges are bucketed by destination with a counting sort (histogram, one-pass
+// look-back scan, scatter), then each row is handled by one warp: forward and reverse entries are sorted
+// by column (in registers by a shuffle network for rows of up to 32 edges, in shared memory up to 256, by
+// a block -- in global memory if need be -- for hub rows of any length), duplicates merged (max), the
+// degree is a left fold in ascending column order (same order as the reference), and the CSR rows are
+// staged per block and written with 16-byte stores.  Seven launches, one host round trip (the exact nnz).
+// HBM-bound: reads M*k*12 B of lists, writes (M+1)*8 + nnz*12 B.
 #include <math.h>
 
 #include <new>
@@ -119,34 +121,30 @@ __global__ void adjacency_kernel(const uint32_t* in_idx, const double* in_val,
 }
 
 // ---- symmetrise -------------------------------------------------------------------------------
+// Reverse edges are bucketed by destination with a counting sort: count (atomics), one-pass scan, scatter.  The scatter
+// takes its slots by counting rev_cnt back DOWN (the order inside a bucket is arbitrary either way: the per-row sort
+// fixes it), which leaves rev_cnt zeroed for the next call's scratch and needs no second counter array.
+// [r_begin, r_end): the rows this call owns (all rows, or this rank's shard of a row-sharded build).
 __global__ void rev_count_kernel(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ cnt, uint64_t m, uint32_t k,
-                                 uint32_t* __restrict__ rev_cnt) {
+                                 uint64_t r_begin, uint64_t r_end, uint32_t* __restrict__ rev_cnt) {
     uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= m * k) return;
     uint64_t i = gid / k; uint32_t t = (uint32_t)(gid % k);
     if (t >= cnt[i]) return;
     uint32_t j = idx[gid];
-    if (j != (uint32_t)i) atomicAdd(&rev_cnt[j], 1u);
+    if (j != (uint32_t)i && j >= r_begin && j < r_end) atomicAdd(&rev_cnt[j - r_begin], 1u);
 }
 __global__ void rev_scatter_kernel(const uint32_t* __restrict__ idx, const double* __restrict__ w, const uint32_t* __restrict__ cnt,
-                                   uint64_t m, uint32_t k, const uint64_t* __restrict__ rev_off, uint32_t* __restrict__ fill,
-                                   uint32_t* __restrict__ rev_src, double* __restrict__ rev_w) {
+                                   uint64_t m, uint32_t k, uint64_t r_begin, uint64_t r_end, const uint64_t* __restrict__ rev_off,
+                                   uint32_t* __restrict__ rev_cnt, uint32_t* __restrict__ rev_src, double* __restrict__ rev_w) {
     uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= m * k) return;
     uint64_t i = gid / k; uint32_t t = (uint32_t)(gid % k);
     if (t >= cnt[i]) return;
     uint32_t j = idx[gid];
-    if (j == (uint32_t)i) return;
-    uint64_t o = rev_off[j] + atomicAdd(&fill[j], 1u);
+    if (j == (uint32_t)i || j < r_begin || j >= r_end) return;
+    uint64_t o = rev_off[j - r_begin] + (atomicSub(&rev_cnt[j - r_begin], 1u) - 1u);
     rev_src[o] = (uint32_t)i; rev_w[o] = w[gid];
-}
-__global__ void row_len_kernel(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ rev_cnt, uint64_t m,
-                               uint32_t* __restrict__ len, uint32_t* __restrict__ max_len) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t l = 0;
-    if (i < m) { l = cnt[i] + rev_cnt[i]; len[i] = l; }
-    for (int o = 16; o; o >>= 1) l = max(l, __shfl_down_sync(FULL, l, o));
-    if ((threadIdx.x & 31) == 0 && l) atomicMax(max_len, l);
 }
 
 // Bitonic sort of P (power of two) (col, w) pairs in shared memory by (col asc, w desc), by NT
@@ -172,108 +170,191 @@ __device__ void bitonic_sort_pairs(uint32_t* col, double* w, uint32_t P, uint32_
     group_sync<BLOCK>();
 }
 
-// Pass A: per row, merge forward + reverse entries, sort by column, dedupe (max), write the unique
-// neighbours to tmp at tmp_off[i], the unique count to ulen[i], the degree (left fold, ascending
-// column) to deg[i].  BLOCK = false: one warp per row, rows with len <= CAP; BLOCK = true: one block
-// per row from `row_list`.
-template <bool BLOCK, uint32_t CAP>
-__global__ void lap_merge_rows_kernel(const uint32_t* __restrict__ a_idx, const double* __restrict__ a_w,
-                                      const uint32_t* __restrict__ a_cnt, uint32_t k, const uint64_t* __restrict__ rev_off,
-                                      const uint32_t* __restrict__ rev_src, const double* __restrict__ rev_w,
-                                      const uint32_t* __restrict__ len, const uint64_t* __restrict__ tmp_off, uint64_t m,
-                                      const uint32_t* __restrict__ row_list, uint32_t n_list, uint32_t warp_cap,
-                                      uint32_t* __restrict__ tmp_col, double* __restrict__ tmp_w, uint32_t* __restrict__ ulen,
-                                      double* __restrict__ deg) {
+// Work descriptor shared by the row kernels.  Row i (global index) of the owned range has its forward list at
+// a_idx[i * k ..], its reverse bucket at rev_off[i - r_begin], and its scratch segment for the merged, de-duplicated
+// neighbours at tmp[(i - r_begin) * k + rev_off[i - r_begin] ..] (capacity k + bucket length: no second scan).
+struct MergeArgs {
+    const uint32_t* a_idx; const double* a_w; const uint32_t* a_cnt; uint32_t k;
+    const uint64_t* rev_off; const uint32_t* rev_src; const double* rev_w;
+    uint64_t r_begin, n_rows;
+    uint32_t* tmp_col; double* tmp_w; uint32_t* ulen; double* deg; uint32_t* row_nnz;   // row_nnz: ulen + 1 (null when normalised)
+    uint32_t* long_list; uint32_t* n_long;   // rows the warp kernel leaves to the block kernel
+};
+
+// Pass A, rows of up to 32 incident edges (the common case: k forward + about as many reverse after sparsification):
+// one warp per row, ONE entry per lane, sorted in registers by (column, slot) with a 15-step shuffle network; a column
+// that comes from both directions keeps the larger weight (reference: identical for a symmetric metric, max otherwise).
+// Rows of 33..256 edges are sorted in shared memory by the same warp; longer ones go to the block kernel's list.
+template <uint32_t CAP>
+__global__ void __launch_bounds__(256) lap_merge_rows_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t nt = BLOCK ? blockDim.x : 32;
-    const uint32_t tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
-    const uint32_t groups = BLOCK ? 1 : blockDim.x >> 5, grp = BLOCK ? 0 : threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, grp = threadIdx.x >> 5, groups = blockDim.x >> 5;
     double* sw = reinterpret_cast<double*>(smem_raw) + (size_t)grp * CAP;
     uint32_t* scol = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)groups * CAP) + (size_t)grp * CAP;
-    __shared__ uint32_t s_count;
-
-    uint64_t i;
-    if (BLOCK) { if (blockIdx.x >= n_list) return; i = row_list[blockIdx.x]; }
-    else { i = (uint64_t)blockIdx.x * groups + grp; if (i >= m) return; }
-    const uint32_t l = len[i];
-    if (!BLOCK && l > warp_cap) return;  // long rows go to the block kernel
-    if (l == 0) { if (tid == 0) { ulen[i] = 0; deg[i] = 0.0; } return; }
-    uint32_t P = 2; while (P < l) P <<= 1;
-    const uint32_t fc = a_cnt[i];
-    const uint64_t ro = rev_off[i];
-    for (uint32_t t = tid; t < P; t += nt) {
+    const uint64_t li = (uint64_t)blockIdx.x * groups + grp;
+    if (li >= a.n_rows) return;
+    const uint64_t i = a.r_begin + li;
+    const uint32_t fc = a.a_cnt[i];
+    const uint64_t ro = a.rev_off[li];
+    const uint32_t rl = (uint32_t)(a.rev_off[li + 1] - ro);
+    const uint32_t l = fc + rl;
+    const uint64_t to = li * a.k + ro;
+    if (l == 0) { if (lane == 0) { a.ulen[li] = 0; a.deg[li] = 0.0; if (a.row_nnz) a.row_nnz[li] = 1; } return; }
+    if (l > CAP) { if (lane == 0) a.long_list[atomicAdd(a.n_long, 1u)] = (uint32_t)li; return; }
+    uint32_t u = 0;   // unique neighbours
+    bool in_regs = l <= 32;
+    if (in_regs) {
         uint32_t c = SFB_IDX_NONE; double w = 0.0;
-        if (t < fc) { c = a_idx[i * k + t]; w = a_w[i * k + t]; if (c == (uint32_t)i) c = SFB_IDX_NONE; }
-        else if (t < l) { c = rev_src[ro + (t - fc)]; w = rev_w[ro + (t - fc)]; }
-        scol[t] = c; sw[t] = w;
+        if (lane < fc) { c = a.a_idx[i * a.k + lane]; w = a.a_w[i * a.k + lane]; if (c == (uint32_t)i) c = SFB_IDX_NONE; }
+        else if (lane < l) { c = a.rev_src[ro + (lane - fc)]; w = a.rev_w[ro + (lane - fc)]; }
+        unsigned long long key = ((unsigned long long)c << 32) | lane;
+#pragma unroll
+        for (uint32_t size = 2; size <= 32; size <<= 1)
+#pragma unroll
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(FULL, key, stride);
+                const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+                key = take_min ? (other < key ? other : key) : (other > key ? other : key);
+            }
+        const uint32_t col = (uint32_t)(key >> 32);
+        const double ws = __shfl_sync(FULL, w, (int)(key & 31u));
+        const uint32_t col_prev = __shfl_up_sync(FULL, col, 1), col_prev2 = __shfl_up_sync(FULL, col, 2), col_next = __shfl_down_sync(FULL, col, 1);
+        const double w_next = __shfl_down_sync(FULL, ws, 1);
+        const bool valid = col != SFB_IDX_NONE;
+        // a column normally occurs at most twice (once forward, once reverse); lists from the host may repeat one more often
+        if (__any_sync(FULL, valid && lane >= 2 && col == col_prev && col == col_prev2)) in_regs = false;
+        else {
+            const bool head = valid && (lane == 0 || col != col_prev);
+            const double wh = (lane < 31 && col_next == col && w_next > ws) ? w_next : ws;   // duplicates -> max
+            const uint32_t hb = __ballot_sync(FULL, head);
+            const uint32_t pos = __popc(hb & ((1u << lane) - 1u));
+            u = __popc(hb);
+            if (head) { a.tmp_col[to + pos] = col; a.tmp_w[to + pos] = wh; sw[pos] = wh; }
+            __syncwarp();
+        }
     }
-    bitonic_sort_pairs<BLOCK>(scol, sw, P, tid, nt);
-    // heads of runs of equal column; sorted (col asc, w desc) => the head carries the max weight
-    const uint64_t to = tmp_off[i];
-    uint32_t base = 0;
-    if (BLOCK) { if (tid == 0) s_count = 0; __syncthreads(); }
-    for (uint32_t t0 = 0; t0 < P; t0 += nt) {
-        uint32_t t = t0 + tid;
-        bool head = t < P && scol[t] != SFB_IDX_NONE && (t == 0 || scol[t] != scol[t - 1]);
-        uint32_t b = __ballot_sync(FULL, head);
-        uint32_t pos;
-        if (BLOCK) {
-            // per-warp slots reserved in order: warps of the block handle ascending t ranges, so a
-            // block-wide ordered scan is needed; do it with one shared counter per 32-chunk serially
-            __shared__ uint32_t warp_base[32];
-            if ((tid & 31) == 0) warp_base[tid >> 5] = __popc(b);
-            __syncthreads();
-            uint32_t pre = 0;
-            for (uint32_t wv = 0; wv < (tid >> 5); ++wv) pre += warp_base[wv];
-            uint32_t tot = 0;
-            for (uint32_t wv = 0; wv < (nt >> 5); ++wv) tot += warp_base[wv];
-            pos = s_count + pre + __popc(b & ((1u << (tid & 31)) - 1u));
+    if (!in_regs) {
+        uint32_t P = 2; while (P < l) P <<= 1;
+        for (uint32_t t = lane; t < P; t += 32) {
+            uint32_t c = SFB_IDX_NONE; double w = 0.0;
+            if (t < fc) { c = a.a_idx[i * a.k + t]; w = a.a_w[i * a.k + t]; if (c == (uint32_t)i) c = SFB_IDX_NONE; }
+            else if (t < l) { c = a.rev_src[ro + (t - fc)]; w = a.rev_w[ro + (t - fc)]; }
+            scol[t] = c; sw[t] = w;
+        }
+        bitonic_sort_pairs<false>(scol, sw, P, lane, 32);
+        // heads of runs of equal column; sorted (col asc, w desc) => the head carries the max weight
+        uint32_t base = 0;
+        for (uint32_t t0 = 0; t0 < P; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            uint32_t c = SFB_IDX_NONE; double w = 0.0; bool head = false;
+            if (t < P) { c = scol[t]; w = sw[t]; head = c != SFB_IDX_NONE && (t == 0 || c != scol[t - 1]); }
+            const uint32_t b = __ballot_sync(FULL, head);
+            const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+            __syncwarp();
+            if (head) { a.tmp_col[to + pos] = c; a.tmp_w[to + pos] = w; sw[pos] = w; }   // compacted in place for the fold below (pos <= t)
+            __syncwarp();
+            base += __popc(b);
+        }
+        u = base;
+    }
+    // degree: left fold over the unique neighbours in ascending column order (laplacian.rs:371)
+    if (lane == 0) {
+        double s = 0.0;
+        for (uint32_t t = 0; t < u; ++t) s = __dadd_rn(s, sw[t]);
+        a.ulen[li] = u; a.deg[li] = s;
+        if (a.row_nnz) a.row_nnz[li] = u + 1;
+    }
+}
+
+// Pass A for the long rows (hubs: in-degree is unbounded).  One block per listed row, any length: the entries are
+// gathered into the row's scratch segment in global memory, sorted there by an ascending-only bitonic network (first
+// step of every merge mirrored, so a padding element -- virtual index >= len, key +inf -- never has to move below a real
+// one and the network works on lengths that are not powers of two), then de-duplicated and folded in place.  Rows
+// that fit shared memory (<= SMEM_CAP) are sorted there instead.
+template <uint32_t SMEM_CAP>
+__global__ void __launch_bounds__(1024) lap_merge_long_kernel(MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sw = reinterpret_cast<double*>(smem_raw);
+    uint32_t* scol = reinterpret_cast<uint32_t*>(sw + SMEM_CAP);
+    __shared__ uint32_t s_count, s_warp[32];
+    __shared__ double s_deg;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x, n_long = *a.n_long;
+    for (uint32_t item = blockIdx.x; item < n_long; item += gridDim.x) {
+        const uint64_t li = a.long_list[item], i = a.r_begin + li;
+        const uint32_t fc = a.a_cnt[i];
+        const uint64_t ro = a.rev_off[li];
+        const uint32_t rl = (uint32_t)(a.rev_off[li + 1] - ro), l = fc + rl;
+        const uint64_t to = li * a.k + ro;
+        uint32_t* gcol = a.tmp_col + to; double* gw = a.tmp_w + to;
+        const bool in_smem = l <= SMEM_CAP;
+        uint32_t* col = in_smem ? scol : gcol; double* wv = in_smem ? sw : gw;
+        uint32_t P = 2; while (P < l) P <<= 1;
+        for (uint32_t t = tid; t < (in_smem ? P : l); t += nt) {
+            uint32_t c = SFB_IDX_NONE; double w = 0.0;
+            if (t < fc) { c = a.a_idx[i * a.k + t]; w = a.a_w[i * a.k + t]; if (c == (uint32_t)i) c = SFB_IDX_NONE; }
+            else if (t < l) { c = a.rev_src[ro + (t - fc)]; w = a.rev_w[ro + (t - fc)]; }
+            col[t] = c; wv[t] = w;
+        }
+        __syncthreads();
+        // ascending-only bitonic network over P virtual slots; slots >= len hold (+inf) and are never touched
+        const uint32_t len = in_smem ? P : l;
+        for (uint32_t size = 2; size <= P; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = tid; t < P / 2; t += nt) {
+                    uint32_t lo, hi;
+                    if (stride == size >> 1) { const uint32_t blk = t / stride, off = t % stride; lo = blk * size + off; hi = blk * size + size - 1 - off; }   // mirrored first step
+                    else { lo = 2 * t - (t & (stride - 1)); hi = lo + stride; }
+                    if (hi < len) {
+                        const uint32_t ca = col[lo], cb = col[hi];
+                        const double wa = wv[lo], wb = wv[hi];
+                        if (ca > cb || (ca == cb && wa < wb)) { col[lo] = cb; col[hi] = ca; wv[lo] = wb; wv[hi] = wa; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // heads of runs (col asc, w desc: the head carries the max weight), compacted in order, chunk by chunk
+        if (tid == 0) { s_count = 0; s_deg = 0.0; }
+        __syncthreads();
+        for (uint32_t t0 = 0; t0 < l; t0 += nt) {
+            const uint32_t t = t0 + tid;
+            uint32_t c = SFB_IDX_NONE; double w = 0.0; bool head = false;
+            if (t < l) { c = col[t]; w = wv[t]; head = c != SFB_IDX_NONE && (t == 0 || c != col[t - 1]); }
+            const uint32_t b = __ballot_sync(FULL, head);
+            if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(b);
+            __syncthreads();   // every read of this chunk is done: the compacted writes below land at or before it
+            uint32_t pre = 0, tot = 0;
+            for (uint32_t wq = 0; wq < (nt >> 5); ++wq) { const uint32_t v = s_warp[wq]; if (wq < (tid >> 5)) pre += v; tot += v; }
+            const uint32_t pos = s_count + pre + __popc(b & ((1u << (tid & 31)) - 1u));
+            if (head) { gcol[pos] = c; gw[pos] = w; }
             __syncthreads();
             if (tid == 0) s_count += tot;
             __syncthreads();
-        } else {
-            pos = base + __popc(b & ((1u << tid) - 1u));
-            base += __popc(b);
         }
-        if (head) { tmp_col[to + pos] = scol[t]; tmp_w[to + pos] = sw[t]; }
-    }
-    group_sync<BLOCK>();
-    const uint32_t u = BLOCK ? s_count : base;
-    if (tid == 0) {
-        // degree: left fold over the unique neighbours in ascending column order (laplacian.rs:371)
-        double s = 0.0;
-        uint32_t prev = SFB_IDX_NONE;
-        for (uint32_t t = 0; t < P; ++t) {
-            uint32_t c = scol[t];
-            if (c == SFB_IDX_NONE) break;
-            if (c != prev) s = __dadd_rn(s, sw[t]);
-            prev = c;
+        // degree: left fold in ascending column order, one thread (a hub's fold is as sequential as the reference's)
+        if (tid == 0) {
+            const uint32_t u = s_count;
+            double s = 0.0;
+            for (uint32_t t = 0; t < u; ++t) s = __dadd_rn(s, gw[t]);
+            a.ulen[li] = u; a.deg[li] = s;
+            if (a.row_nnz) a.row_nnz[li] = u + 1;
         }
-        ulen[i] = u; deg[i] = s;
+        __syncthreads();
     }
 }
 
-// rows longer than `warp_cap`: compact their indices
-__global__ void long_rows_kernel(const uint32_t* __restrict__ len, uint64_t m, uint32_t warp_cap, uint32_t* __restrict__ list,
-                                 uint32_t* __restrict__ n_list) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m && len[i] > warp_cap) list[atomicAdd(n_list, 1u)] = (uint32_t)i;
-}
-
-// Pass B: CSR row lengths.
+// Pass B (normalised form only): CSR row lengths after the |v| <= 1e-9 drop rule.
 __global__ void csr_row_nnz_kernel(const uint32_t* __restrict__ ulen, const double* __restrict__ deg,
-                                   const uint64_t* __restrict__ tmp_off, const uint32_t* __restrict__ tmp_col,
-                                   const double* __restrict__ tmp_w, uint64_t m, int normalised, double thr,
-                                   uint32_t* __restrict__ row_nnz) {
+                                   const uint64_t* __restrict__ rev_off, uint32_t k, const uint32_t* __restrict__ tmp_col,
+                                   const double* __restrict__ tmp_w, uint64_t m, double thr, uint32_t* __restrict__ row_nnz) {
     const int lane = threadIdx.x & 31;
     const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= m) return;
     const uint32_t u = ulen[i];
-    if (!normalised) { if (lane == 0) row_nnz[i] = u + 1; return; }
     const double di = deg[i];
     uint32_t n = 0;
     if (di > thr) {
-        const uint64_t to = tmp_off[i];
+        const uint64_t to = i * k + rev_off[i];
         for (uint32_t t0 = 0; t0 < u; t0 += 32) {
             uint32_t t = t0 + lane;
             bool ok = false;
@@ -288,56 +369,92 @@ __global__ void csr_row_nnz_kernel(const uint32_t* __restrict__ ulen, const doub
     if (lane == 0) row_nnz[i] = n;
 }
 
-// Pass C: emit CSR rows (one warp per row, any length), diagonal inserted in column order.
-__global__ void csr_emit_kernel(const uint32_t* __restrict__ ulen, const double* __restrict__ deg,
-                                const uint64_t* __restrict__ tmp_off, const uint32_t* __restrict__ tmp_col,
-                                const double* __restrict__ tmp_w, uint64_t m, int normalised, double thr,
-                                const uint64_t* __restrict__ indptr, uint32_t* __restrict__ indices, double* __restrict__ data) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= m) return;
-    const uint32_t u = ulen[i];
-    const double di = deg[i];
-    const uint64_t to = tmp_off[i];
-    const uint64_t o = indptr[i];
-    if (normalised && !(di > thr)) return;  // isolated node: empty row (surfface-core laplacian.rs:349-353)
-    const double diag_val = normalised ? 1.0 : di;
-    // phase 1: kept entries left of the diagonal
-    uint32_t n_left = 0;
-    for (uint32_t t0 = 0; t0 < u; t0 += 32) {
-        uint32_t t = t0 + lane;
-        bool left = false;
-        if (t < u) {
-            uint32_t c = tmp_col[to + t];
-            bool ok = true;
-            if (normalised) {
-                double dj = deg[c];
-                ok = dj > thr && fabs(__ddiv_rn(tmp_w[to + t], __dsqrt_rn(__dmul_rn(di, dj)))) > 1e-9;
+// Pass C: emit CSR rows.  A block takes a run of consecutive rows, assembles their entries (diagonal inserted in column
+// order) in shared memory and writes the run's contiguous slice of `indices` / `data` with 16-byte stores where the
+// slice is aligned, scalar stores at its ragged ends; runs whose slice does not fit are written row by row.
+// r_begin: global index of local row 0 (the diagonal's column).
+constexpr uint32_t EMIT_ROWS = 64, EMIT_CAP = 4032;
+__global__ void __launch_bounds__(256) csr_emit_kernel(const uint32_t* __restrict__ ulen, const double* __restrict__ deg,
+                                                       const uint64_t* __restrict__ rev_off, uint32_t k, const uint32_t* __restrict__ tmp_col,
+                                                       const double* __restrict__ tmp_w, uint64_t m, uint64_t r_begin, int normalised, double thr,
+                                                       const uint64_t* __restrict__ indptr, uint32_t* __restrict__ indices, double* __restrict__ data) {
+    __shared__ __align__(16) double s_val[EMIT_CAP];
+    __shared__ __align__(16) uint32_t s_col[EMIT_CAP];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint64_t row0 = (uint64_t)blockIdx.x * EMIT_ROWS;
+    if (row0 >= m) return;
+    const uint64_t row1 = row0 + EMIT_ROWS < m ? row0 + EMIT_ROWS : m;
+    const uint64_t o0 = indptr[row0], o1 = indptr[row1];
+    const bool staged = o1 - o0 <= EMIT_CAP;
+    for (uint64_t i = row0 + wid; i < row1; i += nw) {
+        const uint32_t u = ulen[i];
+        const double di = deg[i];
+        if (normalised && !(di > thr)) continue;  // isolated node: empty row (surfface-core laplacian.rs:349-353)
+        const uint64_t to = i * k + rev_off[i];
+        const uint64_t o = indptr[i];
+        const uint32_t gi = (uint32_t)(r_begin + i);
+        const double diag_val = normalised ? 1.0 : di;
+        uint32_t* oc = staged ? s_col + (o - o0) : indices + o;
+        double* ov = staged ? s_val + (o - o0) : data + o;
+        // phase 1: kept entries left of the diagonal
+        uint32_t n_left = 0;
+        for (uint32_t t0 = 0; t0 < u; t0 += 32) {
+            uint32_t t = t0 + lane;
+            bool left = false;
+            if (t < u) {
+                uint32_t c = tmp_col[to + t];
+                bool ok = true;
+                if (normalised) {
+                    double dj = deg[c];
+                    ok = dj > thr && fabs(__ddiv_rn(tmp_w[to + t], __dsqrt_rn(__dmul_rn(di, dj)))) > 1e-9;
+                }
+                left = ok && c < gi;
             }
-            left = ok && c < (uint32_t)i;
+            n_left += __popc(__ballot_sync(FULL, left));
         }
-        n_left += __popc(__ballot_sync(FULL, left));
+        if (lane == 0) { oc[n_left] = gi; ov[n_left] = diag_val; }
+        // phase 2: place the kept entries; those right of the diagonal shift by one
+        uint32_t done = 0;
+        for (uint32_t t0 = 0; t0 < u; t0 += 32) {
+            uint32_t t = t0 + lane;
+            uint32_t c = SFB_IDX_NONE; double v = 0.0; bool ok = false;
+            if (t < u) {
+                c = tmp_col[to + t];
+                if (!normalised) { v = -tmp_w[to + t]; ok = true; }
+                else {
+                    double dj = deg[c];
+                    if (dj > thr) { v = -__ddiv_rn(tmp_w[to + t], __dsqrt_rn(__dmul_rn(di, dj))); ok = fabs(v) > 1e-9; }
+                }
+            }
+            uint32_t okb = __ballot_sync(FULL, ok);
+            if (ok) {
+                uint32_t dst = done + __popc(okb & ((1u << lane) - 1u)) + (c > gi ? 1u : 0u);
+                oc[dst] = c; ov[dst] = v;
+            }
+            done += __popc(okb);
+        }
     }
-    if (lane == 0) { indices[o + n_left] = (uint32_t)i; data[o + n_left] = diag_val; }
-    // phase 2: place the kept entries; those right of the diagonal shift by one
-    uint32_t done = 0;
-    for (uint32_t t0 = 0; t0 < u; t0 += 32) {
-        uint32_t t = t0 + lane;
-        uint32_t c = SFB_IDX_NONE; double v = 0.0; bool ok = false;
-        if (t < u) {
-            c = tmp_col[to + t];
-            if (!normalised) { v = -tmp_w[to + t]; ok = true; }
-            else {
-                double dj = deg[c];
-                if (dj > thr) { v = -__ddiv_rn(tmp_w[to + t], __dsqrt_rn(__dmul_rn(di, dj))); ok = fabs(v) > 1e-9; }
-            }
-        }
-        uint32_t okb = __ballot_sync(FULL, ok);
-        if (ok) {
-            uint64_t dst = o + done + __popc(okb & ((1u << lane) - 1u)) + (c > (uint32_t)i ? 1u : 0u);
-            indices[dst] = c; data[dst] = v;
-        }
-        done += __popc(okb);
+    if (!staged) return;
+    __syncthreads();
+    // the run's slice [o0, o1): scalar head up to the next 16-byte boundary, vector body, scalar tail
+    const uint32_t n = (uint32_t)(o1 - o0);
+    {   // data (f64): 2 per vector
+        const uint32_t head = (uint32_t)((2 - (o0 & 1)) & 1) < n ? (uint32_t)((2 - (o0 & 1)) & 1) : n;
+        const uint32_t body = (n - head) / 2;
+        if (threadIdx.x < head) data[o0 + threadIdx.x] = s_val[threadIdx.x];
+        double2* dst = reinterpret_cast<double2*>(data + o0 + head);
+        for (uint32_t v = threadIdx.x; v < body; v += blockDim.x) dst[v] = make_double2(s_val[head + 2 * v], s_val[head + 2 * v + 1]);
+        for (uint32_t t = head + 2 * body + threadIdx.x; t < n; t += blockDim.x) data[o0 + t] = s_val[t];
+    }
+    {   // indices (u32): 4 per vector
+        const uint32_t mis = (uint32_t)(o0 & 3), h0 = (4 - mis) & 3;
+        const uint32_t head = h0 < n ? h0 : n;
+        const uint32_t body = (n - head) / 4;
+        if (threadIdx.x < head) indices[o0 + threadIdx.x] = s_col[threadIdx.x];
+        uint4* dst = reinterpret_cast<uint4*>(indices + o0 + head);
+        for (uint32_t v = threadIdx.x; v < body; v += blockDim.x)
+            dst[v] = make_uint4(s_col[head + 4 * v], s_col[head + 4 * v + 1], s_col[head + 4 * v + 2], s_col[head + 4 * v + 3]);
+        for (uint32_t t = head + 4 * body + threadIdx.x; t < n; t += blockDim.x) indices[o0 + t] = s_col[t];
     }
 }
 
@@ -440,113 +557,105 @@ extern "C" int32_t sfb_sparsify_sfgrass(sfb_ctx* ctx, sfb_adj* a, double ratio, 
     return SFB_OK;
 }
 
-extern "C" int32_t sfb_laplacian_build(sfb_ctx* ctx, const sfb_adj* a, const sfb_lap_params* prm, sfb_csr** out) {
-    if (!ctx || !a || !prm || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+// rows [r_begin, r_end) of the Laplacian of the graph in `a` (all of its lists are needed: the reverse edges of a row
+// live in other rows' lists).  One device pass, one host round trip (the exact nnz, to size the CSR arrays).
+static int32_t laplacian_build_rows(sfb_ctx* ctx, const sfb_adj* a, const sfb_lap_params* prm, uint64_t r_begin, uint64_t r_end, sfb_csr** out) {
     *out = nullptr;
-    const uint64_t m = a->rows; const uint32_t k = a->k;
+    const uint64_t m = a->rows, nr = r_end - r_begin; const uint32_t k = a->k;
     StageTimer timer(ctx, &ctx->times.ms_laplacian);
-    constexpr uint32_t WARP_CAP = 256, BLOCK_CAP = 8192;
+    constexpr uint32_t WARP_CAP = 256, BLOCK_SMEM_CAP = 8192;
 
-    DevBuf rev_cnt, fill, rev_off, len, tmp_off, max_len;
-    SFB_CUDA(ctx, rev_cnt.alloc(sizeof(uint32_t) * m));
-    SFB_CUDA(ctx, fill.alloc(sizeof(uint32_t) * m));
-    SFB_CUDA(ctx, rev_off.alloc(sizeof(uint64_t) * (m + 1)));
-    SFB_CUDA(ctx, len.alloc(sizeof(uint32_t) * m));
-    SFB_CUDA(ctx, tmp_off.alloc(sizeof(uint64_t) * (m + 1)));
-    SFB_CUDA(ctx, max_len.alloc(2 * sizeof(uint32_t)));
-    SFB_CUDA(ctx, cudaMemsetAsync(rev_cnt.p, 0, sizeof(uint32_t) * m, ctx->stream));
-    SFB_CUDA(ctx, cudaMemsetAsync(fill.p, 0, sizeof(uint32_t) * m, ctx->stream));
-    SFB_CUDA(ctx, cudaMemsetAsync(max_len.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    // buffers sized from the N * k bound: the build never waits for a count
+    DevBuf rev_cnt, rev_off, rev_src, rev_w, tmp_col, tmp_w, ulen, deg, row_nnz, long_list, n_long;
+    const uint64_t rev_cap = m * k;   // every directed edge lands in at most one owned bucket
+    SFB_CUDA(ctx, rev_cnt.alloc(sizeof(uint32_t) * nr));
+    SFB_CUDA(ctx, rev_off.alloc(sizeof(uint64_t) * (nr + 1)));
+    SFB_CUDA(ctx, rev_src.alloc(sizeof(uint32_t) * rev_cap));
+    SFB_CUDA(ctx, rev_w.alloc(sizeof(double) * rev_cap));
+    SFB_CUDA(ctx, tmp_col.alloc(sizeof(uint32_t) * (nr * k + rev_cap)));
+    SFB_CUDA(ctx, tmp_w.alloc(sizeof(double) * (nr * k + rev_cap)));
+    SFB_CUDA(ctx, ulen.alloc(sizeof(uint32_t) * nr));
+    SFB_CUDA(ctx, deg.alloc(sizeof(double) * (prm->normalised ? m : nr)));
+    SFB_CUDA(ctx, row_nnz.alloc(sizeof(uint32_t) * nr));
+    SFB_CUDA(ctx, long_list.alloc(sizeof(uint32_t) * nr));
+    SFB_CUDA(ctx, n_long.alloc(sizeof(uint32_t)));
+    SFB_CUDA(ctx, cudaMemsetAsync(rev_cnt.p, 0, sizeof(uint32_t) * nr, ctx->stream));
+    SFB_CUDA(ctx, cudaMemsetAsync(n_long.p, 0, sizeof(uint32_t), ctx->stream));
 
-    rev_count_kernel<<<div_up(m * k, 256), 256, 0, ctx->stream>>>(a->idx, a->cnt, m, k, rev_cnt.as<uint32_t>());
+    rev_count_kernel<<<div_up(m * k, 256), 256, 0, ctx->stream>>>(a->idx, a->cnt, m, k, r_begin, r_end, rev_cnt.as<uint32_t>());
     SFB_LAUNCH_CHECK(ctx);
-    SFB_TRY(sfb_scan_exclusive_u64(ctx, rev_cnt.as<uint32_t>(), m, rev_off.as<uint64_t>()));
-    uint64_t n_rev = 0;
-    SFB_CUDA(ctx, cudaMemcpyAsync(&n_rev, rev_off.as<uint64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-
-    DevBuf rev_src, rev_w;
-    SFB_CUDA(ctx, rev_src.alloc(sizeof(uint32_t) * n_rev));
-    SFB_CUDA(ctx, rev_w.alloc(sizeof(double) * n_rev));
-    rev_scatter_kernel<<<div_up(m * k, 256), 256, 0, ctx->stream>>>(a->idx, a->w, a->cnt, m, k, rev_off.as<uint64_t>(),
-                                                                    fill.as<uint32_t>(), rev_src.as<uint32_t>(), rev_w.as<double>());
+    SFB_TRY(sfb_scan_exclusive_u64(ctx, rev_cnt.as<uint32_t>(), nr, rev_off.as<uint64_t>()));
+    rev_scatter_kernel<<<div_up(m * k, 256), 256, 0, ctx->stream>>>(a->idx, a->w, a->cnt, m, k, r_begin, r_end, rev_off.as<uint64_t>(),
+                                                                    rev_cnt.as<uint32_t>(), rev_src.as<uint32_t>(), rev_w.as<double>());
     SFB_LAUNCH_CHECK(ctx);
-    row_len_kernel<<<div_up(m, 256), 256, 0, ctx->stream>>>(a->cnt, rev_cnt.as<uint32_t>(), m, len.as<uint32_t>(), max_len.as<uint32_t>());
-    SFB_LAUNCH_CHECK(ctx);
-    SFB_TRY(sfb_scan_exclusive_u64(ctx, len.as<uint32_t>(), m, tmp_off.as<uint64_t>()));
-    uint64_t n_tmp = 0; uint32_t h_max_len = 0;
-    SFB_CUDA(ctx, cudaMemcpyAsync(&n_tmp, tmp_off.as<uint64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SFB_CUDA(ctx, cudaMemcpyAsync(&h_max_len, max_len.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (h_max_len > BLOCK_CAP)
-        return sfb_fail(ctx, SFB_EUNSUPPORTED, "a node has %u incident directed edges; this build sorts rows of up to %u", h_max_len, BLOCK_CAP);
 
-    DevBuf tmp_col, tmp_w, ulen, deg, row_nnz;
-    SFB_CUDA(ctx, tmp_col.alloc(sizeof(uint32_t) * n_tmp));
-    SFB_CUDA(ctx, tmp_w.alloc(sizeof(double) * n_tmp));
-    SFB_CUDA(ctx, ulen.alloc(sizeof(uint32_t) * m));
-    SFB_CUDA(ctx, deg.alloc(sizeof(double) * m));
-    SFB_CUDA(ctx, row_nnz.alloc(sizeof(uint32_t) * m));
-
+    MergeArgs ma{a->idx, a->w, a->cnt, k, rev_off.as<uint64_t>(), rev_src.as<uint32_t>(), rev_w.as<double>(), r_begin, nr,
+                 tmp_col.as<uint32_t>(), tmp_w.as<double>(), ulen.as<uint32_t>(), deg.as<double>(),
+                 prm->normalised ? nullptr : row_nnz.as<uint32_t>(), long_list.as<uint32_t>(), n_long.as<uint32_t>()};
     {
         const int groups = 8;
-        size_t smem = (size_t)groups * WARP_CAP * (sizeof(double) + sizeof(uint32_t));
-        auto kern = lap_merge_rows_kernel<false, WARP_CAP>;
+        const size_t smem = (size_t)groups * WARP_CAP * (sizeof(double) + sizeof(uint32_t));
+        auto kern = lap_merge_rows_kernel<WARP_CAP>;
         SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<div_up(m, groups), groups * 32, smem, ctx->stream>>>(a->idx, a->w, a->cnt, k, rev_off.as<uint64_t>(), rev_src.as<uint32_t>(),
-                                                                    rev_w.as<double>(), len.as<uint32_t>(), tmp_off.as<uint64_t>(), m, nullptr, 0,
-                                                                    WARP_CAP, tmp_col.as<uint32_t>(), tmp_w.as<double>(), ulen.as<uint32_t>(), deg.as<double>());
+        kern<<<div_up(nr, groups), groups * 32, smem, ctx->stream>>>(ma);
         SFB_LAUNCH_CHECK(ctx);
     }
-    if (h_max_len > WARP_CAP) {
-        DevBuf list;
-        SFB_CUDA(ctx, list.alloc(sizeof(uint32_t) * m));
-        uint32_t* n_list_d = max_len.as<uint32_t>() + 1;
-        long_rows_kernel<<<div_up(m, 256), 256, 0, ctx->stream>>>(len.as<uint32_t>(), m, WARP_CAP, list.as<uint32_t>(), n_list_d);
-        SFB_LAUNCH_CHECK(ctx);
-        uint32_t n_list = 0;
-        SFB_CUDA(ctx, cudaMemcpyAsync(&n_list, n_list_d, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        size_t smem = (size_t)BLOCK_CAP * (sizeof(double) + sizeof(uint32_t));
-        auto kern = lap_merge_rows_kernel<true, BLOCK_CAP>;
+    {   // hub rows (in-degree is unbounded): the kernel reads the list length on the device and leaves at once when it is empty
+        const size_t smem = (size_t)BLOCK_SMEM_CAP * (sizeof(double) + sizeof(uint32_t));
+        auto kern = lap_merge_long_kernel<BLOCK_SMEM_CAP>;
         SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<n_list, 256, smem, ctx->stream>>>(a->idx, a->w, a->cnt, k, rev_off.as<uint64_t>(), rev_src.as<uint32_t>(), rev_w.as<double>(),
-                                                 len.as<uint32_t>(), tmp_off.as<uint64_t>(), m, list.as<uint32_t>(), n_list, WARP_CAP,
-                                                 tmp_col.as<uint32_t>(), tmp_w.as<double>(), ulen.as<uint32_t>(), deg.as<double>());
+        kern<<<2 * ctx->sm_count, 1024, smem, ctx->stream>>>(ma);
         SFB_LAUNCH_CHECK(ctx);
-        SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    csr_row_nnz_kernel<<<div_up(m * 32, 256), 256, 0, ctx->stream>>>(ulen.as<uint32_t>(), deg.as<double>(), tmp_off.as<uint64_t>(),
-                                                                     tmp_col.as<uint32_t>(), tmp_w.as<double>(), m, prm->normalised,
-                                                                     prm->weight_threshold, row_nnz.as<uint32_t>());
-    SFB_LAUNCH_CHECK(ctx);
+    if (prm->normalised) {   // needs the degree of every neighbour: full range only (checked by the caller)
+        csr_row_nnz_kernel<<<div_up(nr * 32, 256), 256, 0, ctx->stream>>>(ulen.as<uint32_t>(), deg.as<double>(), rev_off.as<uint64_t>(), k,
+                                                                         tmp_col.as<uint32_t>(), tmp_w.as<double>(), nr, prm->weight_threshold, row_nnz.as<uint32_t>());
+        SFB_LAUNCH_CHECK(ctx);
+    }
 
     sfb_csr* L = new (std::nothrow) sfb_csr();
     if (!L) return SFB_ENOMEM;
-    L->ctx = ctx; L->rows = m;
-    L->symmetric = 1;   // union / max symmetrisation, L_ij and L_ji are the same expression of (w, d_i, d_j): symmetric bit for bit
-    if (sfb_dev_alloc(ctx, (void**)&L->indptr, sizeof(uint64_t) * (m + 1)) != cudaSuccess) { sfb_csr_free(L); return sfb_fail(ctx, SFB_ENOMEM, "indptr"); }
-    int32_t st = sfb_scan_exclusive_u64(ctx, row_nnz.as<uint32_t>(), m, L->indptr);
+    L->ctx = ctx; L->rows = nr; L->row0 = r_begin; L->cols = m;
+    L->symmetric = nr == m ? 1 : 0;   // union / max symmetrisation, L_ij and L_ji are the same expression of (w, d_i, d_j): symmetric bit for bit
+    if (sfb_dev_alloc(ctx, (void**)&L->indptr, sizeof(uint64_t) * (nr + 1)) != cudaSuccess) { sfb_csr_free(L); return sfb_fail(ctx, SFB_ENOMEM, "indptr"); }
+    int32_t st = sfb_scan_exclusive_u64(ctx, row_nnz.as<uint32_t>(), nr, L->indptr);
     if (st != SFB_OK) { sfb_csr_free(L); return st; }
-    cudaMemcpyAsync(&L->nnz, L->indptr + m, 8, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(&L->nnz, L->indptr + nr, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the one host round trip: the exact nnz sizes the CSR arrays
+    if (e != cudaSuccess) { sfb_csr_free(L); return sfb_fail(ctx, SFB_ECUDA, "Laplacian assembly: %s", cudaGetErrorString(e)); }
     if (sfb_dev_alloc(ctx, (void**)&L->indices, sizeof(uint32_t) * (L->nnz ? L->nnz : 1)) != cudaSuccess ||
         sfb_dev_alloc(ctx, (void**)&L->data, sizeof(double) * (L->nnz ? L->nnz : 1)) != cudaSuccess) {
         sfb_csr_free(L);
         return sfb_fail(ctx, SFB_ENOMEM, "CSR arrays (%llu nnz)", (unsigned long long)L->nnz);
     }
-    csr_emit_kernel<<<div_up(m * 32, 256), 256, 0, ctx->stream>>>(ulen.as<uint32_t>(), deg.as<double>(), tmp_off.as<uint64_t>(),
-                                                                  tmp_col.as<uint32_t>(), tmp_w.as<double>(), m, prm->normalised,
-                                                                  prm->weight_threshold, L->indptr, L->indices, L->data);
+    csr_emit_kernel<<<div_up(nr, EMIT_ROWS), 256, 0, ctx->stream>>>(ulen.as<uint32_t>(), deg.as<double>(), rev_off.as<uint64_t>(), k,
+                                                                     tmp_col.as<uint32_t>(), tmp_w.as<double>(), nr, r_begin, prm->normalised,
+                                                                     prm->weight_threshold, L->indptr, L->indices, L->data);
     ctx->times.kernel_launches++;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    timer.stop();   // synchronises: the scratch may go back to the cache
+    e = cudaGetLastError();
     if (e != cudaSuccess) { sfb_csr_free(L); return sfb_fail(ctx, SFB_ECUDA, "CSR emit: %s", cudaGetErrorString(e)); }
     *out = L;
     return SFB_OK;
 }
 
+extern "C" int32_t sfb_laplacian_build(sfb_ctx* ctx, const sfb_adj* a, const sfb_lap_params* prm, sfb_csr** out) {
+    if (!ctx || !a || !prm || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    return laplacian_build_rows(ctx, a, prm, 0, a->rows, out);
+}
+
+extern "C" int32_t sfb_laplacian_build_rows(sfb_ctx* ctx, const sfb_adj* a, const sfb_lap_params* prm, uint64_t row_begin, uint64_t row_end,
+                                            sfb_csr** out) {
+    if (!ctx || !a || !prm || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (row_begin >= row_end || row_end > a->rows) return sfb_fail(ctx, SFB_EINVAL, "bad row range [%llu, %llu) of %llu", (unsigned long long)row_begin, (unsigned long long)row_end, (unsigned long long)a->rows);
+    if (prm->normalised && (row_begin != 0 || row_end != a->rows))
+        return sfb_fail(ctx, SFB_EUNSUPPORTED, "the normalised form needs the degree of every neighbour: build all rows");
+    return laplacian_build_rows(ctx, a, prm, row_begin, row_end, out);
+}
+
 extern "C" int32_t sfb_spmv(sfb_ctx* ctx, const sfb_csr* L, const double* x, double* y) {
     if (!ctx || !L || !x || !y) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (L->cols && L->cols != L->rows) return sfb_fail(ctx, SFB_EINVAL, "a row shard of a Laplacian is not a square operator");
     DevBuf dx, dy;
     SFB_CUDA(ctx, dx.alloc(sizeof(double) * L->rows));
     SFB_CUDA(ctx, dy.alloc(sizeof(double) * L->rows));
@@ -560,6 +669,7 @@ extern "C" int32_t sfb_spmv(sfb_ctx* ctx, const sfb_csr* L, const double* x, dou
 
 extern "C" int32_t sfb_rayleigh_quotient(sfb_ctx* ctx, const sfb_csr* L, const double* x, double* out) {
     if (!ctx || !L || !x || !out) return sfb_fail(ctx, SFB_EINVAL, "null argument");
+    if (L->cols && L->cols != L->rows) return sfb_fail(ctx, SFB_EINVAL, "a row shard of a Laplacian is not a square operator");
     const int nb = 64;
     DevBuf dx, dy, part;
     SFB_CUDA(ctx, dx.alloc(sizeof(double) * L->rows));

@@ -62,6 +62,7 @@ extern "C" {
     pub fn sfb_adj_from_host(ctx: *mut sfb_ctx, idx: *const u32, w: *const f64, cnt: *const u32, rows: u64, k: u32, out: *mut *mut sfb_adj) -> i32;
     pub fn sfb_adj_free(adj: *mut sfb_adj);
     pub fn sfb_laplacian_build(ctx: *mut sfb_ctx, adj: *const sfb_adj, params: *const sfb_lap_params, out: *mut *mut sfb_csr) -> i32;
+    pub fn sfb_laplacian_build_rows(ctx: *mut sfb_ctx, adj: *const sfb_adj, params: *const sfb_lap_params, row_begin: u64, row_end: u64, out: *mut *mut sfb_csr) -> i32;
     pub fn sfb_csr_shape(L: *const sfb_csr, rows: *mut u64, nnz: *mut u64) -> i32;
     pub fn sfb_csr_copy(ctx: *mut sfb_ctx, L: *const sfb_csr, indptr: *mut u64, indices: *mut u32, data: *mut f64) -> i32;
     pub fn sfb_csr_from_host(ctx: *mut sfb_ctx, rows: u64, indptr: *const u64, indices: *const u32, data: *const f64, out: *mut *mut sfb_csr) -> i32;

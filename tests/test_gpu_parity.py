@@ -216,6 +216,45 @@ def test_laplacian_hub_rows(sfb, oracle, ctx):
     assert_csr_equal(a.laplacian().to_host(), oracle.laplacian(idx, w, cnt), data_exact=True)
 
 
+def test_laplacian_hub_beyond_shared_memory(sfb, oracle, ctx):
+    """A star: 20 000 nodes all point at node 0 (plus a second hub of 9 000), so two rows have more incident edges than
+    the 8192 a block sorts in shared memory: they are sorted in global memory.  The reference has no such limit."""
+    m, k = 20001, 3
+    rng = np.random.default_rng(9)
+    idx = np.full((m, k), 0xFFFFFFFF, np.uint32); w = np.zeros((m, k)); cnt = np.zeros(m, np.uint32)
+    for i in range(1, m):
+        nb = [0] + ([7] if i % 2 == 0 and i < 18000 and i != 7 else []) + [int(rng.integers(1, m))]
+        nb = [j for t, j in enumerate(nb) if j != i and j not in nb[:t]]
+        idx[i, :len(nb)] = nb; w[i, :len(nb)] = rng.uniform(0.1, 1.0, len(nb)); cnt[i] = len(nb)
+    idx[0, :2] = [5, 7]; w[0, :2] = [0.9, 0.3]; cnt[0] = 2      # duplicates of reverse edges: max of the two weights
+    L = sfb.Adjacency.from_host(ctx, idx, w, cnt).laplacian()
+    want = oracle.laplacian(idx, w, cnt)
+    assert_csr_equal(L.to_host(), want, data_exact=True)
+    assert np.diff(want[0].astype(np.int64)).max() > 8192
+
+
+@pytest.mark.parametrize("m,kd,k", [(3000, 12, 16), (777, 5, 40)])
+def test_laplacian_row_shards_concatenate_to_the_full_matrix(sfb, oracle, ctx, m, kd, k):
+    """sfb_laplacian_build_rows: the rows a rank owns, from the all-gathered lists."""
+    x = np.random.default_rng(m).normal(size=(m, kd))
+    a = ctx.matrix(x).knn(k, sfb.METRIC_L2SQ, screen=sfb.SCREEN_EXACT_F64).adjacency(2.0, 1.0)
+    full = a.laplacian().to_host()
+    cuts = [0, m // 3 + 1, m // 3 + 2, m - 5, m]
+    ptr, ind, dat = [np.zeros(1, np.uint64)], [], []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        sh = a.laplacian(rows=(lo, hi))
+        assert sh.shape[0] == hi - lo
+        p, i, d = sh.to_host()
+        ptr.append(p[1:] + ptr[-1][-1]); ind.append(i); dat.append(d)
+        with pytest.raises(sfb.SfbError):   # a shard is not a square operator
+            sh.spmv(np.ones(hi - lo))
+    assert np.array_equal(np.concatenate(ptr), full[0]) and np.array_equal(np.concatenate(ind), full[1]) and np.array_equal(np.concatenate(dat), full[2])
+    with pytest.raises(sfb.SfbError):
+        a.laplacian(rows=(5, 5))
+    with pytest.raises(sfb.SfbError):
+        a.laplacian(normalised=True, rows=(0, 10))
+
+
 def test_laplacian_asymmetric_weights_take_max(sfb, oracle, ctx):
     idx = np.array([[1, 2], [0, 2], [0, 0xFFFFFFFF]], np.uint32)
     w = np.array([[0.5, 0.25], [0.75, 0.125], [0.3, 0.0]])
