@@ -345,6 +345,15 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
             gm &= gm - 1;
             const uint32_t jb = col0 + 4u * (uint32_t)q;
             float k0, k1, k2, k3;
+#ifdef SFB_SELECT_BRANCHLESS
+            k0 = key[28]; k1 = key[29]; k2 = key[30]; k3 = key[31];
+#pragma unroll
+            for (int qq = 6; qq >= 0; --qq) {
+                const bool sel = q == qq;
+                k0 = sel ? key[4 * qq] : k0; k1 = sel ? key[4 * qq + 1] : k1; k2 = sel ? key[4 * qq + 2] : k2; k3 = sel ? key[4 * qq + 3] : k3;
+            }
+            if (false)
+#endif
             switch (q) {
                 case 0: k0 = key[0]; k1 = key[1]; k2 = key[2]; k3 = key[3]; break;
                 case 1: k0 = key[4]; k1 = key[5]; k2 = key[6]; k3 = key[7]; break;
