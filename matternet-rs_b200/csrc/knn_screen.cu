@@ -345,6 +345,15 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
             gm &= gm - 1;
             const uint32_t jb = col0 + 4u * (uint32_t)q;
             float k0, k1, k2, k3;
+#ifdef SFB_SELECT_BRANCHLESS
+            k0 = key[28]; k1 = key[29]; k2 = key[30]; k3 = key[31];
+#pragma unroll
+            for (int qq = 6; qq >= 0; --qq) {
+                const bool sel = q == qq;
+                k0 = sel ? key[4 * qq] : k0; k1 = sel ? key[4 * qq + 1] : k1; k2 = sel ? key[4 * qq + 2] : k2; k3 = sel ? key[4 * qq + 3] : k3;
+            }
+            if (false)
+#endif
             switch (q) {
                 case 0: k0 = key[0]; k1 = key[1]; k2 = key[2]; k3 = key[3]; break;
                 case 1: k0 = key[4]; k1 = key[5]; k2 = key[6]; k3 = key[7]; break;
@@ -378,6 +387,90 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const floa
 #ifdef SFB_SCREEN_PROFILE
     if (prof) { atomicAdd(&g_screen_dbg[0], (unsigned long long)(clock64() - t_in)); atomicAdd(&g_screen_dbg[1], 1ull); }
 #endif
+}
+
+// ---- eight epilogue warps on one set of row buffers (experiment) ------------------------------------------------
+// Warps w and w + 4 read the same 32 TMEM lanes (same query rows), four 32-column chunks each.  A row's count and
+// threshold live in shared memory; slots are reserved with atomicAdd; after every chunk the pair meets at a named
+// barrier that also ORs "some row is within 64 slots of its capacity": only then the rows to prune are agreed on
+// (from counts that no longer move), split between the two warps, pruned, and written back between two more barriers.
+__device__ __forceinline__ bool pair_bar_or(int id, bool q) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %2, 0;\n\tbarrier.cta.red.or.pred p, %1, 64, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"(id), "r"((uint32_t)q) : "memory");
+    return r != 0;
+}
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("barrier.cta.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <bool L2>
+__device__ __forceinline__ void filter_chunk_shared(const uint32_t (&v)[32], const float* __restrict__ nqv, uint32_t col0, uint64_t n_rows,
+                                                    bool row_valid, uint2* my_buf, uint32_t* s_cnt_row, float* s_thr_row,
+                                                    uint32_t cap, uint32_t kprime, int lane, int group, int bar_id) {
+    float key[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        key[c] = __uint_as_float(v[c]);
+        if (L2) key[c] = fmaf(2.0f, key[c], -nqv[c]);
+    }
+    float g[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmax3(key[4 * q], key[4 * q + 1], key[4 * q + 2]), key[4 * q + 3]);
+    const float m = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
+    const float thr = *s_thr_row;
+    const bool hit = m > thr;
+    if (__any_sync(FULL, hit)) {
+        if (hit && row_valid) {
+            const uint32_t n_rows32 = (uint32_t)n_rows;
+            uint32_t gm = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gm |= (g[q] > thr ? 1u : 0u) << q;
+            do {
+                const int q = __ffs(gm) - 1;
+                gm &= gm - 1;
+                const uint32_t jb = col0 + 4u * (uint32_t)q;
+                float k0, k1, k2, k3;
+                switch (q) {
+                    case 0: k0 = key[0]; k1 = key[1]; k2 = key[2]; k3 = key[3]; break;
+                    case 1: k0 = key[4]; k1 = key[5]; k2 = key[6]; k3 = key[7]; break;
+                    case 2: k0 = key[8]; k1 = key[9]; k2 = key[10]; k3 = key[11]; break;
+                    case 3: k0 = key[12]; k1 = key[13]; k2 = key[14]; k3 = key[15]; break;
+                    case 4: k0 = key[16]; k1 = key[17]; k2 = key[18]; k3 = key[19]; break;
+                    case 5: k0 = key[20]; k1 = key[21]; k2 = key[22]; k3 = key[23]; break;
+                    case 6: k0 = key[24]; k1 = key[25]; k2 = key[26]; k3 = key[27]; break;
+                    default: k0 = key[28]; k1 = key[29]; k2 = key[30]; k3 = key[31]; break;
+                }
+                const bool h0 = k0 > thr && jb < n_rows32, h1 = k1 > thr && jb + 1 < n_rows32;
+                const bool h2 = k2 > thr && jb + 2 < n_rows32, h3 = k3 > thr && jb + 3 < n_rows32;
+                const uint32_t nh = (uint32_t)h0 + (uint32_t)h1 + (uint32_t)h2 + (uint32_t)h3;
+                if (nh) {
+                    uint32_t pos = atomicAdd(s_cnt_row, nh);   // both warps of the pair append to this row
+                    if (h0) __stcg(my_buf + pos++, make_uint2(__float_as_uint(k0), jb));
+                    if (h1) __stcg(my_buf + pos++, make_uint2(__float_as_uint(k1), jb + 1));
+                    if (h2) __stcg(my_buf + pos++, make_uint2(__float_as_uint(k2), jb + 2));
+                    if (h3) __stcg(my_buf + pos++, make_uint2(__float_as_uint(k3), jb + 3));
+                }
+            } while (gm);
+        }
+    }
+    __syncwarp();
+    // every chunk: meet the partner warp; the later of the two reads of a row's count sees both warps' appends
+    const bool near_full = *s_cnt_row + 64 > cap;
+    if (pair_bar_or(bar_id, near_full)) {
+        // counts are frozen now (nobody appends before the last barrier below)
+        uint32_t cnt = *s_cnt_row;
+        float thr2 = *s_thr_row;
+        const uint32_t need = __ballot_sync(FULL, cnt + 64 > cap);
+        uint32_t mine = 0, nm = need;
+        int turn = 0;
+        while (nm) { const int L = __ffs(nm) - 1; nm &= nm - 1; if ((turn++ & 1) == group) mine |= 1u << L; }
+        if (mine) {
+            if (cap <= 128) prune_rows<4>(mine, my_buf, cnt, thr2, kprime, lane);
+            else prune_rows<8>(mine, my_buf, cnt, thr2, kprime, lane);
+        }
+        pair_bar(bar_id);   // the partner has read the old counts
+        if ((mine >> lane) & 1u) { *s_cnt_row = cnt; *s_thr_row = thr2; }
+        pair_bar(bar_id);   // new counts / thresholds visible to both
+    }
 }
 
 template <bool L2, bool DUMP>
@@ -533,8 +626,9 @@ struct Screen2Args {
 
 constexpr int P_BM = 128, P_BNH = 128, P_SLAB_BYTES = 128 * BK * 2;  // 16 KB: one k-block of 128 rows
 
-template <bool L2>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SCREEN_THREADS, 1)
+constexpr int SCREEN_THREADS8 = 320;  // + warps 6-9: the second epilogue group
+template <bool L2, bool EW8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EW8 ? SCREEN_THREADS8 : SCREEN_THREADS, 1)
 knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmA, Screen2Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // carve: A slabs [kblocks] | B stages [stages] | barriers | tmem ptr | nq tiles (L2)
@@ -548,6 +642,8 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
     uint64_t* aempty_bar = afull_bar + 1;    // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty_bar + 1);
     float* s_nq = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][BN]
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_nq + 2 * BN);   // [128] (EW8)
+    float* s_thr = reinterpret_cast<float*>(s_cnt + 128);              // [128] (EW8)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -559,7 +655,7 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         for (uint32_t s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }  // 4 epilogue warps x 2 CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW8 ? 16 : 8); }  // epilogue warps x 2 CTAs
         mbar_init(afull_bar, 1); mbar_init(aempty_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 1) {
@@ -641,6 +737,76 @@ knn_screen_pair_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
                 }
                 umma_commit_pair(aempty_bar);   // A may be overwritten once every MMA of this item has retired
             }
+        }
+    } else if (EW8) {
+        // ===== epilogue, two warps per 32 query rows: group 0 takes columns 0-127 of a tile, group 1 columns 128-255 =====
+        const int quarter = warp & 3, group = (warp - 2) >> 2, bar_id = 2 + quarter;
+        const int row_in_tile = quarter * 32 + lane;
+        const int etid = threadIdx.x - 64;
+        const uint32_t l_tempty0 = mapa_u32(&tempty_bar[0], 0), l_tempty1 = mapa_u32(&tempty_bar[1], 0);
+        uint32_t tc = 0;
+        SFB_FOR_EACH_ITEM {
+            SFB_ITEM_RANGE
+            const uint64_t row_local = (uint64_t)mb2 * 256 + rank * P_BM + row_in_tile;
+            const bool row_valid = row_local < a.nq;
+            const size_t slot = (size_t)(row_valid ? row_local : 0) * a.n_splits + split;
+            uint2* my_buf = a.buf + slot * a.cap;
+            if (group == 0) {
+                uint32_t c0 = 0; float t0 = -INFINITY;
+                if (chunk != 0 && row_valid) { c0 = a.out_cnt[slot]; t0 = a.out_thr[slot]; }
+                if (a.dbg == 3) t0 = INFINITY;
+                s_cnt[row_in_tile] = c0; s_thr[row_in_tile] = t0;
+            }
+            pair_bar(bar_id);
+            for (uint32_t t = t_lo; t < t_hi; ++t, ++tc) {
+                const uint32_t as = tc & 1, aphase = (tc >> 1) & 1;
+                const uint32_t n0 = t * BN;
+                if (L2) {
+                    float* dst = s_nq + as * BN;
+                    for (int c = etid; c < BN; c += 256) dst[c] = (uint64_t)n0 + c < a.n_rows ? __ldg(a.nq32 + n0 + c) : INFINITY;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t half = (uint32_t)group * (BN / 2);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half;
+                const float* nqt = s_nq + as * BN + half;
+                uint32_t va[32], vb[32];
+                if (a.dbg == 0 || a.dbg >= 3) {
+                    tmem_ld32(taddr, va);
+#pragma unroll 1
+                    for (int ch = 0; ch < BN / 64; ch += 2) {
+                        tmem_ld_wait();
+                        tmem_ld32(taddr + (ch + 1) * 32, vb);
+                        filter_chunk_shared<L2>(va, nqt + ch * 32, n0 + half + ch * 32, a.n_rows, row_valid, my_buf, s_cnt + row_in_tile, s_thr + row_in_tile,
+                                                a.cap, a.kprime, lane, group, bar_id);
+                        tmem_ld_wait();
+                        if (ch + 2 < BN / 64) tmem_ld32(taddr + (ch + 2) * 32, va);
+                        filter_chunk_shared<L2>(vb, nqt + (ch + 1) * 32, n0 + half + (ch + 1) * 32, a.n_rows, row_valid, my_buf, s_cnt + row_in_tile,
+                                                s_thr + row_in_tile, a.cap, a.kprime, lane, group, bar_id);
+                    }
+                } else if (a.dbg == 1) {
+                    uint32_t acc = 0;
+#pragma unroll 1
+                    for (int ch = 0; ch < BN / 64; ++ch) {
+                        tmem_ld32(taddr + ch * 32, va);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc ^= va[c];
+                    }
+                    if (acc == 0x12345678u) s_thr[row_in_tile] = 0.0f;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(as ? l_tempty1 : l_tempty0);
+            }
+            pair_bar(bar_id);   // both warps are done with the item: the row state can be parked
+            if (group == 0 && row_valid) {
+                uint32_t c1 = s_cnt[row_in_tile]; float t1 = s_thr[row_in_tile];
+                if (a.dbg == 3) { c1 = 0; t1 = -INFINITY; }
+                a.out_cnt[slot] = c1; a.out_thr[slot] = t1;
+            }
+            pair_bar(bar_id);   // ... before group 0 re-initialises it for the next item
         }
     } else {
         // ===== epilogue: thread = query row =====
@@ -1079,6 +1245,12 @@ int32_t launch_screen(sfb_ctx* ctx, const Prepared& P, int metric, ScreenArgs& s
     return SFB_OK;
 }
 
+// SFB_SCREEN_EW8=1: the eight-warp epilogue on shared row buffers (experiment)
+static bool screen_ew8() {
+    static const bool on = [] { const char* e = getenv("SFB_SCREEN_EW8"); return e && e[0] == '1'; }();
+    return on;
+}
+
 int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2Args& sa, void* a_base, uint64_t a_rows) {
     CUtensorMap tm, tmA;
     SFB_TRY(make_tmap(ctx, &tm, P.q.p, P.mpad, P.kpad, P_BM, P.bf16));
@@ -1086,7 +1258,7 @@ int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2A
     // M = 256 across the pair, N = 256
     const uint32_t fmt = P.bf16 ? 1u : 0u;
     sa.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-    const size_t fixed = 1024 + 22 * 8 + 16 + 2 * BN * sizeof(float);
+    const size_t fixed = 1024 + 22 * 8 + 16 + 2 * BN * sizeof(float) + 1024;   // + row counts / thresholds of the 8-warp epilogue
     const size_t budget = ctx->smem_optin ? ctx->smem_optin : 232448;
     const size_t room = (budget - fixed) / P_SLAB_BYTES;   // 16 KB slabs that fit
     if (sa.kblocks + 5 <= room) {
@@ -1105,13 +1277,15 @@ int32_t launch_screen_pair(sfb_ctx* ctx, const Prepared& P, int metric, Screen2A
     const uint32_t n_slots = sa.n_mb2 * sa.n_splits;
     uint32_t pairs = (uint32_t)ctx->sm_count / 2;
     if (pairs > n_slots) pairs = n_slots;
-    if (metric == SFB_METRIC_COSINE) {
-        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_screen_pair_kernel<false><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, tmA, sa);
-    } else {
-        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_screen_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_screen_pair_kernel<true><<<2 * pairs, SCREEN_THREADS, smem, ctx->stream>>>(tm, tmA, sa);
-    }
+    const bool ew8 = screen_ew8();
+    auto launch = [&](auto kernel, int threads) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<2 * pairs, threads, smem, ctx->stream>>>(tm, tmA, sa);
+        return cudaSuccess;
+    };
+    if (metric == SFB_METRIC_COSINE) SFB_CUDA(ctx, ew8 ? launch(knn_screen_pair_kernel<false, true>, SCREEN_THREADS8) : launch(knn_screen_pair_kernel<false, false>, SCREEN_THREADS));
+    else SFB_CUDA(ctx, ew8 ? launch(knn_screen_pair_kernel<true, true>, SCREEN_THREADS8) : launch(knn_screen_pair_kernel<true, false>, SCREEN_THREADS));
     SFB_LAUNCH_CHECK(ctx);
     sfb_side_job_fire(ctx);   // a pending feature-graph Gram rides beside the resident screen CTAs
     return SFB_OK;
@@ -1139,7 +1313,7 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
     const bool cosine = p->metric == SFB_METRIC_COSINE;
     uint32_t slack = 64;   // appends a row's buffer takes between two prunes (minus the 32 a chunk may add)
     if (const char* e = getenv("SFB_SCREEN_SLACK")) { int v = atoi(e); if (v >= 64) slack = (uint32_t)v; }
-    uint32_t cap = (kprime + slack + 31) / 32 * 32;
+    uint32_t cap = (kprime + slack + (screen_ew8() ? 32u : 0u) + 31) / 32 * 32;   // the 8-warp epilogue reserves 64 slots per chunk round
     if (cap > MAX_CAP) cap = MAX_CAP;
     const uint32_t tiles_total = (uint32_t)(P.mpad / BN);
     const bool use_pair = pair_kernel_applies(P);
@@ -1253,7 +1427,7 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     // k' candidates survive per row and corpus split; the buffer has 64 slots of slack between prunes.
     // Measured at C2 (k = 16): k' = 96 / 64 / 48 / 32 / 24 take 814 / 717 / 689 / 662 / 645 ms of screen and leave
     // 0 / 0 / 0 / 9 / 3366 rows to the next level.
-    const uint32_t kp_max = MAX_CAP - 64;
+    const uint32_t kp_max = MAX_CAP - (screen_ew8() ? 96 : 64);
     uint32_t kprime = p->k_prime ? p->k_prime : (3 * p->k / 2 + 7) / 8 * 8;   // 1.5k (C5-like, k = 64: k' = 128 / 96 -> 980 / 895 ms), at least 32
     bool kp_forced = p->k_prime != 0;
     if (const char* e = getenv("SFB_SCREEN_KPRIME")) { int v = atoi(e); if (v > 0 && !p->k_prime) { kprime = (uint32_t)v; kp_forced = true; } }  // tuning aid
