@@ -122,8 +122,9 @@ extern "C" int32_t sfb_knn_build_columns_sharded(sfb_ctx* ctx, const sfb_mat* x,
 // the persistent screen kernel is enqueued, so its CTAs run beside the screen's; _end joins, all-reduces (sharded),
 // and selects.  If no screen runs before _end, the job simply runs there.
 int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uint32_t m, uint64_t kd, int metric, double* g,
-                        uint32_t t0, uint32_t t1, bool small_smem);
-void sfb_gram_tile_range(const sfb_ctx* ctx, uint32_t m, int collective, uint32_t* t0, uint32_t* t1);
+                        uint32_t gt, uint32_t t0, uint32_t t1, bool small_smem);
+uint32_t sfb_gram_tile_edge(const sfb_ctx* ctx, uint32_t m, int collective);
+void sfb_gram_tile_range(const sfb_ctx* ctx, uint32_t m, uint32_t gt, int collective, uint32_t* t0, uint32_t* t1);
 int32_t sfb_gram_finish(sfb_ctx* ctx, double* g, uint32_t m, int metric, uint32_t k, double eps, uint64_t q_begin, uint64_t nq,
                         uint32_t* out_idx, double* out_dist, uint32_t* out_cnt, int collective);
 
@@ -134,6 +135,7 @@ struct sfb_pending {
     int collective = 0;
     bool dense = false, launched = false;
     bool deferred = false;   // not worth hiding: _end runs the tiles stand-alone
+    uint32_t gt = 16;        // pair-tile edge (knn_exact.cu: sfb_gram_tile_edge)
     double* g = nullptr;   // 2 * m * m doubles
 };
 
@@ -144,11 +146,11 @@ void sfb_side_job_fire(sfb_ctx* ctx) {
     if (!ctx->side) return;   // _begin could not create the side stream: _end runs the job inline
     const uint32_t m = pd->x->cols;
     uint32_t t0, t1;
-    sfb_gram_tile_range(ctx, m, pd->collective, &t0, &t1);
+    sfb_gram_tile_range(ctx, m, pd->gt, pd->collective, &t0, &t1);
     // side_fork was recorded by _begin (after the matrix upload and the memset of g) -- NOT here: an event recorded
     // now would sit behind the screen kernel that was just enqueued
     cudaStreamWaitEvent(ctx->side, ctx->side_fork, 0);
-    if (sfb_gram_launch(ctx, ctx->side, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, t0, t1, true) != SFB_OK) return;
+    if (sfb_gram_launch(ctx, ctx->side, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, pd->gt, t0, t1, true) != SFB_OK) return;
     cudaEventRecord(ctx->side_done, ctx->side);
     pd->launched = true;
 }
@@ -175,7 +177,8 @@ extern "C" int32_t sfb_knn_build_columns_begin(sfb_ctx* ctx, const sfb_mat* x, c
         // gets one CTA per SM and ~45 ns per fold step; otherwise _end runs it stand-alone on every SM (C4, 3072
         // features x 100k items: 18.5k tiles would take 0.5 s co-resident against a 60 ms screen, 0.11 s alone).
         uint32_t t0, t1;
-        sfb_gram_tile_range(ctx, (uint32_t)nodes, pd->collective, &t0, &t1);
+        pd->gt = sfb_gram_tile_edge(ctx, (uint32_t)nodes, pd->collective);
+        sfb_gram_tile_range(ctx, (uint32_t)nodes, pd->gt, pd->collective, &t0, &t1);
         const double tiles_per_cta = ceil((double)(t1 - t0) / (double)ctx->sm_count);
         const double gram_s = tiles_per_cta * (double)dims * 45e-9;
         const double screen_s = 2.0 * (double)dims * (double)dims * (double)nodes / (double)(ctx->world > 0 ? ctx->world : 1) / 1.1e15;
@@ -201,8 +204,8 @@ extern "C" int32_t sfb_knn_build_columns_end(sfb_ctx* ctx, sfb_pending* pd, sfb_
         if (ctx->side_job == pd || pd->deferred) {   // no screen ran in between, or not worth hiding: run the Gram tiles now, on the main stream
             ctx->side_job = nullptr;
             uint32_t t0, t1;
-            sfb_gram_tile_range(ctx, m, pd->collective, &t0, &t1);
-            if (st == SFB_OK) st = sfb_gram_launch(ctx, ctx->stream, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, t0, t1, false);
+            sfb_gram_tile_range(ctx, m, pd->gt, pd->collective, &t0, &t1);
+            if (st == SFB_OK) st = sfb_gram_launch(ctx, ctx->stream, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, pd->gt, t0, t1, false);
         } else if (pd->launched) {
             cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0);
         } else if (st == SFB_OK) st = sfb_fail(ctx, SFB_ECUDA, "the side launch of the Gram tiles failed");

@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(THREADS) knn_exact_kernel(ExactArgs a) {
     }
     __syncthreads();
 
+    // a fallback call brings a handful of rows: thread groups whose four query rows are all padding skip the FP64 work
+    // (they still stage tiles and meet the barriers)
+    const bool rows_live = q0 + (uint64_t)ty * 4 < a.nq;
     const uint64_t n_tiles = (a.m + TC - 1) / TC;
     const uint64_t t_begin = (uint64_t)blockIdx.y * a.tiles_per_split;
     uint64_t t_end = t_begin + a.tiles_per_split;
@@ -100,6 +103,7 @@ __global__ void __launch_bounds__(THREADS) knn_exact_kernel(ExactArgs a) {
             }
             if (d0 == 0 && tid < TC) cn[tid] = (COS && c0 + tid < a.m) ? a.norms[c0 + tid] : 0.0;
             __syncthreads();
+            if (rows_live)
 #pragma unroll
             for (int d = 0; d < KC; ++d) {
                 double q[4], c[4];
@@ -217,8 +221,8 @@ __global__ void knn_merge_kernel(const uint32_t* __restrict__ pidx, const double
 // and writes the raw sums G[i][j] (= G[j][i]: products commute) for tiles on or above the diagonal.
 // The diagonal G[i][i] is the squared norm, the same left fold as row_norms_kernel.
 // FP64-pipe bound: m^2/2 * N multiply + add pairs; at m = 384 the 300 tiles fill 148 SMs.
-constexpr int GT = 16;   // pair tile edge; GCH (template) = dimensions per staged chunk: 64 standalone (32 KB of shared memory),
-                        // 16 when the kernel runs beside a resident screen CTA (8 KB fit next to its 216 of 227 KB)
+// GCH (template) = dimensions per staged chunk: 64 standalone (32 KB of shared memory), 16 when the kernel runs beside a
+// resident screen CTA (8 KB fit next to its 216 of 227 KB)
 
 __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, int bytes, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -227,11 +231,15 @@ __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc,
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 
-template <bool COS, int VEC, int GCH>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
+// GTILE: pair-tile edge.  16: thread = 2 x 2 pairs (four chains per thread).  8: thread = 1 pair -- four times as many,
+// shorter-lived CTAs; used when a rank's share of the tiles would otherwise leave most SMs without a chain (every chain
+// is N steps long whatever the tile count: with G ranks the 16-edge tiling gives each rank 300 / G CTAs of two warps).
+template <bool COS, int VEC, int GCH, int GTILE>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
 __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G, uint32_t tile0,
                                                        uint32_t n_tiles) {
-    __shared__ __align__(16) double sa[2][GCH][GT], sb[2][GCH][GT];
-    const uint32_t T = (m + GT - 1) / GT;
+    constexpr int R = GTILE / 8;
+    __shared__ __align__(16) double sa[2][GCH][GTILE], sb[2][GCH][GTILE];
+    const uint32_t T = (m + GTILE - 1) / GTILE;
     // a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: beside the screen kernel the grid is capped at one CTA per SM
     for (uint32_t tt = blockIdx.x; tt < n_tiles; tt += gridDim.x) {
     // decode the upper-triangular tile index
@@ -239,10 +247,10 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
     while (rem >= T - ti) { rem -= T - ti; ++ti; }
     const uint32_t tj = ti + rem;
     const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
-    const uint32_t ci = ti * GT, cj = tj * GT;
+    const uint32_t ci = ti * GTILE, cj = tj * GTILE;
 
     auto stage = [&](int buf, uint64_t n0) {
-        constexpr int PIECES = GT / VEC;            // pieces per 16-column strip row
+        constexpr int PIECES = GTILE / VEC;            // pieces per strip row
         for (int e = tid; e < GCH * PIECES; e += 64) {
             const int r = e / PIECES, pc = (e % PIECES) * VEC;
             const uint64_t n = n0 + r;
@@ -255,7 +263,11 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+    double acc[R][R];
+#pragma unroll
+    for (int di = 0; di < R; ++di)
+#pragma unroll
+        for (int dj = 0; dj < R; ++dj) acc[di][dj] = 0.0;
     const uint64_t n_chunks = (kd + GCH - 1) / GCH;
     stage(0, 0);
     for (uint64_t c = 0; c < n_chunks; ++c) {
@@ -267,27 +279,24 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
         const int lim = left < (uint64_t)GCH ? (int)left : GCH;
 #pragma unroll 8
         for (int n = 0; n < lim; ++n) {
-            const double2 a = *reinterpret_cast<const double2*>(&sa[buf][n][2 * ty]);
-            const double2 b = *reinterpret_cast<const double2*>(&sb[buf][n][2 * tx]);
-            if (COS) {
-                a00 = __dadd_rn(a00, __dmul_rn(a.x, b.x)); a01 = __dadd_rn(a01, __dmul_rn(a.x, b.y));
-                a10 = __dadd_rn(a10, __dmul_rn(a.y, b.x)); a11 = __dadd_rn(a11, __dmul_rn(a.y, b.y));
-            } else {
-                double t;
-                t = __dadd_rn(a.x, -b.x); a00 = __dadd_rn(a00, __dmul_rn(t, t));
-                t = __dadd_rn(a.x, -b.y); a01 = __dadd_rn(a01, __dmul_rn(t, t));
-                t = __dadd_rn(a.y, -b.x); a10 = __dadd_rn(a10, __dmul_rn(t, t));
-                t = __dadd_rn(a.y, -b.y); a11 = __dadd_rn(a11, __dmul_rn(t, t));
-            }
+            double av[R], bv[R];
+#pragma unroll
+            for (int d = 0; d < R; ++d) { av[d] = sa[buf][n][R * ty + d]; bv[d] = sb[buf][n][R * tx + d]; }
+#pragma unroll
+            for (int di = 0; di < R; ++di)
+#pragma unroll
+                for (int dj = 0; dj < R; ++dj) {
+                    if (COS) acc[di][dj] = __dadd_rn(acc[di][dj], __dmul_rn(av[di], bv[dj]));
+                    else { const double t = __dadd_rn(av[di], -bv[dj]); acc[di][dj] = __dadd_rn(acc[di][dj], __dmul_rn(t, t)); }
+                }
         }
         __syncthreads();
     }
-    const uint32_t i0 = ci + 2 * ty, j0 = cj + 2 * tx;
-    const double acc[2][2] = {{a00, a01}, {a10, a11}};
+    const uint32_t i0 = ci + R * ty, j0 = cj + R * tx;
 #pragma unroll
-    for (int di = 0; di < 2; ++di)
+    for (int di = 0; di < R; ++di)
 #pragma unroll
-        for (int dj = 0; dj < 2; ++dj) {
+        for (int dj = 0; dj < R; ++dj) {
             const uint32_t i = i0 + di, j = j0 + dj;
             if (i < m && j < m) { G[(uint64_t)i * m + j] = acc[di][dj]; G[(uint64_t)j * m + i] = acc[di][dj]; }
         }
@@ -372,31 +381,41 @@ bool sfb_dense_shape(uint64_t nodes, uint64_t dims) { return nodes <= 4096 && di
 // kNN over few nodes with very long rows, from the DIMS-MAJOR matrix xd[kd][m] (see gram_tile_kernel).
 int32_t sfb_comm_allreduce_sum_f64(sfb_ctx* ctx, double* buf, size_t n);
 
+// Pair-tile edge for this call: 16 (thread = 2 x 2 pairs), or 8 (thread = one pair) when the 16-edge tiling would give this
+// rank fewer CTAs than a quarter of its SMs -- the sharded builds at 8 GPUs.  SFB_GRAM_GT=8 / 16 forces it (tests, A/B).
+uint32_t sfb_gram_tile_edge(const sfb_ctx* ctx, uint32_t m, int collective) {
+    if (const char* e = getenv("SFB_GRAM_GT")) { const int v = atoi(e); if (v == 8 || v == 16) return (uint32_t)v; }
+    const uint32_t T = (m + 15) / 16, tiles = T * (T + 1) / 2;
+    const uint32_t world = collective && ctx->world > 1 ? (uint32_t)ctx->world : 1u;
+    return (tiles + world - 1) / world * 4 <= (uint32_t)ctx->sm_count ? 8u : 16u;
+}
+
 // raw pair sums of tiles [t0, t1) into g (m x m doubles) on `stream`; small_smem: the 8 KB variant that co-resides
 // with the screen kernel
 int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uint32_t m, uint64_t kd, int metric, double* g,
-                        uint32_t t0, uint32_t t1, bool small_smem) {
+                        uint32_t gt, uint32_t t0, uint32_t t1, bool small_smem) {
     if (t1 <= t0) return SFB_OK;
     const uint32_t nt = t1 - t0;
     const bool cos = metric == SFB_METRIC_COSINE, even = (m & 1u) == 0 && (reinterpret_cast<uintptr_t>(xd) & 15u) == 0;
     // beside the screen kernel: at most one CTA per SM, so that a CTA placed before the screen's never keeps the
     // screen's 216 KB from fitting (two of them would)
     const uint32_t grid = small_smem && nt > (uint32_t)ctx->sm_count ? (uint32_t)ctx->sm_count : nt;
-#define SFB_GRAM(C_, V_, G_) gram_tile_kernel<C_, V_, G_><<<grid, 64, 0, stream>>>(xd, m, kd, g, t0, nt)
-    if (small_smem) {
-        if (cos) { if (even) SFB_GRAM(true, 2, 16); else SFB_GRAM(true, 1, 16); }
-        else { if (even) SFB_GRAM(false, 2, 16); else SFB_GRAM(false, 1, 16); }
-    } else {
-        if (cos) { if (even) SFB_GRAM(true, 2, 64); else SFB_GRAM(true, 1, 64); }
-        else { if (even) SFB_GRAM(false, 2, 64); else SFB_GRAM(false, 1, 64); }
-    }
+#define SFB_GRAM(C_, V_, G_, T_) gram_tile_kernel<C_, V_, G_, T_><<<grid, 64, 0, stream>>>(xd, m, kd, g, t0, nt)
+#define SFB_GRAM_CV(G_, T_)                                                           \
+    do {                                                                              \
+        if (cos) { if (even) SFB_GRAM(true, 2, G_, T_); else SFB_GRAM(true, 1, G_, T_); }   \
+        else { if (even) SFB_GRAM(false, 2, G_, T_); else SFB_GRAM(false, 1, G_, T_); }     \
+    } while (0)
+    if (gt == 8) { if (small_smem) SFB_GRAM_CV(16, 8); else SFB_GRAM_CV(64, 8); }
+    else { if (small_smem) SFB_GRAM_CV(16, 16); else SFB_GRAM_CV(64, 16); }
+#undef SFB_GRAM_CV
 #undef SFB_GRAM
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
 }
 
-void sfb_gram_tile_range(const sfb_ctx* ctx, uint32_t m, int collective, uint32_t* t0, uint32_t* t1) {
-    const uint32_t T = (m + GT - 1) / GT, tiles = T * (T + 1) / 2;
+void sfb_gram_tile_range(const sfb_ctx* ctx, uint32_t m, uint32_t gt, int collective, uint32_t* t0, uint32_t* t1) {
+    const uint32_t T = (m + gt - 1) / gt, tiles = T * (T + 1) / 2;
     *t0 = 0; *t1 = tiles;
     if (collective && ctx->world > 1) {
         const uint32_t per = (tiles + (uint32_t)ctx->world - 1) / (uint32_t)ctx->world;
@@ -426,9 +445,10 @@ int32_t sfb_knn_dense(sfb_ctx* ctx, const double* xd, uint32_t m, uint64_t kd, i
     DevBuf g;  // [0, m*m): raw sums, [m*m, 2*m*m): keys
     SFB_CUDA(ctx, g.alloc(sizeof(double) * 2 * (size_t)m * m));
     uint32_t t0, t1;
-    sfb_gram_tile_range(ctx, m, collective, &t0, &t1);
+    const uint32_t gt = sfb_gram_tile_edge(ctx, m, collective);
+    sfb_gram_tile_range(ctx, m, gt, collective, &t0, &t1);
     if (collective && ctx->world > 1) SFB_CUDA(ctx, cudaMemsetAsync(g.p, 0, sizeof(double) * (size_t)m * m, ctx->stream));
-    SFB_TRY(sfb_gram_launch(ctx, ctx->stream, xd, m, kd, metric, g.as<double>(), t0, t1, false));
+    SFB_TRY(sfb_gram_launch(ctx, ctx->stream, xd, m, kd, metric, g.as<double>(), gt, t0, t1, false));
     return sfb_gram_finish(ctx, g.as<double>(), m, metric, k, eps, q_begin, nq, out_idx, out_dist, out_cnt, collective);
 }
 
@@ -438,7 +458,9 @@ int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int m
     if (nq == 0) return SFB_OK;
     if (k == 0 || k > 128) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k must be in 1..128 (got %u)", k);
     const uint64_t q_tiles = (nq + TQ - 1) / TQ, n_tiles = (x->rows + TC - 1) / TC;
-    uint64_t want = 2ull * ctx->sm_count;
+    // one query tile (a fallback of a few rows): only one or two warps per CTA carry FP64 work, so spread the corpus
+    // over four CTAs per SM instead of two
+    uint64_t want = (q_tiles == 1 ? 4ull : 2ull) * ctx->sm_count;
     uint32_t csplits = 1;
     if (q_tiles < want) {
         csplits = (uint32_t)((want + q_tiles - 1) / q_tiles);

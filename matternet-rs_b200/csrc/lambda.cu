@@ -216,7 +216,8 @@ __global__ void lambda_kernel(LambdaArgs a) {
         double e_raw = 0.0;
         if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
         double g = 0.0;
-        if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
+        // a NaN sum: the taumode form tests `<= 1e-12 -> 0` and lets it propagate through f64::clamp (taumode.rs:385-407), the energy form tests `> 1e-12` (energymaps.rs:1006)
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE ? !(ssum <= 1e-12) : (ssum > 1e-12)) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
         double lam;
         if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
             const double tau = a.tau_in ? a.tau_in[i] : warp_select_tau(xs, f, a.tau_mode, a.tau_value, hist, lane);
@@ -442,7 +443,8 @@ __global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
         double e_raw = 0.0;
         if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
         double g = 0.0;
-        if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
+        // a NaN sum: the taumode form tests `<= 1e-12 -> 0` and lets it propagate through f64::clamp (taumode.rs:385-407), the energy form tests `> 1e-12` (energymaps.rs:1006)
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE ? !(ssum <= 1e-12) : (ssum > 1e-12)) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
         double lam;
         if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
             const double tau = a.tau_in ? a.tau_in[i] : warp_select_tau_fast(xs, f, a.tau_mode, a.tau_value, lane, hist);
@@ -469,7 +471,10 @@ __global__ void __launch_bounds__(256) lambda_sym_kernel(LambdaSymArgs a) {
 // combines, blends and writes 32 consecutive lambdas; the running min / max feed the normalisation without a second pass.
 constexpr int LT_TS = 33;          // tile row stride in doubles (odd: the transposing store is conflict-free)
 
-struct __align__(16) EdgeRec { double w; uint32_t coff; uint32_t roff; };   // w = -L_rc; offsets = index * LT_TS; roff bit 31: first edge of its row
+// w = -L_rc; coff / roff = BYTE offsets of x_c / x_r in the tile (index * LT_TS * 8).  First edge of a row: roff bit 31 set, and --
+// when every weight of the matrix is positive (meta.any_nonpos == 0: the Laplacians built here) -- w stored NEGATED, so the edge
+// loop tests one sign bit and multiplies by |w| (an operand modifier) instead of masking a flag out of an offset.
+struct __align__(16) EdgeRec { double w; uint32_t coff; uint32_t roff; };
 
 struct PackMeta { uint32_t ne; uint32_t any_defect; uint32_t any_nonpos; uint32_t pad; };
 
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(1024) lambda_pack_kernel(const uint64_t* __res
         for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
             const uint32_t c = indices[e];
             if (c > r) {
-                EdgeRec rec; rec.w = -data[e]; rec.coff = c * LT_TS; rec.roff = r * LT_TS | (first ? 0x80000000u : 0u);
+                EdgeRec rec; rec.w = -data[e]; rec.coff = c * (LT_TS * 8); rec.roff = r * (LT_TS * 8) | (first ? 0x80000000u : 0u);
                 recs[o++] = rec; first = false;
                 nonpos = nonpos || !(rec.w > 0.0);
             }
@@ -512,6 +517,7 @@ __global__ void __launch_bounds__(1024) lambda_pack_kernel(const uint64_t* __res
     }
     __syncthreads();
     if (r == 0) { meta->ne = s_scan[1023]; meta->any_defect = s_flags[0]; meta->any_nonpos = s_flags[1]; meta->pad = 0; }
+    if (!s_flags[1] && r < f && c_up) { EdgeRec* first = recs + (s_scan[r] - c_up); first->w = -first->w; first->roff &= 0x7FFFFFFFu; }   // row flag = sign of w
 }
 
 __device__ __forceinline__ uint32_t f32_key(float v) { uint32_t u = __float_as_uint(v); return (u >> 31) ? ~u : (u | 0x80000000u); }
@@ -605,6 +611,79 @@ __device__ __forceinline__ bool regs_select2(const double (&v)[E], uint32_t f, i
     return true;
 }
 
+// The common case of the selection above, stripped of everything it does not need: every lane slot holds a finite value
+// (f == 32 E, no NaN / inf in the row).  One pass: f32 images -> min / max -> 256 linear bins counted with shared-memory
+// atomics (one word per bin: the warp's 1 KB scratch) -> the bin that holds rank k1 -> exact ranking of that bin's
+// members; rank k2 = k1 + 1 is the next member of the bin, or, when k1 is the bin's last, the smallest value above it.
+// Returns false (nothing written) when the histogram cannot separate the candidates.
+template <int E>
+__device__ __forceinline__ bool regs_select2_fast(const double (&v)[E], int lane, uint32_t k1, uint32_t k2, uint32_t* scratch, double* out1, double* out2) {
+    float a[E];
+    float fmn = INFINITY, fmx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < E; ++u) { a[u] = __double2float_rn(v[u]); fmn = fminf(fmn, a[u]); fmx = fmaxf(fmx, a[u]); }
+    const float lo = key_f32(__reduce_min_sync(FULL, f32_key(fmn))), hi = key_f32(__reduce_max_sync(FULL, f32_key(fmx)));
+    const float scale = 255.0f / (hi - lo);
+    if (!(scale > 0.0f) || !(scale < 3.0e38f)) return false;   // all equal in f32, or a range that overflows f32
+    uint4* z = reinterpret_cast<uint4*>(scratch);
+    z[lane * 2] = make_uint4(0u, 0u, 0u, 0u); z[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    int q[E];
+#pragma unroll
+    for (int u = 0; u < E; ++u) { q[u] = min((int)((a[u] - lo) * scale), 255); atomicAdd(&scratch[q[u]], 1u); }
+    __syncwarp();
+    const uint4 w0 = z[lane * 2], w1 = z[lane * 2 + 1];   // bins 8 * lane .. 8 * lane + 7
+    const uint32_t c8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    uint32_t s8 = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) s8 += c8[b];
+    uint32_t inc = s8;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    const uint32_t ex = inc - s8;
+    const bool mine = k1 >= ex && k1 < inc;
+    int bin1 = 0; uint32_t below1 = 0, cnt1 = 0;
+    if (mine) {
+        uint32_t run = ex;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { if (k1 >= run && k1 < run + c8[b]) { bin1 = lane * 8 + b; below1 = run; cnt1 = c8[b]; } run += c8[b]; }
+    }
+    const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
+    bin1 = __shfl_sync(FULL, bin1, src); below1 = __shfl_sync(FULL, below1, src); cnt1 = __shfl_sync(FULL, cnt1, src);
+    if (cnt1 > 64) return false;
+    __syncwarp();
+    double* cand = reinterpret_cast<double*>(scratch);   // [0, 64): words 0 .. 127; slot counter in word 128
+    if (lane == 0) scratch[128] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < E; ++u) if (q[u] == bin1) cand[atomicAdd(&scratch[128], 1u)] = v[u];
+    __syncwarp();
+    const uint32_t t1 = k1 - below1;
+    const bool need2 = k2 != k1, same_bin = t1 + 1 < cnt1;
+    double r1 = 0.0, r2 = 0.0; bool h1 = false, h2 = false;
+    for (uint32_t j = lane; j < cnt1; j += 32) {
+        const double cj = cand[j];
+        uint32_t rk = 0;
+        for (uint32_t i = 0; i < cnt1; ++i) { const double ci = cand[i]; rk += (ci < cj || (ci == cj && i < j)) ? 1u : 0u; }
+        if (rk == t1) { r1 = cj; h1 = true; }
+        if (rk == t1 + 1) { r2 = cj; h2 = true; }
+    }
+    const double va = __shfl_sync(FULL, r1, __ffs(__ballot_sync(FULL, h1)) - 1);
+    double vb = va;
+    if (need2) {
+        if (same_bin) vb = __shfl_sync(FULL, r2, __ffs(__ballot_sync(FULL, h2)) - 1);
+        else {   // the next larger value lives in a later bin
+            double nx = INFINITY;
+#pragma unroll
+            for (int u = 0; u < E; ++u) if (q[u] > bin1) nx = fmin(nx, v[u]);
+            vb = warp_min_d(nx);
+        }
+    }
+    __syncwarp();
+    *out1 = va; *out2 = vb;
+    return true;
+}
+
 // exact selection of rank k among the finite register entries by bisection on the order-preserving 64-bit image (rare path)
 template <int E>
 __device__ double regs_select_exact(const double (&v)[E], uint32_t f, int lane, uint32_t k) {
@@ -628,6 +707,24 @@ template <int E>
 __device__ __forceinline__ double regs_select_tau(const double (&v)[E], uint32_t f, int lane, int mode, double value, uint32_t* scratch) {
     const double FLOOR = 1e-10;
     if (mode == SFB_TAU_FIXED) return (isfinite(value) && value > 0.0) ? value : FLOOR;
+    if (mode != SFB_TAU_MEAN && f == 32u * E) {
+        // full lanes: is every entry finite?  (exponent field of the high word below 0x7FF)
+        bool fin = true;
+#pragma unroll
+        for (int u = 0; u < E; ++u) fin = fin && ((uint32_t)__double2hiint(v[u]) & 0x7FF00000u) != 0x7FF00000u;
+        if (__all_sync(FULL, fin)) {
+            uint32_t k1, k2;
+            if (mode == SFB_TAU_PERCENTILE) {
+                const double pp = value < 0.0 ? 0.0 : (value > 1.0 ? 1.0 : value);
+                k1 = k2 = (uint32_t)round((double)(f - 1) * pp);
+            } else { k1 = f / 2 - 1; k2 = f / 2; }   // f = 32 E is even
+            double a, b;
+            if (regs_select2_fast<E>(v, lane, k1, k2, scratch, &a, &b)) {
+                const double r = k1 == k2 ? a : 0.5 * (a + b);
+                return r > FLOOR ? r : FLOOR;
+            }
+        }
+    }
     uint32_t n = 0; double s = 0.0;
 #pragma unroll
     for (int u = 0; u < E; ++u) if ((uint32_t)(lane + 32 * u) < f && isfinite(v[u])) { ++n; s += v[u]; }
@@ -658,6 +755,9 @@ struct LambdaTileArgs {
     unsigned long long* minmax;   // [0]: min of lambda, [1]: max(0, lambda), as order-preserving keys (atomicMin / atomicMax); may be null
 };
 
+__device__ __forceinline__ double lt_ld(const double* lane_base, uint32_t byte_off) {
+    return *reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(lane_base) + byte_off);
+}
 __device__ __forceinline__ void lt_cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -751,34 +851,35 @@ __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_t
                 __syncwarp();
                 const uint4* rr = ring + (c & 1) * 32;
                 const uint32_t cnt = min(32u, e_hi - e_lo - c * 32);
-                if (c == 0) xa = xs_lane[rr[0].w & 0x7FFFFFFFu];
+                if (c == 0) xa = lt_ld(xs_lane, rr[0].w & 0x7FFFFFFFu);
                 if (!nonpos) {
+                    // every weight positive: a negative w marks the first edge of a row
                     uint32_t j = 0;
 #pragma unroll 2
                     for (; j + 2 <= cnt; j += 2) {
                         const uint4 ra = rr[j], rb = rr[j + 1];
-                        if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
-                        const double d0 = xa - xs_lane[ra.z];
-                        if (rb.w & 0x80000000u) xa = xs_lane[rb.w & 0x7FFFFFFFu];
-                        const double d1 = xa - xs_lane[rb.z];
-                        const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
-                        const double c1 = (__hiloint2double((int)rb.y, (int)rb.x) * d1) * d1;
+                        if ((int)ra.y < 0) xa = lt_ld(xs_lane, ra.w);
+                        const double d0 = xa - lt_ld(xs_lane, ra.z);
+                        if ((int)rb.y < 0) xa = lt_ld(xs_lane, rb.w);
+                        const double d1 = xa - lt_ld(xs_lane, rb.z);
+                        const double c0 = (fabs(__hiloint2double((int)ra.y, (int)ra.x)) * d0) * d0;
+                        const double c1 = (fabs(__hiloint2double((int)rb.y, (int)rb.x)) * d1) * d1;
                         s0 += c0; q0 = fma(c0, c0, q0);
                         s1 += c1; q1 = fma(c1, c1, q1);
                     }
                     if (j < cnt) {
                         const uint4 ra = rr[j];
-                        if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
-                        const double d0 = xa - xs_lane[ra.z];
-                        const double c0 = (__hiloint2double((int)ra.y, (int)ra.x) * d0) * d0;
+                        if ((int)ra.y < 0) xa = lt_ld(xs_lane, ra.w);
+                        const double d0 = xa - lt_ld(xs_lane, ra.z);
+                        const double c0 = (fabs(__hiloint2double((int)ra.y, (int)ra.x)) * d0) * d0;
                         s0 += c0; q0 = fma(c0, c0, q0);
                     }
                 } else {
                     for (uint32_t j = 0; j < cnt; ++j) {
                         const uint4 ra = rr[j];
-                        if (ra.w & 0x80000000u) xa = xs_lane[ra.w & 0x7FFFFFFFu];
+                        if (ra.w & 0x80000000u) xa = lt_ld(xs_lane, ra.w & 0x7FFFFFFFu);
                         const double wv = __hiloint2double((int)ra.y, (int)ra.x);
-                        const double d0 = xa - xs_lane[ra.z];
+                        const double d0 = xa - lt_ld(xs_lane, ra.z);
                         const double c0 = (wv * d0) * d0;
                         sa += c0;
                         if (wv > 0.0) { s0 += c0; q0 = fma(c0, c0, q0); }
@@ -808,7 +909,8 @@ __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_t
             double e_raw = 0.0;
             if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
             double g = 0.0;
-            if (ssum > 1e-12) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
+            // a NaN sum: the taumode form tests `<= 1e-12 -> 0` and lets it propagate through f64::clamp (taumode.rs:385-407), the energy form tests `> 1e-12` (energymaps.rs:1006)
+        if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE ? !(ssum <= 1e-12) : (ssum > 1e-12)) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
             double lam;
             if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
                 if (tau < 0.0) { lam = 0.0; g = 0.0; }

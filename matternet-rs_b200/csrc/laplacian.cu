@@ -179,13 +179,18 @@ struct MergeArgs {
     uint64_t r_begin, n_rows;
     uint32_t* tmp_col; double* tmp_w; uint32_t* ulen; double* deg; uint32_t* row_nnz;   // row_nnz: ulen + 1 (null when normalised)
     uint32_t* long_list; uint32_t* n_long;   // rows the warp kernel leaves to the block kernel
+    // final != 0 (unnormalised form): the scratch segment receives the finished CSR row -- neighbours as -w with the diagonal
+    // (the degree) inserted in column order, ulen + 1 entries -- and the emit pass is a plain segmented copy
+    int final;
 };
+// scratch segment of local row li: capacity k + 1 + bucket length
+__device__ __forceinline__ uint64_t tmp_offset(const MergeArgs& a, uint64_t li, uint64_t ro) { return li * (a.k + 1) + ro; }
 
 // Pass A, rows of up to 32 incident edges (the common case: k forward + about as many reverse after sparsification):
 // one warp per row, ONE entry per lane, sorted in registers by (column, slot) with a 15-step shuffle network; a column
 // that comes from both directions keeps the larger weight (reference: identical for a symmetric metric, max otherwise).
 // Rows of 33..256 edges are sorted in shared memory by the same warp; longer ones go to the block kernel's list.
-template <uint32_t CAP>
+template <uint32_t CAP, bool KEY32>
 __global__ void __launch_bounds__(256) lap_merge_rows_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31, grp = threadIdx.x >> 5, groups = blockDim.x >> 5;
@@ -198,26 +203,47 @@ __global__ void __launch_bounds__(256) lap_merge_rows_kernel(MergeArgs a) {
     const uint64_t ro = a.rev_off[li];
     const uint32_t rl = (uint32_t)(a.rev_off[li + 1] - ro);
     const uint32_t l = fc + rl;
-    const uint64_t to = li * a.k + ro;
-    if (l == 0) { if (lane == 0) { a.ulen[li] = 0; a.deg[li] = 0.0; if (a.row_nnz) a.row_nnz[li] = 1; } return; }
+    const uint64_t to = tmp_offset(a, li, ro);
+    if (l == 0) {
+        if (lane == 0) {
+            a.ulen[li] = 0; a.deg[li] = 0.0;
+            if (a.row_nnz) a.row_nnz[li] = 1;
+            if (a.final) { a.tmp_col[to] = (uint32_t)i; a.tmp_w[to] = 0.0; }   // the diagonal is stored even when it is 0
+        }
+        return;
+    }
     if (l > CAP) { if (lane == 0) a.long_list[atomicAdd(a.n_long, 1u)] = (uint32_t)li; return; }
-    uint32_t u = 0;   // unique neighbours
+    uint32_t u = 0, n_left = 0;   // unique neighbours; those left of the diagonal
     bool in_regs = l <= 32;
     if (in_regs) {
         uint32_t c = SFB_IDX_NONE; double w = 0.0;
         if (lane < fc) { c = a.a_idx[i * a.k + lane]; w = a.a_w[i * a.k + lane]; if (c == (uint32_t)i) c = SFB_IDX_NONE; }
         else if (lane < l) { c = a.rev_src[ro + (lane - fc)]; w = a.rev_w[ro + (lane - fc)]; }
-        unsigned long long key = ((unsigned long long)c << 32) | lane;
+        uint32_t col, slot;
+        if (KEY32) {   // node indices below 2^27: (column, slot) fits one 32-bit key, one shuffle and one min / max per step
+            uint32_t key = c == SFB_IDX_NONE ? 0xFFFFFFFFu : (c << 5 | lane);
 #pragma unroll
-        for (uint32_t size = 2; size <= 32; size <<= 1)
+            for (uint32_t size = 2; size <= 32; size <<= 1)
 #pragma unroll
-            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(FULL, key, stride);
-                const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
-                key = take_min ? (other < key ? other : key) : (other > key ? other : key);
-            }
-        const uint32_t col = (uint32_t)(key >> 32);
-        const double ws = __shfl_sync(FULL, w, (int)(key & 31u));
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    const uint32_t other = __shfl_xor_sync(FULL, key, stride);
+                    const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+                    key = take_min ? min(key, other) : max(key, other);
+                }
+            col = key == 0xFFFFFFFFu ? SFB_IDX_NONE : key >> 5; slot = key & 31u;
+        } else {
+            unsigned long long key = ((unsigned long long)c << 32) | lane;
+#pragma unroll
+            for (uint32_t size = 2; size <= 32; size <<= 1)
+#pragma unroll
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(FULL, key, stride);
+                    const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+                    key = take_min ? (other < key ? other : key) : (other > key ? other : key);
+                }
+            col = (uint32_t)(key >> 32); slot = (uint32_t)key & 31u;
+        }
+        const double ws = __shfl_sync(FULL, w, (int)slot);
         const uint32_t col_prev = __shfl_up_sync(FULL, col, 1), col_prev2 = __shfl_up_sync(FULL, col, 2), col_next = __shfl_down_sync(FULL, col, 1);
         const double w_next = __shfl_down_sync(FULL, ws, 1);
         const bool valid = col != SFB_IDX_NONE;
@@ -229,7 +255,12 @@ __global__ void __launch_bounds__(256) lap_merge_rows_kernel(MergeArgs a) {
             const uint32_t hb = __ballot_sync(FULL, head);
             const uint32_t pos = __popc(hb & ((1u << lane) - 1u));
             u = __popc(hb);
-            if (head) { a.tmp_col[to + pos] = col; a.tmp_w[to + pos] = wh; sw[pos] = wh; }
+            n_left = __popc(__ballot_sync(FULL, head && col < (uint32_t)i));
+            if (head) {
+                sw[pos] = wh;
+                if (a.final) { const uint32_t d = pos + (col > (uint32_t)i ? 1u : 0u); a.tmp_col[to + d] = col; a.tmp_w[to + d] = -wh; }
+                else { a.tmp_col[to + pos] = col; a.tmp_w[to + pos] = wh; }
+            }
             __syncwarp();
         }
     }
@@ -250,8 +281,13 @@ __global__ void __launch_bounds__(256) lap_merge_rows_kernel(MergeArgs a) {
             if (t < P) { c = scol[t]; w = sw[t]; head = c != SFB_IDX_NONE && (t == 0 || c != scol[t - 1]); }
             const uint32_t b = __ballot_sync(FULL, head);
             const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+            n_left += __popc(__ballot_sync(FULL, head && c < (uint32_t)i));
             __syncwarp();
-            if (head) { a.tmp_col[to + pos] = c; a.tmp_w[to + pos] = w; sw[pos] = w; }   // compacted in place for the fold below (pos <= t)
+            if (head) {
+                sw[pos] = w;   // compacted in place for the fold below (pos <= t)
+                if (a.final) { const uint32_t d = pos + (c > (uint32_t)i ? 1u : 0u); a.tmp_col[to + d] = c; a.tmp_w[to + d] = -w; }
+                else { a.tmp_col[to + pos] = c; a.tmp_w[to + pos] = w; }
+            }
             __syncwarp();
             base += __popc(b);
         }
@@ -263,6 +299,7 @@ __global__ void __launch_bounds__(256) lap_merge_rows_kernel(MergeArgs a) {
         for (uint32_t t = 0; t < u; ++t) s = __dadd_rn(s, sw[t]);
         a.ulen[li] = u; a.deg[li] = s;
         if (a.row_nnz) a.row_nnz[li] = u + 1;
+        if (a.final) { a.tmp_col[to + n_left] = (uint32_t)i; a.tmp_w[to + n_left] = s; }
     }
 }
 
@@ -276,18 +313,20 @@ __global__ void __launch_bounds__(1024) lap_merge_long_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sw = reinterpret_cast<double*>(smem_raw);
     uint32_t* scol = reinterpret_cast<uint32_t*>(sw + SMEM_CAP);
-    __shared__ uint32_t s_count, s_warp[32];
-    __shared__ double s_deg;
+    __shared__ uint32_t s_count, s_left, s_warp[32], s_wleft[32];
     const uint32_t tid = threadIdx.x, nt = blockDim.x, n_long = *a.n_long;
     for (uint32_t item = blockIdx.x; item < n_long; item += gridDim.x) {
         const uint64_t li = a.long_list[item], i = a.r_begin + li;
         const uint32_t fc = a.a_cnt[i];
         const uint64_t ro = a.rev_off[li];
         const uint32_t rl = (uint32_t)(a.rev_off[li + 1] - ro), l = fc + rl;
-        const uint64_t to = li * a.k + ro;
+        const uint64_t to = tmp_offset(a, li, ro);
         uint32_t* gcol = a.tmp_col + to; double* gw = a.tmp_w + to;
         const bool in_smem = l <= SMEM_CAP;
-        uint32_t* col = in_smem ? scol : gcol; double* wv = in_smem ? sw : gw;
+        // global workspace: the row's own segment, shifted up by one slot (capacity k + 1 + bucket >= l + 1), so that the
+        // compaction below -- which may move an entry one slot to the right of its rank to make room for the diagonal --
+        // never writes a slot it has not read yet
+        uint32_t* col = in_smem ? scol : gcol + 1; double* wv = in_smem ? sw : gw + 1;
         uint32_t P = 2; while (P < l) P <<= 1;
         for (uint32_t t = tid; t < (in_smem ? P : l); t += nt) {
             uint32_t c = SFB_IDX_NONE; double w = 0.0;
@@ -314,28 +353,32 @@ __global__ void __launch_bounds__(1024) lap_merge_long_kernel(MergeArgs a) {
             }
         }
         // heads of runs (col asc, w desc: the head carries the max weight), compacted in order, chunk by chunk
-        if (tid == 0) { s_count = 0; s_deg = 0.0; }
+        if (tid == 0) { s_count = 0; s_left = 0; }
         __syncthreads();
         for (uint32_t t0 = 0; t0 < l; t0 += nt) {
             const uint32_t t = t0 + tid;
             uint32_t c = SFB_IDX_NONE; double w = 0.0; bool head = false;
             if (t < l) { c = col[t]; w = wv[t]; head = c != SFB_IDX_NONE && (t == 0 || c != col[t - 1]); }
-            const uint32_t b = __ballot_sync(FULL, head);
-            if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(b);
+            const uint32_t b = __ballot_sync(FULL, head), bl = __ballot_sync(FULL, head && c < (uint32_t)i);
+            if ((tid & 31) == 0) { s_warp[tid >> 5] = __popc(b); s_wleft[tid >> 5] = __popc(bl); }
             __syncthreads();   // every read of this chunk is done: the compacted writes below land at or before it
-            uint32_t pre = 0, tot = 0;
-            for (uint32_t wq = 0; wq < (nt >> 5); ++wq) { const uint32_t v = s_warp[wq]; if (wq < (tid >> 5)) pre += v; tot += v; }
+            uint32_t pre = 0, tot = 0, totl = 0;
+            for (uint32_t wq = 0; wq < (nt >> 5); ++wq) { const uint32_t v = s_warp[wq]; if (wq < (tid >> 5)) pre += v; tot += v; totl += s_wleft[wq]; }
             const uint32_t pos = s_count + pre + __popc(b & ((1u << (tid & 31)) - 1u));
-            if (head) { gcol[pos] = c; gw[pos] = w; }
+            if (head) {
+                if (a.final) { const uint32_t d = pos + (c > (uint32_t)i ? 1u : 0u); gcol[d] = c; gw[d] = -w; }
+                else { gcol[pos] = c; gw[pos] = w; }
+            }
             __syncthreads();
-            if (tid == 0) s_count += tot;
+            if (tid == 0) { s_count += tot; s_left += totl; }
             __syncthreads();
         }
         // degree: left fold in ascending column order, one thread (a hub's fold is as sequential as the reference's)
         if (tid == 0) {
-            const uint32_t u = s_count;
+            const uint32_t u = s_count, nl = s_left;
             double s = 0.0;
-            for (uint32_t t = 0; t < u; ++t) s = __dadd_rn(s, gw[t]);
+            if (a.final) { for (uint32_t t = 0; t < u; ++t) s = __dadd_rn(s, -gw[t + (t >= nl ? 1u : 0u)]); gcol[nl] = (uint32_t)i; gw[nl] = s; }
+            else for (uint32_t t = 0; t < u; ++t) s = __dadd_rn(s, gw[t]);
             a.ulen[li] = u; a.deg[li] = s;
             if (a.row_nnz) a.row_nnz[li] = u + 1;
         }
@@ -354,7 +397,7 @@ __global__ void csr_row_nnz_kernel(const uint32_t* __restrict__ ulen, const doub
     const double di = deg[i];
     uint32_t n = 0;
     if (di > thr) {
-        const uint64_t to = i * k + rev_off[i];
+        const uint64_t to = i * (k + 1) + rev_off[i];
         for (uint32_t t0 = 0; t0 < u; t0 += 32) {
             uint32_t t = t0 + lane;
             bool ok = false;
@@ -390,7 +433,7 @@ __global__ void __launch_bounds__(256) csr_emit_kernel(const uint32_t* __restric
         const uint32_t u = ulen[i];
         const double di = deg[i];
         if (normalised && !(di > thr)) continue;  // isolated node: empty row (surfface-core laplacian.rs:349-353)
-        const uint64_t to = i * k + rev_off[i];
+        const uint64_t to = i * (k + 1) + rev_off[i];
         const uint64_t o = indptr[i];
         const uint32_t gi = (uint32_t)(r_begin + i);
         const double diag_val = normalised ? 1.0 : di;
@@ -455,6 +498,41 @@ __global__ void __launch_bounds__(256) csr_emit_kernel(const uint32_t* __restric
         for (uint32_t v = threadIdx.x; v < body; v += blockDim.x)
             dst[v] = make_uint4(s_col[head + 4 * v], s_col[head + 4 * v + 1], s_col[head + 4 * v + 2], s_col[head + 4 * v + 3]);
         for (uint32_t t = head + 4 * body + threadIdx.x; t < n; t += blockDim.x) indices[o0 + t] = s_col[t];
+    }
+}
+
+// Pass C, unnormalised form: the scratch segments already hold the finished rows (lap_merge_*: final != 0); a block
+// takes a run of consecutive rows, whose output is one contiguous slice of `indices` / `data`, and copies it with one
+// thread per PAIR of entries: 16-byte stores of the values, 8-byte stores of the columns (scalar at the ragged ends).
+constexpr uint32_t COPY_ROWS = 128;
+__global__ void __launch_bounds__(256) csr_copy_kernel(const uint64_t* __restrict__ rev_off, uint32_t k, const uint32_t* __restrict__ tmp_col,
+                                                       const double* __restrict__ tmp_w, uint64_t m, const uint64_t* __restrict__ indptr,
+                                                       uint32_t* __restrict__ indices, double* __restrict__ data) {
+    __shared__ uint64_t s_ptr[COPY_ROWS + 1], s_src[COPY_ROWS];
+    const uint64_t row0 = (uint64_t)blockIdx.x * COPY_ROWS;
+    if (row0 >= m) return;
+    const uint32_t nrows = (uint32_t)(row0 + COPY_ROWS < m ? COPY_ROWS : m - row0);
+    for (uint32_t r = threadIdx.x; r <= nrows; r += blockDim.x) {
+        s_ptr[r] = indptr[row0 + r];
+        if (r < nrows) s_src[r] = (row0 + r) * (k + 1) + rev_off[row0 + r];
+    }
+    __syncthreads();
+    const uint64_t o0 = s_ptr[0], o1 = s_ptr[nrows];
+    auto locate = [&](uint64_t e) {   // source position of output entry e: its row by bisection over the run's indptr
+        uint32_t lo = 0, hi = nrows;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_ptr[mid] <= e) lo = mid; else hi = mid; }
+        return s_src[lo] + (e - s_ptr[lo]);
+    };
+    for (uint64_t e = (o0 & ~1ull) + 2ull * threadIdx.x; e < o1; e += 2ull * blockDim.x) {
+        const bool v0 = e >= o0, v1 = e + 1 < o1;
+        uint32_t c0 = 0, c1 = 0; double w0 = 0.0, w1 = 0.0;
+        if (v0) { const uint64_t sp = locate(e); c0 = tmp_col[sp]; w0 = tmp_w[sp]; }
+        if (v1) { const uint64_t sp = locate(e + 1); c1 = tmp_col[sp]; w1 = tmp_w[sp]; }
+        if (v0 && v1) {
+            *reinterpret_cast<double2*>(data + e) = make_double2(w0, w1);
+            *reinterpret_cast<uint2*>(indices + e) = make_uint2(c0, c1);
+        } else if (v0) { data[e] = w0; indices[e] = c0; }
+        else if (v1) { data[e + 1] = w1; indices[e + 1] = c1; }
     }
 }
 
@@ -572,8 +650,8 @@ static int32_t laplacian_build_rows(sfb_ctx* ctx, const sfb_adj* a, const sfb_la
     SFB_CUDA(ctx, rev_off.alloc(sizeof(uint64_t) * (nr + 1)));
     SFB_CUDA(ctx, rev_src.alloc(sizeof(uint32_t) * rev_cap));
     SFB_CUDA(ctx, rev_w.alloc(sizeof(double) * rev_cap));
-    SFB_CUDA(ctx, tmp_col.alloc(sizeof(uint32_t) * (nr * k + rev_cap)));
-    SFB_CUDA(ctx, tmp_w.alloc(sizeof(double) * (nr * k + rev_cap)));
+    SFB_CUDA(ctx, tmp_col.alloc(sizeof(uint32_t) * (nr * (k + 1) + rev_cap)));
+    SFB_CUDA(ctx, tmp_w.alloc(sizeof(double) * (nr * (k + 1) + rev_cap)));
     SFB_CUDA(ctx, ulen.alloc(sizeof(uint32_t) * nr));
     SFB_CUDA(ctx, deg.alloc(sizeof(double) * (prm->normalised ? m : nr)));
     SFB_CUDA(ctx, row_nnz.alloc(sizeof(uint32_t) * nr));
@@ -591,13 +669,19 @@ static int32_t laplacian_build_rows(sfb_ctx* ctx, const sfb_adj* a, const sfb_la
 
     MergeArgs ma{a->idx, a->w, a->cnt, k, rev_off.as<uint64_t>(), rev_src.as<uint32_t>(), rev_w.as<double>(), r_begin, nr,
                  tmp_col.as<uint32_t>(), tmp_w.as<double>(), ulen.as<uint32_t>(), deg.as<double>(),
-                 prm->normalised ? nullptr : row_nnz.as<uint32_t>(), long_list.as<uint32_t>(), n_long.as<uint32_t>()};
+                 prm->normalised ? nullptr : row_nnz.as<uint32_t>(), long_list.as<uint32_t>(), n_long.as<uint32_t>(), prm->normalised ? 0 : 1};
     {
         const int groups = 8;
         const size_t smem = (size_t)groups * WARP_CAP * (sizeof(double) + sizeof(uint32_t));
-        auto kern = lap_merge_rows_kernel<WARP_CAP>;
-        SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<div_up(nr, groups), groups * 32, smem, ctx->stream>>>(ma);
+        if (m < (1ull << 27)) {
+            auto kern = lap_merge_rows_kernel<WARP_CAP, true>;
+            SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<div_up(nr, groups), groups * 32, smem, ctx->stream>>>(ma);
+        } else {
+            auto kern = lap_merge_rows_kernel<WARP_CAP, false>;
+            SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<div_up(nr, groups), groups * 32, smem, ctx->stream>>>(ma);
+        }
         SFB_LAUNCH_CHECK(ctx);
     }
     {   // hub rows (in-degree is unbounded): the kernel reads the list length on the device and leaves at once when it is empty
@@ -628,9 +712,13 @@ static int32_t laplacian_build_rows(sfb_ctx* ctx, const sfb_adj* a, const sfb_la
         sfb_csr_free(L);
         return sfb_fail(ctx, SFB_ENOMEM, "CSR arrays (%llu nnz)", (unsigned long long)L->nnz);
     }
-    csr_emit_kernel<<<div_up(nr, EMIT_ROWS), 256, 0, ctx->stream>>>(ulen.as<uint32_t>(), deg.as<double>(), rev_off.as<uint64_t>(), k,
-                                                                     tmp_col.as<uint32_t>(), tmp_w.as<double>(), nr, r_begin, prm->normalised,
-                                                                     prm->weight_threshold, L->indptr, L->indices, L->data);
+    if (prm->normalised)
+        csr_emit_kernel<<<div_up(nr, EMIT_ROWS), 256, 0, ctx->stream>>>(ulen.as<uint32_t>(), deg.as<double>(), rev_off.as<uint64_t>(), k,
+                                                                         tmp_col.as<uint32_t>(), tmp_w.as<double>(), nr, r_begin, prm->normalised,
+                                                                         prm->weight_threshold, L->indptr, L->indices, L->data);
+    else
+        csr_copy_kernel<<<div_up(nr, COPY_ROWS), 256, 0, ctx->stream>>>(rev_off.as<uint64_t>(), k, tmp_col.as<uint32_t>(), tmp_w.as<double>(), nr,
+                                                                         L->indptr, L->indices, L->data);
     ctx->times.kernel_launches++;
     timer.stop();   // synchronises: the scratch may go back to the cache
     e = cudaGetLastError();
