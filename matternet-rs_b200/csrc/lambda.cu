@@ -765,11 +765,12 @@ __device__ __forceinline__ void lt_cp_async16(void* smem_dst, const void* gsrc) 
 // shared memory: xs [f][LT_TS] | den, defect term, tau [3][32] | one 1 KB region per warp: the tau selection's scratch in
 // phase 1, the ring of edge records in phase 2 (2 x 32 records, filled by cp.async one chunk ahead), the warp's partial sums
 // at the end of phase 2
-template <int VARIANT, int E, int LT_WARPS>
+// FULL: f == 32 E (every lane slot holds an entry): the bounds tests of phase 1 compile away
+template <int VARIANT, int E, int LT_WARPS, bool FULL>
 __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_tile_kernel(LambdaTileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t f = a.f;
+    const uint32_t f = FULL ? 32u * E : a.f;
     double* xs = reinterpret_cast<double*>(smem_raw);                         // [f][LT_TS]
     double* s_den = xs + (((size_t)f * LT_TS + 1) & ~(size_t)1);              // [32]   (16-byte aligned)
     double* s_dfc = s_den + 32;                                               // [32]
@@ -795,7 +796,7 @@ __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_t
         if (PREFETCH) {
             const uint64_t i = i0 + w * IPW;
 #pragma unroll
-            for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; vn[PREFETCH ? u : 0] = (i < a.n && t < f) ? __ldcs(a.x + i * f + t) : 0.0; }
+            for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; vn[PREFETCH ? u : 0] = (i < a.n && (FULL || t < f)) ? __ldcs(a.x + i * f + t) : 0.0; }
         }
 #pragma unroll 1
         for (int qi = 0; qi < IPW; ++qi) {
@@ -808,26 +809,30 @@ __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_t
                 if (qi + 1 < IPW) {
                     const uint64_t i2 = i + 1;
 #pragma unroll
-                    for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; vn[PREFETCH ? u : 0] = (i2 < a.n && t < f) ? __ldcs(a.x + i2 * f + t) : 0.0; }
+                    for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; vn[PREFETCH ? u : 0] = (i2 < a.n && (FULL || t < f)) ? __ldcs(a.x + i2 * f + t) : 0.0; }
                 }
             } else {
 #pragma unroll
-                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; v[u] = (i < a.n && t < f) ? __ldcs(a.x + i * f + t) : 0.0; }
+                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; v[u] = (i < a.n && (FULL || t < f)) ? __ldcs(a.x + i * f + t) : 0.0; }
             }
-            bool zero = true;
-            double den = 0.0, dfc = 0.0;
+            // zero test |v| <= 1e-10 for every entry (taumode.rs:268-274) as one running maximum (a NaN entry fails it, as in
+            // the reference: max keeps the NaN out, so test it apart)
+            double amax = 0.0, den = 0.0, dfc = 0.0;
+            bool any_nan = false;
 #pragma unroll
             for (int u = 0; u < E; ++u) {
                 const uint32_t t = lane + 32 * u;
-                if (t < f) {
+                if (FULL || t < f) {
                     xs[(size_t)t * LT_TS + it] = v[u];
-                    zero = zero && (fabs(v[u]) <= 1e-10);
+                    amax = fmax(amax, fabs(v[u]));
+                    any_nan = any_nan || v[u] != v[u];
                     den = fma(v[u], v[u], den);
                 }
             }
+            const bool zero = amax <= 1e-10 && !any_nan;
             if (has_defect) {
 #pragma unroll
-                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; if (t < f) dfc += (v[u] * a.defect[t]) * v[u]; }
+                for (int u = 0; u < E; ++u) { const uint32_t t = lane + 32 * u; if (FULL || t < f) dfc += (v[u] * a.defect[t]) * v[u]; }
                 dfc = warp_sum(dfc);
             }
             den = warp_sum(den);
@@ -1036,10 +1041,10 @@ namespace {
 
 size_t lt_smem_bytes(uint32_t f, int nw) { return ((((size_t)f * LT_TS + 1) & ~(size_t)1) + 96) * sizeof(double) + (size_t)nw * 1024; }
 
-template <int VARIANT, int E, int NW>
-int32_t lt_launch(sfb_ctx* ctx, const LambdaTileArgs& a) {
+template <int VARIANT, int E, int NW, bool FULL>
+int32_t lt_launch_full(sfb_ctx* ctx, const LambdaTileArgs& a) {
     const size_t smem = lt_smem_bytes(a.f, NW);
-    auto kern = lambda_tile_kernel<VARIANT, E, NW>;
+    auto kern = lambda_tile_kernel<VARIANT, E, NW, FULL>;
     SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     SFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
@@ -1049,6 +1054,10 @@ int32_t lt_launch(sfb_ctx* ctx, const LambdaTileArgs& a) {
     kern<<<(unsigned)(tiles < cap ? tiles : cap), NW * 32, smem, ctx->stream>>>(a);
     SFB_LAUNCH_CHECK(ctx);
     return SFB_OK;
+}
+template <int VARIANT, int E, int NW>
+int32_t lt_launch(sfb_ctx* ctx, const LambdaTileArgs& a) {
+    return a.f == 32u * E ? lt_launch_full<VARIANT, E, NW, true>(ctx, a) : lt_launch_full<VARIANT, E, NW, false>(ctx, a);
 }
 template <int VARIANT>
 int32_t lt_dispatch(sfb_ctx* ctx, const LambdaTileArgs& a) {

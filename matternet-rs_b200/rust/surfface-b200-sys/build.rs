@@ -14,7 +14,9 @@ fn main() {
         println!("cargo:rerun-if-changed={csrc}/{f}");
     }
     b.compile("surfface_b200");
-    println!("cargo:rustc-link-lib=cudart");
+    println!("cargo:rustc-link-lib=static=cudart_static");   // as csrc/Makefile links it
+    println!("cargo:rustc-link-lib=rt");
+    println!("cargo:rustc-link-lib=pthread");
     println!("cargo:rustc-link-lib=cuda");
     println!("cargo:rustc-link-lib=dl");
 }

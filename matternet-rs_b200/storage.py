@@ -6,10 +6,51 @@ Laplacian and a lambda vector built here can be read by the reference's loaders 
         in CSR order: row-major, ascending column)
     save_lambda / load_lambda                 parquet.rs:728-826:
         name_id Utf8 | n_values u64 | row_index u64 | lambda f64
-Files are `<path>/<name_id>.parquet`.  Host-side I/O only (the reference's persistence is not on the compute path)."""
+    save_metadata / load_metadata             parquet.rs:131-170: `<name_id>_metadata.json`, the ArrowSpaceMetadata sidecar the
+        reference writes next to a file when a builder configuration is passed (parquet.rs:486-503,788-806): name_id,
+        timestamp (RFC 3339), n_rows, n_cols, builder_config (serde's externally tagged ConfigValue: {"F64": 0.001},
+        {"Usize": 6}, {"OptionF64": null}, {"TauMode": "Median"}), files {key: FileInfo}
+Files are `<path>/<name_id>.parquet`.  Host-side I/O only (the reference's persistence is not on the compute path; a Rust
+host keeps using the reference's own storage module on the CsMat / Vec the wrapper returns)."""
+import datetime
+import json
 import os
 
 import numpy as np
+
+
+def config_value(v):
+    """A Python value as serde serialises the reference's ConfigValue (surfface-pipeline/src/builder.rs:1531-1544)."""
+    if isinstance(v, dict):          # already tagged
+        return v
+    if isinstance(v, bool):
+        return {"Bool": v}
+    if isinstance(v, int):
+        return {"Usize": v}
+    if isinstance(v, float):
+        return {"F64": v}
+    if isinstance(v, str):
+        return {"String": v}
+    if v is None:
+        return {"OptionF64": None}
+    raise TypeError(f"no ConfigValue form for {type(v).__name__}")
+
+
+def save_metadata(path, name_id, n_rows, n_cols, builder_config, files):
+    """ArrowSpaceMetadata -> `<path>/<name_id>_metadata.json` (parquet.rs:131-145), pretty-printed like serde_json."""
+    meta = {"name_id": name_id, "timestamp": datetime.datetime.now(datetime.timezone.utc).isoformat(),
+            "n_rows": int(n_rows), "n_cols": int(n_cols),
+            "builder_config": {k: config_value(v) for k, v in builder_config.items()}, "files": files}
+    os.makedirs(path, exist_ok=True)
+    out = os.path.join(path, f"{name_id}_metadata.json")
+    with open(out, "w") as f:
+        json.dump(meta, f, indent=2)
+    return out
+
+
+def load_metadata(path, name_id):
+    with open(os.path.join(path, f"{name_id}_metadata.json")) as f:
+        return json.load(f)
 
 
 def _pa():
@@ -18,8 +59,9 @@ def _pa():
     return pa, pq
 
 
-def save_sparse_matrix(indptr, indices, data, path, name_id, n_cols=None):
-    """CSR (as returned by Csr.to_host()) -> `<path>/<name_id>.parquet` in the reference's COO schema."""
+def save_sparse_matrix(indptr, indices, data, path, name_id, n_cols=None, builder_config=None):
+    """CSR (as returned by Csr.to_host()) -> `<path>/<name_id>.parquet` in the reference's COO schema; with a
+    builder_config also the `<name_id>_metadata.json` sidecar (parquet.rs:486-503)."""
     pa, pq = _pa()
     indptr = np.asarray(indptr, dtype=np.uint64)
     n_rows = len(indptr) - 1
@@ -39,26 +81,41 @@ def save_sparse_matrix(indptr, indices, data, path, name_id, n_cols=None):
     os.makedirs(path, exist_ok=True)
     out = os.path.join(path, f"{name_id}.parquet")
     pq.write_table(table.cast(schema), out, compression="snappy")
+    if builder_config is not None:
+        save_metadata(path, name_id, n_rows, n_cols, builder_config,
+                      {"matrix": {"filename": f"{name_id}.parquet", "file_type": "sparse", "rows": n_rows, "cols": int(n_cols),
+                                  "nnz": nnz, "size_bytes": os.path.getsize(out)}})
     return out
 
 
 def load_sparse_matrix(file_path):
-    """The reference's COO Parquet -> (indptr u64, indices u32, data f64, (n_rows, n_cols)); triplets are summed into CSR
-    in (row, col) order like sprs' TriMat::to_csr."""
+    """The reference's COO Parquet -> (indptr u64, indices u32, data f64, (n_rows, n_cols)).  Triplets are ordered by
+    (row, col) and duplicates of a position SUMMED, like sprs' TriMat::to_csr (parquet.rs:520-590)."""
     pa, pq = _pa()
     t = pq.read_table(file_path)
-    n_rows, n_cols = int(t["n_rows"][0].as_py()), int(t["n_cols"][0].as_py())
+    if t.num_rows == 0:
+        raise ValueError("empty sparse-matrix file: the dimensions live in its rows")
+    n_rows, n_cols, nnz = int(t["n_rows"][0].as_py()), int(t["n_cols"][0].as_py()), int(t["nnz"][0].as_py())
+    if nnz != t.num_rows:
+        raise ValueError(f"file declares nnz = {nnz} but holds {t.num_rows} triplets")
     row = t["row"].to_numpy().astype(np.int64)
     col = t["col"].to_numpy().astype(np.int64)
     val = t["value"].to_numpy().astype(np.float64)
+    if row.max() >= n_rows or col.max() >= n_cols:
+        raise ValueError("triplet outside the declared shape")
     order = np.lexsort((col, row))
     row, col, val = row[order], col[order], val[order]
+    first = np.ones(len(row), bool)
+    first[1:] = (row[1:] != row[:-1]) | (col[1:] != col[:-1])
+    starts = np.nonzero(first)[0]
+    val = np.add.reduceat(val, starts)
+    row, col = row[starts], col[starts]
     indptr = np.zeros(n_rows + 1, np.uint64)
     np.add.at(indptr, row + 1, 1)
     return np.cumsum(indptr).astype(np.uint64), col.astype(np.uint32), val, (n_rows, n_cols)
 
 
-def save_lambda(lambdas, path, name_id):
+def save_lambda(lambdas, path, name_id, builder_config=None):
     pa, pq = _pa()
     lam = np.asarray(lambdas, dtype=np.float64)
     if lam.size == 0:
@@ -74,6 +131,10 @@ def save_lambda(lambdas, path, name_id):
     os.makedirs(path, exist_ok=True)
     out = os.path.join(path, f"{name_id}.parquet")
     pq.write_table(table.cast(schema), out, compression="snappy")
+    if builder_config is not None:   # parquet.rs:788-806
+        save_metadata(path, name_id, n, 1, builder_config,
+                      {"lambda_vector": {"filename": f"{name_id}.parquet", "file_type": "lambda_vector", "rows": n, "cols": 1,
+                                         "nnz": None, "size_bytes": os.path.getsize(out)}})
     return out
 
 
