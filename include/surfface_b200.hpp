@@ -9,6 +9,8 @@
 //   TauMode, TauMode::compute_taumode_lambdas_parallel            src_legacy/taumode.rs:16-23,117-214 (+ core.rs:1427-1443)
 //   SfGrassSparsifier::sparsify_graph                             src_legacy/sparsification.rs:14-113
 //   LaplacianConfig, LaplacianOutput, LaplacianStage::execute     surfface-core/src/laplacian.rs:49-219
+//   compute_tau_mode_gpu                                          surfface-core/src/spectral/bridge.rs:27-32
+//   CoreTauMode, compute_tau                                      surfface-core/src/taumode.rs:12-65
 //   compute_jl_dimension, ImplicitProjection, project_matrix      src_legacy/reduction.rs:117-248
 //   SortedLambdas::{build_from, to_vec, range_bylambda}           src_legacy/sorted_index.rs:8-79
 // The reference panics (assert! / panic!) on bad input; the mirror throws surfface_b200::Error carrying the status
@@ -257,6 +259,34 @@ public:
     }
     LaplacianConfig config;
 };
+
+// Stage D seam of the successor: compute_tau_mode_gpu(&LaplacianOutput, data: &[f32], n_items, n_features) -> Vec<f64>
+// (surfface-core/src/spectral/bridge.rs:27-32): Rayleigh + Dirichlet per item in f32 semantics, widened to f64, not
+// normalised.  `data` crosses PCIe as f32 and is widened on the device.
+inline std::vector<double> compute_tau_mode_gpu(const LaplacianOutput& laplacian, const std::vector<float>& data, size_t n_items, size_t n_features) {
+    if (data.size() != n_items * n_features) throw Error(SFB_EINVAL, "data must be n_items x n_features");
+    Context& ctx = Context::thread_default();
+    std::vector<double> out(n_items);
+    ctx.check(sfb_compute_tau_mode_lambdas(ctx.get(), laplacian.device.get(), data.data(), n_items, (uint32_t)n_features, out.data()));
+    return out;
+}
+
+// TauMode of the successor (surfface-core/src/taumode.rs:12-23): tau is resolved from the lambda DISTRIBUTION.
+struct CoreTauMode {
+    int kind = SFB_TAU_MEDIAN;
+    float value = 0.f;
+    static CoreTauMode Median() { return {SFB_TAU_MEDIAN, 0.f}; }
+    static CoreTauMode Mean() { return {SFB_TAU_MEAN, 0.f}; }
+    static CoreTauMode Fixed(float t) { return {SFB_TAU_FIXED, t}; }
+    static CoreTauMode Percentile(float p) { return {SFB_TAU_PERCENTILE, p}; }
+};
+// compute_tau(lambdas: &[f32], mode: &TauMode) -> f32 (surfface-core/src/taumode.rs:37-65)
+inline float compute_tau(const std::vector<float>& lambdas, const CoreTauMode& mode = CoreTauMode::Median()) {
+    Context& ctx = Context::thread_default();
+    float out = 0.f;
+    ctx.check(sfb_compute_tau(ctx.get(), lambdas.empty() ? nullptr : lambdas.data(), lambdas.size(), mode.kind, mode.value, &out));
+    return out;
+}
 
 // ---- JL projection ahead of lambda (src_legacy/reduction.rs) -----------------------------------------------------
 inline size_t compute_jl_dimension(size_t n_points, size_t original_dim, double epsilon) {

@@ -32,6 +32,7 @@ void orc_normalise_lambdas(double* lam, uint64_t n, double* stats);
 uint64_t orc_jl_dimension(uint64_t n_points, uint64_t original_dim, double epsilon);
 void orc_project_rows(const double* x, uint64_t n, uint32_t f, const double* samples, uint32_t r, double* out);
 int orc_sorted_lambdas(const double* lam, uint64_t n, double* out_lambda, uint32_t* out_idx, double* out_std_dev);
+float orc_compute_tau_core(const float* lambdas, uint64_t n, int mode, float value);
 }
 
 static int failures = 0;
@@ -231,7 +232,34 @@ static void test_projection_and_sorted_lambdas() {
     CHECK(threw, "empty lambdas must be refused");
 }
 
+// Stage D seam (surfface-core/src/tests/test_spectral.rs:30-80,165-185: finite lambdas, zero-vector safety) and compute_tau
+static void test_stage_d_seam() {
+    // Stage C on 3 features / 4 centroids, then compute_tau_mode_gpu on two items (test_spectral.rs:38-78)
+    const std::vector<float> means = {1.0f, 0.9f, 0.1f, 0.8f, 1.0f, 0.2f, 0.2f, 0.1f, 1.0f, 0.5f, 0.5f, 0.5f};
+    const std::vector<float> vars(12, 0.1f);
+    LaplacianConfig cfg; cfg.k_neighbors = 2;
+    LaplacianOutput lap = LaplacianStage(cfg).execute(means, vars, 4, 3);
+    CHECK(lap.n_features == 3 && lap.nnz > 0, "Stage C output");
+    const double* d00 = lap.matrix.get(0, 0);
+    CHECK(d00 && std::fabs(*d00 - 1.0) < 1e-5, "L_sym diagonal is 1 for connected nodes");
+    const std::vector<float> data = {1.0f, 0.0f, 0.0f, 0.5f, 0.5f, 0.5f};
+    std::vector<double> lambdas = compute_tau_mode_gpu(lap, data, 2, 3);
+    CHECK(lambdas.size() == 2 && std::isfinite(lambdas[0]) && std::isfinite(lambdas[1]), "lambdas finite");
+    // zero vector: finite (test_zero_vector_safety)
+    std::vector<double> z = compute_tau_mode_gpu(lap, {0.f, 0.f, 0.f, 1.f, 1.f, 1.f}, 2, 3);
+    CHECK(std::isfinite(z[0]) && std::isfinite(z[1]), "zero vector is safe");
+    // compute_tau against the oracle's restatement of taumode.rs:37-65
+    std::mt19937 rng(5);
+    std::vector<float> lam(1001);
+    for (auto& v : lam) v = std::generate_canonical<float, 24>(rng);
+    lam[17] = NAN; lam[400] = INFINITY;
+    const CoreTauMode modes[] = {CoreTauMode::Median(), CoreTauMode::Mean(), CoreTauMode::Fixed(0.25f), CoreTauMode::Fixed(-1.f), CoreTauMode::Percentile(0.9f)};
+    for (const auto& m : modes) CHECK(compute_tau(lam, m) == orc_compute_tau_core(lam.data(), lam.size(), m.kind, m.value), "compute_tau mode %d", m.kind);
+    CHECK(compute_tau({}, CoreTauMode::Median()) == 1e-9f, "empty distribution -> TAU_FLOOR");
+}
+
 int main() {
+    test_stage_d_seam();
     test_basic_laplacian_construction();
     test_laplacian_mathematical_properties();
     test_with_adjacency_output();
