@@ -163,7 +163,7 @@ def build_once(sfb, ctx, X, wl, rank, world, out_lambda=None, keep=False):
     # the feature graph (the reference's call shape: nodes = columns) is registered first and runs on a side stream
     # beside the item graph's tensor-core screen; .end() joins it
     pend = X.knn_columns_begin(feature_k(wl), sfb.METRIC_COSINE, sharded=world > 1)
-    g = _timed(ctx, "knn", lambda: X.knn(wl["k"], wl["metric"], q_begin=lo, q_end=hi))
+    g = _timed(ctx, "knn", lambda: X.knn(wl["k"], wl["metric"], q_begin=lo, q_end=hi, sharded=world > 1))
     st = g.stats()
     if world > 1:
         g_all = _timed(ctx, "allgather", lambda: g.allgather(n))
@@ -260,6 +260,17 @@ def run_ours(args):
     ms_total, wall_ms = float(t[0]), float(t[1])
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3)
+    # per-rank view of the same steps: a sharded step ends when the slowest rank does (the GPUs of a box are power-capped differently)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([ms / args.steps, sum(s_["ms_screen"] for s_ in stats) / len(stats), sum(s_["ms_rescore"] for s_ in stats) / len(stats),
+                             sum(s_["ms_prepare"] for s_ in stats) / len(stats), sum(s_["ms_fallback"] for s_ in stats) / len(stats),
+                             tm["ms_knn"] / args.steps, tm["ms_laplacian"] / args.steps, tm["ms_lambda"] / args.steps, tm.get("ms_comm", 0.0) / args.steps],
+                            device="cuda", dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        names = ("ms_step", "ms_screen", "ms_rescore", "ms_prepare", "ms_fallback", "ms_knn", "ms_laplacian", "ms_lambda", "ms_comm")
+        per_rank = {nm: [round(float(a[i]), 2) for a in allr] for i, nm in enumerate(names)}
 
     # ---- the energy pipeline's diffusion pass (config c5), timed apart from the build ----------
     diffusion = None
@@ -379,6 +390,8 @@ def run_ours(args):
             "gpu_launches": int(tm["kernel_launches"]),
             "clocks": clocks, "roofline": roof, "roofline_stages": stages, "e2e": e2e,
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if diffusion is not None:
             line["diffusion"] = diffusion
         if verify is not None:

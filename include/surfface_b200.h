@@ -333,6 +333,7 @@ typedef struct {
     uint64_t kernel_launches; /* kernels of this library launched since ctx creation */
     double ms_lambda_kernel;  /* the per-item lambda kernel alone (inside ms_lambda)         */
     double ms_diffuse;        /* sfb_diffuse                                                  */
+    double ms_comm;           /* NCCL exchanges (all-gathers, all-reduces), incl. waiting for the slowest rank */
 } sfb_stage_times;
 int32_t sfb_timings(const sfb_ctx* ctx, sfb_stage_times* out);
 /* device stopwatch on the context's stream (CUDA events): start, run any calls, stop -> ms */
@@ -353,6 +354,11 @@ int32_t sfb_mat_allgather_rows(sfb_ctx* ctx, const sfb_mat* shard, uint64_t tota
  * (few columns, many rows) the exact f64 pair sums are split across the ranks and all-reduced (each sum is
  * produced by exactly one rank, so the result has the same bits as the single-GPU build). */
 int32_t sfb_knn_build_columns_sharded(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* params, sfb_knn** out);
+/* sfb_knn_build as a COLLECTIVE: every rank passes the same (replicated) matrix and its own ceil-split query shard in
+ * params->q_begin / q_end.  Same result as sfb_knn_build; the operand preparation of the tensor-core screen (row norms,
+ * 16-bit conversion, rounding residuals: one pass over the f64 matrix) is done by each rank for its own rows only and
+ * all-gathered over NVLink. */
+int32_t sfb_knn_build_sharded(sfb_ctx* ctx, const sfb_mat* rows, const sfb_knn_params* params, sfb_knn** out);
 /* gathers equal row shards of every rank into a full-M kNN handle (all ranks get a copy) */
 int32_t sfb_knn_allgather(sfb_ctx* ctx, const sfb_knn* shard, uint64_t total_rows, sfb_knn** out);
 /* lambda over this rank's rows of X, min/max all-reduced, normalised, all-gathered into out (total_rows) */

@@ -204,10 +204,13 @@ class Matrix(_Handle):
         return out
 
     def knn(self, k, metric=METRIC_COSINE, eps=math.inf, screen=SCREEN_AUTO, k_prime=0, q_begin=0, q_end=0,
-            allow_fallback=True):
+            allow_fallback=True, sharded=False):
+        """sharded=True: the collective form (every rank of the communicator calls it with the same matrix and its own
+        ceil-split [q_begin, q_end)): the operand preparation is split across the ranks."""
         p = _ffi.KnnParams(metric, k, float(eps), screen, k_prime, q_begin, q_end, int(allow_fallback))
         h = C.c_void_p()
-        self.ctx.check(lib().sfb_knn_build(self.ctx._h, self._h, C.byref(p), C.byref(h)))
+        fn = lib().sfb_knn_build_sharded if sharded else lib().sfb_knn_build
+        self.ctx.check(fn(self.ctx._h, self._h, C.byref(p), C.byref(h)))
         return KnnGraph(self.ctx, h)
 
     def knn_columns(self, k, metric=METRIC_COSINE, eps=math.inf, screen=SCREEN_AUTO, sharded=False):

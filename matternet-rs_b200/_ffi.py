@@ -61,7 +61,7 @@ class LaplacianConfigC(C.Structure):
 class StageTimes(C.Structure):
     _fields_ = [("ms_h2d", C.c_double), ("ms_knn", C.c_double), ("ms_adjacency", C.c_double),
                 ("ms_laplacian", C.c_double), ("ms_lambda", C.c_double), ("ms_d2h", C.c_double),
-                ("kernel_launches", C.c_uint64), ("ms_lambda_kernel", C.c_double), ("ms_diffuse", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("ms_lambda_kernel", C.c_double), ("ms_diffuse", C.c_double), ("ms_comm", C.c_double)]
 
 
 # every symbol include/surfface_b200.h declares: name -> (restype, argtypes)
@@ -87,6 +87,7 @@ SYMBOLS = {
     "sfb_mat_copy_rows": (C.c_int32, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "sfb_mat_free": (None, [_P]),
     "sfb_knn_build": (C.c_int32, [_P, _P, C.POINTER(KnnParams), _PP]),
+    "sfb_knn_build_sharded": (C.c_int32, [_P, _P, C.POINTER(KnnParams), _PP]),
     "sfb_knn_build_columns": (C.c_int32, [_P, _P, C.POINTER(KnnParams), _PP]),
     "sfb_knn_build_columns_sharded": (C.c_int32, [_P, _P, C.POINTER(KnnParams), _PP]),
     "sfb_knn_build_columns_begin": (C.c_int32, [_P, _P, C.POINTER(KnnParams), C.c_int32, _PP]),

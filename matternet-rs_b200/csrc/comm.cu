@@ -97,6 +97,7 @@ void sfb_comm_destroy(sfb_ctx* ctx) {
 int32_t sfb_comm_allreduce_sum_f64(sfb_ctx* ctx, double* buf, size_t n) {
     if (ctx->world == 1) return SFB_OK;
     if (!ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    StageTimer tc(ctx, &ctx->times.ms_comm);
     SFB_NCCL(ctx, nccl()->AllReduce(buf, buf, n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return SFB_OK;
 }
@@ -105,6 +106,22 @@ int32_t sfb_comm_allreduce_sum_f32(sfb_ctx* ctx, float* buf, size_t n) {
     if (ctx->world == 1) return SFB_OK;
     if (!ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
     SFB_NCCL(ctx, nccl()->AllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return SFB_OK;
+}
+
+// in-place all-gather of equal byte slots: rank r's slot is base + r * bytes_per_rank
+int32_t sfb_comm_allgather_bytes(sfb_ctx* ctx, void* base, size_t bytes_per_rank) {
+    if (ctx->world == 1) return SFB_OK;
+    if (!ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    StageTimer tc(ctx, &ctx->times.ms_comm);
+    SFB_NCCL(ctx, nccl()->AllGather((const char*)base + (size_t)ctx->rank * bytes_per_rank, base, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return SFB_OK;
+}
+int32_t sfb_comm_allreduce_max_u64(sfb_ctx* ctx, unsigned long long* buf, size_t n) {
+    if (ctx->world == 1) return SFB_OK;
+    if (!ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    StageTimer tc(ctx, &ctx->times.ms_comm);
+    SFB_NCCL(ctx, nccl()->AllReduce(buf, buf, n, ncclUint64, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return SFB_OK;
 }
 
@@ -151,6 +168,7 @@ extern "C" int32_t sfb_knn_allgather(sfb_ctx* ctx, const sfb_knn* shard, uint64_
     SFB_CUDA(ctx, cudaMemcpyAsync(my_cnt, shard->cnt, sizeof(uint32_t) * shard->rows, cudaMemcpyDeviceToDevice, ctx->stream));
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     // the three lists in one grouped call: one launch, one pass over the NVLink rings
+    StageTimer tc(ctx, &ctx->times.ms_comm);
     SFB_NCCL(ctx, nccl()->GroupStart());
     ncclResult_t r1 = nccl()->AllGather(my_idx, g->idx, S * k, ncclUint32, comm, ctx->stream);
     ncclResult_t r2 = nccl()->AllGather(my_dist, g->dist, S * k, ncclFloat64, comm, ctx->stream);
@@ -211,6 +229,7 @@ extern "C" int32_t sfb_lambda_allgather(sfb_ctx* ctx, const sfb_csr* L, const sf
     ctx->lambda_sharded = false;
     SFB_TRY(st);
     if (world > 1) {   // global min / max(0, .) (core.rs:1345-1346), on the device values: no host round trip
+        StageTimer tc(ctx, &ctx->times.ms_comm);
         ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
         SFB_NCCL(ctx, nccl()->GroupStart());
         ncclResult_t r1 = nccl()->AllReduce(mm.p, mm.p, 1, ncclFloat64, ncclMin, comm, ctx->stream);

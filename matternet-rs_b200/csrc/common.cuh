@@ -32,6 +32,7 @@ struct sfb_ctx {
     // NCCL (loaded lazily, comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    bool knn_collective = false;   // inside sfb_knn_build_sharded: operand preparation is split across the ranks (knn_screen.cu)
     bool lambda_sharded = false;   // inside sfb_lambda_allgather: per-rank totals of CORE_F32SEM are all-reduced (lambda.cu)
 };
 
@@ -160,6 +161,8 @@ int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int m
                       const uint32_t* query_rows /* device, or null */, uint64_t nq, uint64_t q_begin,
                       uint32_t* out_idx, double* out_dist, uint32_t* out_cnt);
 void sfb_comm_destroy(sfb_ctx* ctx);
+int32_t sfb_comm_allgather_bytes(sfb_ctx* ctx, void* base, size_t bytes_per_rank);   // comm.cu: in-place, slot r = base + r * bytes
+int32_t sfb_comm_allreduce_max_u64(sfb_ctx* ctx, unsigned long long* buf, size_t n);
 int32_t sfb_mat_alloc(sfb_ctx* ctx, uint64_t rows, uint32_t cols, sfb_mat** out);  // api.cu: uninitialised rows x cols f64
 // launches the registered side job, if any (called right after the screen kernel is enqueued, so that the persistent
 // screen CTAs are placed first and the side kernel's small CTAs fill in beside them)

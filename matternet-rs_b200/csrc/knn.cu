@@ -67,11 +67,20 @@ static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_no
             view.d = tmp.as<double>(); view.rows = nodes; view.cols = (uint32_t)dims; view.owns = false;
         }
         DevBuf norms;
+        const bool shared_work = ctx->knn_collective && ctx->world > 1;
+        const uint64_t nw = shared_work ? (uint64_t)ctx->world : 1, S = (nodes + nw - 1) / nw;
         if (st == SFB_OK) {
-            cudaError_t e = (sfb_tls_ctx = ctx, norms.alloc(sizeof(double) * nodes));
+            cudaError_t e = (sfb_tls_ctx = ctx, norms.alloc(sizeof(double) * nw * S));
             if (e != cudaSuccess) st = sfb_fail(ctx, SFB_ENOMEM, "norms: %s", cudaGetErrorString(e));
         }
-        if (st == SFB_OK && p->metric == SFB_METRIC_COSINE) st = sfb_row_norms(ctx, &view, norms.as<double>());
+        if (st == SFB_OK && p->metric == SFB_METRIC_COSINE) {
+            if (!shared_work) st = sfb_row_norms(ctx, &view, norms.as<double>());
+            else {   // the norms of this rank's rows, all-gathered
+                const uint64_t r0 = (uint64_t)ctx->rank * S < nodes ? (uint64_t)ctx->rank * S : nodes, r1 = r0 + S < nodes ? r0 + S : nodes;
+                if (r1 > r0) { sfb_mat part = view; part.d = view.d + r0 * view.cols; part.rows = r1 - r0; st = sfb_row_norms(ctx, &part, norms.as<double>() + r0); }
+                if (st == SFB_OK) st = sfb_comm_allgather_bytes(ctx, norms.p, (size_t)S * sizeof(double));
+            }
+        }
         tr.mark("norms");
         if (screen == SFB_SCREEN_AUTO) {
             // the screen pays off once the pair count dwarfs its fixed costs and k' stays small
@@ -104,6 +113,16 @@ static int32_t knn_build_any(sfb_ctx* ctx, const sfb_mat* x, bool columns_are_no
 
 extern "C" int32_t sfb_knn_build(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, sfb_knn** out) {
     return knn_build_any(ctx, x, false, p, out, 0);
+}
+
+// The COLLECTIVE form for a row-sharded build: every rank passes the same matrix and its own query shard.
+extern "C" int32_t sfb_knn_build_sharded(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, sfb_knn** out) {
+    if (!ctx) return SFB_EINVAL;
+    if (ctx->world > 1 && !ctx->nccl_comm) return sfb_fail(ctx, SFB_ENCCL, "communicator not initialised");
+    ctx->knn_collective = true;
+    const int32_t st = knn_build_any(ctx, x, false, p, out, 0);
+    ctx->knn_collective = false;
+    return st;
 }
 
 extern "C" int32_t sfb_knn_build_columns(sfb_ctx* ctx, const sfb_mat* x, const sfb_knn_params* p, sfb_knn** out) {

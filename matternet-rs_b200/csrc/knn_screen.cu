@@ -135,14 +135,15 @@ __global__ void absmax_kernel(const double* __restrict__ x, uint64_t n, unsigned
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));  // non-negative doubles order as integers
 }
 
-// One warp per row.  aux[0..M): |q_i|, [M..2M): |delta_i|, [2M..3M): |q_i|^2 (f64).  gmax[0] = max |q|, gmax[1] = max |delta|.
+// One warp per row of [row0, row0 + nrows).  aux[3 i + {0, 1, 2}] = |q_i|, |delta_i|, |q_i|^2 (f64).  gmax[0] = max |q|, gmax[1] = max |delta|.
 template <bool BF16>
-__global__ void prepare_kernel(const double* __restrict__ x, const double* __restrict__ norms, uint64_t m, uint32_t kd,
+__global__ void prepare_kernel(const double* __restrict__ x, const double* __restrict__ norms, uint64_t row0, uint64_t nrows, uint32_t kd,
                                uint32_t kpad, int cosine, double scale, uint16_t* __restrict__ q, float* __restrict__ nq32,
                                double* __restrict__ aux, unsigned long long* __restrict__ gmax) {
     const int lane = threadIdx.x & 31;
-    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= m) return;
+    const uint64_t li = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (li >= nrows) return;
+    const uint64_t i = row0 + li;
     double mul = scale;
     if (cosine) { double nrm = norms[i]; mul = nrm > 0.0 ? scale / nrm : 0.0; }
     if (!isfinite(mul)) mul = 0.0;
@@ -167,7 +168,7 @@ __global__ void prepare_kernel(const double* __restrict__ x, const double* __res
     if (lane == 0) {
         double qn = sqrt(sq) * (1.0 + 1e-12), dn = sqrt(sd) * (1.0 + 1e-12);
         if (!isfinite(dn)) dn = INFINITY;
-        aux[i] = qn; aux[m + i] = dn; aux[2 * m + i] = sq;
+        aux[3 * i] = qn; aux[3 * i + 1] = dn; aux[3 * i + 2] = sq;
         nq32[i] = (float)sq;
         atomicMax(&gmax[0], (unsigned long long)__double_as_longlong(qn));
         atomicMax(&gmax[1], (unsigned long long)__double_as_longlong(dn));
@@ -938,7 +939,7 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
     const uint64_t orow = (uint64_t)gi - a.out_base;
     const double* xi = a.x + (uint64_t)gi * a.kd;
     const double ni = COS ? a.norms[gi] : 0.0;
-    const double qn = a.aux[gi], dn = a.aux[a.m + gi], q2 = a.aux[2 * a.m + gi];
+    const double qn = a.aux[3 * (size_t)gi], dn = a.aux[3 * (size_t)gi + 1], q2 = a.aux[3 * (size_t)gi + 2];
     const double s2 = a.scale * a.scale;
     // error model of the screen key (see the header comment of this file)
     const double cos_margin = ((a.gamma * qn + dn) * a.nmax + a.scale * a.dmax) * (1.0 + 1e-6) + s2 * 1e-9;  // key units
@@ -1187,22 +1188,37 @@ struct Prepared {
     bool bf16 = false;
 };
 
+// `ctx->knn_collective` (sfb_knn_build_sharded: every rank of the communicator is in this call with the same matrix): each
+// rank converts the rows of its own ceil-split shard and the operands, their norms and residuals are all-gathered over NVLink
+// instead of being recomputed on every GPU.
 int32_t prepare_operands(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int metric, bool bf16, Prepared* P) {
     const uint64_t m = x->rows;
+    const bool shared_work = ctx->knn_collective && ctx->world > 1;
+    const uint64_t world = shared_work ? (uint64_t)ctx->world : 1, S = (m + world - 1) / world;
+    const uint64_t r0 = shared_work ? ((uint64_t)ctx->rank * S < m ? (uint64_t)ctx->rank * S : m) : 0;
+    const uint64_t r1 = shared_work ? (r0 + S < m ? r0 + S : m) : m;
     P->bf16 = bf16;
     P->kpad = (x->cols + BK - 1) / BK * BK;
     P->mpad = (m + BN - 1) / BN * BN;
-    SFB_CUDA(ctx, P->q.alloc((size_t)P->mpad * P->kpad * 2));
-    SFB_CUDA(ctx, P->nq32.alloc(sizeof(float) * P->mpad));
-    SFB_CUDA(ctx, P->aux.alloc(sizeof(double) * 3 * m));
+    const uint64_t rows_alloc = P->mpad > world * S ? P->mpad : world * S;   // equal-count all-gather slots
+    SFB_CUDA(ctx, P->q.alloc((size_t)rows_alloc * P->kpad * 2));
+    SFB_CUDA(ctx, P->nq32.alloc(sizeof(float) * rows_alloc));
+    SFB_CUDA(ctx, P->aux.alloc(sizeof(double) * 3 * rows_alloc));
     SFB_CUDA(ctx, P->gmax.alloc(4 * sizeof(unsigned long long)));
-    SFB_CUDA(ctx, cudaMemsetAsync(P->q.p, 0, (size_t)P->mpad * P->kpad * 2, ctx->stream));
+    SFB_CUDA(ctx, cudaMemsetAsync(P->q.p, 0, (size_t)rows_alloc * P->kpad * 2, ctx->stream));
     SFB_CUDA(ctx, cudaMemsetAsync(P->gmax.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (shared_work) {
+        SFB_CUDA(ctx, cudaMemsetAsync(P->nq32.p, 0, sizeof(float) * rows_alloc, ctx->stream));
+        SFB_CUDA(ctx, cudaMemsetAsync(P->aux.p, 0, sizeof(double) * 3 * rows_alloc, ctx->stream));
+    }
     const bool cosine = metric == SFB_METRIC_COSINE;
     P->scale = COS_SCALE;
     if (!cosine) {
-        absmax_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(x->d, m * x->cols, P->gmax.as<unsigned long long>() + 2);
-        SFB_LAUNCH_CHECK(ctx);
+        if (r1 > r0) {
+            absmax_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(x->d + r0 * x->cols, (r1 - r0) * x->cols, P->gmax.as<unsigned long long>() + 2);
+            SFB_LAUNCH_CHECK(ctx);
+        }
+        if (shared_work) SFB_TRY(sfb_comm_allreduce_max_u64(ctx, P->gmax.as<unsigned long long>() + 2, 1));   // non-negative doubles order as integers
         double amax = 0.0;
         SFB_CUDA(ctx, cudaMemcpyAsync(&amax, P->gmax.as<unsigned long long>() + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
         SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1212,13 +1228,21 @@ int32_t prepare_operands(sfb_ctx* ctx, const sfb_mat* x, const double* norms, in
         if (amax > 0.0) { frexp(amax, &e); e = 8 - e; }
         P->scale = ldexp(1.0, e);
     }
-    if (bf16)
-        prepare_kernel<true><<<div_up(m * 32, 256), 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, P->kpad, cosine, P->scale, P->q.as<uint16_t>(),
-                                                                            P->nq32.as<float>(), P->aux.as<double>(), P->gmax.as<unsigned long long>());
-    else
-        prepare_kernel<false><<<div_up(m * 32, 256), 256, 0, ctx->stream>>>(x->d, norms, m, x->cols, P->kpad, cosine, P->scale, P->q.as<uint16_t>(),
-                                                                             P->nq32.as<float>(), P->aux.as<double>(), P->gmax.as<unsigned long long>());
-    SFB_LAUNCH_CHECK(ctx);
+    if (r1 > r0) {
+        if (bf16)
+            prepare_kernel<true><<<div_up((r1 - r0) * 32, 256), 256, 0, ctx->stream>>>(x->d, norms, r0, r1 - r0, x->cols, P->kpad, cosine, P->scale, P->q.as<uint16_t>(),
+                                                                                      P->nq32.as<float>(), P->aux.as<double>(), P->gmax.as<unsigned long long>());
+        else
+            prepare_kernel<false><<<div_up((r1 - r0) * 32, 256), 256, 0, ctx->stream>>>(x->d, norms, r0, r1 - r0, x->cols, P->kpad, cosine, P->scale, P->q.as<uint16_t>(),
+                                                                                       P->nq32.as<float>(), P->aux.as<double>(), P->gmax.as<unsigned long long>());
+        SFB_LAUNCH_CHECK(ctx);
+    }
+    if (shared_work) {
+        SFB_TRY(sfb_comm_allgather_bytes(ctx, P->q.p, (size_t)S * P->kpad * 2));
+        SFB_TRY(sfb_comm_allgather_bytes(ctx, P->nq32.p, (size_t)S * sizeof(float)));
+        SFB_TRY(sfb_comm_allgather_bytes(ctx, P->aux.p, (size_t)S * 3 * sizeof(double)));
+        SFB_TRY(sfb_comm_allreduce_max_u64(ctx, P->gmax.as<unsigned long long>(), 2));
+    }
     double g[2];
     SFB_CUDA(ctx, cudaMemcpyAsync(g, P->gmax.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

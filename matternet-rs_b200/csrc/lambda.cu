@@ -1504,7 +1504,7 @@ extern "C" int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, doubl
     SFB_CUDA(ctx, cudaFuncSetAttribute(diffuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t want = (x->rows + wpb - 1) / wpb;
     unsigned grid = (unsigned)(want < (uint64_t)ctx->sm_count * 4 ? want : (uint64_t)ctx->sm_count * 4);
-    StageTimer t(ctx, &ctx->times.ms_lambda);
+    StageTimer t(ctx, &ctx->times.ms_diffuse);
     diffuse_kernel<<<grid, wpb * 32, smem, ctx->stream>>>(L->indptr, L->indices, L->data, x->cols, x->d, x->rows, eta, steps);
     SFB_LAUNCH_CHECK(ctx);
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

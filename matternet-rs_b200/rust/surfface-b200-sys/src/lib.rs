@@ -26,7 +26,7 @@ pub struct sfb_graph_params { pub eps: f64, pub k: u32, pub topk: u32, pub p: f6
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct sfb_laplacian_config { pub k_neighbors: u32, pub variance_regularizer: f32, pub normalize: i32, pub weight_threshold: f32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct sfb_stage_times { pub ms_h2d: f64, pub ms_knn: f64, pub ms_adjacency: f64, pub ms_laplacian: f64, pub ms_lambda: f64, pub ms_d2h: f64, pub kernel_launches: u64, pub ms_lambda_kernel: f64, pub ms_diffuse: f64 }
+pub struct sfb_stage_times { pub ms_h2d: f64, pub ms_knn: f64, pub ms_adjacency: f64, pub ms_laplacian: f64, pub ms_lambda: f64, pub ms_d2h: f64, pub kernel_launches: u64, pub ms_lambda_kernel: f64, pub ms_diffuse: f64, pub ms_comm: f64 }
 
 extern "C" {
     pub fn sfb_abi_version() -> i32;
@@ -47,6 +47,7 @@ extern "C" {
     pub fn sfb_mat_copy_rows(ctx: *mut sfb_ctx, a: *const sfb_mat, row0: u64, nrows: u64, out: *mut f64) -> i32;
     pub fn sfb_mat_free(a: *mut sfb_mat);
     pub fn sfb_knn_build(ctx: *mut sfb_ctx, rows: *const sfb_mat, params: *const sfb_knn_params, out: *mut *mut sfb_knn) -> i32;
+    pub fn sfb_knn_build_sharded(ctx: *mut sfb_ctx, rows: *const sfb_mat, params: *const sfb_knn_params, out: *mut *mut sfb_knn) -> i32;
     pub fn sfb_knn_build_columns(ctx: *mut sfb_ctx, x: *const sfb_mat, params: *const sfb_knn_params, out: *mut *mut sfb_knn) -> i32;
     pub fn sfb_knn_shape(g: *const sfb_knn, rows: *mut u64, k: *mut u32, q_begin: *mut u64) -> i32;
     pub fn sfb_knn_copy(ctx: *mut sfb_ctx, g: *const sfb_knn, idx: *mut u32, dist: *mut f64, cnt: *mut u32) -> i32;

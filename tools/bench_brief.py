@@ -20,6 +20,9 @@ for path in sys.argv[1:]:
         print("  e2e %.4g  ms/step %.2f" % (d["e2e"]["value"], d["e2e"]["ms_per_step"]))
     if d.get("diffusion"):
         print("  diffusion", d["diffusion"])
+    if d.get("per_rank"):
+        for k, v in d["per_rank"].items():
+            print("  per-rank %-12s %s" % (k, v))
     print("  verify", d.get("verify"))
     print("  clocks", d.get("clocks"))
     if d.get("cpu_baseline"):
