@@ -767,7 +767,7 @@ __device__ __forceinline__ void lt_cp_async16(void* smem_dst, const void* gsrc) 
 // at the end of phase 2
 // FULL: f == 32 E (every lane slot holds an entry): the bounds tests of phase 1 compile away
 template <int VARIANT, int E, int LT_WARPS, bool FULL>
-__global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? 2 : 1) lambda_tile_kernel(LambdaTileArgs a) {
+__global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? (E <= 4 ? 4 : 2) : 1) lambda_tile_kernel(LambdaTileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t f = FULL ? 32u * E : a.f;
@@ -1049,7 +1049,7 @@ int32_t lt_launch_full(sfb_ctx* ctx, const LambdaTileArgs& a) {
     int per_sm = 1;
     SFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 8) per_sm = 8;
     const uint64_t tiles = (a.n + 31) / 32, cap = (uint64_t)ctx->sm_count * per_sm;
     kern<<<(unsigned)(tiles < cap ? tiles : cap), NW * 32, smem, ctx->stream>>>(a);
     SFB_LAUNCH_CHECK(ctx);

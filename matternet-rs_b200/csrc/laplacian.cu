@@ -182,6 +182,7 @@ struct MergeArgs {
     // final != 0 (unnormalised form): the scratch segment receives the finished CSR row -- neighbours as -w with the diagonal
     // (the degree) inserted in column order, ulen + 1 entries -- and the emit pass is a plain segmented copy
     int final;
+    int slots64;   // node indices below 2^26: rows of 33..64 edges are sorted in registers too (two entries per lane)
 };
 // scratch segment of local row li: capacity k + 1 + bucket length
 __device__ __forceinline__ uint64_t tmp_offset(const MergeArgs& a, uint64_t li, uint64_t ro) { return li * (a.k + 1) + ro; }
@@ -262,6 +263,80 @@ __global__ void __launch_bounds__(256) lap_merge_rows_kernel(MergeArgs a) {
                 else { a.tmp_col[to + pos] = col; a.tmp_w[to + pos] = wh; }
             }
             __syncwarp();
+        }
+    }
+    if (KEY32 && !in_regs && l <= 64 && a.slots64) {
+        // 33..64 edges (k = 64 graphs after sparsification): two entries per lane, element e = lane (+ 32), one 64-key bitonic
+        // network: stride 32 is a compare-exchange between the lane's own two keys, smaller strides are shuffles
+        uint32_t key[2]; double w[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t t = lane + 32 * h;
+            uint32_t c = SFB_IDX_NONE; w[h] = 0.0;
+            if (t < fc) { c = a.a_idx[i * a.k + t]; w[h] = a.a_w[i * a.k + t]; if (c == (uint32_t)i) c = SFB_IDX_NONE; }
+            else if (t < l) { c = a.rev_src[ro + (t - fc)]; w[h] = a.rev_w[ro + (t - fc)]; }
+            key[h] = c == SFB_IDX_NONE ? 0xFFFFFFFFu : (c << 6 | t);
+        }
+#pragma unroll
+        for (uint32_t size = 2; size <= 64; size <<= 1)
+#pragma unroll
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                if (stride == 32) {   // partner of element lane is element lane + 32; size = 64: ascending
+                    const uint32_t lo = min(key[0], key[1]), hi = max(key[0], key[1]);
+                    key[0] = lo; key[1] = hi;
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t e = lane + 32 * h;
+                        const uint32_t other = __shfl_xor_sync(FULL, key[h], stride);
+                        const bool take_min = ((e & size) == 0) == ((e & stride) == 0);
+                        key[h] = take_min ? min(key[h], other) : max(key[h], other);
+                    }
+                }
+            }
+        uint32_t col[2]; double ws[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            col[h] = key[h] == 0xFFFFFFFFu ? SFB_IDX_NONE : key[h] >> 6;
+            const uint32_t slot = key[h] & 63u;
+            const double wa = __shfl_sync(FULL, w[0], (int)(slot & 31u)), wb = __shfl_sync(FULL, w[1], (int)(slot & 31u));
+            ws[h] = slot < 32u ? wa : wb;
+        }
+        // neighbours in sorted order: element e - 1 / e - 2 / e + 1 of (lane, h)
+        const uint32_t c0_up1 = __shfl_up_sync(FULL, col[0], 1), c1_up1 = __shfl_up_sync(FULL, col[1], 1);
+        const uint32_t c0_up2 = __shfl_up_sync(FULL, col[0], 2), c1_up2 = __shfl_up_sync(FULL, col[1], 2);
+        const uint32_t c0_last = __shfl_sync(FULL, col[0], 31), c0_last2 = __shfl_sync(FULL, col[0], 30);
+        const uint32_t c0_dn = __shfl_down_sync(FULL, col[0], 1), c1_dn = __shfl_down_sync(FULL, col[1], 1), c1_first = __shfl_sync(FULL, col[1], 0);
+        const double w0_dn = __shfl_down_sync(FULL, ws[0], 1), w1_dn = __shfl_down_sync(FULL, ws[1], 1), w1_first = __shfl_sync(FULL, ws[1], 0);
+        const uint32_t prev[2] = {lane ? c0_up1 : SFB_IDX_NONE, lane ? c1_up1 : c0_last};
+        const uint32_t prev2[2] = {lane >= 2 ? c0_up2 : SFB_IDX_NONE, lane >= 2 ? c1_up2 : (lane == 1 ? c0_last : c0_last2)};
+        const uint32_t next[2] = {lane < 31 ? c0_dn : c1_first, lane < 31 ? c1_dn : SFB_IDX_NONE};
+        const double wnext[2] = {lane < 31 ? w0_dn : w1_first, w1_dn};
+        bool triple = false, head[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool valid = col[h] != SFB_IDX_NONE;
+            const bool has_prev = h == 1 || lane > 0, has_prev2 = h == 1 || lane > 1;
+            triple = triple || (valid && has_prev2 && col[h] == prev[h] && col[h] == prev2[h]);
+            head[h] = valid && (!has_prev || col[h] != prev[h]);
+        }
+        if (!__any_sync(FULL, triple)) {
+            const uint32_t hb0 = __ballot_sync(FULL, head[0]), hb1 = __ballot_sync(FULL, head[1]);
+            const uint32_t lt = (1u << lane) - 1u;
+            const uint32_t pos[2] = {(uint32_t)__popc(hb0 & lt), (uint32_t)(__popc(hb0) + __popc(hb1 & lt))};
+            u = __popc(hb0) + __popc(hb1);
+            n_left = __popc(__ballot_sync(FULL, head[0] && col[0] < (uint32_t)i)) + __popc(__ballot_sync(FULL, head[1] && col[1] < (uint32_t)i));
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (head[h]) {
+                    const bool dup = next[h] == col[h] && !(h == 1 && lane == 31);
+                    const double wh = (dup && wnext[h] > ws[h]) ? wnext[h] : ws[h];   // duplicates -> max
+                    sw[pos[h]] = wh;
+                    if (a.final) { const uint32_t d = pos[h] + (col[h] > (uint32_t)i ? 1u : 0u); a.tmp_col[to + d] = col[h]; a.tmp_w[to + d] = -wh; }
+                    else { a.tmp_col[to + pos[h]] = col[h]; a.tmp_w[to + pos[h]] = wh; }
+                }
+            __syncwarp();
+            in_regs = true;
         }
     }
     if (!in_regs) {
@@ -669,7 +744,7 @@ static int32_t laplacian_build_rows(sfb_ctx* ctx, const sfb_adj* a, const sfb_la
 
     MergeArgs ma{a->idx, a->w, a->cnt, k, rev_off.as<uint64_t>(), rev_src.as<uint32_t>(), rev_w.as<double>(), r_begin, nr,
                  tmp_col.as<uint32_t>(), tmp_w.as<double>(), ulen.as<uint32_t>(), deg.as<double>(),
-                 prm->normalised ? nullptr : row_nnz.as<uint32_t>(), long_list.as<uint32_t>(), n_long.as<uint32_t>(), prm->normalised ? 0 : 1};
+                 prm->normalised ? nullptr : row_nnz.as<uint32_t>(), long_list.as<uint32_t>(), n_long.as<uint32_t>(), prm->normalised ? 0 : 1, m < (1ull << 26) ? 1 : 0};
     {
         const int groups = 8;
         const size_t smem = (size_t)groups * WARP_CAP * (sizeof(double) + sizeof(uint32_t));
