@@ -234,11 +234,14 @@ __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc,
 // GTILE: pair-tile edge.  16: thread = 2 x 2 pairs (four chains per thread).  8: thread = 1 pair -- four times as many,
 // shorter-lived CTAs; used when a rank's share of the tiles would otherwise leave most SMs without a chain (every chain
 // is N steps long whatever the tile count: with G ranks the 16-edge tiling gives each rank 300 / G CTAs of two warps).
-template <bool COS, int VEC, int GCH, int GTILE>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
+// NST: stages of the cp.async ring.  A chunk is consumed in GCH * (GTILE / 8)^2 * 4 FP64-pipe cycles per warp -- a few
+// hundred at most -- while a global -> shared copy takes ~1000: with two stages the kernel waited for memory four steps out
+// of five (27 ns per fold step standalone, 45 ns in the 16-dimension variant).  NST - 1 chunks are kept in flight.
+template <bool COS, int VEC, int GCH, int GTILE, int NST>  // VEC doubles per cp.async: 2 when m is even (16-byte aligned strips), else 1
 __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G, uint32_t tile0,
                                                        uint32_t n_tiles) {
     constexpr int R = GTILE / 8;
-    __shared__ __align__(16) double sa[2][GCH][GTILE], sb[2][GCH][GTILE];
+    __shared__ __align__(16) double sa[NST][GCH][GTILE], sb[NST][GCH][GTILE];
     const uint32_t T = (m + GTILE - 1) / GTILE;
     // a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: beside the screen kernel the grid is capped at one CTA per SM
     for (uint32_t tt = blockIdx.x; tt < n_tiles; tt += gridDim.x) {
@@ -248,17 +251,22 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
     const uint32_t tj = ti + rem;
     const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
     const uint32_t ci = ti * GTILE, cj = tj * GTILE;
+    const uint64_t n_chunks = (kd + GCH - 1) / GCH;
 
-    auto stage = [&](int buf, uint64_t n0) {
-        constexpr int PIECES = GTILE / VEC;            // pieces per strip row
-        for (int e = tid; e < GCH * PIECES; e += 64) {
-            const int r = e / PIECES, pc = (e % PIECES) * VEC;
-            const uint64_t n = n0 + r;
-            const bool rv = n < kd;
-            const double* src = xd + (rv ? n : 0) * m;
-            const bool va = rv && ci + pc + VEC <= m, vb = rv && cj + pc + VEC <= m;
-            cp_async_zfill(&sa[buf][r][pc], va ? src + ci + pc : xd, VEC * 8, va);
-            cp_async_zfill(&sb[buf][r][pc], vb ? src + cj + pc : xd, VEC * 8, vb);
+    auto stage = [&](uint64_t c) {   // chunk c -> ring slot c % NST; one commit group per call, empty past the end
+        if (c < n_chunks) {
+            const int buf = (int)(c % NST);
+            const uint64_t n0 = c * GCH;
+            constexpr int PIECES = GTILE / VEC;            // pieces per strip row
+            for (int e = tid; e < GCH * PIECES; e += 64) {
+                const int r = e / PIECES, pc = (e % PIECES) * VEC;
+                const uint64_t n = n0 + r;
+                const bool rv = n < kd;
+                const double* src = xd + (rv ? n : 0) * m;
+                const bool va = rv && ci + pc + VEC <= m, vb = rv && cj + pc + VEC <= m;
+                cp_async_zfill(&sa[buf][r][pc], va ? src + ci + pc : xd, VEC * 8, va);
+                cp_async_zfill(&sb[buf][r][pc], vb ? src + cj + pc : xd, VEC * 8, vb);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -268,12 +276,12 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
     for (int di = 0; di < R; ++di)
 #pragma unroll
         for (int dj = 0; dj < R; ++dj) acc[di][dj] = 0.0;
-    const uint64_t n_chunks = (kd + GCH - 1) / GCH;
-    stage(0, 0);
+#pragma unroll
+    for (int c = 0; c < NST - 1; ++c) stage((uint64_t)c);
     for (uint64_t c = 0; c < n_chunks; ++c) {
-        const int buf = (int)(c & 1);
-        if (c + 1 < n_chunks) { stage(buf ^ 1, (c + 1) * GCH); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int buf = (int)(c % NST);
+        stage(c + NST - 1);   // its slot was consumed in the previous iteration (barrier at its end)
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
         __syncthreads();
         const uint64_t left = kd - c * GCH;
         const int lim = left < (uint64_t)GCH ? (int)left : GCH;
@@ -292,6 +300,7 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
         }
         __syncthreads();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     const uint32_t i0 = ci + R * ty, j0 = cj + R * tx;
 #pragma unroll
     for (int di = 0; di < R; ++di)
@@ -400,14 +409,15 @@ int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uin
     // beside the screen kernel: at most one CTA per SM, so that a CTA placed before the screen's never keeps the
     // screen's 216 KB from fitting (two of them would)
     const uint32_t grid = small_smem && nt > (uint32_t)ctx->sm_count ? (uint32_t)ctx->sm_count : nt;
-#define SFB_GRAM(C_, V_, G_, T_) gram_tile_kernel<C_, V_, G_, T_><<<grid, 64, 0, stream>>>(xd, m, kd, g, t0, nt)
-#define SFB_GRAM_CV(G_, T_)                                                           \
-    do {                                                                              \
-        if (cos) { if (even) SFB_GRAM(true, 2, G_, T_); else SFB_GRAM(true, 1, G_, T_); }   \
-        else { if (even) SFB_GRAM(false, 2, G_, T_); else SFB_GRAM(false, 1, G_, T_); }     \
+#define SFB_GRAM(C_, V_, G_, T_, S_) gram_tile_kernel<C_, V_, G_, T_, S_><<<grid, 64, 0, stream>>>(xd, m, kd, g, t0, nt)
+#define SFB_GRAM_CV(G_, T_, S_)                                                               \
+    do {                                                                                      \
+        if (cos) { if (even) SFB_GRAM(true, 2, G_, T_, S_); else SFB_GRAM(true, 1, G_, T_, S_); }   \
+        else { if (even) SFB_GRAM(false, 2, G_, T_, S_); else SFB_GRAM(false, 1, G_, T_, S_); }     \
     } while (0)
-    if (gt == 8) { if (small_smem) SFB_GRAM_CV(16, 8); else SFB_GRAM_CV(64, 8); }
-    else { if (small_smem) SFB_GRAM_CV(16, 16); else SFB_GRAM_CV(64, 16); }
+    // shared memory: 2 * NST * GCH * GTILE * 8 bytes -- 8 KB beside the screen (its CTA leaves ~11 KB), 32 KB standalone
+    if (gt == 8) { if (small_smem) SFB_GRAM_CV(16, 8, 4); else SFB_GRAM_CV(32, 8, 8); }
+    else { if (small_smem) SFB_GRAM_CV(16, 16, 2); else SFB_GRAM_CV(32, 16, 4); }
 #undef SFB_GRAM_CV
 #undef SFB_GRAM
     SFB_LAUNCH_CHECK(ctx);

@@ -1016,6 +1016,69 @@ __global__ void diffuse_kernel(const uint64_t* __restrict__ indptr, const uint32
     }
 }
 
+// diffusion, lane = item: a CTA stages a tile of 32 item rows transposed (as the lambda tile kernel does), keeps the whole CSR
+// of L in shared memory as (value, byte offset of the column) records, and runs the steps between two tiles in shared memory:
+// the row's record is one broadcast read for the warp, x[c] of 32 items one conflict-free read.  Every (L x)_r is the row's
+// left fold with separately rounded multiply and add (graph.rs:486-493), so the result has the reference's bits.  One HBM
+// read and one write of the rows, whatever the number of steps.
+struct __align__(16) DiffRec { double v; uint32_t coff; uint32_t pad; };
+__global__ void diffuse_pack_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const double* __restrict__ data,
+                                    uint32_t f, DiffRec* __restrict__ recs, uint32_t* __restrict__ ptr) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > f) return;
+    ptr[r] = (uint32_t)indptr[r];
+    if (r == f) return;
+    for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) { DiffRec d; d.v = data[e]; d.coff = indices[e] * (LT_TS * 8); d.pad = 0; recs[e] = d; }
+}
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) diffuse_tile_kernel(const DiffRec* __restrict__ recs, const uint32_t* __restrict__ ptr, uint32_t nnz, uint32_t f,
+                                                               double* __restrict__ x, uint64_t n, double eta, uint32_t steps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t tile = ((size_t)f * LT_TS + 1) & ~(size_t)1;
+    double* t0 = reinterpret_cast<double*>(smem_raw);
+    double* t1 = t0 + tile;
+    DiffRec* s_rec = reinterpret_cast<DiffRec*>(t1 + tile);
+    uint32_t* s_ptr = reinterpret_cast<uint32_t*>(s_rec + nnz);
+    for (uint32_t e = threadIdx.x; e < nnz; e += NW * 32) s_rec[e] = recs[e];
+    for (uint32_t r = threadIdx.x; r <= f; r += NW * 32) s_ptr[r] = ptr[r];
+    __syncthreads();
+    const uint64_t n_tiles = (n + 31) / 32;
+    constexpr int IPW = 32 / NW;
+    for (uint64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const uint64_t i0 = tl * 32;
+#pragma unroll
+        for (int qi = 0; qi < IPW; ++qi) {
+            const int it = w * IPW + qi;
+            const uint64_t i = i0 + it;
+            for (uint32_t t = lane; t < f; t += 32) t0[(size_t)t * LT_TS + it] = i < n ? __ldcs(x + i * f + t) : 0.0;
+        }
+        __syncthreads();
+        double* cur = t0; double* nxt = t1;
+        for (uint32_t s = 0; s < steps; ++s) {
+            const unsigned char* cur_lane = reinterpret_cast<const unsigned char*>(cur + lane);
+            for (uint32_t r = w; r < f; r += NW) {
+                double sum = 0.0;
+                const uint32_t e1 = s_ptr[r + 1];
+                for (uint32_t e = s_ptr[r]; e < e1; ++e) {
+                    const DiffRec d = s_rec[e];
+                    sum = __dadd_rn(sum, __dmul_rn(d.v, *reinterpret_cast<const double*>(cur_lane + d.coff)));
+                }
+                nxt[(size_t)r * LT_TS + lane] = __dadd_rn(cur[(size_t)r * LT_TS + lane], -__dmul_rn(eta, sum));
+            }
+            __syncthreads();
+            double* tmp = cur; cur = nxt; nxt = tmp;
+        }
+#pragma unroll
+        for (int qi = 0; qi < IPW; ++qi) {
+            const int it = w * IPW + qi;
+            const uint64_t i = i0 + it;
+            if (i < n) for (uint32_t t = lane; t < f; t += 32) x[i * f + t] = cur[(size_t)t * LT_TS + it];
+        }
+        __syncthreads();
+    }
+}
+
 // tau and the zero-vector test of every row (select_tau on the item, taumode.rs:174-175, and :268-274), for items that are
 // projected before the Rayleigh quotient: both are taken from the UNPROJECTED vector.  One warp per row; -1 marks a zero vector.
 __global__ void tau_rows_kernel(const double* __restrict__ x, uint64_t n, uint32_t f, int tau_mode, double tau_value, double* __restrict__ tau_out) {
@@ -1496,6 +1559,30 @@ extern "C" int32_t sfb_diffuse(sfb_ctx* ctx, const sfb_csr* L, sfb_mat* x, doubl
     if (!ctx || !L || !x) return sfb_fail(ctx, SFB_EINVAL, "null argument");
     if (L->cols && L->cols != L->rows) return sfb_fail(ctx, SFB_EINVAL, "a row shard of a Laplacian is not a square operator");
     if (L->rows != x->cols) return sfb_fail(ctx, SFB_EINVAL, "Laplacian rows %llu must match feature count %u", (unsigned long long)L->rows, x->cols);  // energymaps.rs:507-512
+    {   // tile kernel when two transposed tiles and the CSR records fit shared memory
+        const uint32_t f = x->cols;
+        const size_t tile = (((size_t)f * LT_TS + 1) & ~(size_t)1) * sizeof(double);
+        const size_t smem_t = 2 * tile + (size_t)L->nnz * sizeof(DiffRec) + ((size_t)f + 1) * sizeof(uint32_t) + 16;
+        if (smem_t <= (ctx->smem_optin ? ctx->smem_optin : 232448) && L->nnz < 0xFFFFFFFFull && f <= 0x7FFFFFFFu / (LT_TS * 8) && !getenv("SFB_DIFFUSE_ROWWISE")) {
+            DevBuf recs, ptr;
+            SFB_CUDA(ctx, recs.alloc(sizeof(DiffRec) * (L->nnz ? L->nnz : 1)));
+            SFB_CUDA(ctx, ptr.alloc(sizeof(uint32_t) * ((size_t)f + 1)));
+            StageTimer t(ctx, &ctx->times.ms_diffuse);
+            diffuse_pack_kernel<<<div_up((uint64_t)f + 1, 128), 128, 0, ctx->stream>>>(L->indptr, L->indices, L->data, f, recs.as<DiffRec>(), ptr.as<uint32_t>());
+            SFB_LAUNCH_CHECK(ctx);
+            auto kern = diffuse_tile_kernel<8>;
+            SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            int per_sm = 1;
+            SFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem_t));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 4) per_sm = 4;
+            const uint64_t tiles = (x->rows + 31) / 32, cap = (uint64_t)ctx->sm_count * per_sm;
+            kern<<<(unsigned)(tiles < cap ? tiles : cap), 256, smem_t, ctx->stream>>>(recs.as<DiffRec>(), ptr.as<uint32_t>(), (uint32_t)L->nnz, f, x->d, x->rows, eta, steps);
+            SFB_LAUNCH_CHECK(ctx);
+            t.stop();   // synchronises: the records may be released
+            return SFB_OK;
+        }
+    }
     size_t per_warp = (size_t)x->cols * 2 * sizeof(double);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;

@@ -88,6 +88,24 @@ def test_knn_columns_feature_graph(sfb, oracle, ctx, metric, n_items, n_feat, k)
     assert_knn_equal(m.knn_columns(k, metric, eps=eps).to_host(), oracle.knn(oracle.transpose(x), k, metric, eps))
 
 
+@pytest.mark.parametrize("gt", ["8", "16"])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, monkeypatch):
+    """Both pair-tile edges of the feature-graph Gram kernel (thread = 2 x 2 pairs / one pair), the stand-alone ring and the
+    small one that rides beside the screen, on shapes with ragged tiles, odd node counts and a dimension count that is not a
+    multiple of the staged chunk: every pair sum is the reference's left fold, so the lists are bit-exact."""
+    monkeypatch.setenv("SFB_GRAM_GT", gt)
+    for n_items, n_feat, k in ((4101, 37, 5), (6000, 130, 16), (5003, 64, 8)):
+        x = np.random.default_rng(n_items + metric).normal(size=(n_items, n_feat))
+        m = ctx.matrix(x)
+        want = oracle.knn(oracle.transpose(x), k, metric)
+        assert_knn_equal(m.knn_columns(k, metric).to_host(), want)
+        pend = m.knn_columns_begin(k, metric)      # fired beside the screen of the next knn()
+        g = m.knn(4, sfb.METRIC_COSINE, screen=sfb.SCREEN_F16)
+        assert_knn_equal(pend.end().to_host(), want)
+        g.free()
+
+
 def test_knn_columns_many_nodes(sfb, oracle, ctx):
     """Columns as nodes when the shape is NOT the feature-graph shape: falls back to a node-major copy."""
     x = np.random.default_rng(77).normal(size=(40, 600))
@@ -370,13 +388,17 @@ def test_lambda_kats(sfb, oracle, ctx):
         c.lambdas(ctx.matrix(np.ones((2, 4))))
 
 
-def test_diffusion_bit_exact(sfb, oracle, ctx):
-    x = np.random.default_rng(34).normal(size=(300, 40))
-    L = feature_laplacian(oracle, x, 3)
+@pytest.mark.parametrize("n,f,topk", [(300, 40, 3), (1000, 128, 4), (77, 200, 8), (33, 384, 16), (1, 64, 3)])
+def test_diffusion_bit_exact(sfb, oracle, ctx, n, f, topk):
+    """Both diffusion kernels (the tile kernel when two tiles and L fit shared memory, the row-wise one otherwise):
+    every (L x)_r is the reference's left fold, so the rows come out bit for bit, ragged tiles included."""
+    x = np.random.default_rng(34 + n).normal(size=(n, f))
+    L = feature_laplacian(oracle, np.random.default_rng(f).normal(size=(max(n, 64), f)), topk)
     c = sfb.Csr.from_host(ctx, *L)
-    for steps in (1, 4):
+    for steps in (1, 4, 5):
         m = ctx.matrix(x).diffuse(c, 0.1, steps)
         assert np.array_equal(m.rows(), oracle.diffuse(*L, x, 0.1, steps))
+    assert np.array_equal(ctx.matrix(x).diffuse(c, 0.1, 0).rows(), x)
 
 
 # ---- reference-shaped entry points ------------------------------------------------------------
