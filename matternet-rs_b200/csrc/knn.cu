@@ -153,7 +153,8 @@ struct sfb_pending {
     sfb_knn_params p{};
     int collective = 0;
     bool dense = false, launched = false;
-    bool deferred = false;   // not worth hiding: _end runs the tiles stand-alone
+    bool deferred = false;   // no side stream (or a tiny problem): _end runs the tiles inline
+    bool after_screen = false;   // fired when the screen kernel has FINISHED: runs beside the rescore, the exchanges and the item Laplacian
     uint32_t gt = 16;        // pair-tile edge (knn_exact.cu: sfb_gram_tile_edge)
     double* g = nullptr;   // 2 * m * m doubles
 };
@@ -166,10 +167,11 @@ void sfb_side_job_fire(sfb_ctx* ctx) {
     const uint32_t m = pd->x->cols;
     uint32_t t0, t1;
     sfb_gram_tile_range(ctx, m, pd->gt, pd->collective, &t0, &t1);
-    // side_fork was recorded by _begin (after the matrix upload and the memset of g) -- NOT here: an event recorded
-    // now would sit behind the screen kernel that was just enqueued
+    // co-resident: side_fork was recorded by _begin (after the matrix upload and the memset of g) -- NOT here: an event
+    // recorded now would sit behind the screen kernel that was just enqueued.  after_screen: that is exactly what is wanted.
+    if (pd->after_screen) cudaEventRecord(ctx->side_fork, ctx->stream);
     cudaStreamWaitEvent(ctx->side, ctx->side_fork, 0);
-    if (sfb_gram_launch(ctx, ctx->side, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, pd->gt, t0, t1, true) != SFB_OK) return;
+    if (sfb_gram_launch(ctx, ctx->side, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, pd->gt, t0, t1, !pd->after_screen) != SFB_OK) return;
     cudaEventRecord(ctx->side_done, ctx->side);
     pd->launched = true;
 }
@@ -192,18 +194,28 @@ extern "C" int32_t sfb_knn_build_columns_begin(sfb_ctx* ctx, const sfb_mat* x, c
             cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming);
         }
-        // Hide it only if it can finish behind the screen that is about to run on this matrix: beside the screen the kernel
-        // gets one CTA per SM and ~45 ns per fold step; otherwise _end runs it stand-alone on every SM (C4, 3072
-        // features x 100k items: 18.5k tiles would take 0.5 s co-resident against a 60 ms screen, 0.11 s alone).
+        // Two ways to keep the chains off the critical path, both on the side stream, both fired by the next screen launch:
+        //   co-resident   one small CTA per SM BESIDE the screen's: a fold step then takes ~200 ns (edge-16 tiles) / ~110 ns
+        //                 (edge 8) instead of ~10-30, because the screen's epilogue warps own the issue slots -- fine while
+        //                 tiles per CTA x N steps still finish before the screen does (C2 on one GPU: 3 x 10^6 x 200 ns < 650 ms);
+        //   after-screen  the stand-alone kernel, released by an event behind the screen kernel: it runs beside the rescore,
+        //                 the fallback, the list exchange and the item Laplacian, which leave the FP64 pipe idle (every
+        //                 sharded C2 build: at N = 8 the co-resident chain left 17-26 ms exposed behind an 80 ms screen).
         uint32_t t0, t1;
         pd->gt = sfb_gram_tile_edge(ctx, (uint32_t)nodes, pd->collective);
         sfb_gram_tile_range(ctx, (uint32_t)nodes, pd->gt, pd->collective, &t0, &t1);
         const double tiles_per_cta = ceil((double)(t1 - t0) / (double)ctx->sm_count);
-        const double gram_s = tiles_per_cta * (double)dims * 45e-9;
+        const double co_s = tiles_per_cta * (double)dims * (pd->gt == 8 ? 110e-9 : 200e-9);
         const double screen_s = 2.0 * (double)dims * (double)dims * (double)nodes / (double)(ctx->world > 0 ? ctx->world : 1) / 1.1e15;
-        const bool hide = gram_s < 0.8 * screen_s && dims >= 4096 && !getenv("SFB_NO_SIDE_STREAM");
-        if (hide && ctx->side) { cudaEventRecord(ctx->side_fork, ctx->stream); ctx->side_job = pd; }   // fired by the next screen launch, or by _end
-        pd->deferred = !(hide && ctx->side);
+        bool co = co_s < 0.9 * screen_s;
+        if (const char* e = getenv("SFB_GRAM_MODE")) { if (e[0] == 'c') co = true; else if (e[0] == 'a') co = false; }
+        const bool side = ctx->side && dims >= 4096 && !getenv("SFB_NO_SIDE_STREAM");
+        if (side) {
+            pd->after_screen = !co;
+            if (co) cudaEventRecord(ctx->side_fork, ctx->stream);
+            ctx->side_job = pd;   // fired by the next screen launch, or by _end
+        }
+        pd->deferred = !side;
     }
     *out = pd;
     return SFB_OK;

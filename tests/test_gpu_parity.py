@@ -88,13 +88,15 @@ def test_knn_columns_feature_graph(sfb, oracle, ctx, metric, n_items, n_feat, k)
     assert_knn_equal(m.knn_columns(k, metric, eps=eps).to_host(), oracle.knn(oracle.transpose(x), k, metric, eps))
 
 
+@pytest.mark.parametrize("mode", ["co", "after"])
 @pytest.mark.parametrize("gt", ["8", "16"])
 @pytest.mark.parametrize("metric", [0, 1])
-def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, monkeypatch):
+def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, mode, monkeypatch):
     """Both pair-tile edges of the feature-graph Gram kernel (thread = 2 x 2 pairs / one pair), the stand-alone ring and the
     small one that rides beside the screen, on shapes with ragged tiles, odd node counts and a dimension count that is not a
     multiple of the staged chunk: every pair sum is the reference's left fold, so the lists are bit-exact."""
     monkeypatch.setenv("SFB_GRAM_GT", gt)
+    monkeypatch.setenv("SFB_GRAM_MODE", mode)   # beside the screen kernel / released when it has finished
     for n_items, n_feat, k in ((4101, 37, 5), (6000, 130, 16), (5003, 64, 8)):
         x = np.random.default_rng(n_items + metric).normal(size=(n_items, n_feat))
         m = ctx.matrix(x)
