@@ -209,7 +209,8 @@ extern "C" int32_t sfb_knn_build_columns_begin(sfb_ctx* ctx, const sfb_mat* x, c
         const double screen_s = 2.0 * (double)dims * (double)dims * (double)nodes / (double)(ctx->world > 0 ? ctx->world : 1) / 1.1e15;
         bool co = co_s < 0.9 * screen_s;
         if (const char* e = getenv("SFB_GRAM_MODE")) { if (e[0] == 'c') co = true; else if (e[0] == 'a') co = false; }
-        const bool side = ctx->side && dims >= 4096 && !getenv("SFB_NO_SIDE_STREAM");
+        // chains of less than half a millisecond are not worth a side slot: _end runs them inline (and such builds may be stacked)
+        const bool side = ctx->side && dims >= 4096 && (double)dims * 30e-9 > 0.5e-3 && !getenv("SFB_NO_SIDE_STREAM");
         if (side) {
             pd->after_screen = !co;
             if (co) cudaEventRecord(ctx->side_fork, ctx->stream);

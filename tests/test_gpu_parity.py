@@ -97,7 +97,7 @@ def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, mode, monk
     multiple of the staged chunk: every pair sum is the reference's left fold, so the lists are bit-exact."""
     monkeypatch.setenv("SFB_GRAM_GT", gt)
     monkeypatch.setenv("SFB_GRAM_MODE", mode)   # beside the screen kernel / released when it has finished
-    for n_items, n_feat, k in ((4101, 37, 5), (6000, 130, 16), (5003, 64, 8)):
+    for n_items, n_feat, k in ((20000, 37, 5), (6000, 130, 16), (17001, 64, 8)):   # two long enough for the side stream, one run inline
         x = np.random.default_rng(n_items + metric).normal(size=(n_items, n_feat))
         m = ctx.matrix(x)
         want = oracle.knn(oracle.transpose(x), k, metric)
