@@ -313,6 +313,88 @@ __global__ void __launch_bounds__(64) gram_tile_kernel(const double* __restrict_
     }
 }
 
+// ---- the same chains without shared memory: one WARP per pair tile, operands in a register ring -----------------------
+// A chain is N dependent FP64 adds whatever the tile shape, so the kernel's time is N x (time per fold step); the
+// shared-memory kernel above pays a cp.async wait and two CTA barriers per chunk and can look ahead only as far as its
+// ring is deep -- 48 steps in the 8 KB that fit beside a resident screen CTA, where a global load takes several
+// microseconds (measured: ~100 ns per step co-resident, 17-26 ms of an 8-GPU C2 step exposed).  Here a warp owns a
+// GT x GT tile (lane = (ty, tx) of a 4 x 8 grid, RA x RB chains per lane) and streams its two column strips straight
+// into REGISTERS: a round is 8 fold steps, its 8 x GT + 8 x GT operands are RA + 2 RB coalesced loads (each lane holds a
+// different element), D - 1 rounds are in flight, and a step fetches its operands from the holding lanes by shuffle.  No
+// shared memory (any number of warps co-reside with the screen CTA: its 192 threads x 168 registers leave half the
+// register file), no barriers, 8 (D - 1) steps of look-ahead (88 at GT = 8).
+template <bool COS, int GT>
+__global__ void __launch_bounds__(32, 12) gram_warp_kernel(const double* __restrict__ xd, uint32_t m, uint64_t kd, double* __restrict__ G,
+                                                       uint32_t tile0, uint32_t n_tiles) {
+    constexpr int RA = GT / 4, RB = GT / 8;      // rows ty + 4 da, columns tx + 8 db
+    constexpr int NB = 2 * RB;                   // b loads per round: steps 0-3 and 4-7 of each 8-column group
+    constexpr int D = GT == 8 ? 12 : 6;          // rounds in flight (D * (RA + NB) doubles of ring per lane)
+    const int lane = threadIdx.x, ty = lane >> 3, tx = lane & 7;
+    const uint32_t T = (m + GT - 1) / GT;
+    const uint64_t n_rounds = (kd + 7) / 8;
+    for (uint32_t tt = blockIdx.x; tt < n_tiles; tt += gridDim.x) {
+        uint32_t ti = 0, rem = tt + tile0;
+        while (rem >= T - ti) { rem -= T - ti; ++ti; }
+        const uint32_t ci = ti * GT, cj = (ti + rem) * GT;
+        // this lane's slots of a round: a[q] = x[n0 + lane / 4][ci + lane % 4 + 4 q], b[q] = x[n0 + lane / 8 + 4 (q & 1)][cj + lane % 8 + 8 (q / 2)]
+        const uint32_t a_s = lane >> 2, a_c = ci + (lane & 3), b_s = lane >> 3, b_c = cj + (lane & 7);
+        const double* pa = xd + (uint64_t)a_s * m + a_c;      // both advance 8 rows per round
+        const double* pb = xd + (uint64_t)b_s * m + b_c;
+        const uint64_t m4 = 4ull * m, m8 = 8ull * m;
+        uint32_t colmask = 0;                                  // bit q: a column in range, bit 8 + g: b column group in range
+#pragma unroll
+        for (int q = 0; q < RA; ++q) colmask |= (a_c + 4 * q < m ? 1u : 0u) << q;
+#pragma unroll
+        for (int g = 0; g < RB; ++g) colmask |= (b_c + 8 * g < m ? 1u : 0u) << (8 + g);
+        uint64_t n_next = 0;                                   // first row of the next round to load
+        double ra[D][RA], rb[D][NB];
+        auto load_round = [&](double (&a)[RA], double (&b)[NB]) {
+            const bool va = n_next + a_s < kd, vb0 = n_next + b_s < kd, vb1 = n_next + b_s + 4 < kd;
+#pragma unroll
+            for (int q = 0; q < RA; ++q) a[q] = (va && (colmask >> q & 1u)) ? __ldg(pa + 4 * q) : 0.0;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) b[q] = (((q & 1) ? vb1 : vb0) && (colmask >> (8 + (q >> 1)) & 1u)) ? __ldg(pb + (q & 1) * m4 + 8 * (q >> 1)) : 0.0;
+            pa += m8; pb += m8; n_next += 8;
+        };
+        double acc[RA][RB];
+#pragma unroll
+        for (int da = 0; da < RA; ++da)
+#pragma unroll
+            for (int db = 0; db < RB; ++db) acc[da][db] = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) load_round(ra[d], rb[d]);
+        // rounds past the end hold zeros: x + 0 * 0 = x, the chain's bits do not change
+        for (uint64_t base = 0; base < n_rounds; base += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    double av[RA], bv[RB];
+#pragma unroll
+                    for (int da = 0; da < RA; ++da) av[da] = __shfl_sync(0xffffffffu, ra[d][da], s * 4 + ty);
+#pragma unroll
+                    for (int db = 0; db < RB; ++db) bv[db] = __shfl_sync(0xffffffffu, rb[d][2 * db + (s >> 2)], (s & 3) * 8 + tx);
+#pragma unroll
+                    for (int da = 0; da < RA; ++da)
+#pragma unroll
+                        for (int db = 0; db < RB; ++db) {
+                            if (COS) acc[da][db] = __dadd_rn(acc[da][db], __dmul_rn(av[da], bv[db]));
+                            else { const double t = __dadd_rn(av[da], -bv[db]); acc[da][db] = __dadd_rn(acc[da][db], __dmul_rn(t, t)); }
+                        }
+                }
+                load_round(ra[d], rb[d]);   // refill the slot just consumed: D - 1 rounds stay in flight
+            }
+        }
+#pragma unroll
+        for (int da = 0; da < RA; ++da)
+#pragma unroll
+            for (int db = 0; db < RB; ++db) {
+                const uint32_t i = ci + ty + 4 * da, j = cj + tx + 8 * db;
+                if (i < m && j < m) { G[(uint64_t)i * m + j] = acc[da][db]; G[(uint64_t)j * m + i] = acc[da][db]; }
+            }
+    }
+}
+
 // raw sums G -> distance keys, written behind G (cosine: the norms are the square roots of the diagonal)
 template <bool COS>
 __global__ void gram_keys_kernel(double* __restrict__ G, uint32_t m, int metric, double* __restrict__ norms) {
@@ -405,6 +487,16 @@ int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uin
                         uint32_t gt, uint32_t t0, uint32_t t1, bool small_smem) {
     if (t1 <= t0) return SFB_OK;
     const uint32_t nt = t1 - t0;
+    if (!getenv("SFB_GRAM_SMEM")) {
+        // one warp per tile; beside the screen kernel at most two warps per SM walk the tiles (the screen CTA's registers must
+        // still fit wherever the block scheduler puts them)
+        const uint32_t cap = 2u * (uint32_t)ctx->sm_count, wgrid = small_smem && nt > cap ? cap : nt;
+        const bool c = metric == SFB_METRIC_COSINE;
+        if (gt == 8) { if (c) gram_warp_kernel<true, 8><<<wgrid, 32, 0, stream>>>(xd, m, kd, g, t0, nt); else gram_warp_kernel<false, 8><<<wgrid, 32, 0, stream>>>(xd, m, kd, g, t0, nt); }
+        else { if (c) gram_warp_kernel<true, 16><<<wgrid, 32, 0, stream>>>(xd, m, kd, g, t0, nt); else gram_warp_kernel<false, 16><<<wgrid, 32, 0, stream>>>(xd, m, kd, g, t0, nt); }
+        SFB_LAUNCH_CHECK(ctx);
+        return SFB_OK;
+    }
     const bool cos = metric == SFB_METRIC_COSINE, even = (m & 1u) == 0 && (reinterpret_cast<uintptr_t>(xd) & 15u) == 0;
     // beside the screen kernel: at most one CTA per SM, so that a CTA placed before the screen's never keeps the
     // screen's 216 KB from fitting (two of them would)

@@ -88,14 +88,18 @@ def test_knn_columns_feature_graph(sfb, oracle, ctx, metric, n_items, n_feat, k)
     assert_knn_equal(m.knn_columns(k, metric, eps=eps).to_host(), oracle.knn(oracle.transpose(x), k, metric, eps))
 
 
+@pytest.mark.parametrize("kernel", ["regs", "smem"])
 @pytest.mark.parametrize("mode", ["co", "after"])
 @pytest.mark.parametrize("gt", ["8", "16"])
 @pytest.mark.parametrize("metric", [0, 1])
-def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, mode, monkeypatch):
-    """Both pair-tile edges of the feature-graph Gram kernel (thread = 2 x 2 pairs / one pair), the stand-alone ring and the
-    small one that rides beside the screen, on shapes with ragged tiles, odd node counts and a dimension count that is not a
-    multiple of the staged chunk: every pair sum is the reference's left fold, so the lists are bit-exact."""
+def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, mode, kernel, monkeypatch):
+    """Both pair-tile edges of the feature-graph Gram kernels -- the warp-per-tile kernel with its operands in a register ring
+    (default) and the shared-memory ring (SFB_GRAM_SMEM) -- stand-alone and beside the screen, on shapes with ragged tiles,
+    odd node counts and a dimension count that is not a multiple of a round / staged chunk: every pair sum is the reference's
+    left fold, so the lists are bit-exact."""
     monkeypatch.setenv("SFB_GRAM_GT", gt)
+    if kernel == "smem":
+        monkeypatch.setenv("SFB_GRAM_SMEM", "1")
     monkeypatch.setenv("SFB_GRAM_MODE", mode)   # beside the screen kernel / released when it has finished
     for n_items, n_feat, k in ((20000, 37, 5), (6000, 130, 16), (17001, 64, 8)):   # two long enough for the side stream, one run inline
         x = np.random.default_rng(n_items + metric).normal(size=(n_items, n_feat))
