@@ -253,13 +253,15 @@ __device__ __forceinline__ double warp_max_d(double v) {
     return v;
 }
 
+// STRIDE: doubles between consecutive entries (1: a row; ITEMS + 1: one item of a transposed tile)
 // value of 0-based rank `rank` among the finite entries of xs[0..f); *n_le = number of finite entries <= that value
+template <int STRIDE = 1>
 __device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, int lane, uint32_t* n_le, uint32_t* hist /* 256 u32 of this warp */) {
     double lo = -INFINITY, hi = INFINITY;   // candidates: finite v with lo <= v <= hi
     uint32_t below = 0;                     // finite entries < lo
     double mn = INFINITY, mx = -INFINITY;
     uint32_t cnt = 0;
-    for (uint32_t t = lane; t < f; t += 32) { const double v = xs[t]; if (isfinite(v)) { mn = fmin(mn, v); mx = fmax(mx, v); ++cnt; } }
+    for (uint32_t t = lane; t < f; t += 32) { const double v = xs[(size_t)t * STRIDE]; if (isfinite(v)) { mn = fmin(mn, v); mx = fmax(mx, v); ++cnt; } }
     mn = warp_min_d(mn); mx = warp_max_d(mx); cnt = warp_sum_u(cnt);
     for (int iter = 0; iter < 40; ++iter) {
         lo = mn; hi = mx;
@@ -271,7 +273,7 @@ __device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, i
         for (int b = lane; b < 256; b += 32) hist[b] = 0;
         __syncwarp();
         for (uint32_t t = lane; t < f; t += 32) {
-            const double v = xs[t];
+            const double v = xs[(size_t)t * STRIDE];
             if (isfinite(v) && v >= lo && v <= hi) { int q = (int)((v - lo) * scale); q = q > 255 ? 255 : q; atomicAdd(&hist[q], 1u); }
         }
         __syncwarp();
@@ -293,7 +295,7 @@ __device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, i
         // recurse into bin `cut`: its min, max and population
         double nmn = INFINITY, nmx = -INFINITY; uint32_t ncnt = 0;
         for (uint32_t t = lane; t < f; t += 32) {
-            const double v = xs[t];
+            const double v = xs[(size_t)t * STRIDE];
             if (isfinite(v) && v >= lo && v <= hi) {
                 int q = (int)((v - lo) * scale); q = q > 255 ? 255 : q;
                 if ((uint32_t)q == cut) { nmn = fmin(nmn, v); nmx = fmax(nmx, v); ++ncnt; }
@@ -309,10 +311,10 @@ __device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, i
     bool first = true;
     for (;;) {
         double cand = INFINITY;
-        for (uint32_t t = lane; t < f; t += 32) { const double v = xs[t]; if (isfinite(v) && v >= lo && v <= hi && (first || v > last)) cand = fmin(cand, v); }
+        for (uint32_t t = lane; t < f; t += 32) { const double v = xs[(size_t)t * STRIDE]; if (isfinite(v) && v >= lo && v <= hi && (first || v > last)) cand = fmin(cand, v); }
         cand = warp_min_d(cand);
         uint32_t mult = 0;
-        for (uint32_t t = lane; t < f; t += 32) mult += xs[t] == cand ? 1u : 0u;
+        for (uint32_t t = lane; t < f; t += 32) mult += xs[(size_t)t * STRIDE] == cand ? 1u : 0u;
         mult = warp_sum_u(mult);
         if (target < seen + mult || !(cand < INFINITY)) { *n_le = below + seen + mult; return cand; }
         seen += mult; last = cand; first = false;
@@ -320,11 +322,12 @@ __device__ double warp_kth_finite(const double* xs, uint32_t f, uint32_t rank, i
 }
 
 // TauMode::select_tau (taumode.rs:29-70) with the quantised selection
+template <int STRIDE = 1>
 __device__ double warp_select_tau_fast(const double* xs, uint32_t f, int mode, double value, int lane, uint32_t* hist) {
     const double FLOOR = 1e-10;
     if (mode == SFB_TAU_FIXED) return (isfinite(value) && value > 0.0) ? value : FLOOR;
     uint32_t n = 0; double s = 0.0;
-    for (uint32_t t = lane; t < f; t += 32) { double v = xs[t]; if (isfinite(v)) { ++n; s += v; } }
+    for (uint32_t t = lane; t < f; t += 32) { double v = xs[(size_t)t * STRIDE]; if (isfinite(v)) { ++n; s += v; } }
     n = warp_sum_u(n);
     if (n == 0) return FLOOR;
     if (mode == SFB_TAU_MEAN) { double mean = warp_sum(s) / (double)n; return mean > FLOOR ? mean : FLOOR; }
@@ -332,15 +335,15 @@ __device__ double warp_select_tau_fast(const double* xs, uint32_t f, int mode, d
     double r;
     if (mode == SFB_TAU_PERCENTILE) {
         double pp = value < 0.0 ? 0.0 : (value > 1.0 ? 1.0 : value);
-        r = warp_kth_finite(xs, f, (uint32_t)round((double)(n - 1) * pp), lane, &n_le, hist);
+        r = warp_kth_finite<STRIDE>(xs, f, (uint32_t)round((double)(n - 1) * pp), lane, &n_le, hist);
     } else if (n & 1u) {
-        r = warp_kth_finite(xs, f, n / 2, lane, &n_le, hist);
+        r = warp_kth_finite<STRIDE>(xs, f, n / 2, lane, &n_le, hist);
     } else {
-        const double a = warp_kth_finite(xs, f, n / 2 - 1, lane, &n_le, hist);
+        const double a = warp_kth_finite<STRIDE>(xs, f, n / 2 - 1, lane, &n_le, hist);
         double b = a;
         if (n_le <= n / 2) {   // rank n/2 is the next larger value
             b = INFINITY;
-            for (uint32_t t = lane; t < f; t += 32) { double v = xs[t]; if (isfinite(v) && v > a) b = fmin(b, v); }
+            for (uint32_t t = lane; t < f; t += 32) { double v = xs[(size_t)t * STRIDE]; if (isfinite(v) && v > a) b = fmin(b, v); }
             b = warp_min_d(b);
         }
         r = 0.5 * (a + b);
@@ -478,32 +481,36 @@ struct __align__(16) EdgeRec { double w; uint32_t coff; uint32_t roff; };
 
 struct PackMeta { uint32_t ne; uint32_t any_defect; uint32_t any_nonpos; uint32_t pad; };
 
-// one CTA, thread = row (F <= 1024): strict upper triangle in CSR order -> EdgeRec list, row-sum defects, flags
+// one CTA, thread = a run of ceil(F / 1024) consecutive rows: strict upper triangle in CSR order -> EdgeRec list, row-sum
+// defects, flags.  stride_bytes: bytes between consecutive features of the staged tile (LT_TS * 8, or (ITEMS + 1) * 8 for
+// the narrow tiles of lambda_tile_narrow_kernel)
 __global__ void __launch_bounds__(1024) lambda_pack_kernel(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
-                                                           const double* __restrict__ data, uint32_t f, EdgeRec* __restrict__ recs,
+                                                           const double* __restrict__ data, uint32_t f, uint32_t stride_bytes, EdgeRec* __restrict__ recs,
                                                            double* __restrict__ defect, PackMeta* __restrict__ meta) {
     __shared__ uint32_t s_scan[1024];
     __shared__ uint32_t s_flags[2];
-    const uint32_t r = threadIdx.x;
-    if (r < 2) s_flags[r] = 0;
+    const uint32_t t = threadIdx.x, rpt = (f + 1023) / 1024;
+    const uint32_t r_lo = t * rpt < f ? t * rpt : f, r_hi = r_lo + rpt < f ? r_lo + rpt : f;
+    if (t < 2) s_flags[t] = 0;
     uint32_t c_up = 0;
-    if (r < f) for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) c_up += indices[e] > r ? 1u : 0u;
-    s_scan[r] = c_up;
+    for (uint32_t r = r_lo; r < r_hi; ++r)
+        for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) c_up += indices[e] > r ? 1u : 0u;
+    s_scan[t] = c_up;
     __syncthreads();
     for (uint32_t o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
-        uint32_t v = r >= o ? s_scan[r - o] : 0u;
+        uint32_t v = t >= o ? s_scan[t - o] : 0u;
         __syncthreads();
-        s_scan[r] += v;
+        s_scan[t] += v;
         __syncthreads();
     }
-    if (r < f) {
-        uint32_t o = s_scan[r] - c_up;
+    uint32_t o = s_scan[t] - c_up;
+    for (uint32_t r = r_lo; r < r_hi; ++r) {
         double d = 0.0, fold = 0.0;
         bool first = true, nonpos = false;
         for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
             const uint32_t c = indices[e];
             if (c > r) {
-                EdgeRec rec; rec.w = -data[e]; rec.coff = c * (LT_TS * 8); rec.roff = r * (LT_TS * 8) | (first ? 0x80000000u : 0u);
+                EdgeRec rec; rec.w = -data[e]; rec.coff = c * stride_bytes; rec.roff = r * stride_bytes | (first ? 0x80000000u : 0u);
                 recs[o++] = rec; first = false;
                 nonpos = nonpos || !(rec.w > 0.0);
             }
@@ -516,8 +523,16 @@ __global__ void __launch_bounds__(1024) lambda_pack_kernel(const uint64_t* __res
         if (nonpos) s_flags[1] = 1;
     }
     __syncthreads();
-    if (r == 0) { meta->ne = s_scan[1023]; meta->any_defect = s_flags[0]; meta->any_nonpos = s_flags[1]; meta->pad = 0; }
-    if (!s_flags[1] && r < f && c_up) { EdgeRec* first = recs + (s_scan[r] - c_up); first->w = -first->w; first->roff &= 0x7FFFFFFFu; }   // row flag = sign of w
+    if (t == 0) { meta->ne = s_scan[1023]; meta->any_defect = s_flags[0]; meta->any_nonpos = s_flags[1]; meta->pad = 0; }
+    if (!s_flags[1]) {   // every weight positive: the row flag becomes the sign of w
+        uint32_t q = s_scan[t] - c_up;
+        for (uint32_t r = r_lo; r < r_hi; ++r) {
+            uint32_t cu = 0;
+            for (uint64_t e = indptr[r]; e < indptr[r + 1]; ++e) cu += indices[e] > r ? 1u : 0u;
+            if (cu) { EdgeRec* first = recs + q; first->w = -first->w; first->roff &= 0x7FFFFFFFu; }
+            q += cu;
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t f32_key(float v) { uint32_t u = __float_as_uint(v); return (u >> 31) ? ~u : (u | 0x80000000u); }
@@ -938,6 +953,159 @@ __global__ void __launch_bounds__(LT_WARPS * 32, LT_WARPS == 8 ? (E <= 4 ? 4 : 2
     }
 }
 
+// ---- narrow tiles: F beyond the 32-item tile (768 < F <= 3111) ---------------------------------------------------
+// A 32-item tile of F = 3072 would need 811 KB.  Here a tile holds ITEMS = 16 or 8 items (row stride ITEMS + 1 doubles:
+// 1646 / 3111 features fit the 227 KB) and a warp walks SUB = 32 / ITEMS edges at a time: lane = (edge slot, item).  The
+// record is no longer warp-uniform (SUB distinct 16-byte reads, broadcast inside a slot's lanes), x_r is fetched per edge
+// (no run of equal rows to ride on) and the lanes of an item meet in a shuffle reduction at the end of the slice; the sums
+// are reordered exactly as much as in the 32-item kernel (eight warp slices, then SUB slots), inside the 1e-9 of the
+// contract.  Phase 1 streams each item row once (coalesced, eight loads in flight per lane) into the transposed tile and
+// selects tau from the tile column with the strided quantised selection.
+template <int VARIANT, int ITEMS>
+__global__ void __launch_bounds__(256, 1) lambda_tile_narrow_kernel(LambdaTileArgs a) {
+    constexpr int NW = 8, TS = ITEMS + 1, SUB = 32 / ITEMS, IPW = ITEMS / NW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t f = a.f;
+    double* xs = reinterpret_cast<double*>(smem_raw);                         // [f][TS]
+    double* s_den = xs + (((size_t)f * TS + 1) & ~(size_t)1);                 // [ITEMS]   (16-byte aligned)
+    double* s_dfc = s_den + ITEMS;
+    double* s_tau = s_dfc + ITEMS;                                            // < 0: zero vector
+    unsigned char* region0 = reinterpret_cast<unsigned char*>(s_tau + ITEMS);
+    unsigned char* region = region0 + (size_t)w * 1024;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(region);                  // phase 1: 256-bin histogram
+    uint4* ring = reinterpret_cast<uint4*>(region);                           // phase 2: [2][32] records
+    double* part = reinterpret_cast<double*>(region);                         // end of phase 2: [3][ITEMS]
+    const uint32_t ne = a.meta->ne;
+    const bool has_defect = a.meta->any_defect != 0, nonpos = a.meta->any_nonpos != 0;
+    const uint32_t e_lo = (uint32_t)((uint64_t)ne * w / NW), e_hi = (uint32_t)((uint64_t)ne * (w + 1) / NW);
+    const uint32_t n_chunks = (e_hi - e_lo + 31) / 32;
+    const int item = lane & (ITEMS - 1), sub = lane / ITEMS;
+    const double* xs_item = xs + item;
+    double run_mn = INFINITY, run_mx = 0.0;
+    const uint64_t n_tiles = (a.n + ITEMS - 1) / ITEMS;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t i0 = tile * ITEMS;
+        // ---- phase 1: warp w stages items w * IPW .. + IPW - 1
+#pragma unroll 1
+        for (int qi = 0; qi < IPW; ++qi) {
+            const int it = w * IPW + qi;
+            const uint64_t i = i0 + it;
+            const bool live = i < a.n;
+            const double* xr = a.x + (live ? i : 0) * f;
+            double amax = 0.0, den = 0.0, dfc = 0.0;
+            bool any_nan = false;
+#pragma unroll 8
+            for (uint32_t t = lane; t < f; t += 32) {
+                const double v = live ? __ldcs(xr + t) : 0.0;
+                xs[(size_t)t * TS + it] = v;
+                amax = fmax(amax, fabs(v));
+                any_nan = any_nan || v != v;
+                den = fma(v, v, den);
+                if (has_defect) dfc += (v * a.defect[t]) * v;
+            }
+            const bool zero = amax <= 1e-10 && !any_nan;
+            den = warp_sum(den);
+            if (has_defect) dfc = warp_sum(dfc);
+            __syncwarp();
+            double tau = 0.0;
+            if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
+                if (a.tau_in) tau = live ? a.tau_in[i] : -1.0;
+                else if (__all_sync(FULL, zero)) tau = -1.0;                // taumode.rs:268-274
+                else tau = warp_select_tau_fast<TS>(xs + it, f, a.tau_mode, a.tau_value, lane, scratch);
+            }
+            if (lane == 0) { s_den[it] = den; s_dfc[it] = dfc; s_tau[it] = tau; }
+        }
+        __syncthreads();
+        // ---- phase 2: this warp's slice of the edge list, SUB edges per step, records one chunk ahead in the ring
+        double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0, sa = 0.0;
+        if (n_chunks) {
+            { const uint32_t e = e_lo + lane; if (e < e_hi) lt_cp_async16(&ring[lane], a.recs + e); asm volatile("cp.async.commit_group;" ::: "memory"); }
+            { const uint32_t e = e_lo + 32 + lane; if (e < e_hi) lt_cp_async16(&ring[32 + lane], a.recs + e); asm volatile("cp.async.commit_group;" ::: "memory"); }
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+                const uint4* rr = ring + (c & 1) * 32;
+                const uint32_t cnt = min(32u, e_hi - e_lo - c * 32);
+                if (!nonpos) {
+                    uint32_t j = sub;
+                    for (; j + SUB < cnt; j += 2 * SUB) {
+                        const uint4 ra = rr[j], rb = rr[j + SUB];
+                        const double d0 = lt_ld(xs_item, ra.w) - lt_ld(xs_item, ra.z);
+                        const double d1 = lt_ld(xs_item, rb.w) - lt_ld(xs_item, rb.z);
+                        const double c0 = (fabs(__hiloint2double((int)ra.y, (int)ra.x)) * d0) * d0;
+                        const double c1 = (fabs(__hiloint2double((int)rb.y, (int)rb.x)) * d1) * d1;
+                        s0 += c0; q0 = fma(c0, c0, q0);
+                        s1 += c1; q1 = fma(c1, c1, q1);
+                    }
+                    if (j < cnt) {
+                        const uint4 ra = rr[j];
+                        const double d0 = lt_ld(xs_item, ra.w) - lt_ld(xs_item, ra.z);
+                        const double c0 = (fabs(__hiloint2double((int)ra.y, (int)ra.x)) * d0) * d0;
+                        s0 += c0; q0 = fma(c0, c0, q0);
+                    }
+                } else {
+                    for (uint32_t j = sub; j < cnt; j += SUB) {
+                        const uint4 ra = rr[j];
+                        const double wv = __hiloint2double((int)ra.y, (int)ra.x);
+                        const double d0 = lt_ld(xs_item, ra.w & 0x7FFFFFFFu) - lt_ld(xs_item, ra.z);
+                        const double c0 = (wv * d0) * d0;
+                        sa += c0;
+                        if (wv > 0.0) { s0 += c0; q0 = fma(c0, c0, q0); }
+                    }
+                }
+                __syncwarp();
+                { const uint32_t e = e_lo + (c + 2) * 32 + lane; if (e < e_hi) lt_cp_async16(&ring[(c & 1) * 32 + lane], a.recs + e); asm volatile("cp.async.commit_group;" ::: "memory"); }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
+        s0 += s1; q0 += q1;
+        if (!nonpos) sa = s0;
+#pragma unroll
+        for (int o = ITEMS; o < 32; o <<= 1) {   // the SUB edge slots of an item
+            s0 += __shfl_xor_sync(FULL, s0, o); q0 += __shfl_xor_sync(FULL, q0, o); sa += __shfl_xor_sync(FULL, sa, o);
+        }
+        if (sub == 0) { part[item] = s0; part[ITEMS + item] = q0; part[2 * ITEMS + item] = sa; }
+        __syncthreads();
+        // ---- phase 3: combine, blend, write
+        if (w == 0 && lane < ITEMS) {
+            const uint64_t i = i0 + lane;
+            double ssum = 0.0, qsum = 0.0, sall = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) {
+                const double* pw = reinterpret_cast<const double*>(region0 + (size_t)ww * 1024);
+                ssum += pw[lane]; qsum += pw[ITEMS + lane]; sall += pw[2 * ITEMS + lane];
+            }
+            const double den = s_den[lane], num = s_dfc[lane] + sall, tau = s_tau[lane];
+            if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) { ssum *= 2.0; qsum *= 2.0; }   // both triangles (taumode.rs:371-383)
+            double e_raw = 0.0;
+            if (den > 1e-12) { e_raw = num / den; if (!(e_raw > 0.0)) e_raw = 0.0; }
+            double g = 0.0;
+            // NaN sums: see lambda_tile_kernel
+            if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE ? !(ssum <= 1e-12) : (ssum > 1e-12)) { g = qsum / (ssum * ssum); g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g); }
+            double lam;
+            if (VARIANT == SFB_LAMBDA_LEGACY_TAUMODE) {
+                if (tau < 0.0) { lam = 0.0; g = 0.0; }
+                else lam = tau * (e_raw / (e_raw + tau)) + (1.0 - tau) * g;       // taumode.rs:306-310
+            } else lam = e_raw;
+            if (i < a.n) {
+                a.out_lambda[i] = lam;
+                if (a.out_disp) a.out_disp[i] = g;
+                run_mn = fmin(run_mn, lam); run_mx = fmax(run_mx, lam);
+            }
+        }
+        __syncthreads();
+    }
+    if (w == 0 && a.minmax) {
+        run_mn = warp_min_d(run_mn); run_mx = warp_max_d(run_mx);
+        if (lane == 0) {
+            if (run_mn == run_mn) atomicMin(&a.minmax[0], (unsigned long long)sort_key(run_mn));
+            if (run_mx == run_mx) atomicMax(&a.minmax[1], (unsigned long long)sort_key(run_mx));
+        }
+    }
+}
+
 // minmax keys -> {min, max(0, .)} as doubles (the input of the NCCL min / max exchange and of the normalisation)
 __global__ void minmax_keys_kernel(const unsigned long long* __restrict__ keys, double* __restrict__ out) {
     out[0] = key_value(keys[0]); out[1] = key_value(keys[1]);
@@ -1122,8 +1290,24 @@ template <int VARIANT, int E, int NW>
 int32_t lt_launch(sfb_ctx* ctx, const LambdaTileArgs& a) {
     return a.f == 32u * E ? lt_launch_full<VARIANT, E, NW, true>(ctx, a) : lt_launch_full<VARIANT, E, NW, false>(ctx, a);
 }
+constexpr uint32_t LT_MAX_F = 768, LTN_MAX_F16 = 1646, LTN_MAX_F8 = 3111;   // 32-, 16-, 8-item tiles in 227 KB
+uint32_t lt_items(uint32_t f) { return f <= LT_MAX_F ? 32u : (f <= LTN_MAX_F16 ? 16u : 8u); }
+size_t ltn_smem_bytes(uint32_t f, uint32_t items) { return ((((size_t)f * (items + 1) + 1) & ~(size_t)1) + 3 * items) * sizeof(double) + 8 * 1024; }
+
+template <int VARIANT, int ITEMS>
+int32_t ltn_launch(sfb_ctx* ctx, const LambdaTileArgs& a) {
+    const size_t smem = ltn_smem_bytes(a.f, ITEMS);
+    auto kern = lambda_tile_narrow_kernel<VARIANT, ITEMS>;
+    SFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t tiles = (a.n + ITEMS - 1) / ITEMS, cap = (uint64_t)ctx->sm_count;
+    kern<<<(unsigned)(tiles < cap ? tiles : cap), 256, smem, ctx->stream>>>(a);
+    SFB_LAUNCH_CHECK(ctx);
+    return SFB_OK;
+}
+
 template <int VARIANT>
 int32_t lt_dispatch(sfb_ctx* ctx, const LambdaTileArgs& a) {
+    if (a.f > LT_MAX_F) return a.f <= LTN_MAX_F16 ? ltn_launch<VARIANT, 16>(ctx, a) : ltn_launch<VARIANT, 8>(ctx, a);
     const uint32_t e = (a.f + 31) / 32;
     if (e <= 4) return lt_launch<VARIANT, 4, 8>(ctx, a);
     if (e <= 8) return lt_launch<VARIANT, 8, 8>(ctx, a);
@@ -1152,7 +1336,8 @@ static int32_t lt_pack(sfb_ctx* ctx, const sfb_csr* L) {
         sfb_dev_free(ctx, recs); sfb_dev_free(ctx, defect); sfb_dev_free(ctx, meta);
         return sfb_fail(ctx, SFB_ENOMEM, "packed Laplacian");
     }
-    lambda_pack_kernel<<<1, 1024, 0, ctx->stream>>>(L->indptr, L->indices, L->data, f, (EdgeRec*)recs, (double*)defect, (PackMeta*)meta);
+    lambda_pack_kernel<<<1, 1024, 0, ctx->stream>>>(L->indptr, L->indices, L->data, f, (lt_items(f) == 32 ? (uint32_t)LT_TS : lt_items(f) + 1) * 8u,
+                                                    (EdgeRec*)recs, (double*)defect, (PackMeta*)meta);
     ctx->times.kernel_launches++;
     if (cudaGetLastError() != cudaSuccess) { sfb_dev_free(ctx, recs); sfb_dev_free(ctx, defect); sfb_dev_free(ctx, meta); return sfb_fail(ctx, SFB_ECUDA, "lambda_pack_kernel launch failed"); }
     L->lt_recs = recs; L->lt_defect = defect; L->lt_meta = meta;
@@ -1190,8 +1375,8 @@ int32_t sfb_lambda_device(sfb_ctx* ctx, const sfb_csr* L, const double* x_dev, u
         SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         L->symmetric = hb ? 0 : 1;
     }
-    // tile kernel (lane = item): LEGACY_TAUMODE / ENERGY_NODE, symmetric L, F <= 768
-    if (sym_variant && L->symmetric == 1 && f <= 768 && L->nnz / 2 < 0x7FFFFFFFull / LT_TS && !getenv("SFB_LAMBDA_ROWWISE") && !getenv("SFB_LAMBDA_SYM")) {
+    // tile kernels (lane = item): LEGACY_TAUMODE / ENERGY_NODE, symmetric L, F <= 768 (32-item tiles) or <= 3111 (16 / 8 items)
+    if (sym_variant && L->symmetric == 1 && f <= (getenv("SFB_LAMBDA_NO_NARROW") ? LT_MAX_F : LTN_MAX_F8) && L->nnz / 2 < 0x7FFFFFFFull / LT_TS && !getenv("SFB_LAMBDA_ROWWISE") && !getenv("SFB_LAMBDA_SYM")) {
         SFB_TRY(lt_pack(ctx, L));
         DevBuf keys;
         if (d_mm) {

@@ -464,9 +464,11 @@ def test_config_c1_exact(sfb, oracle, ctx, screen):
 
 # ---- the lambda tile kernel (lane = item) at the shapes of the configs ----------------------------------------------
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("n,f,topk", [(1000, 128, 4), (777, 200, 8), (2000, 384, 16), (300, 512, 16), (200, 768, 16), (33, 40, 3), (1, 64, 3)])
+@pytest.mark.parametrize("n,f,topk", [(1000, 128, 4), (777, 200, 8), (2000, 384, 16), (300, 512, 16), (200, 768, 16), (33, 40, 3), (1, 64, 3),
+                                      (100, 769, 8), (37, 1646, 6), (21, 1647, 6), (50, 3072, 8), (9, 3111, 4), (12, 3112, 4)])
 def test_lambda_tile_kernel_shapes(sfb, oracle, ctx, variant, n, f, topk):
-    """Every register-block size of the tile kernel (E = 4 .. 24 values per lane), ragged tails (n not a multiple of 32),
+    """Every register-block size of the tile kernel (E = 4 .. 24 values per lane), the 16- and 8-item tiles beyond 768
+    features (and the row-wise kernel past their 3111), ragged tails (n not a multiple of the tile),
     a Laplacian built on the device (symmetric by construction, defect 0) and one from the host with a non-zero row-sum
     defect and a positive off-diagonal entry (the general edge loop)."""
     rng = np.random.default_rng(n * 7 + f)
@@ -496,18 +498,18 @@ def test_lambda_tile_kernel_shapes(sfb, oracle, ctx, variant, n, f, topk):
     assert np.allclose(lam, o_lam, rtol=RTOL, atol=1e-13) and np.allclose(disp, o_g, rtol=RTOL, atol=1e-15)
 
 
-def test_lambda_tile_kernel_tau_edge_cases(sfb, oracle, ctx):
-    """Median / percentile selection in registers: all-equal rows, two-valued rows, heavy duplicates around the median,
+@pytest.mark.parametrize("f", [96, 1000, 2000])
+def test_lambda_tile_kernel_tau_edge_cases(sfb, oracle, ctx, f):
+    """Median / percentile selection in registers (f = 96) and over a column of a narrow tile (f = 1000, 2000): all-equal rows, two-valued rows, heavy duplicates around the median,
     rows whose values collapse in f32 (the quantised histogram cannot separate them: exact path), huge dynamic range,
     NaN / inf entries (select_tau keeps the finite ones, taumode.rs:41,50)."""
-    f = 96
     rng = np.random.default_rng(5)
     base = rng.normal(size=(64, f))
     L = feature_laplacian(oracle, base, 4)
     c = sfb.Csr.from_host(ctx, *L)
     x = rng.normal(size=(40, f))
     x[0] = 3.0
-    x[1, :48] = 1.0; x[1, 48:] = 2.0
+    x[1, :f // 2] = 1.0; x[1, f // 2:] = 2.0
     x[2] = np.round(x[2])                                   # many duplicates
     x[3] = 1.0 + np.arange(f) * 1e-13                       # equal in f32
     x[4] = 1e300 * np.sign(x[4]) * np.abs(x[4])             # f32 overflow in the quantisation
