@@ -195,20 +195,22 @@ extern "C" int32_t sfb_knn_build_columns_begin(sfb_ctx* ctx, const sfb_mat* x, c
             cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming);
         }
         // Two ways to keep the chains off the critical path, both on the side stream, both fired by the next screen launch:
-        //   co-resident   one small CTA per SM BESIDE the screen's: a fold step then takes ~200 ns (edge-16 tiles) / ~110 ns
-        //                 (edge 8) instead of ~10-30, because the screen's epilogue warps own the issue slots -- fine while
-        //                 tiles per CTA x N steps still finish before the screen does (C2 on one GPU: 3 x 10^6 x 200 ns < 650 ms);
-        //   after-screen  the stand-alone kernel, released by an event behind the screen kernel: it runs beside the rescore,
-        //                 the fallback, the list exchange and the item Laplacian, which leave the FP64 pipe idle (every
-        //                 sharded C2 build: at N = 8 the co-resident chain left 17-26 ms exposed behind an 80 ms screen).
+        //   co-resident   warps BESIDE the screen's CTAs, operands in a register ring (gram_warp_kernel, 8 x 8 pair tiles, at most
+        //                 two warps per SM): ~50 ns per fold step there, and the screen does not notice (tools/gram_probe.py: one
+        //                 rank's share of C2 at 8 GPUs rides a 98 ms screen for -0.5 ms) -- the choice while tiles per warp x N
+        //                 steps finish before the screen does;
+        //   after-screen  the stand-alone shared-memory kernel, released by an event behind the screen kernel: it runs beside the
+        //                 rescore, the fallback, the list exchange and the item Laplacian, which leave the FP64 pipe idle.
         uint32_t t0, t1;
-        pd->gt = sfb_gram_tile_edge(ctx, (uint32_t)nodes, pd->collective);
-        sfb_gram_tile_range(ctx, (uint32_t)nodes, pd->gt, pd->collective, &t0, &t1);
-        const double tiles_per_cta = ceil((double)(t1 - t0) / (double)ctx->sm_count);
-        const double co_s = tiles_per_cta * (double)dims * (pd->gt == 8 ? 110e-9 : 200e-9);
+        const char* gt_forced = getenv("SFB_GRAM_GT");
+        const uint32_t gt_co = gt_forced ? sfb_gram_tile_edge(ctx, (uint32_t)nodes, pd->collective) : 8u;
+        sfb_gram_tile_range(ctx, (uint32_t)nodes, gt_co, pd->collective, &t0, &t1);
+        const double tiles_per_warp = ceil((double)(t1 - t0) / (2.0 * (double)ctx->sm_count));
+        const double co_s = tiles_per_warp * (double)dims * (gt_co == 8 ? 60e-9 : 140e-9);
         const double screen_s = 2.0 * (double)dims * (double)dims * (double)nodes / (double)(ctx->world > 0 ? ctx->world : 1) / 1.1e15;
         bool co = co_s < 0.9 * screen_s;
         if (const char* e = getenv("SFB_GRAM_MODE")) { if (e[0] == 'c') co = true; else if (e[0] == 'a') co = false; }
+        pd->gt = co ? gt_co : sfb_gram_tile_edge(ctx, (uint32_t)nodes, pd->collective);
         // chains of less than half a millisecond are not worth a side slot: _end runs them inline (and such builds may be stacked)
         const bool side = ctx->side && dims >= 4096 && (double)dims * 30e-9 > 0.5e-3 && !getenv("SFB_NO_SIDE_STREAM");
         if (side) {
@@ -236,6 +238,7 @@ extern "C" int32_t sfb_knn_build_columns_end(sfb_ctx* ctx, sfb_pending* pd, sfb_
         if (ctx->side_job == pd || pd->deferred) {   // no screen ran in between, or not worth hiding: run the Gram tiles now, on the main stream
             ctx->side_job = nullptr;
             uint32_t t0, t1;
+            pd->gt = sfb_gram_tile_edge(ctx, m, pd->collective);   // the stand-alone tiling
             sfb_gram_tile_range(ctx, m, pd->gt, pd->collective, &t0, &t1);
             if (st == SFB_OK) st = sfb_gram_launch(ctx, ctx->stream, pd->x->d, m, pd->x->rows, pd->p.metric, pd->g, pd->gt, t0, t1, false);
         } else if (pd->launched) {

@@ -184,6 +184,152 @@ __global__ void __launch_bounds__(THREADS) knn_exact_kernel(ExactArgs a) {
     }
 }
 
+// ---- a handful of query rows (the rows the screen could not certify: a few per million) ---------------------------
+// The 64 x 64 tile kernel above leaves all but one thread group idle for such a call and stages its operands with
+// synchronous loads: 4 ms for three rows at 1M x 384, latency-bound.  Here a thread owns one CORPUS row of a 128-row tile
+// and carries the chains of all NQ query rows (NQ x 2 FP64 instructions per dimension on every lane), the corpus chunk
+// (16 dimensions x 128 rows, row stride 17 doubles: conflict-free for lane = row) and the matching query chunk come
+// through a cp.async ring that runs ahead across tile boundaries, and the selection is the same thresholded warp insert.
+// Same left folds, same bits.  Reads the corpus once: HBM-bound from about four rows down, FP64-bound above.
+constexpr int FEW_TC = 128, FEW_KC = 16, FEW_CS = 17, FEW_NST = 4;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 8 : 0;   // src-size 0: zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+template <int NQ> __host__ __device__ constexpr size_t few_smem_doubles(uint32_t k) {
+    return (size_t)FEW_NST * (FEW_TC * FEW_CS + FEW_KC * NQ) + (size_t)NQ * (FEW_TC + 1) + NQ + (size_t)NQ * k;
+}
+
+template <bool COS, int NQ>
+__global__ void __launch_bounds__(FEW_TC) knn_exact_few_kernel(ExactArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* cs = reinterpret_cast<double*>(smem_raw);                       // [NST][TC][CS]
+    double* qs = cs + (size_t)FEW_NST * FEW_TC * FEW_CS;                   // [NST][KC][NQ]
+    double* keys = qs + (size_t)FEW_NST * FEW_KC * NQ;                     // [NQ][TC + 1]
+    double* qn = keys + (size_t)NQ * (FEW_TC + 1);                         // [NQ]
+    double* ld = qn + NQ;                                                  // [NQ][k]
+    uint32_t* li = reinterpret_cast<uint32_t*>(ld + (size_t)NQ * a.k);     // [NQ][k]
+    uint32_t* gq = li + (size_t)NQ * a.k;                                  // [NQ]
+    uint32_t* lcnt = gq + NQ;                                              // [NQ]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < NQ) {
+        uint32_t g = SFB_IDX_NONE;
+        if ((uint64_t)tid < a.nq) g = a.query_rows ? a.query_rows[tid] : (uint32_t)(a.q_begin + tid);
+        gq[tid] = g; lcnt[tid] = 0;
+        qn[tid] = (COS && g != SFB_IDX_NONE) ? a.norms[g] : 0.0;
+    }
+    __syncthreads();
+    const uint64_t n_tiles = (a.m + FEW_TC - 1) / FEW_TC;
+    const uint64_t t_begin = (uint64_t)blockIdx.x * a.tiles_per_split;
+    const uint64_t t_end = t_begin + a.tiles_per_split < n_tiles ? t_begin + a.tiles_per_split : n_tiles;
+    const uint32_t n_kc = (a.kd + FEW_KC - 1) / FEW_KC;
+    const uint64_t n_steps = t_end > t_begin ? (t_end - t_begin) * n_kc : 0;   // (tile, chunk) pairs, in order
+
+    auto stage = [&](uint64_t s) {
+        if (s < n_steps) {
+            const int buf = (int)(s % FEW_NST);
+            const uint64_t tile = t_begin + s / n_kc;
+            const uint32_t d0 = (uint32_t)(s % n_kc) * FEW_KC;
+            double* cb = cs + (size_t)buf * FEW_TC * FEW_CS;
+            // 128 rows x 16 dimensions, 8 bytes per copy: lanes walk a row's 128-byte run
+#pragma unroll 4
+            for (int e = tid; e < FEW_TC * FEW_KC; e += FEW_TC) {
+                const int r = e / FEW_KC, d = e % FEW_KC;
+                const uint64_t row = tile * FEW_TC + r;
+                const bool v = row < a.m && d0 + d < a.kd;
+                cp_async8(cb + r * FEW_CS + d, v ? a.x + row * a.kd + d0 + d : a.x, v);
+            }
+#pragma unroll
+            for (int e = tid; e < NQ * FEW_KC; e += FEW_TC) {   // the query chunk, [dimension][query]
+                const int sq = e / FEW_KC, sd = e % FEW_KC;
+                const uint32_t sg = gq[sq];
+                const bool v = sg != SFB_IDX_NONE && d0 + sd < a.kd;
+                cp_async8(qs + (size_t)buf * FEW_KC * NQ + sd * NQ + sq, v ? a.x + (uint64_t)sg * a.kd + d0 + sd : a.x, v);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    double acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+#pragma unroll
+    for (int c = 0; c < FEW_NST - 1; ++c) stage((uint64_t)c);
+    for (uint64_t s = 0; s < n_steps; ++s) {
+        const int buf = (int)(s % FEW_NST);
+        stage(s + FEW_NST - 1);   // the slot consumed in the previous iteration (barrier at its end)
+        asm volatile("cp.async.wait_group %0;" ::"n"(FEW_NST - 1) : "memory");
+        __syncthreads();
+        const double* cb = cs + (size_t)buf * FEW_TC * FEW_CS + tid * FEW_CS;
+        const double* qb = qs + (size_t)buf * FEW_KC * NQ;
+#pragma unroll
+        for (int d = 0; d < FEW_KC; ++d) {
+            const double c = cb[d];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (COS) acc[q] = __dadd_rn(acc[q], __dmul_rn(qb[d * NQ + q], c));
+                else { const double t = __dadd_rn(qb[d * NQ + q], -c); acc[q] = __dadd_rn(acc[q], __dmul_rn(t, t)); }
+            }
+        }
+        if ((s + 1) % n_kc == 0) {
+            // end of a tile: keys, then the selection (warp w owns query rows w, w + 4, ...)
+            const uint64_t c0 = (t_begin + s / n_kc) * FEW_TC, crow = c0 + tid;
+            const double cn = (COS && crow < a.m) ? a.norms[crow] : 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                double key;
+                if (COS) {
+                    const double denom = __dmul_rn(qn[q], cn);
+                    double cosv = 0.0;
+                    if (denom > 1e-12) { cosv = __ddiv_rn(acc[q], denom); if (cosv < -1.0) cosv = -1.0; else if (cosv > 1.0) cosv = 1.0; }
+                    const double rect = cosv > 0.0 ? cosv : 0.0;
+                    key = __dadd_rn(1.0, -rect);
+                } else key = a.metric == SFB_METRIC_L2 ? __dsqrt_rn(acc[q]) : acc[q];
+                keys[q * (FEW_TC + 1) + tid] = key;
+                acc[q] = 0.0;
+            }
+            __syncthreads();
+            for (int q = warp; q < NQ; q += FEW_TC / 32) {
+                const uint32_t g = gq[q];
+                if (g == SFB_IDX_NONE) continue;
+                double* rld = ld + (size_t)q * a.k;
+                uint32_t* rli = li + (size_t)q * a.k;
+                uint32_t c = lcnt[q];
+#pragma unroll 1
+                for (int part = 0; part < FEW_TC / 32; ++part) {
+                    const double key = keys[q * (FEW_TC + 1) + part * 32 + lane];
+                    const uint64_t j = c0 + part * 32 + lane;
+                    const double thr_d = c == a.k ? rld[a.k - 1] : INFINITY;
+                    const uint32_t thr_i = c == a.k ? rli[a.k - 1] : SFB_IDX_NONE;
+                    const bool pr = j < a.m && (uint32_t)j != g && key <= a.eps && topk_key_less(key, (uint32_t)j, thr_d, thr_i);
+                    uint32_t b = __ballot_sync(0xffffffffu, pr);
+                    while (b) {
+                        const int src = __ffs(b) - 1; b &= b - 1;
+                        warp_list_insert(rld, rli, c, a.k, __shfl_sync(0xffffffffu, key, src), (uint32_t)(c0 + part * 32 + src), lane);
+                    }
+                }
+                if (lane == 0) lcnt[q] = c;
+            }
+        }
+        __syncthreads();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int q = warp; q < NQ; q += FEW_TC / 32) {
+        if ((uint64_t)q >= a.nq) continue;
+        const uint32_t c = lcnt[q];
+        const size_t o = ((size_t)q * a.csplits + blockIdx.x) * a.k;
+        for (uint32_t t = lane; t < a.k; t += 32) {
+            a.out_idx[o + t] = t < c ? li[(size_t)q * a.k + t] : SFB_IDX_NONE;
+            a.out_dist[o + t] = t < c ? ld[(size_t)q * a.k + t] : INFINITY;
+        }
+        if (lane == 0) a.out_cnt[(size_t)q * a.csplits + blockIdx.x] = c;
+    }
+}
+
 // merge csplits partial lists per query: one warp per query row
 __global__ void knn_merge_kernel(const uint32_t* __restrict__ pidx, const double* __restrict__ pdist,
                                  const uint32_t* __restrict__ pcnt, uint64_t nq, uint32_t csplits, uint32_t k,
@@ -487,7 +633,9 @@ int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uin
                         uint32_t gt, uint32_t t0, uint32_t t1, bool small_smem) {
     if (t1 <= t0) return SFB_OK;
     const uint32_t nt = t1 - t0;
-    if (!getenv("SFB_GRAM_SMEM")) {
+    // beside a screen: the register-ring kernel (hidden completely at one rank's share of C2 at 8 GPUs, where the 8 KB ring left
+    // 17-32 ms exposed); alone: the shared-memory ring (14 against 24 ns per fold step).  SFB_GRAM_SMEM / SFB_GRAM_REGS force one.
+    if (small_smem ? !getenv("SFB_GRAM_SMEM") : getenv("SFB_GRAM_REGS") != nullptr) {
         // one warp per tile; beside the screen kernel at most two warps per SM walk the tiles (the screen CTA's registers must
         // still fit wherever the block scheduler puts them)
         const uint32_t cap = 2u * (uint32_t)ctx->sm_count, wgrid = small_smem && nt > cap ? cap : nt;
@@ -559,6 +707,44 @@ int32_t sfb_knn_exact(sfb_ctx* ctx, const sfb_mat* x, const double* norms, int m
                       uint32_t* out_cnt) {
     if (nq == 0) return SFB_OK;
     if (k == 0 || k > 128) return sfb_fail(ctx, SFB_EUNSUPPORTED, "k must be in 1..128 (got %u)", k);
+    if (nq <= 16 && x->rows >= 16384 && !getenv("SFB_EXACT_NO_FEW")) {
+        // a handful of rows against a long corpus: knn_exact_few_kernel, the corpus split over every SM, then the merge
+        const uint64_t n_tiles_f = (x->rows + FEW_TC - 1) / FEW_TC;
+        const int nqt = nq <= 4 ? 4 : (nq <= 8 ? 8 : 16);
+        const size_t smem = (nqt == 4 ? few_smem_doubles<4>(k) : nqt == 8 ? few_smem_doubles<8>(k) : few_smem_doubles<16>(k)) * sizeof(double) +
+                            sizeof(uint32_t) * ((size_t)nqt * k + 2 * nqt);
+        int per_sm = (int)((ctx->smem_optin ? ctx->smem_optin : 232448) / (smem + 1024));
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm >= 1) {
+            uint64_t want = (uint64_t)ctx->sm_count * per_sm;
+            if (want > n_tiles_f) want = n_tiles_f;
+            const uint32_t tps = (uint32_t)((n_tiles_f + want - 1) / want);
+            const uint32_t splits = (uint32_t)((n_tiles_f + tps - 1) / tps);
+            DevBuf pidx, pdist, pcnt;
+            SFB_CUDA(ctx, pidx.alloc(sizeof(uint32_t) * nq * splits * k));
+            SFB_CUDA(ctx, pdist.alloc(sizeof(double) * nq * splits * k));
+            SFB_CUDA(ctx, pcnt.alloc(sizeof(uint32_t) * nq * splits));
+            ExactArgs a{x->d, norms, x->rows, x->cols, metric, k, eps, query_rows, nq, q_begin, splits, tps,
+                        pidx.as<uint32_t>(), pdist.as<double>(), pcnt.as<uint32_t>()};
+            const bool cos = metric == SFB_METRIC_COSINE;
+#define SFB_FEW(C_, Q_)                                                                                                        \
+    do {                                                                                                                       \
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_exact_few_kernel<C_, Q_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        knn_exact_few_kernel<C_, Q_><<<splits, FEW_TC, smem, ctx->stream>>>(a);                                                \
+    } while (0)
+            if (cos) { if (nqt == 4) SFB_FEW(true, 4); else if (nqt == 8) SFB_FEW(true, 8); else SFB_FEW(true, 16); }
+            else { if (nqt == 4) SFB_FEW(false, 4); else if (nqt == 8) SFB_FEW(false, 8); else SFB_FEW(false, 16); }
+#undef SFB_FEW
+            SFB_LAUNCH_CHECK(ctx);
+            const int wpb = 4;
+            const size_t msmem = (size_t)wpb * k * (sizeof(double) + sizeof(uint32_t));
+            knn_merge_kernel<<<div_up(nq, wpb), wpb * 32, msmem, ctx->stream>>>(pidx.as<uint32_t>(), pdist.as<double>(), pcnt.as<uint32_t>(), nq, splits, k,
+                                                                                 out_idx, out_dist, out_cnt);
+            SFB_LAUNCH_CHECK(ctx);
+            SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // partial buffers die with this scope
+            return SFB_OK;
+        }
+    }
     const uint64_t q_tiles = (nq + TQ - 1) / TQ, n_tiles = (x->rows + TC - 1) / TC;
     // one query tile (a fallback of a few rows): only one or two warps per CTA carry FP64 work, so spread the corpus
     // over four CTAs per SM instead of two

@@ -94,12 +94,11 @@ def test_knn_columns_feature_graph(sfb, oracle, ctx, metric, n_items, n_feat, k)
 @pytest.mark.parametrize("metric", [0, 1])
 def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, mode, kernel, monkeypatch):
     """Both pair-tile edges of the feature-graph Gram kernels -- the warp-per-tile kernel with its operands in a register ring
-    (default) and the shared-memory ring (SFB_GRAM_SMEM) -- stand-alone and beside the screen, on shapes with ragged tiles,
+    (the default beside a screen) and the shared-memory ring (the default alone) -- each stand-alone and beside the screen, on shapes with ragged tiles,
     odd node counts and a dimension count that is not a multiple of a round / staged chunk: every pair sum is the reference's
     left fold, so the lists are bit-exact."""
     monkeypatch.setenv("SFB_GRAM_GT", gt)
-    if kernel == "smem":
-        monkeypatch.setenv("SFB_GRAM_SMEM", "1")
+    monkeypatch.setenv("SFB_GRAM_SMEM" if kernel == "smem" else "SFB_GRAM_REGS", "1")   # either kernel in both roles
     monkeypatch.setenv("SFB_GRAM_MODE", mode)   # beside the screen kernel / released when it has finished
     for n_items, n_feat, k in ((20000, 37, 5), (6000, 130, 16), (17001, 64, 8)):   # two long enough for the side stream, one run inline
         x = np.random.default_rng(n_items + metric).normal(size=(n_items, n_feat))
@@ -110,6 +109,26 @@ def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, mode, kern
         g = m.knn(4, sfb.METRIC_COSINE, screen=sfb.SCREEN_F16)
         assert_knn_equal(pend.end().to_host(), want)
         g.free()
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2])
+@pytest.mark.parametrize("n,d,k", [(20011, 37, 16), (16384, 384, 16), (17000, 5, 128), (18000, 16, 3)])
+def test_knn_exact_few_rows(sfb, oracle, ctx, metric, n, d, k, monkeypatch):
+    """A handful of query rows against a long corpus -- the shape of the screen's fallback -- take the one-corpus-row-per-lane
+    kernel: 1 to 8 rows, at the start and at the ragged end of the corpus, with duplicate rows (index ties), a zero row and a
+    distance cap; the same bits as the tile kernel (SFB_EXACT_NO_FEW) and as the oracle."""
+    rng = np.random.default_rng(n + d + metric)
+    x = rng.normal(size=(n, d))
+    x[7] = x[3]; x[n - 2] = x[3]; x[11] = 0.0; x[n - 1] = x[n - 5]
+    m = ctx.matrix(x)
+    for q0, q1 in ((0, 1), (2, 5), (3, 7), (4, 9), (5, 13), (n - 8, n), (n - 1, n)):
+        want = oracle.knn(x, k, metric, query_rows=np.arange(q0, q1, dtype=np.uint32))
+        assert_knn_equal(m.knn(k, metric, screen=sfb.SCREEN_EXACT_F64, q_begin=q0, q_end=q1).to_host(), want)
+    eps = float(np.median(want[1][np.isfinite(want[1])]))
+    want = oracle.knn(x, k, metric, eps, query_rows=np.arange(2, 8, dtype=np.uint32))
+    assert_knn_equal(m.knn(k, metric, eps=eps, screen=sfb.SCREEN_EXACT_F64, q_begin=2, q_end=8).to_host(), want)
+    monkeypatch.setenv("SFB_EXACT_NO_FEW", "1")
+    assert_knn_equal(m.knn(k, metric, eps=eps, screen=sfb.SCREEN_EXACT_F64, q_begin=2, q_end=8).to_host(), want)
 
 
 def test_knn_columns_many_nodes(sfb, oracle, ctx):
@@ -474,7 +493,7 @@ def test_lambda_tile_kernel_shapes(sfb, oracle, ctx, variant, n, f, topk):
     rng = np.random.default_rng(n * 7 + f)
     x = rng.normal(size=(n, f)) * rng.uniform(0.1, 3.0, size=(1, f)) + 0.3
     if n > 8:
-        x[1] = 0.0; x[2] = -4.0; x[5, ::2] = x[5, 1::2][: len(x[5, ::2])]
+        x[1] = 0.0; x[2] = -4.0; x[5, : 2 * (f // 2) : 2] = x[5, 1::2]
     xm = ctx.matrix(x)
     gf = xm.knn_columns(min(topk, f - 1), sfb.METRIC_COSINE)
     Lf = gf.adjacency(2.0, 1.0).laplacian()
