@@ -373,6 +373,15 @@ def run_ours(args):
                                "frac": lap_bytes / (lap_ms * 1e-3) / 1e9 / pk["hbm"],
                                "note": "lists N*k*12 + N*4 read, (N+1)*8 + nnz*12 written; ms covers both Laplacians of a step"}
 
+    rs_ms, rs_cand = stats[-1]["ms_rescore"], stats[-1]["candidates_rescored"]
+    if rs_ms > 0 and rs_cand:
+        rs_bytes = (rs_cand + stats[-1]["rows"]) * d * 8.0   # the gathered candidate rows + each query row once
+        stages["rescore"] = {"kernel": "knn_rescore_kernel", "bound": "hbm", "bytes": rs_bytes, "ms": rs_ms,
+                             "achieved": rs_bytes / (rs_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": rs_bytes / (rs_ms * 1e-3) / 1e9 / pk["hbm"],
+                             "candidates_per_row": rs_cand / max(1, stats[-1]["rows"]),
+                             "note": "(candidates + rows) * D * 8 bytes of row gathers (rank 0's shard); every distance is one FP64 chain of D dependent adds"}
+
     if rank == 0:
         line = {
             "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -386,7 +395,7 @@ def run_ours(args):
             "knn_ms_steps": [[round(s_[k_], 2) for k_ in ("ms_prepare", "ms_screen", "ms_rescore")] for s_ in stats],
             "stages_ms_per_step": {kk: tm[kk] / args.steps for kk in ("ms_knn", "ms_adjacency", "ms_laplacian", "ms_lambda") if kk in tm},
             "knn": {kk: stats[-1][kk] for kk in ("rows", "rows_certified", "rows_fallback", "k_prime", "screen_used", "ms_prepare",
-                                                 "ms_screen", "ms_rescore", "ms_fallback", "max_margin", "rows_rescreened", "ms_rescreen")},
+                                                 "ms_screen", "ms_rescore", "ms_fallback", "max_margin", "rows_rescreened", "ms_rescreen", "candidates_rescored")},
             "gpu_launches": int(tm["kernel_launches"]),
             "clocks": clocks, "roofline": roof, "roofline_stages": stages, "e2e": e2e,
         }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SFB_ABI_VERSION 3
+#define SFB_ABI_VERSION 4
 #define SFB_IDX_NONE 0xFFFFFFFFu
 
 typedef enum {
@@ -126,6 +126,7 @@ typedef struct {
     double max_margin;        /* largest per-row screen margin used                          */
     uint64_t rows_rescreened; /* rows the first screen level left to the k' = 192 re-screen   */
     double ms_rescreen;       /* gather + re-screen + rescore of those rows                   */
+    uint64_t candidates_rescored; /* corpus rows gathered and rescored in f64: rescore traffic = this x dims x 8 bytes */
 } sfb_knn_stats;
 
 int32_t sfb_knn_build(sfb_ctx* ctx, const sfb_mat* rows, const sfb_knn_params* params, sfb_knn** out);

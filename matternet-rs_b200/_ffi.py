@@ -32,7 +32,8 @@ class KnnStats(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("rows_certified", C.c_uint64), ("rows_fallback", C.c_uint64),
                 ("k_prime", C.c_uint32), ("screen_used", C.c_int32), ("ms_prepare", C.c_double),
                 ("ms_screen", C.c_double), ("ms_rescore", C.c_double), ("ms_fallback", C.c_double),
-                ("max_margin", C.c_double), ("rows_rescreened", C.c_uint64), ("ms_rescreen", C.c_double)]
+                ("max_margin", C.c_double), ("rows_rescreened", C.c_uint64), ("ms_rescreen", C.c_double),
+                ("candidates_rescored", C.c_uint64)]
 
 
 class AdjParams(C.Structure):

@@ -898,6 +898,7 @@ struct RescoreArgs {
     uint32_t* out_idx; double* out_dist; uint32_t* out_cnt;
     uint32_t* fb_rows; uint32_t* fb_count;  // uncertified rows (global indices)
     double* max_margin;
+    unsigned long long* n_cand;   // corpus rows rescored (a statistic: the rescore's traffic is n_cand x dims x 8 bytes)
     const uint32_t* qlist;  // null: query row rl is global row q_begin + rl; else global row qlist[rl] (re-screen of uncertified rows)
     uint64_t out_base;      // results of global row g go to output row g - out_base
 };
@@ -921,17 +922,21 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
 }
 
-template <bool COS>
-__global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
+// NST: stages of the per-warp tile ring.  The gather is latency-bound: a warp waits for a chunk it issued one iteration
+// earlier, ~3 us under load against ~0.4 us of folds, so the HBM rate is (bytes in flight) / latency -- 2.4 TB/s at C2 with two
+// stages (one chunk in flight per warp, eight warps per SM).  Three stages keep two chunks in flight; they fit twice per SM
+// up to k = 64 (the screen keys of the filter phase share the ring's memory), else the kernel runs with two.
+template <bool COS, int NST>
+__global__ void __launch_bounds__(128, NST == 2 ? 4 : 2) knn_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* dbase = reinterpret_cast<double*>(smem_raw);
-    double* tile = dbase + (size_t)w * (2 * RS_TILE);   // 2 x { [32][33] candidate tile + query chunk [32] }
-    double* ld = dbase + (size_t)wpb * (2 * RS_TILE) + (size_t)w * a.k;
-    uint32_t* ubase = reinterpret_cast<uint32_t*>(dbase + (size_t)wpb * (2 * RS_TILE + a.k));
+    double* tile = dbase + (size_t)w * (NST * RS_TILE);   // NST x { [32][33] candidate tile + query chunk [32] }
+    double* ld = dbase + (size_t)wpb * (NST * RS_TILE) + (size_t)w * a.k;
+    uint32_t* ubase = reinterpret_cast<uint32_t*>(dbase + (size_t)wpb * (NST * RS_TILE + a.k));
     uint32_t* li = ubase + (size_t)w * a.k;
-    float* skey = reinterpret_cast<float*>(ubase + (size_t)wpb * a.k) + (size_t)w * RS_MAXC;
-    uint32_t* sidx = ubase + (size_t)wpb * (a.k + RS_MAXC) + (size_t)w * RS_MAXC;
+    float* skey = reinterpret_cast<float*>(tile);         // filter phase only: RS_MAXC floats at the head of the (still idle) ring
+    uint32_t* sidx = ubase + (size_t)wpb * a.k + (size_t)w * RS_MAXC;
 
     const uint64_t rl = (uint64_t)blockIdx.x * wpb + w;
     if (rl >= a.nq) return;
@@ -1027,27 +1032,30 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
     uint32_t c = 0;
     auto run_batch = [&](uint32_t mine, uint32_t nb) {
         double acc = 0.0;
-        // cp.async (8 bytes per lane: one 256-byte row segment per instruction), two tiles in flight:
-        // the gather of chunk c + 1 overlaps the folds of chunk c
-        auto issue = [&](int buf, uint32_t d0) {
-            double* tb = tile + buf * RS_TILE;
-            const bool dv = d0 + lane < a.kd;
-            const uint32_t dd = dv ? d0 + lane : 0u;
-            for (uint32_t r = 0; r < nb; ++r) {
-                const uint32_t j = __shfl_sync(FULL, mine, r);
-                cp_async8(&tb[r * 33 + lane], a.x + (uint64_t)j * a.kd + dd, dv);
+        // cp.async (8 bytes per lane: one 256-byte row segment per instruction), NST - 1 chunks in flight:
+        // the gathers of chunks c + 1 .. c + NST - 1 overlap the folds of chunk c
+        const uint32_t n_chunks = (a.kd + 31) / 32;
+        auto issue = [&](uint32_t ci) {   // chunk ci into slot ci % NST; one commit group per call, empty past the end
+            if (ci < n_chunks) {
+                double* tb = tile + (ci % NST) * RS_TILE;
+                const uint32_t d0 = ci * 32;
+                const bool dv = d0 + lane < a.kd;
+                const uint32_t dd = dv ? d0 + lane : 0u;
+                for (uint32_t r = 0; r < nb; ++r) {
+                    const uint32_t j = __shfl_sync(FULL, mine, r);
+                    cp_async8(&tb[r * 33 + lane], a.x + (uint64_t)j * a.kd + dd, dv);
+                }
+                cp_async8(&tb[33 * 32 + lane], xi + dd, dv);
             }
-            cp_async8(&tb[33 * 32 + lane], xi + dd, dv);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        const uint32_t n_chunks = (a.kd + 31) / 32;
-        issue(0, 0);
+#pragma unroll
+        for (int s = 0; s < NST - 1; ++s) issue((uint32_t)s);
         for (uint32_t ci = 0; ci < n_chunks; ++ci) {
-            const int buf = (int)(ci & 1u);
-            if (ci + 1 < n_chunks) { issue(buf ^ 1, (ci + 1) * 32); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            issue(ci + NST - 1);   // its slot was consumed in the previous iteration (__syncwarp at its end)
+            asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
             __syncwarp();
-            const double* tb = tile + buf * RS_TILE;
+            const double* tb = tile + (ci % NST) * RS_TILE;
             const double* qc = tb + 33 * 32;
             const uint32_t d0 = ci * 32, lim = a.kd - d0 < 32 ? a.kd - d0 : 32;
             if (lane < (int)nb) {
@@ -1056,8 +1064,9 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
                     else { double t = __dadd_rn(qc[d], -tb[lane * 33 + d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
                 }
             }
-            __syncwarp();   // the tile is rewritten two iterations from now
+            __syncwarp();   // the slot is refilled by the next iteration's issue
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         double key = INFINITY;
         if (mine != SFB_IDX_NONE) {
             if (COS) {
@@ -1078,6 +1087,7 @@ __global__ void __launch_bounds__(128, 4) knn_rescore_kernel(RescoreArgs a) {
             warp_list_insert(ld, li, c, a.k, kd_, jj, lane);
         }
     };
+    if (lane == 0) atomicAdd(a.n_cand, (unsigned long long)(use_list ? n_list : total));
     if (use_list) {
         for (uint32_t b = 0; b < n_list; b += 32)
             run_batch(b + lane < n_list ? sidx[b + lane] : SFB_IDX_NONE, n_list - b < 32 ? n_list - b : 32);
@@ -1415,18 +1425,22 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
     RescoreArgs ra{x->d, norms, m, x->cols, p->metric, p->k, p->eps, a_row0, nq, sa.n_splits, cap,
                    sa.buf, sa.out_cnt, sa.out_thr, P.aux.as<double>(), P.nmax, P.dmax, gamma, P.scale,
                    out->idx, out->dist, out->cnt, fb_rows, reinterpret_cast<uint32_t*>(fb_count),
-                   reinterpret_cast<double*>(fb_count + 1), qlist, out_base};
+                   reinterpret_cast<double*>(fb_count + 1), reinterpret_cast<unsigned long long*>(fb_count + 4), qlist, out_base};
     {
         StageTimer t(ctx, nullptr);
         const int wpb = 4;
-        size_t smem = (size_t)wpb * ((2 * RS_TILE + p->k) * sizeof(double) + (p->k + 2 * RS_MAXC) * sizeof(uint32_t));
-        if (cosine) {
-            SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knn_rescore_kernel<true><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);
-        } else {
-            SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            knn_rescore_kernel<false><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);
-        }
+        auto rs_smem = [&](int nst) { return (size_t)wpb * ((nst * RS_TILE + p->k) * sizeof(double) + (p->k + RS_MAXC) * sizeof(uint32_t)); };
+        // three stages while two CTAs still fit an SM (228 KB, 1 KB reserved per CTA): k <= 64
+        const bool three = 2 * (rs_smem(3) + 1024) <= 228u * 1024u && !getenv("SFB_RESCORE_NST2");
+        const size_t smem = rs_smem(three ? 3 : 2);
+#define SFB_RESCORE(C_, N_)                                                                                                      \
+    do {                                                                                                                         \
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<C_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        knn_rescore_kernel<C_, N_><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);                                        \
+    } while (0)
+        if (cosine) { if (three) SFB_RESCORE(true, 3); else SFB_RESCORE(true, 2); }
+        else { if (three) SFB_RESCORE(false, 3); else SFB_RESCORE(false, 2); }
+#undef SFB_RESCORE
         SFB_LAUNCH_CHECK(ctx);
         *ms_rescore += t.stop();   // synchronises: the candidate buffers may be released on return
     }
@@ -1471,18 +1485,19 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
     tr.mark("prepare");
     DevBuf fb_rows, fb_rows2, fb_count;
     SFB_CUDA(ctx, fb_rows.alloc(nq * sizeof(uint32_t)));
-    SFB_CUDA(ctx, fb_count.alloc(4 * sizeof(uint64_t)));
-    SFB_CUDA(ctx, cudaMemsetAsync(fb_count.p, 0, 4 * sizeof(uint64_t), ctx->stream));
+    SFB_CUDA(ctx, fb_count.alloc(8 * sizeof(uint64_t)));   // level 1: [0] uncertified rows, [1] max margin, [4] rows rescored; level 2: [2], [3], [6]
+    SFB_CUDA(ctx, cudaMemsetAsync(fb_count.p, 0, 8 * sizeof(uint64_t), ctx->stream));
     uint64_t* fbc = fb_count.as<uint64_t>();
 
     // level 1
     SFB_TRY(screen_level(ctx, x, norms, p, P, kprime, P.q.p, P.mpad, q_begin, nq, nullptr, q_begin, out, fb_rows.as<uint32_t>(), fbc,
                          &st.ms_screen, &st.ms_rescore));
-    uint64_t h[4];
-    SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t h[8];
+    SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
     SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     uint32_t n_fb = (uint32_t)(h[0] & 0xFFFFFFFFu);
     memcpy(&st.max_margin, &h[1], 8);
+    st.candidates_rescored = h[4];
     const uint32_t* fb_final = fb_rows.as<uint32_t>();
     tr.mark("level 1");
 
@@ -1504,9 +1519,10 @@ int32_t sfb_knn_screened(sfb_ctx* ctx, const sfb_mat* x, const double* norms, co
         double ms_s = 0.0, ms_r = 0.0;
         SFB_TRY(screen_level(ctx, x, norms, p, P, kp_max, qa.p, a_rows, 0, n_fb, fb_rows.as<uint32_t>(), q_begin, out, fb_rows2.as<uint32_t>(),
                              fbc + 2, &ms_s, &ms_r));
-        SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        SFB_CUDA(ctx, cudaMemcpyAsync(h, fb_count.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
         SFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         n_fb = (uint32_t)(h[2] & 0xFFFFFFFFu);
+        st.candidates_rescored += h[6];
         fb_final = fb_rows2.as<uint32_t>();
         st.ms_rescreen = t.stop();
         tr.mark("level 2");

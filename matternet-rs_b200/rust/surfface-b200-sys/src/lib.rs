@@ -17,7 +17,8 @@ pub const SFB_IDX_NONE: u32 = 0xFFFF_FFFF;
 pub struct sfb_knn_params { pub metric: i32, pub k: u32, pub eps: f64, pub screen: i32, pub k_prime: u32, pub q_begin: u64, pub q_end: u64, pub allow_fallback: i32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct sfb_knn_stats { pub rows: u64, pub rows_certified: u64, pub rows_fallback: u64, pub k_prime: u32, pub screen_used: i32, pub ms_prepare: f64,
-                           pub ms_screen: f64, pub ms_rescore: f64, pub ms_fallback: f64, pub max_margin: f64, pub rows_rescreened: u64, pub ms_rescreen: f64 }
+                           pub ms_screen: f64, pub ms_rescore: f64, pub ms_fallback: f64, pub max_margin: f64, pub rows_rescreened: u64, pub ms_rescreen: f64,
+                           pub candidates_rescored: u64 }
 #[repr(C)] #[derive(Clone, Copy)] pub struct sfb_adj_params { pub p: f64, pub sigma: f64, pub sparsify: i32 }
 #[repr(C)] #[derive(Clone, Copy)] pub struct sfb_lap_params { pub normalised: i32, pub weight_threshold: f64 }
 #[repr(C)] #[derive(Clone, Copy)] pub struct sfb_lambda_params { pub variant: i32, pub tau_mode: i32, pub tau_value: f64, pub normalise_minmax: i32 }

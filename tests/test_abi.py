@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(sfb):
         assert hasattr(L, n), f"{n} declared in the header but not exported"
         assert n in _ffi.SYMBOLS, f"{n} has no ctypes signature"
     assert set(_ffi.SYMBOLS) == set(names)
-    assert L.sfb_abi_version() == 3
+    assert L.sfb_abi_version() == 4
 
 
 def test_no_cpu_fallback(sfb):
