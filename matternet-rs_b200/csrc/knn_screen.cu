@@ -915,7 +915,21 @@ struct RescoreArgs {
 //   certify  row i is certified iff its exact k-th distance is below the proven lower bound on the
 //            distance of everything that was not rescored; otherwise it goes to the exact fallback.
 constexpr uint32_t RS_MAXC = 256;  // candidates a row can bring to the filter; beyond that all are rescored
-constexpr int RS_TILE = 33 * 32 + 32;
+// per-warp tile of one ring stage: NB candidate rows x 32 dimensions at row stride LD doubles, + the query chunk [32].
+//   cp.async path  32 rows, stride 33 (conflict-free for lane = row)
+//   bulk path      30 rows, stride 34: a row chunk is ONE 256-byte cp.async.bulk (16-byte aligned destination: even stride;
+//                  lane = row reads are then 2-way conflicted, which the fold does not notice), 30 rows so that three CTAs of
+//                  four warps fit an SM
+template <bool BULK> struct RsGeom { static constexpr int LD = BULK ? 34 : 33, NB = BULK ? 30 : 32, TILE = NB * LD + 32; };
+__host__ __device__ constexpr size_t rs_warp_bytes(bool bulk, int nst, uint32_t k) {
+    return ((size_t)nst * (bulk ? RsGeom<true>::TILE : RsGeom<false>::TILE) * sizeof(double) + (bulk ? (size_t)nst * 8 : 0) +
+            (size_t)k * (sizeof(double) + sizeof(uint32_t)) + RS_MAXC * sizeof(uint32_t) + 15) & ~(size_t)15;   // 16-byte aligned per warp
+}
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
     const int n = valid ? 8 : 0;   // src-size 0: zero fill
@@ -926,19 +940,35 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
 // earlier, ~3 us under load against ~0.4 us of folds, so the HBM rate is (bytes in flight) / latency -- 2.4 TB/s at C2 with two
 // stages (one chunk in flight per warp, eight warps per SM).  Three stages keep two chunks in flight; they fit twice per SM
 // up to k = 64 (the screen keys of the filter phase share the ring's memory), else the kernel runs with two.
-template <bool COS, int NST>
-__global__ void __launch_bounds__(128, NST == 2 ? 4 : 2) knn_rescore_kernel(RescoreArgs a) {
+//
+// BULK: the row chunks come by cp.async.bulk (the TMA engine's linear copy: one 256-byte request per candidate row and chunk,
+// issued by the lane that owns the row, completion counted in bytes on a per-stage mbarrier) instead of 8-byte cp.async, which
+// costs the LSU one 8-byte element per lane and instruction: at C2 the kernel moved ~8 bytes per clock and SM whatever the ring
+// depth, and only more resident warps made it faster.  Needs 16-byte aligned row chunks (even D, aligned base).
+template <bool COS, int NST, bool BULK>
+__global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double* dbase = reinterpret_cast<double*>(smem_raw);
-    double* tile = dbase + (size_t)w * (NST * RS_TILE);   // NST x { [32][33] candidate tile + query chunk [32] }
-    double* ld = dbase + (size_t)wpb * (NST * RS_TILE) + (size_t)w * a.k;
-    uint32_t* ubase = reinterpret_cast<uint32_t*>(dbase + (size_t)wpb * (NST * RS_TILE + a.k));
-    uint32_t* li = ubase + (size_t)w * a.k;
+    constexpr int RS_LD = RsGeom<BULK>::LD, RS_NB = RsGeom<BULK>::NB, RS_TILE = RsGeom<BULK>::TILE;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // per warp: NST tiles | NST mbarriers (BULK) | list distances [k] | list indices [k] | candidate indices [RS_MAXC]
+    unsigned char* wbase = smem_raw + (size_t)w * rs_warp_bytes(BULK, NST, a.k);
+    double* tile = reinterpret_cast<double*>(wbase);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tile + (size_t)NST * RS_TILE);
+    double* ld = reinterpret_cast<double*>(bars + (BULK ? NST : 0));
+    uint32_t* li = reinterpret_cast<uint32_t*>(ld + a.k);
+    uint32_t* sidx = li + a.k;
     float* skey = reinterpret_cast<float*>(tile);         // filter phase only: RS_MAXC floats at the head of the (still idle) ring
-    uint32_t* sidx = ubase + (size_t)wpb * a.k + (size_t)w * RS_MAXC;
+    uint32_t phase = 0;                                   // BULK: parity of each stage's barrier, one bit per stage
+    if (BULK) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
-    const uint64_t rl = (uint64_t)blockIdx.x * wpb + w;
+    const uint64_t rl = (uint64_t)blockIdx.x * (blockDim.x >> 5) + w;
     if (rl >= a.nq) return;
     const uint32_t gi = a.qlist ? a.qlist[rl] : (uint32_t)(a.q_begin + rl);
     const uint64_t orow = (uint64_t)gi - a.out_base;
@@ -1035,38 +1065,55 @@ __global__ void __launch_bounds__(128, NST == 2 ? 4 : 2) knn_rescore_kernel(Resc
         // cp.async (8 bytes per lane: one 256-byte row segment per instruction), NST - 1 chunks in flight:
         // the gathers of chunks c + 1 .. c + NST - 1 overlap the folds of chunk c
         const uint32_t n_chunks = (a.kd + 31) / 32;
-        auto issue = [&](uint32_t ci) {   // chunk ci into slot ci % NST; one commit group per call, empty past the end
+        auto issue = [&](uint32_t ci) {   // chunk ci into slot ci % NST; cp.async: one commit group per call, empty past the end
             if (ci < n_chunks) {
-                double* tb = tile + (ci % NST) * RS_TILE;
+                const uint32_t slot = ci % NST;
+                double* tb = tile + slot * RS_TILE;
                 const uint32_t d0 = ci * 32;
-                const bool dv = d0 + lane < a.kd;
-                const uint32_t dd = dv ? d0 + lane : 0u;
-                for (uint32_t r = 0; r < nb; ++r) {
-                    const uint32_t j = __shfl_sync(FULL, mine, r);
-                    cp_async8(&tb[r * 33 + lane], a.x + (uint64_t)j * a.kd + dd, dv);
+                if (BULK) {
+                    const uint32_t bytes = (a.kd - d0 < 32 ? a.kd - d0 : 32) * 8;
+                    // the slot's previous contents were read (or, in the filter phase, written) through the generic proxy
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (lane == 0) mbar_expect_tx(&bars[slot], (nb + 1) * bytes);
+                    __syncwarp();
+                    if (lane < (int)nb) bulk_g2s(&tb[lane * RS_LD], a.x + (uint64_t)mine * a.kd + d0, bytes, &bars[slot]);
+                    if (lane == 31) bulk_g2s(&tb[RS_LD * RS_NB], xi + d0, bytes, &bars[slot]);
+                } else {
+                    const bool dv = d0 + lane < a.kd;
+                    const uint32_t dd = dv ? d0 + lane : 0u;
+                    for (uint32_t r = 0; r < nb; ++r) {
+                        const uint32_t j = __shfl_sync(FULL, mine, r);
+                        cp_async8(&tb[r * RS_LD + lane], a.x + (uint64_t)j * a.kd + dd, dv);
+                    }
+                    cp_async8(&tb[RS_LD * RS_NB + lane], xi + dd, dv);
                 }
-                cp_async8(&tb[33 * 32 + lane], xi + dd, dv);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (!BULK) asm volatile("cp.async.commit_group;" ::: "memory");
         };
 #pragma unroll
         for (int s = 0; s < NST - 1; ++s) issue((uint32_t)s);
         for (uint32_t ci = 0; ci < n_chunks; ++ci) {
             issue(ci + NST - 1);   // its slot was consumed in the previous iteration (__syncwarp at its end)
-            asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
-            __syncwarp();
+            if (BULK) {
+                const uint32_t slot = ci % NST;
+                mbar_wait(&bars[slot], (phase >> slot) & 1u);
+                phase ^= 1u << slot;
+            } else {
+                asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
+                __syncwarp();
+            }
             const double* tb = tile + (ci % NST) * RS_TILE;
-            const double* qc = tb + 33 * 32;
+            const double* qc = tb + RS_LD * RS_NB;
             const uint32_t d0 = ci * 32, lim = a.kd - d0 < 32 ? a.kd - d0 : 32;
             if (lane < (int)nb) {
                 for (uint32_t d = 0; d < lim; ++d) {
-                    if (COS) acc = __dadd_rn(acc, __dmul_rn(qc[d], tb[lane * 33 + d]));
-                    else { double t = __dadd_rn(qc[d], -tb[lane * 33 + d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
+                    if (COS) acc = __dadd_rn(acc, __dmul_rn(qc[d], tb[lane * RS_LD + d]));
+                    else { double t = __dadd_rn(qc[d], -tb[lane * RS_LD + d]); acc = __dadd_rn(acc, __dmul_rn(t, t)); }
                 }
             }
             __syncwarp();   // the slot is refilled by the next iteration's issue
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!BULK) asm volatile("cp.async.wait_group 0;" ::: "memory");
         double key = INFINITY;
         if (mine != SFB_IDX_NONE) {
             if (COS) {
@@ -1089,14 +1136,15 @@ __global__ void __launch_bounds__(128, NST == 2 ? 4 : 2) knn_rescore_kernel(Resc
     };
     if (lane == 0) atomicAdd(a.n_cand, (unsigned long long)(use_list ? n_list : total));
     if (use_list) {
-        for (uint32_t b = 0; b < n_list; b += 32)
-            run_batch(b + lane < n_list ? sidx[b + lane] : SFB_IDX_NONE, n_list - b < 32 ? n_list - b : 32);
+        for (uint32_t b = 0; b < n_list; b += RS_NB)
+            run_batch(lane < RS_NB && b + lane < n_list ? sidx[b + lane] : SFB_IDX_NONE, n_list - b < (uint32_t)RS_NB ? n_list - b : RS_NB);
     } else {
         for (uint32_t s = 0; s < a.n_splits; ++s) {
             const size_t slot = (size_t)rl * a.n_splits + s;
             const uint32_t n = a.cnt[slot];
             const uint2* cand = a.buf + slot * a.cap;
-            for (uint32_t b = 0; b < n; b += 32) run_batch(b + lane < n ? cand[b + lane].y : SFB_IDX_NONE, n - b < 32 ? n - b : 32);
+            for (uint32_t b = 0; b < n; b += RS_NB)
+                run_batch(lane < RS_NB && b + lane < n ? cand[b + lane].y : SFB_IDX_NONE, n - b < (uint32_t)RS_NB ? n - b : RS_NB);
         }
     }
 
@@ -1429,17 +1477,23 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
     {
         StageTimer t(ctx, nullptr);
         const int wpb = 4;
-        auto rs_smem = [&](int nst) { return (size_t)wpb * ((nst * RS_TILE + p->k) * sizeof(double) + (p->k + RS_MAXC) * sizeof(uint32_t)); };
-        // three stages while two CTAs still fit an SM (228 KB, 1 KB reserved per CTA): k <= 64
-        const bool three = 2 * (rs_smem(3) + 1024) <= 228u * 1024u && !getenv("SFB_RESCORE_NST2");
-        const size_t smem = rs_smem(three ? 3 : 2);
-#define SFB_RESCORE(C_, N_)                                                                                                      \
-    do {                                                                                                                         \
-        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<C_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        knn_rescore_kernel<C_, N_><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);                                        \
+        // bulk (TMA) gathers need 16-byte aligned row chunks; SFB_RESCORE_LSU forces the cp.async path, SFB_RESCORE_NST its ring depth
+        const bool bulk = (x->cols & 1u) == 0 && (reinterpret_cast<uintptr_t>(x->d) & 15u) == 0 && !getenv("SFB_RESCORE_LSU");
+        int nst = 2;
+        if (const char* e = getenv("SFB_RESCORE_NST")) { if (atoi(e) == 3) nst = 3; }
+        const size_t smem = (size_t)wpb * rs_warp_bytes(bulk, nst, p->k);
+#define SFB_RESCORE(C_, N_, B_)                                                                                                      \
+    do {                                                                                                                             \
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<C_, N_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        knn_rescore_kernel<C_, N_, B_><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);                                        \
     } while (0)
-        if (cosine) { if (three) SFB_RESCORE(true, 3); else SFB_RESCORE(true, 2); }
-        else { if (three) SFB_RESCORE(false, 3); else SFB_RESCORE(false, 2); }
+#define SFB_RESCORE_C(C_)                                                              \
+    do {                                                                               \
+        if (bulk) { if (nst == 3) SFB_RESCORE(C_, 3, true); else SFB_RESCORE(C_, 2, true); }   \
+        else { if (nst == 3) SFB_RESCORE(C_, 3, false); else SFB_RESCORE(C_, 2, false); }      \
+    } while (0)
+        if (cosine) SFB_RESCORE_C(true); else SFB_RESCORE_C(false);
+#undef SFB_RESCORE_C
 #undef SFB_RESCORE
         SFB_LAUNCH_CHECK(ctx);
         *ms_rescore += t.stop();   // synchronises: the candidate buffers may be released on return
