@@ -620,10 +620,14 @@ int32_t sfb_comm_allreduce_sum_f64(sfb_ctx* ctx, double* buf, size_t n);
 
 // Pair-tile edge for this call: 16 (thread = 2 x 2 pairs), or 8 (thread = one pair) when the 16-edge tiling would give this
 // rank fewer CTAs than a quarter of its SMs -- the sharded builds at 8 GPUs.  SFB_GRAM_GT=8 / 16 forces it (tests, A/B).
+// 32 (thread = 4 x 4 pairs) when even that tiling gives every SM four CTAs: with thousands of nodes (C4: 3072) the chains are
+// plentiful and the kernel is bound by the FP64 pipe, where 16 chains per thread halve the shared-memory reads per multiply-add.
 uint32_t sfb_gram_tile_edge(const sfb_ctx* ctx, uint32_t m, int collective) {
-    if (const char* e = getenv("SFB_GRAM_GT")) { const int v = atoi(e); if (v == 8 || v == 16) return (uint32_t)v; }
+    if (const char* e = getenv("SFB_GRAM_GT")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) return (uint32_t)v; }
     const uint32_t T = (m + 15) / 16, tiles = T * (T + 1) / 2;
     const uint32_t world = collective && ctx->world > 1 ? (uint32_t)ctx->world : 1u;
+    const uint32_t T32 = (m + 31) / 32, tiles32 = T32 * (T32 + 1) / 2;
+    if (tiles32 / world >= 4u * (uint32_t)ctx->sm_count) return 32u;
     return (tiles + world - 1) / world * 4 <= (uint32_t)ctx->sm_count ? 8u : 16u;
 }
 
@@ -635,7 +639,7 @@ int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uin
     const uint32_t nt = t1 - t0;
     // beside a screen: the register-ring kernel (hidden completely at one rank's share of C2 at 8 GPUs, where the 8 KB ring left
     // 17-32 ms exposed); alone: the shared-memory ring (14 against 24 ns per fold step).  SFB_GRAM_SMEM / SFB_GRAM_REGS force one.
-    if (small_smem ? !getenv("SFB_GRAM_SMEM") : getenv("SFB_GRAM_REGS") != nullptr) {
+    if (gt != 32 && (small_smem ? !getenv("SFB_GRAM_SMEM") : getenv("SFB_GRAM_REGS") != nullptr)) {
         // one warp per tile; beside the screen kernel at most two warps per SM walk the tiles (the screen CTA's registers must
         // still fit wherever the block scheduler puts them)
         const uint32_t cap = 2u * (uint32_t)ctx->sm_count, wgrid = small_smem && nt > cap ? cap : nt;
@@ -657,6 +661,7 @@ int32_t sfb_gram_launch(sfb_ctx* ctx, cudaStream_t stream, const double* xd, uin
     } while (0)
     // shared memory: 2 * NST * GCH * GTILE * 8 bytes -- 8 KB beside the screen (its CTA leaves ~11 KB), 32 KB standalone
     if (gt == 8) { if (small_smem) SFB_GRAM_CV(16, 8, 4); else SFB_GRAM_CV(32, 8, 8); }
+    else if (gt == 32) SFB_GRAM_CV(16, 32, 3);   // 24 KB; never the choice beside a screen
     else { if (small_smem) SFB_GRAM_CV(16, 16, 2); else SFB_GRAM_CV(32, 16, 4); }
 #undef SFB_GRAM_CV
 #undef SFB_GRAM

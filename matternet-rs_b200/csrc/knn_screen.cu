@@ -1477,8 +1477,11 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
     {
         StageTimer t(ctx, nullptr);
         const int wpb = 4;
-        // bulk (TMA) gathers need 16-byte aligned row chunks; SFB_RESCORE_LSU forces the cp.async path, SFB_RESCORE_NST its ring depth
-        const bool bulk = (x->cols & 1u) == 0 && (reinterpret_cast<uintptr_t>(x->d) & 15u) == 0 && !getenv("SFB_RESCORE_LSU");
+        // Measured (C2 / C4, ms): cp.async two stages 27.3 / 136, three 33.4 / 133; bulk two stages 29.1 / 142, three 38.3 / 142 --
+        // neither the gather mechanism nor the ring depth is the limit, the number of resident warps is (three CTAs per SM with two
+        // stages).  Default: cp.async, two stages.  SFB_RESCORE_BULK=1 selects the bulk gathers (16-byte aligned row chunks: even D),
+        // SFB_RESCORE_NST=3 the deeper ring.
+        const bool bulk = (x->cols & 1u) == 0 && (reinterpret_cast<uintptr_t>(x->d) & 15u) == 0 && getenv("SFB_RESCORE_BULK") != nullptr;
         int nst = 2;
         if (const char* e = getenv("SFB_RESCORE_NST")) { if (atoi(e) == 3) nst = 3; }
         const size_t smem = (size_t)wpb * rs_warp_bytes(bulk, nst, p->k);

@@ -90,7 +90,7 @@ def test_knn_columns_feature_graph(sfb, oracle, ctx, metric, n_items, n_feat, k)
 
 @pytest.mark.parametrize("kernel", ["regs", "smem"])
 @pytest.mark.parametrize("mode", ["co", "after"])
-@pytest.mark.parametrize("gt", ["8", "16"])
+@pytest.mark.parametrize("gt", ["8", "16", "32"])
 @pytest.mark.parametrize("metric", [0, 1])
 def test_knn_columns_gram_tile_variants(sfb, oracle, ctx, gt, metric, mode, kernel, monkeypatch):
     """Both pair-tile edges of the feature-graph Gram kernels -- the warp-per-tile kernel with its operands in a register ring

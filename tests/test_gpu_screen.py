@@ -64,8 +64,8 @@ def test_knn_screen_parity_gaussian(sfb, oracle, ctx, screen, metric, m, kd, k):
 def test_knn_screen_parity_clustered(sfb, oracle, ctx, metric, gather, monkeypatch):
     """Tight clusters: neighbour gaps comparable to the fp16 margin -> many rows fall back; still exact.  Both gather paths
     of the rescore kernel (cp.async.bulk row chunks / 8-byte cp.async) at both ring depths."""
-    if gather.startswith("lsu"):
-        monkeypatch.setenv("SFB_RESCORE_LSU", "1")
+    if gather.startswith("bulk"):
+        monkeypatch.setenv("SFB_RESCORE_BULK", "1")
     monkeypatch.setenv("SFB_RESCORE_NST", gather[-1])
     m = ctx.generate(sfb.SYNTH_CLUSTERED, 7, 20000, 128, 32, 0.3)
     x = oracle.generate_rows(1, 7, 0, 20000, 128, 32, 0.3)
