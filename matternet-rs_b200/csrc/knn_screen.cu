@@ -920,9 +920,11 @@ constexpr uint32_t RS_MAXC = 256;  // candidates a row can bring to the filter; 
 //   bulk path      30 rows, stride 34: a row chunk is ONE 256-byte cp.async.bulk (16-byte aligned destination: even stride;
 //                  lane = row reads are then 2-way conflicted, which the fold does not notice), 30 rows so that three CTAs of
 //                  four warps fit an SM
-template <bool BULK> struct RsGeom { static constexpr int LD = BULK ? 34 : 33, NB = BULK ? 30 : 32, TILE = NB * LD + 32; };
-__host__ __device__ constexpr size_t rs_warp_bytes(bool bulk, int nst, uint32_t k) {
-    return ((size_t)nst * (bulk ? RsGeom<true>::TILE : RsGeom<false>::TILE) * sizeof(double) + (bulk ? (size_t)nst * 8 : 0) +
+//   CH = 16        (cp.async path) half the chunk: half a warp per row and copy instruction, stride 17, 4.4 KB per stage -- twice
+//                  the resident warps for the same shared memory
+template <bool BULK, int CH> struct RsGeom { static constexpr int LD = BULK ? 34 : CH + 1, NB = BULK ? 30 : 32, TILE = NB * LD + CH; };
+__host__ __device__ constexpr size_t rs_warp_bytes(bool bulk, int ch, int nst, uint32_t k) {
+    return ((size_t)nst * (bulk ? RsGeom<true, 32>::TILE : (ch == 16 ? RsGeom<false, 16>::TILE : RsGeom<false, 32>::TILE)) * sizeof(double) + (bulk ? (size_t)nst * 8 : 0) +
             (size_t)k * (sizeof(double) + sizeof(uint32_t)) + RS_MAXC * sizeof(uint32_t) + 15) & ~(size_t)15;   // 16-byte aligned per warp
 }
 
@@ -945,13 +947,14 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
 // issued by the lane that owns the row, completion counted in bytes on a per-stage mbarrier) instead of 8-byte cp.async, which
 // costs the LSU one 8-byte element per lane and instruction: at C2 the kernel moved ~8 bytes per clock and SM whatever the ring
 // depth, and only more resident warps made it faster.  Needs 16-byte aligned row chunks (even D, aligned base).
-template <bool COS, int NST, bool BULK>
+template <bool COS, int NST, bool BULK, int CH>
 __global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescore_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int RS_LD = RsGeom<BULK>::LD, RS_NB = RsGeom<BULK>::NB, RS_TILE = RsGeom<BULK>::TILE;
+    static_assert(!BULK || CH == 32, "the bulk path moves 32-dimension chunks");
+    constexpr int RS_LD = RsGeom<BULK, CH>::LD, RS_NB = RsGeom<BULK, CH>::NB, RS_TILE = RsGeom<BULK, CH>::TILE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     // per warp: NST tiles | NST mbarriers (BULK) | list distances [k] | list indices [k] | candidate indices [RS_MAXC]
-    unsigned char* wbase = smem_raw + (size_t)w * rs_warp_bytes(BULK, NST, a.k);
+    unsigned char* wbase = smem_raw + (size_t)w * rs_warp_bytes(BULK, CH, NST, a.k);
     double* tile = reinterpret_cast<double*>(wbase);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tile + (size_t)NST * RS_TILE);
     double* ld = reinterpret_cast<double*>(bars + (BULK ? NST : 0));
@@ -1013,12 +1016,14 @@ __global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescor
 #pragma unroll
             for (int u = 0; u < (int)(RS_MAXC / 32); ++u) { const uint32_t e = lane + 32 * u; key[u] = e < n_list ? f32_sortable(skey[e]) : 0u; }
             uint32_t prefix = 0, want = a.k;
+            const int nreg = (int)((n_list + 31) / 32);   // registers that hold a key (warp-uniform): ~3 of the 8 at C2
 #pragma unroll 1
             for (int b = 31; b >= 0; --b) {
                 const uint32_t bit = 1u << b, hi = b == 31 ? 0u : ~((bit << 1) - 1u);
                 uint32_t c = 0;
 #pragma unroll
-                for (int u = 0; u < (int)(RS_MAXC / 32); ++u) c += __popc(__ballot_sync(FULL, (key[u] & hi) == (prefix & hi) && (key[u] & bit)));
+                for (int u = 0; u < (int)(RS_MAXC / 32); ++u)
+                    if (u < nreg) c += __popc(__ballot_sync(FULL, (key[u] & hi) == (prefix & hi) && (key[u] & bit)));
                 if (c >= want) prefix |= bit; else want -= c;
             }
             const double sk = (double)sortable_f32(prefix);   // k-th largest screen key among the other rows
@@ -1064,12 +1069,12 @@ __global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescor
         double acc = 0.0;
         // cp.async (8 bytes per lane: one 256-byte row segment per instruction), NST - 1 chunks in flight:
         // the gathers of chunks c + 1 .. c + NST - 1 overlap the folds of chunk c
-        const uint32_t n_chunks = (a.kd + 31) / 32;
+        const uint32_t n_chunks = (a.kd + CH - 1) / CH;
         auto issue = [&](uint32_t ci) {   // chunk ci into slot ci % NST; cp.async: one commit group per call, empty past the end
             if (ci < n_chunks) {
                 const uint32_t slot = ci % NST;
                 double* tb = tile + slot * RS_TILE;
-                const uint32_t d0 = ci * 32;
+                const uint32_t d0 = ci * CH;
                 if (BULK) {
                     const uint32_t bytes = (a.kd - d0 < 32 ? a.kd - d0 : 32) * 8;
                     // the slot's previous contents were read (or, in the filter phase, written) through the generic proxy
@@ -1078,7 +1083,7 @@ __global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescor
                     __syncwarp();
                     if (lane < (int)nb) bulk_g2s(&tb[lane * RS_LD], a.x + (uint64_t)mine * a.kd + d0, bytes, &bars[slot]);
                     if (lane == 31) bulk_g2s(&tb[RS_LD * RS_NB], xi + d0, bytes, &bars[slot]);
-                } else {
+                } else if (CH == 32) {
                     const bool dv = d0 + lane < a.kd;
                     const uint32_t dd = dv ? d0 + lane : 0u;
                     for (uint32_t r = 0; r < nb; ++r) {
@@ -1086,6 +1091,17 @@ __global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescor
                         cp_async8(&tb[r * RS_LD + lane], a.x + (uint64_t)j * a.kd + dd, dv);
                     }
                     cp_async8(&tb[RS_LD * RS_NB + lane], xi + dd, dv);
+                } else {
+                    // half a warp per row: lanes 0-15 row r, lanes 16-31 row r + 1
+                    const uint32_t hl = lane & 15u, hr = (uint32_t)lane >> 4;
+                    const bool dv = d0 + hl < a.kd;
+                    const uint32_t dd = dv ? d0 + hl : 0u;
+                    for (uint32_t r = 0; r < nb; r += 2) {
+                        const uint32_t rr = r + hr;
+                        const uint32_t j = __shfl_sync(FULL, mine, rr & 31u);
+                        if (rr < nb) cp_async8(&tb[rr * RS_LD + hl], a.x + (uint64_t)j * a.kd + dd, dv);
+                    }
+                    if (hr == 0) cp_async8(&tb[RS_LD * RS_NB + hl], xi + dd, dv);
                 }
             }
             if (!BULK) asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1104,7 +1120,7 @@ __global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescor
             }
             const double* tb = tile + (ci % NST) * RS_TILE;
             const double* qc = tb + RS_LD * RS_NB;
-            const uint32_t d0 = ci * 32, lim = a.kd - d0 < 32 ? a.kd - d0 : 32;
+            const uint32_t d0 = ci * CH, lim = a.kd - d0 < (uint32_t)CH ? a.kd - d0 : CH;
             if (lane < (int)nb) {
                 for (uint32_t d = 0; d < lim; ++d) {
                     if (COS) acc = __dadd_rn(acc, __dmul_rn(qc[d], tb[lane * RS_LD + d]));
@@ -1127,6 +1143,27 @@ __global__ void __launch_bounds__(128, BULK ? 3 : (NST == 2 ? 4 : 2)) knn_rescor
         uint32_t ti = c == a.k ? li[a.k - 1] : SFB_IDX_NONE;
         bool pass = mine != SFB_IDX_NONE && mine != gi && key <= a.eps && topk_key_less(key, mine, td, ti);
         uint32_t bal = __ballot_sync(FULL, pass);
+        if (c == 0) {
+            // first batch into an empty list (the only batch of most rows): one 15-step bitonic network over the lanes in the
+            // (distance, index) order instead of ~20 serial list insertions
+            double sk_ = pass ? key : INFINITY;
+            uint32_t si_ = pass ? mine : SFB_IDX_NONE;
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    const double ok = __shfl_xor_sync(FULL, sk_, j);
+                    const uint32_t oi = __shfl_xor_sync(FULL, si_, j);
+                    const bool want_min = ((lane & j) == 0) == ((lane & k2) == 0);
+                    const bool swap = want_min ? topk_key_less(ok, oi, sk_, si_) : topk_key_less(sk_, si_, ok, oi);
+                    if (swap) { sk_ = ok; si_ = oi; }
+                }
+            const uint32_t nv = __popc(bal);
+            c = nv < a.k ? nv : a.k;
+            if ((uint32_t)lane < c) { ld[lane] = sk_; li[lane] = si_; }
+            __syncwarp();
+            bal = 0;
+        }
         while (bal) {
             int src = __ffs(bal) - 1; bal &= bal - 1;
             double kd_ = __shfl_sync(FULL, key, src);
@@ -1479,21 +1516,25 @@ int32_t screen_level(sfb_ctx* ctx, const sfb_mat* x, const double* norms, const 
         const int wpb = 4;
         // Measured (C2 / C4, ms): cp.async two stages 27.3 / 136, three 33.4 / 133; bulk two stages 29.1 / 142, three 38.3 / 142 --
         // neither the gather mechanism nor the ring depth is the limit, the number of resident warps is (three CTAs per SM with two
-        // stages).  Default: cp.async, two stages.  SFB_RESCORE_BULK=1 selects the bulk gathers (16-byte aligned row chunks: even D),
-        // SFB_RESCORE_NST=3 the deeper ring.
+        // stages; ncu: issue slots 42 % busy, stalls on fixed-latency dependencies and shared-memory loads, DRAM 3.7 TB/s at full
+        // clock).  Default: cp.async, two stages.  SFB_RESCORE_BULK=1 selects the bulk gathers (16-byte aligned row chunks: even D),
+        // SFB_RESCORE_NST=3 the deeper ring, SFB_RESCORE_CH=16 / 32 the chunk.
         const bool bulk = (x->cols & 1u) == 0 && (reinterpret_cast<uintptr_t>(x->d) & 15u) == 0 && getenv("SFB_RESCORE_BULK") != nullptr;
-        int nst = 2;
+        int nst = 2, ch = 32;
         if (const char* e = getenv("SFB_RESCORE_NST")) { if (atoi(e) == 3) nst = 3; }
-        const size_t smem = (size_t)wpb * rs_warp_bytes(bulk, nst, p->k);
-#define SFB_RESCORE(C_, N_, B_)                                                                                                      \
-    do {                                                                                                                             \
-        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<C_, N_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        knn_rescore_kernel<C_, N_, B_><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);                                        \
+        if (const char* e = getenv("SFB_RESCORE_CH")) { if (atoi(e) == 16) ch = 16; }
+        if (bulk) ch = 32;
+        const size_t smem = (size_t)wpb * rs_warp_bytes(bulk, ch, nst, p->k);
+#define SFB_RESCORE(C_, N_, B_, H_)                                                                                                      \
+    do {                                                                                                                                 \
+        SFB_CUDA(ctx, cudaFuncSetAttribute(knn_rescore_kernel<C_, N_, B_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        knn_rescore_kernel<C_, N_, B_, H_><<<div_up(nq, wpb), wpb * 32, smem, ctx->stream>>>(ra);                                        \
     } while (0)
-#define SFB_RESCORE_C(C_)                                                              \
-    do {                                                                               \
-        if (bulk) { if (nst == 3) SFB_RESCORE(C_, 3, true); else SFB_RESCORE(C_, 2, true); }   \
-        else { if (nst == 3) SFB_RESCORE(C_, 3, false); else SFB_RESCORE(C_, 2, false); }      \
+#define SFB_RESCORE_C(C_)                                                                            \
+    do {                                                                                             \
+        if (bulk) { if (nst == 3) SFB_RESCORE(C_, 3, true, 32); else SFB_RESCORE(C_, 2, true, 32); } \
+        else if (ch == 16) { if (nst == 3) SFB_RESCORE(C_, 3, false, 16); else SFB_RESCORE(C_, 2, false, 16); } \
+        else { if (nst == 3) SFB_RESCORE(C_, 3, false, 32); else SFB_RESCORE(C_, 2, false, 32); }    \
     } while (0)
         if (cosine) SFB_RESCORE_C(true); else SFB_RESCORE_C(false);
 #undef SFB_RESCORE_C

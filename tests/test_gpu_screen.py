@@ -59,13 +59,15 @@ def test_knn_screen_parity_gaussian(sfb, oracle, ctx, screen, metric, m, kd, k):
     print(st)
 
 
-@pytest.mark.parametrize("gather", ["bulk2", "bulk3", "lsu2", "lsu3"])
+@pytest.mark.parametrize("gather", ["bulk2", "bulk3", "lsu2", "lsu3", "half2", "half3"])
 @pytest.mark.parametrize("metric", [0, 1])
 def test_knn_screen_parity_clustered(sfb, oracle, ctx, metric, gather, monkeypatch):
     """Tight clusters: neighbour gaps comparable to the fp16 margin -> many rows fall back; still exact.  Both gather paths
-    of the rescore kernel (cp.async.bulk row chunks / 8-byte cp.async) at both ring depths."""
+    of the rescore kernel (cp.async.bulk row chunks / 8-byte cp.async, the latter with 32- and 16-dimension chunks) at both
+    ring depths."""
     if gather.startswith("bulk"):
         monkeypatch.setenv("SFB_RESCORE_BULK", "1")
+    monkeypatch.setenv("SFB_RESCORE_CH", "16" if gather.startswith("half") else "32")
     monkeypatch.setenv("SFB_RESCORE_NST", gather[-1])
     m = ctx.generate(sfb.SYNTH_CLUSTERED, 7, 20000, 128, 32, 0.3)
     x = oracle.generate_rows(1, 7, 0, 20000, 128, 32, 0.3)
