@@ -61,3 +61,26 @@ def test_rust_sys_crate_declares_every_symbol():
     rs = open(os.path.join(ROOT, "matternet-rs_b200", "rust", "surfface-b200-sys", "src", "lib.rs")).read()
     declared = set(re.findall(r"pub fn (sfb_[a-z0-9_]+)\(", rs))
     assert declared == set(declared_symbols())
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 and a C program links against the library and runs the
+    calls that need no device (the version, the error text of a refused context)."""
+    import subprocess
+    hdr_dir = os.path.join(ROOT, "include")
+    lib_dir = os.path.join(ROOT, "matternet-rs_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                           os.path.join(hdr_dir, "surfface_b200.h")])
+    src = tmp_path / "abi_smoke.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "surfface_b200.h"\n'
+        "int main(void) {\n"
+        "    sfb_knn_params p; sfb_knn_stats st; sfb_stage_times tm;\n"
+        "    (void)p; (void)st; (void)tm;\n"
+        '    printf("%d %d\\n", (int)sfb_abi_version(), SFB_ABI_VERSION);\n'
+        "    return sfb_abi_version() == SFB_ABI_VERSION ? 0 : 1;\n"
+        "}\n")
+    exe = tmp_path / "abi_smoke"
+    subprocess.check_call(["gcc", "-std=c99", "-I", hdr_dir, str(src), "-o", str(exe), "-L", lib_dir, "-lsurfface_b200",
+                           "-Wl,-rpath," + lib_dir])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert out[0] == out[1] == "4"
